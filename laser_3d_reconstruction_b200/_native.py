@@ -1,0 +1,290 @@
+"""ctypes binding of libl3d.so (include/l3d.h).
+
+There is NO CPU fallback: if the shared library is missing it is built with nvcc; if that fails, or
+if no CUDA device is visible when a context is requested, an exception is raised.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libl3d.so")
+_lib = None
+_lock = threading.Lock()
+
+
+class L3DError(RuntimeError):
+    pass
+
+
+class SgbmParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff",
+        "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")]
+
+
+class WlsParams(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("sigma_color", C.c_double), ("min_disp", C.c_int),
+                ("num_disp", C.c_int), ("dd_radius", C.c_int), ("lrc_thresh", C.c_int)]
+
+
+class DepthConfig(C.Structure):
+    _fields_ = [("left", SgbmParams), ("right", SgbmParams), ("wls", WlsParams),
+                ("use_wls", C.c_int), ("use_maps", C.c_int), ("use_Q", C.c_int), ("Q", C.c_double * 16)]
+
+
+class StegerParams(C.Structure):
+    _fields_ = [("variant", C.c_int), ("sigma", C.c_double), ("bright_thr", C.c_int),
+                ("resp_thr", C.c_double), ("roi", C.c_int * 4), ("hsv_lo", C.c_int * 3), ("hsv_hi", C.c_int * 3)]
+
+
+class ReconParams(C.Structure):
+    _fields_ = [("kind", C.c_int), ("K", C.c_double * 9), ("plane", C.c_double * 4),
+                ("use_refraction", C.c_int), ("n_water", C.c_double), ("fx", C.c_double),
+                ("baseline", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("min_disparity", C.c_double), ("window", C.c_int)]
+
+
+class PipelineConfig(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int), ("depth", DepthConfig), ("extractor", C.c_int),
+                ("steger", StegerParams), ("simple_hsv_lo", C.c_int * 3), ("simple_hsv_hi", C.c_int * 3),
+                ("simple_bright_thr", C.c_int), ("simple_min_area", C.c_double), ("recon", ReconParams),
+                ("max_points", C.c_int), ("lanes", C.c_int)]
+
+
+STEGER_FAST, STEGER_IMPROVED, STEGER_OPTIMIZED, STEGER_HYBRID = 0, 1, 2, 3
+EXTRACT_SIMPLE = 4
+RECON_PLANE, RECON_DEPTH, RECON_DISPARITY, RECON_DISPARITY_MEDIAN = 0, 1, 2, 3
+
+EXPORTS = (
+    "l3d_ctx_create l3d_ctx_destroy l3d_last_error l3d_sync l3d_device_count l3d_version l3d_launch_count "
+    "l3d_set_rectify_maps l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_debug l3d_sgbm_volume_rows "
+    "l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
+    "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_pipeline_create l3d_pipeline_destroy "
+    "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
+    "l3d_pipeline_launch_count l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
+    "l3d_host_alloc l3d_host_free l3d_dev_alloc l3d_dev_free l3d_memcpy_h2d l3d_memcpy_d2h"
+).split()
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load (building if necessary) libl3d.so.  Raises if it cannot be produced."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            from . import build as _b
+            _b.build()
+        lib = C.CDLL(_LIB_PATH)
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise L3DError("libl3d.so does not export %s" % name)
+        lib.l3d_last_error.restype = C.c_char_p
+        lib.l3d_version.restype = C.c_char_p
+        lib.l3d_launch_count.restype = C.c_longlong
+        lib.l3d_pipeline_launch_count.restype = C.c_longlong
+        lib.l3d_pipeline_last_ms.restype = C.c_float
+        lib.l3d_host_alloc.restype = C.c_void_p
+        lib.l3d_host_alloc.argtypes = [C.c_long]
+        lib.l3d_host_free.argtypes = [C.c_void_p]
+        lib.l3d_dev_alloc.restype = C.c_void_p
+        lib.l3d_dev_alloc.argtypes = [C.c_void_p, C.c_long]
+        lib.l3d_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.l3d_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        lib.l3d_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        lib.l3d_ctx_destroy.argtypes = [C.c_void_p]
+        lib.l3d_last_error.argtypes = [C.c_void_p]
+        lib.l3d_sync.argtypes = [C.c_void_p]
+        lib.l3d_launch_count.argtypes = [C.c_void_p]
+        lib.l3d_pipeline_destroy.argtypes = [C.c_void_p]
+        lib.l3d_pipeline_launch_count.argtypes = [C.c_void_p]
+        lib.l3d_pipeline_last_ms.argtypes = [C.c_void_p]
+        _lib = lib
+        return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One GPU context (stream + scratch).  Not thread-safe; create one per thread."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.l3d_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self.lib.l3d_last_error(None).decode()
+            raise L3DError("l3d_ctx_create(device=%d) failed (%d): %s" % (device, rc, msg))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.l3d_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise L3DError("%s failed (%d): %s" % (what, rc, self.lib.l3d_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return int(self.lib.l3d_launch_count(self.h))
+
+    # ---- stage wrappers (host numpy in / out) ---------------------------------------------
+    def set_rectify_maps(self, eye, mapx, mapy):
+        mapx, mapy = _arr(mapx, np.float32), _arr(mapy, np.float32)
+        if mapx.shape != mapy.shape or mapx.ndim != 2:
+            raise ValueError("rectification maps must be two HxW float32 arrays")
+        H, W = mapx.shape
+        self.check(self.lib.l3d_set_rectify_maps(self.h, int(eye), _ptr(mapx), _ptr(mapy), W, H), "l3d_set_rectify_maps")
+        return W, H
+
+    def remap_gray(self, eye, src_bgr, out_shape):
+        src = _arr(src_bgr, np.uint8)
+        if src.ndim != 3 or src.shape[2] != 3:
+            raise ValueError("remap_gray expects an HxWx3 uint8 image")
+        H, W = out_shape
+        rect = np.empty((H, W, 3), np.uint8)
+        gray = np.empty((H, W), np.uint8)
+        self.check(self.lib.l3d_remap_gray(self.h, int(eye), _ptr(src), src.shape[1], src.shape[0],
+                                           C.c_long(src.strides[0]), _ptr(rect), _ptr(gray)), "l3d_remap_gray")
+        return rect, gray
+
+    def bgr2gray(self, bgr):
+        bgr = _arr(bgr, np.uint8)
+        out = np.empty(bgr.shape[:2], np.uint8)
+        self.check(self.lib.l3d_bgr2gray(self.h, _ptr(bgr), bgr.shape[1], bgr.shape[0], _ptr(out)), "l3d_bgr2gray")
+        return out
+
+    def sgbm_compute(self, params, left, right, want_raw=False, want_volumes=False):
+        left, right = _arr(left, np.uint8), _arr(right, np.uint8)
+        if left.ndim != 2 or left.shape != right.shape:
+            raise ValueError("StereoSGBM.compute expects two single-channel uint8 images of equal size")
+        H, W = left.shape
+        disp = np.empty((H, W), np.int16)
+        raw = np.empty((H, W), np.int16) if want_raw else None
+        Cv = Sv = None
+        if want_volumes:
+            hv = self.lib.l3d_sgbm_volume_rows(C.byref(params), W, H)
+            if hv <= 0:
+                raise L3DError("unsupported StereoSGBM parameters")
+            minD, D = params.minDisparity, params.numDisparities
+            width1 = max((W + min(minD, 0)) - max(minD + D, 0), 0)
+            Cv = np.zeros((hv, width1, D), np.int16)
+            Sv = np.zeros((hv, width1, D), np.int16)
+        self.check(self.lib.l3d_sgbm_debug(self.h, C.byref(params), _ptr(left), _ptr(right), W, H, _ptr(disp),
+                                           _ptr(raw), _ptr(Cv), _ptr(Sv)), "l3d_sgbm_compute")
+        out = [disp]
+        if want_raw:
+            out.append(raw)
+        if want_volumes:
+            out += [Cv, Sv]
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def median3_s16(self, a):
+        a = _arr(a, np.int16)
+        out = np.empty_like(a)
+        self.check(self.lib.l3d_median3_s16(self.h, _ptr(a), a.shape[1], a.shape[0], _ptr(out)), "l3d_median3_s16")
+        return out
+
+    def filter_speckles(self, a, new_val, max_size, max_diff):
+        a = _arr(a, np.int16).copy()
+        self.check(self.lib.l3d_filter_speckles(self.h, _ptr(a), a.shape[1], a.shape[0], int(new_val), int(max_size),
+                                                int(max_diff)), "l3d_filter_speckles")
+        return a
+
+    def wls_filter(self, params, dl, dr, guide, want_conf=False):
+        dl, dr, guide = _arr(dl, np.int16), _arr(dr, np.int16), _arr(guide, np.uint8)
+        if dl.shape != dr.shape or dl.shape != guide.shape[:2] or guide.ndim != 2:
+            raise ValueError("wls filter expects int16 disparities and a single-channel guide of equal size")
+        H, W = dl.shape
+        out = np.empty((H, W), np.int16)
+        conf = np.empty((H, W), np.float32) if want_conf else None
+        self.check(self.lib.l3d_wls_filter(self.h, C.byref(params), _ptr(dl), _ptr(dr), _ptr(guide), W, H, _ptr(out),
+                                           _ptr(conf)), "l3d_wls_filter")
+        return (out, conf) if want_conf else out
+
+    def disp_to_depth(self, disp16, Q=None):
+        disp16 = _arr(disp16, np.int16)
+        out = np.empty(disp16.shape, np.float32)
+        q = _arr(Q, np.float64).reshape(16) if Q is not None else None
+        self.check(self.lib.l3d_disp_to_depth(self.h, _ptr(disp16), disp16.shape[1], disp16.shape[0], _ptr(q), _ptr(out)),
+                   "l3d_disp_to_depth")
+        return out
+
+    def compute_depth(self, cfg, left_bgr, right_bgr, want_disp=False):
+        l, r = _arr(left_bgr, np.uint8), _arr(right_bgr, np.uint8)
+        if l.ndim != 3 or l.shape[2] != 3 or l.shape != r.shape:
+            raise ValueError("compute_depth expects two HxWx3 uint8 images of equal size")
+        H, W = l.shape[:2]
+        rect = np.empty((H, W, 3), np.uint8)
+        depth = np.empty((H, W), np.float32)
+        disp = np.empty((H, W), np.int16) if want_disp else None
+        self.check(self.lib.l3d_compute_depth(self.h, C.byref(cfg), _ptr(l), _ptr(r), W, H, C.c_long(3 * W), _ptr(rect),
+                                              _ptr(depth), _ptr(disp)), "l3d_compute_depth")
+        return (rect, depth, disp) if want_disp else (rect, depth)
+
+    def simple_extract(self, bgr, hsv_lo, hsv_hi, bright_thr, min_area, want_masks=False):
+        bgr = _arr(bgr, np.uint8)
+        if bgr.ndim != 3 or bgr.shape[2] != 3:
+            raise ValueError("SimpleLaserExtractor expects an HxWx3 BGR uint8 image")
+        H, W = bgr.shape[:2]
+        lo = (C.c_int * 3)(*[int(v) for v in hsv_lo])
+        hi = (C.c_int * 3)(*[int(v) for v in hsv_hi])
+        xy = np.empty((H, 2), np.float64)
+        n = C.c_int(0)
+        m1 = np.empty((H, W), np.uint8) if want_masks else None
+        m2 = np.empty((H, W), np.uint8) if want_masks else None
+        self.check(self.lib.l3d_simple_extract(self.h, _ptr(bgr), W, H, lo, hi, int(bright_thr), C.c_double(min_area),
+                                               _ptr(m1), _ptr(m2), _ptr(xy), C.byref(n)), "l3d_simple_extract")
+        pts = xy[:n.value]
+        return (pts, m1, m2) if want_masks else pts
+
+    def steger_extract(self, params, img):
+        img = _arr(img, np.uint8)
+        channels = 1 if img.ndim == 2 else img.shape[2]
+        H, W = img.shape[:2]
+        cap = 4 * max(W, H) + 4096
+        while True:
+            xy = np.empty((cap, 2), np.float32)
+            n = C.c_int(0)
+            self.check(self.lib.l3d_steger_extract(self.h, C.byref(params), _ptr(img), channels, W, H, _ptr(xy), cap,
+                                                   C.byref(n)), "l3d_steger_extract")
+            if n.value <= cap:
+                return xy[:n.value]
+            cap = n.value
+
+    def reconstruct(self, params, xy, img=None):
+        xy = _arr(xy, np.float64).reshape(-1, 2)
+        n = xy.shape[0]
+        out = np.empty((max(n, 1), 3), np.float64)
+        n_out = C.c_int(0)
+        W = H = 0
+        if img is not None:
+            img = _arr(img, np.float32)
+            H, W = img.shape
+        self.check(self.lib.l3d_reconstruct(self.h, C.byref(params), _ptr(xy), n, _ptr(img), W, H, _ptr(out),
+                                            C.byref(n_out)), "l3d_reconstruct")
+        return out[:n_out.value]

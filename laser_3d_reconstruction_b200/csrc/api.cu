@@ -1,0 +1,736 @@
+// api.cu -- the C ABI of include/l3d.h: context, host<->device marshalling, frame pipeline.
+#include <stdexcept>
+
+#include "common.cuh"
+
+namespace l3d {
+
+static std::string g_create_err;
+
+void set_err(std::string* err, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (err) *err = buf;
+}
+
+void* Lane::get(Slot s, size_t bytes) {
+    DevBuf& b = bufs[s];
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return b.p;
+    if (b.p) {
+        cudaStreamSynchronize(stream);  // earlier work may still read the old buffer
+        cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        char msg[256];
+        snprintf(msg, sizeof(msg), "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        throw std::runtime_error(msg);
+    }
+    b.cap = want;
+    return b.p;
+}
+
+void Lane::release() {
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    for (auto e : ev_pool) cudaEventDestroy(e);
+    ev_pool.clear(); timers.clear(); ev_used = 0;
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+}
+
+cudaEvent_t Lane::new_event() {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_used++];
+}
+void Lane::t_begin(const char* name) {
+    if (!timing) return;
+    TimerRec r; r.a = new_event(); r.b = nullptr;
+    cudaEventRecord(r.a, stream);
+    timers[name].push_back(r);
+}
+void Lane::t_end(const char* name) {
+    if (!timing) return;
+    auto& v = timers[name];
+    if (v.empty() || v.back().b) return;
+    v.back().b = new_event();
+    cudaEventRecord(v.back().b, stream);
+}
+void Lane::t_reset() { timers.clear(); ev_used = 0; }
+
+}  // namespace l3d
+
+using namespace l3d;
+
+#define API_BEGIN(ctxp)                                                                    \
+    if (!(ctxp)) return L3D_ERR_ARG;                                                       \
+    try {
+#define API_END(ctxp)                                                                      \
+    } catch (const std::exception& ex) {                                                   \
+        (ctxp)->err = ex.what();                                                           \
+        return L3D_ERR_CUDA;                                                               \
+    }
+
+#define CK(ctxp, call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            set_err(&(ctxp)->err, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return L3D_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+#define RC(call) do { int rc__ = (call); if (rc__ != L3D_OK) return rc__; } while (0)
+#define NEED(ctxp, cond, msg) do { if (!(cond)) { set_err(&(ctxp)->err, "invalid argument: %s", msg); return L3D_ERR_ARG; } } while (0)
+
+extern "C" {
+
+const char* l3d_version(void) { return "laser3d-b200 0.1 (sm_100a)"; }
+
+int l3d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int l3d_ctx_create(int device, l3d_ctx** out) {
+    if (!out) return L3D_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_err(&g_create_err, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return L3D_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_err(&g_create_err, "device %d out of range [0,%d)", device, n); return L3D_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { set_err(&g_create_err, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return L3D_ERR_CUDA; }
+    l3d_ctx* c = new l3d_ctx();
+    c->device = device;
+    c->lane.err = &c->err;
+    e = cudaStreamCreateWithFlags(&c->lane.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_err(&g_create_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return L3D_ERR_CUDA; }
+    *out = c;
+    return L3D_OK;
+}
+
+void l3d_ctx_destroy(l3d_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->lane.release();
+    for (auto& m : ctx->maps) if (m.map) cudaFree(m.map);
+    delete ctx;
+}
+
+const char* l3d_last_error(l3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int l3d_sync(l3d_ctx* ctx) {
+    if (!ctx) return L3D_ERR_ARG;
+    CK(ctx, cudaStreamSynchronize(ctx->lane.stream));
+    return L3D_OK;
+}
+
+long long l3d_launch_count(l3d_ctx* ctx) { return ctx ? ctx->lane.launches : 0; }
+
+// ---- small helpers -----------------------------------------------------------------------
+static int h2d(l3d_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->lane.stream));
+    return L3D_OK;
+}
+static int d2h(l3d_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->lane.stream));
+    return L3D_OK;
+}
+static int set_maps(l3d_ctx* ctx, Lane& L, RectMap& m, const float* mapx, const float* mapy, int W, int H) {
+    size_t n = (size_t)W * H;
+    float* tmp = L.get<float>(S_IO_A, 2 * n);
+    CK(ctx, cudaMemcpyAsync(tmp, mapx, n * 4, cudaMemcpyHostToDevice, L.stream));
+    CK(ctx, cudaMemcpyAsync(tmp + n, mapy, n * 4, cudaMemcpyHostToDevice, L.stream));
+    if (m.map) { CK(ctx, cudaStreamSynchronize(L.stream)); cudaFree(m.map); m.map = nullptr; }
+    CK(ctx, cudaMalloc(&m.map, n * sizeof(int2)));
+    m.W = W; m.H = H;
+    RC(dev_build_rectmap(L, tmp, tmp + n, W, H, m.map));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+}
+
+int l3d_set_rectify_maps(l3d_ctx* ctx, int eye, const float* mapx, const float* mapy, int W, int H) {
+    API_BEGIN(ctx)
+    NEED(ctx, eye == 0 || eye == 1, "eye must be 0 (left) or 1 (right)");
+    NEED(ctx, mapx && mapy && W > 0 && H > 0, "maps");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return set_maps(ctx, ctx->lane, ctx->maps[eye], mapx, mapy, W, H);
+    API_END(ctx)
+}
+
+int l3d_remap_gray(l3d_ctx* ctx, int eye, const uint8_t* src_bgr, int sw, int sh, long src_stride,
+                   uint8_t* rect_bgr, uint8_t* gray) {
+    API_BEGIN(ctx)
+    NEED(ctx, eye == 0 || eye == 1, "eye");
+    NEED(ctx, src_bgr && sw > 0 && sh > 0 && src_stride >= 3L * sw, "source image");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    const RectMap& m = ctx->maps[eye];
+    NEED(ctx, m.map, "rectification maps not set for this eye");
+    size_t nsrc = (size_t)src_stride * sh, n = (size_t)m.W * m.H;
+    uint8_t* s = L.get<uint8_t>(S_SRC_L, nsrc);
+    uint8_t* r = L.get<uint8_t>(S_RECT_L, n * 3);
+    uint8_t* g = L.get<uint8_t>(S_GRAY_L, n);
+    RC(h2d(ctx, s, src_bgr, nsrc));
+    RC(dev_remap_gray(L, m, s, sw, sh, src_stride, r, g));
+    if (rect_bgr) RC(d2h(ctx, rect_bgr, r, n * 3));
+    if (gray) RC(d2h(ctx, gray, g, n));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_bgr2gray(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray) {
+    API_BEGIN(ctx)
+    NEED(ctx, bgr && gray && W > 0 && H > 0, "image");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    uint8_t* s = L.get<uint8_t>(S_SRC_L, n * 3);
+    uint8_t* g = L.get<uint8_t>(S_GRAY_L, n);
+    RC(h2d(ctx, s, bgr, n * 3));
+    RC(dev_copy_gray(L, s, W, H, 3L * W, nullptr, g));
+    RC(d2h(ctx, gray, g, n));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_sgbm_volume_rows(const l3d_sgbm_params* p, int W, int H) { return p ? sgbm_volume_rows(*p, W, H) : -1; }
+
+int l3d_sgbm_debug(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left, const uint8_t* right,
+                   int W, int H, int16_t* disp, int16_t* raw, int16_t* C_out, int16_t* S_out) {
+    API_BEGIN(ctx)
+    NEED(ctx, p && left && right && disp && W > 0 && H > 0, "sgbm arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    uint8_t* l = L.get<uint8_t>(S_GRAY_L, n);
+    uint8_t* r = L.get<uint8_t>(S_GRAY_R, n);
+    int16_t* d = L.get<int16_t>(S_DISP_L, n);
+    RC(h2d(ctx, l, left, n));
+    RC(h2d(ctx, r, right, n));
+    SgbmDebug dbg;
+    size_t nvol = 0;
+    if (C_out || S_out) {
+        int hv = sgbm_volume_rows(*p, W, H);
+        NEED(ctx, hv > 0, "sgbm parameters");
+        int minD = p->minDisparity, D = p->numDisparities;
+        int width1 = (W + std::min(minD, 0)) - std::max(minD + D, 0);
+        nvol = width1 > 0 ? (size_t)hv * width1 * D : 0;
+        if (nvol) {
+            int16_t* vols = L.get<int16_t>(S_IO_B, nvol * 2);
+            if (C_out) dbg.C = vols;
+            if (S_out) dbg.S = vols + nvol;
+        }
+    }
+    if (raw) dbg.raw = L.get<int16_t>(S_IO_C, n);
+    RC(dev_sgbm(L, *p, l, r, W, H, d, &dbg));
+    RC(d2h(ctx, disp, d, n * 2));
+    if (raw) RC(d2h(ctx, raw, dbg.raw, n * 2));
+    if (C_out && dbg.C) RC(d2h(ctx, C_out, dbg.C, nvol * 2));
+    if (S_out && dbg.S) RC(d2h(ctx, S_out, dbg.S, nvol * 2));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_sgbm_compute(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left, const uint8_t* right,
+                     int W, int H, int16_t* disp) {
+    return l3d_sgbm_debug(ctx, p, left, right, W, H, disp, nullptr, nullptr, nullptr);
+}
+
+int l3d_median3_s16(l3d_ctx* ctx, const int16_t* src, int W, int H, int16_t* dst) {
+    API_BEGIN(ctx)
+    NEED(ctx, src && dst && W > 0 && H > 0, "image");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    int16_t* a = L.get<int16_t>(S_DISP_L, n);
+    int16_t* b = L.get<int16_t>(S_DISP_R, n);
+    RC(h2d(ctx, a, src, n * 2));
+    RC(dev_median3(L, a, W, H, b));
+    RC(d2h(ctx, dst, b, n * 2));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_filter_speckles(l3d_ctx* ctx, int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff) {
+    API_BEGIN(ctx)
+    NEED(ctx, img && W > 0 && H > 0, "image");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    int16_t* a = L.get<int16_t>(S_DISP_L, n);
+    RC(h2d(ctx, a, img, n * 2));
+    RC(dev_speckles(L, a, W, H, newVal, maxSize, maxDiff));
+    RC(d2h(ctx, img, a, n * 2));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_wls_filter(l3d_ctx* ctx, const l3d_wls_params* p, const int16_t* dl, const int16_t* dr,
+                   const uint8_t* guide, int W, int H, int16_t* out, float* conf_out) {
+    API_BEGIN(ctx)
+    NEED(ctx, p && dl && dr && guide && out && W > 0 && H > 0, "wls arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    int16_t* a = L.get<int16_t>(S_DISP_L, n);
+    int16_t* b = L.get<int16_t>(S_DISP_R, n);
+    int16_t* o = L.get<int16_t>(S_DISP_F, n);
+    uint8_t* g = L.get<uint8_t>(S_GRAY_L, n);
+    float* cf = conf_out ? L.get<float>(S_IO_A, n) : nullptr;
+    RC(h2d(ctx, a, dl, n * 2));
+    RC(h2d(ctx, b, dr, n * 2));
+    RC(h2d(ctx, g, guide, n));
+    RC(dev_wls(L, *p, a, b, g, W, H, o, cf));
+    RC(d2h(ctx, out, o, n * 2));
+    if (conf_out) RC(d2h(ctx, conf_out, cf, n * 4));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_disp_to_depth(l3d_ctx* ctx, const int16_t* disp16, int W, int H, const double* Q, float* depth) {
+    API_BEGIN(ctx)
+    NEED(ctx, disp16 && depth && W > 0 && H > 0, "depth arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    int16_t* a = L.get<int16_t>(S_DISP_F, n);
+    float* d = L.get<float>(S_DEPTH, n);
+    RC(h2d(ctx, a, disp16, n * 2));
+    RC(dev_depth(L, a, W, H, Q, d));
+    RC(d2h(ctx, depth, d, n * 4));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+// get_frames() depth path on device buffers (camera/single_usb_stereo_camera.py:311-359)
+static int depth_path(Lane& L, const l3d_depth_config& cfg, const RectMap* maps, const uint8_t* lsrc,
+                      const uint8_t* rsrc, int W, int H, long stride, uint8_t* rectL, float* depth, int16_t* disp_f) {
+    size_t n = (size_t)W * H;
+    uint8_t* gl = L.get<uint8_t>(S_GRAY_L, n);
+    uint8_t* gr = L.get<uint8_t>(S_GRAY_R, n);
+    if (cfg.use_maps) {
+        L3D_ARG(L, maps[0].map && maps[1].map, "rectification maps not set");
+        L3D_ARG(L, maps[0].W == W && maps[0].H == H && maps[1].W == W && maps[1].H == H, "map size != image size");
+        RC(dev_remap_gray(L, maps[0], lsrc, W, H, stride, rectL, gl));
+        RC(dev_remap_gray(L, maps[1], rsrc, W, H, stride, nullptr, gr));
+    } else {
+        RC(dev_copy_gray(L, lsrc, W, H, stride, rectL, gl));
+        RC(dev_copy_gray(L, rsrc, W, H, stride, nullptr, gr));
+    }
+    int16_t* dl = L.get<int16_t>(S_DISP_L, n);
+    RC(dev_sgbm(L, cfg.left, gl, gr, W, H, dl, nullptr));
+    const int16_t* df = dl;
+    if (cfg.use_wls) {
+        int16_t* dr = L.get<int16_t>(S_DISP_R, n);
+        RC(dev_sgbm(L, cfg.right, gr, gl, W, H, dr, nullptr));
+        RC(dev_wls(L, cfg.wls, dl, dr, gl, W, H, disp_f, nullptr));
+        df = disp_f;
+    } else {
+        L3D_CHECK(L, cudaMemcpyAsync(disp_f, dl, n * 2, cudaMemcpyDeviceToDevice, L.stream));
+    }
+    RC(dev_depth(L, df, W, H, cfg.use_Q ? cfg.Q : nullptr, depth));
+    return L3D_OK;
+}
+
+int l3d_compute_depth(l3d_ctx* ctx, const l3d_depth_config* cfg, const uint8_t* left_bgr, const uint8_t* right_bgr,
+                      int W, int H, long stride, uint8_t* left_rect, float* depth, int16_t* disp_out) {
+    API_BEGIN(ctx)
+    NEED(ctx, cfg && left_bgr && right_bgr && depth && W > 0 && H > 0 && stride >= 3L * W, "compute_depth arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H, ns = (size_t)stride * H;
+    uint8_t* sl = L.get<uint8_t>(S_SRC_L, ns);
+    uint8_t* sr = L.get<uint8_t>(S_SRC_R, ns);
+    uint8_t* rl = L.get<uint8_t>(S_RECT_L, n * 3);
+    float* dp = L.get<float>(S_DEPTH, n);
+    int16_t* df = L.get<int16_t>(S_DISP_F, n);
+    RC(h2d(ctx, sl, left_bgr, ns));
+    RC(h2d(ctx, sr, right_bgr, ns));
+    RC(depth_path(L, *cfg, ctx->maps, sl, sr, W, H, stride, rl, dp, df));
+    if (left_rect) RC(d2h(ctx, left_rect, rl, n * 3));
+    RC(d2h(ctx, depth, dp, n * 4));
+    if (disp_out) RC(d2h(ctx, disp_out, df, n * 2));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_simple_extract(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, const int* hsv_lo, const int* hsv_hi,
+                       int bright_thr, double min_area, uint8_t* mask_morph, uint8_t* mask_final, double* xy, int* n) {
+    API_BEGIN(ctx)
+    NEED(ctx, bgr && hsv_lo && hsv_hi && xy && n && W > 0 && H > 0, "simple_extract arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t np = (size_t)W * H;
+    uint8_t* s = L.get<uint8_t>(S_SRC_L, np * 3);
+    uint8_t* mm = L.get<uint8_t>(S_IO_A, np * 2);
+    double* dxy = L.get<double>(S_SM_XY, (size_t)2 * H + 2);
+    int* dn = (int*)L.get(S_ST_N, 16);
+    RC(h2d(ctx, s, bgr, np * 3));
+    RC(dev_simple(L, s, W, H, hsv_lo, hsv_hi, bright_thr, min_area, mask_morph ? mm : nullptr,
+                  mask_final ? mm + np : nullptr, dxy, dn));
+    RC(d2h(ctx, n, dn, sizeof(int)));
+    if (mask_morph) RC(d2h(ctx, mask_morph, mm, np));
+    if (mask_final) RC(d2h(ctx, mask_final, mm + np, np));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    if (*n > 0) { RC(d2h(ctx, xy, dxy, sizeof(double) * 2 * (size_t)*n)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_steger_extract(l3d_ctx* ctx, const l3d_steger_params* p, const uint8_t* img, int channels, int W, int H,
+                       float* xy, int cap, int* n) {
+    API_BEGIN(ctx)
+    NEED(ctx, p && img && xy && n && cap >= 0 && W > 0 && H > 0, "steger_extract arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t nb = (size_t)W * H * channels;
+    uint8_t* s = L.get<uint8_t>(S_SRC_L, nb);
+    float* dxy = L.get<float>(S_ST_XY, (size_t)2 * std::max(cap, 1));
+    int* dn = (int*)L.get(S_ST_N, 16);
+    RC(h2d(ctx, s, img, nb));
+    RC(dev_steger(L, *p, s, channels, W, H, dxy, cap, dn));
+    RC(d2h(ctx, n, dn, sizeof(int)));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    int m = std::min(*n, cap);
+    if (m > 0) { RC(d2h(ctx, xy, dxy, sizeof(float) * 2 * (size_t)m)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_reconstruct(l3d_ctx* ctx, const l3d_recon_params* p, const double* xy, int n, const float* img, int W,
+                    int H, double* xyz, int* n_out) {
+    API_BEGIN(ctx)
+    NEED(ctx, p && n_out && n >= 0, "reconstruct arguments");
+    *n_out = 0;
+    if (n == 0) return L3D_OK;
+    NEED(ctx, xy && xyz, "reconstruct buffers");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    double* dxy = L.get<double>(S_RC_XY, (size_t)2 * n);
+    double* dxyz = L.get<double>(S_IO_D, (size_t)3 * n);
+    int* dn = (int*)L.get(S_IO_E, 16);
+    float* dimg = nullptr;
+    if (p->kind != L3D_RECON_PLANE) {
+        NEED(ctx, img && W > 0 && H > 0, "reconstruct needs a depth/disparity map");
+        dimg = L.get<float>(S_DEPTH, (size_t)W * H);
+        RC(h2d(ctx, dimg, img, (size_t)W * H * 4));
+    }
+    RC(h2d(ctx, dxy, xy, sizeof(double) * 2 * (size_t)n));
+    RC(dev_recon(L, *p, dxy, nullptr, nullptr, n, dimg, W, H, dxyz, dn));
+    RC(d2h(ctx, n_out, dn, sizeof(int)));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    if (*n_out > 0) { RC(d2h(ctx, xyz, dxyz, sizeof(double) * 3 * (size_t)*n_out)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    return L3D_OK;
+    API_END(ctx)
+}
+
+// ---- raw helpers ---------------------------------------------------------------------------
+void* l3d_host_alloc(long bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void l3d_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* l3d_dev_alloc(l3d_ctx* ctx, long bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { set_err(&ctx->err, "cudaMalloc(%ld) failed", bytes); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void l3d_dev_free(l3d_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+int l3d_memcpy_h2d(l3d_ctx* ctx, void* dst_dev, const void* src, long bytes) {
+    if (!ctx) return L3D_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpy(dst_dev, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return L3D_OK;
+}
+int l3d_memcpy_d2h(l3d_ctx* ctx, void* dst, const void* src_dev, long bytes) {
+    if (!ctx) return L3D_ERR_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpy(dst, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return L3D_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================================
+// frame pipeline: nframes independent frames over `lanes` streams
+// ============================================================================================
+struct FrameOut {
+    uint8_t* rect = nullptr; float* depth = nullptr; int16_t* disp = nullptr;
+    float* xy = nullptr; double* xy64 = nullptr; double* xyz = nullptr; int* n_xy = nullptr; int* n_xyz = nullptr;
+};
+
+struct l3d_pipeline {
+    l3d_ctx* ctx = nullptr;
+    l3d_pipeline_config cfg;
+    std::vector<Lane> lanes;
+    RectMap maps[2];
+    std::vector<FrameOut> outs;   // per frame slot
+    void* arena = nullptr; size_t arena_cap = 0;
+    int* counts_host = nullptr;   // pinned, 2*nframes
+    int counts_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> lane_done;
+    cudaStream_t main = nullptr;
+    float last_ms = 0.f;
+    int last_frames = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int pipe_prepare(l3d_pipeline* p, int nframes) {
+    l3d_ctx* ctx = p->ctx;
+    const int W = p->cfg.W, H = p->cfg.H, cap = p->cfg.max_points;
+    size_t n = (size_t)W * H;
+    size_t per = align_up(n * 3, 256) + align_up(n * 4, 256) + align_up(n * 2, 256) + align_up((size_t)cap * 8, 256) +
+                 align_up((size_t)cap * 16, 256) + align_up((size_t)cap * 24, 256) + 512;
+    size_t need = per * nframes;
+    if (need > p->arena_cap) {
+        for (auto& L : p->lanes) CK(ctx, cudaStreamSynchronize(L.stream));
+        if (p->arena) cudaFree(p->arena);
+        p->arena = nullptr; p->arena_cap = 0;
+        CK(ctx, cudaMalloc(&p->arena, need));
+        p->arena_cap = need;
+        p->outs.clear();
+    }
+    if ((int)p->outs.size() < nframes) {
+        p->outs.resize(nframes);
+        char* base = (char*)p->arena;
+        for (int f = 0; f < nframes; f++) {
+            char* q = base + per * f;
+            FrameOut& o = p->outs[f];
+            o.rect = (uint8_t*)q; q += align_up(n * 3, 256);
+            o.depth = (float*)q; q += align_up(n * 4, 256);
+            o.disp = (int16_t*)q; q += align_up(n * 2, 256);
+            o.xy = (float*)q; q += align_up((size_t)cap * 8, 256);
+            o.xy64 = (double*)q; q += align_up((size_t)cap * 16, 256);
+            o.xyz = (double*)q; q += align_up((size_t)cap * 24, 256);
+            o.n_xy = (int*)q; o.n_xyz = (int*)(q + 256);
+        }
+    }
+    if (p->counts_cap < nframes) {
+        if (p->counts_host) cudaFreeHost(p->counts_host);
+        CK(ctx, cudaMallocHost(&p->counts_host, sizeof(int) * 2 * (size_t)nframes));
+        p->counts_cap = nframes;
+    }
+    return L3D_OK;
+}
+
+// enqueue one frame on lane L (all device pointers)
+static int pipe_frame(l3d_pipeline* p, Lane& L, const uint8_t* l, const uint8_t* r, FrameOut& o) {
+    const l3d_pipeline_config& c = p->cfg;
+    const int W = c.W, H = c.H;
+    RC(depth_path(L, c.depth, p->maps, l, r, W, H, 3L * W, o.rect, o.depth, o.disp));
+    if (c.extractor < 0) {
+        L3D_CHECK(L, cudaMemsetAsync(o.n_xy, 0, sizeof(int), L.stream));
+        L3D_CHECK(L, cudaMemsetAsync(o.n_xyz, 0, sizeof(int), L.stream));
+        return L3D_OK;
+    }
+    const double* xy64 = nullptr; const float* xy32 = nullptr;
+    if (c.extractor == 4) {
+        RC(dev_simple(L, o.rect, W, H, c.simple_hsv_lo, c.simple_hsv_hi, c.simple_bright_thr, c.simple_min_area,
+                      nullptr, nullptr, o.xy64, o.n_xy));
+        xy64 = o.xy64;
+    } else {
+        RC(dev_steger(L, c.steger, o.rect, 3, W, H, o.xy, c.max_points, o.n_xy));
+        xy32 = o.xy;
+    }
+    const float* img = (c.recon.kind == L3D_RECON_PLANE) ? nullptr : o.depth;
+    RC(dev_recon(L, c.recon, xy64, xy32, o.n_xy, c.max_points, img, W, H, o.xyz, o.n_xyz));
+    return L3D_OK;
+}
+
+extern "C" {
+
+int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeline** out) {
+    API_BEGIN(ctx)
+    NEED(ctx, cfg && out, "pipeline_create arguments");
+    NEED(ctx, cfg->W > 1 && cfg->H > 0 && cfg->lanes >= 1 && cfg->lanes <= 64 && cfg->max_points > 0, "pipeline config");
+    NEED(ctx, cfg->extractor >= -1 && cfg->extractor <= 4, "pipeline extractor");
+    if (cfg->extractor == 4) NEED(ctx, cfg->max_points >= cfg->H, "max_points must be >= H for the Simple extractor");
+    CK(ctx, cudaSetDevice(ctx->device));
+    l3d_pipeline* p = new l3d_pipeline();
+    p->ctx = ctx; p->cfg = *cfg;
+    p->lanes.resize(cfg->lanes);
+    for (auto& L : p->lanes) {
+        L.err = &ctx->err;
+        CK(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    }
+    CK(ctx, cudaStreamCreateWithFlags(&p->main, cudaStreamNonBlocking));
+    CK(ctx, cudaEventCreate(&p->ev0));
+    CK(ctx, cudaEventCreate(&p->ev1));
+    p->lane_done.resize(cfg->lanes);
+    for (auto& e : p->lane_done) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = p;
+    return L3D_OK;
+    API_END(ctx)
+}
+
+void l3d_pipeline_destroy(l3d_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    for (auto& L : p->lanes) L.release();
+    for (auto& m : p->maps) if (m.map) cudaFree(m.map);
+    if (p->arena) cudaFree(p->arena);
+    if (p->counts_host) cudaFreeHost(p->counts_host);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    for (auto e : p->lane_done) cudaEventDestroy(e);
+    if (p->main) cudaStreamDestroy(p->main);
+    delete p;
+}
+
+int l3d_pipeline_set_maps(l3d_pipeline* p, int eye, const float* mapx, const float* mapy) {
+    if (!p) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    API_BEGIN(ctx)
+    NEED(ctx, (eye == 0 || eye == 1) && mapx && mapy, "pipeline_set_maps arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return set_maps(ctx, p->lanes[0], p->maps[eye], mapx, mapy, p->cfg.W, p->cfg.H);
+    API_END(ctx)
+}
+
+static int pipe_run(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, bool host_in, int nframes,
+                    float* depth_h, double* xyz_h, int* counts) {
+    l3d_ctx* ctx = p->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    RC(pipe_prepare(p, nframes));
+    const int W = p->cfg.W, H = p->cfg.H, cap = p->cfg.max_points;
+    const size_t nb = (size_t)W * H * 3, n = (size_t)W * H;
+    const int nl = (int)p->lanes.size();
+    for (auto& L : p->lanes) L.t_reset();
+    CK(ctx, cudaEventRecord(p->ev0, p->main));
+    for (auto& L : p->lanes) CK(ctx, cudaStreamWaitEvent(L.stream, p->ev0, 0));
+    for (int f = 0; f < nframes; f++) {
+        Lane& L = p->lanes[f % nl];
+        FrameOut& o = p->outs[f];
+        const uint8_t *l = left + nb * f, *r = right + nb * f;
+        if (host_in) {
+            uint8_t* sl = L.get<uint8_t>(S_SRC_L, nb);
+            uint8_t* sr = L.get<uint8_t>(S_SRC_R, nb);
+            L3D_CHECK(L, cudaMemcpyAsync(sl, l, nb, cudaMemcpyHostToDevice, L.stream));
+            L3D_CHECK(L, cudaMemcpyAsync(sr, r, nb, cudaMemcpyHostToDevice, L.stream));
+            l = sl; r = sr;
+        }
+        RC(pipe_frame(p, L, l, r, o));
+        L3D_CHECK(L, cudaMemcpyAsync(p->counts_host + 2 * f, o.n_xy, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+        L3D_CHECK(L, cudaMemcpyAsync(p->counts_host + 2 * f + 1, o.n_xyz, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+        if (depth_h) L3D_CHECK(L, cudaMemcpyAsync(depth_h + n * f, o.depth, n * 4, cudaMemcpyDeviceToHost, L.stream));
+        if (xyz_h) L3D_CHECK(L, cudaMemcpyAsync(xyz_h + (size_t)cap * 3 * f, o.xyz, (size_t)cap * 24, cudaMemcpyDeviceToHost, L.stream));
+    }
+    for (int i = 0; i < nl; i++) {
+        CK(ctx, cudaEventRecord(p->lane_done[i], p->lanes[i].stream));
+        CK(ctx, cudaStreamWaitEvent(p->main, p->lane_done[i], 0));
+    }
+    CK(ctx, cudaEventRecord(p->ev1, p->main));
+    CK(ctx, cudaEventSynchronize(p->ev1));
+    CK(ctx, cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+    p->last_frames = nframes;
+    if (counts) for (int f = 0; f < nframes; f++) counts[f] = p->counts_host[2 * f + 1];
+    return L3D_OK;
+}
+
+int l3d_pipeline_run_dev(l3d_pipeline* p, const uint8_t* left_dev, const uint8_t* right_dev, int nframes, int* counts) {
+    if (!p) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    API_BEGIN(ctx)
+    NEED(ctx, left_dev && right_dev && nframes > 0, "pipeline_run_dev arguments");
+    return pipe_run(p, left_dev, right_dev, false, nframes, nullptr, nullptr, counts);
+    API_END(ctx)
+}
+
+int l3d_pipeline_run_host(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, int nframes, float* depth,
+                          double* xyz, int* counts) {
+    if (!p) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    API_BEGIN(ctx)
+    NEED(ctx, left && right && nframes > 0, "pipeline_run_host arguments");
+    return pipe_run(p, left, right, true, nframes, depth, xyz, counts);
+    API_END(ctx)
+}
+
+int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* depth, int16_t* disp, float* xy,
+                       double* xyz, int* n_xy, int* n_xyz) {
+    if (!p) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    API_BEGIN(ctx)
+    NEED(ctx, frame >= 0 && frame < p->last_frames, "frame index");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const FrameOut& o = p->outs[frame];
+    size_t n = (size_t)p->cfg.W * p->cfg.H;
+    int nxy = p->counts_host[2 * frame], nxyz = p->counts_host[2 * frame + 1];
+    if (n_xy) *n_xy = nxy;
+    if (n_xyz) *n_xyz = nxyz;
+    if (left_rect) CK(ctx, cudaMemcpy(left_rect, o.rect, n * 3, cudaMemcpyDeviceToHost));
+    if (depth) CK(ctx, cudaMemcpy(depth, o.depth, n * 4, cudaMemcpyDeviceToHost));
+    if (disp) CK(ctx, cudaMemcpy(disp, o.disp, n * 2, cudaMemcpyDeviceToHost));
+    int m = std::min(nxy, p->cfg.max_points);
+    if (xy && m > 0) {
+        if (p->cfg.extractor == 4) {
+            std::vector<double> t((size_t)2 * m);
+            CK(ctx, cudaMemcpy(t.data(), o.xy64, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 2 * m; i++) xy[i] = (float)t[i];
+        } else CK(ctx, cudaMemcpy(xy, o.xy, sizeof(float) * 2 * m, cudaMemcpyDeviceToHost));
+    }
+    if (xyz && nxyz > 0) CK(ctx, cudaMemcpy(xyz, o.xyz, sizeof(double) * 3 * nxyz, cudaMemcpyDeviceToHost));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+long long l3d_pipeline_launch_count(l3d_pipeline* p) {
+    long long s = 0;
+    if (p) for (auto& L : p->lanes) s += L.launches;
+    return s;
+}
+
+int l3d_pipeline_set_timing(l3d_pipeline* p, int on) {
+    if (!p) return L3D_ERR_ARG;
+    for (auto& L : p->lanes) L.timing = on != 0;
+    return L3D_OK;
+}
+
+float l3d_pipeline_last_ms(l3d_pipeline* p) { return p ? p->last_ms : 0.f; }
+
+int l3d_pipeline_kernel_time(l3d_pipeline* p, const char* which, float* ms, int* launches) {
+    if (!p || !which || !ms || !launches) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    float tot = 0.f; int cnt = 0;
+    for (auto& L : p->lanes) {
+        auto it = L.timers.find(which);
+        if (it == L.timers.end()) continue;
+        for (auto& r : it->second) {
+            if (!r.b) continue;
+            float t = 0.f;
+            CK(ctx, cudaEventSynchronize(r.b));
+            CK(ctx, cudaEventElapsedTime(&t, r.a, r.b));
+            tot += t; cnt++;
+        }
+    }
+    *ms = tot; *launches = cnt;
+    return L3D_OK;
+}
+
+}  // extern "C"

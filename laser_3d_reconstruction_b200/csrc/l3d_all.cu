@@ -1,0 +1,11 @@
+// l3d_all.cu -- single translation unit of libl3d.so (kernels launch each other's helpers, so
+// everything is compiled together without relocatable device code).
+#include "common.cuh"
+#include "ccl.cuh"
+#include "remap.cu"
+#include "sgbm.cu"
+#include "post.cu"
+#include "wls.cu"
+#include "laser.cu"
+#include "recon.cu"
+#include "api.cu"

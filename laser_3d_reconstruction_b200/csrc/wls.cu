@@ -1,0 +1,272 @@
+// wls.cu -- K3: confidence-weighted WLS disparity filter + K5a disparity -> depth.
+// Replaces wls_filter.filter(dl, left_gray, disparity_map_right=dr) and the depth conversion of
+// the reference (camera/single_usb_stereo_camera.py:277-282 setup, :328-346).
+//
+// cv2.ximgproc is absent from the image, so this follows the published opencv_contrib algorithm
+// (disparity_filters.cpp + fgs_filter.cpp) as restated in oracle/csrc/orc_wls.c; every f32
+// operation is issued unfused and in the oracle's order, so the two agree bit for bit.
+//
+// Stages (ROI = columns [x0, W), x0 = max(0, minD + numD)):
+//   wls_hbox / wls_vbox_conf   (2r+1)^2 box mean of d and d^2 -> variance -> 1 - 0.001 var
+//   wls_lrc                    LR-consistency confidence, FGS right-hand sides, guide weights
+//   fgs_hpass / fgs_vpass      3 x (row solves, column solves), Thomas algorithm, one line per
+//                              thread, numerator and denominator solved together
+//   wls_finalize               num/(den+eps) -> int16 (half-even, saturated)
+#include "common.cuh"
+
+namespace l3d {
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+// horizontal (2r+1) sums of d and d*d for the left ROI (x0..) and the right ROI (0..)
+__global__ void wls_hbox_kernel(const int16_t* __restrict__ dl, const int16_t* __restrict__ dr, int W, int x0,
+                                int w, int h, int r, float* __restrict__ aL, float* __restrict__ bL,
+                                float* __restrict__ aR, float* __restrict__ bR) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const int16_t* rl = dl + (size_t)y * W + x0;
+    const int16_t* rr = dr + (size_t)y * W;
+    float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f;
+    for (int k = -r; k <= r; k++) {
+        int xx = reflect101(x + k, w);
+        float v = (float)rl[xx], u = (float)rr[xx];
+        sa = __fadd_rn(sa, v); sb = __fadd_rn(sb, __fmul_rn(v, v));
+        ta = __fadd_rn(ta, u); tb = __fadd_rn(tb, __fmul_rn(u, u));
+    }
+    size_t i = (size_t)y * w + x;
+    aL[i] = sa; bL[i] = sb; aR[i] = ta; bR[i] = tb;
+}
+
+__global__ void wls_vbox_conf_kernel(const float* __restrict__ aL, const float* __restrict__ bL,
+                                     const float* __restrict__ aR, const float* __restrict__ bR, int w, int h,
+                                     int r, float* __restrict__ cl, float* __restrict__ cr) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const float inv = __fdiv_rn(1.0f, (float)((2 * r + 1) * (2 * r + 1)));
+    float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f;
+    for (int k = -r; k <= r; k++) {
+        size_t j = (size_t)reflect101(y + k, h) * w + x;
+        sa = __fadd_rn(sa, aL[j]); sb = __fadd_rn(sb, bL[j]);
+        ta = __fadd_rn(ta, aR[j]); tb = __fadd_rn(tb, bR[j]);
+    }
+    float ma = __fmul_rn(sa, inv), mb = __fmul_rn(sb, inv);
+    float c = __fsub_rn(1.0f, __fmul_rn(0.001f, __fsub_rn(mb, __fmul_rn(ma, ma))));
+    size_t i = (size_t)y * w + x;
+    cl[i] = c < 0.f ? 0.f : c;
+    ma = __fmul_rn(ta, inv); mb = __fmul_rn(tb, inv);
+    c = __fsub_rn(1.0f, __fmul_rn(0.001f, __fsub_rn(mb, __fmul_rn(ma, ma))));
+    cr[i] = c < 0.f ? 0.f : c;
+}
+
+__global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __restrict__ dr,
+                               const uint8_t* __restrict__ guide, const float* __restrict__ lut, int W, int x0,
+                               int w, int h, int thresh, const float* __restrict__ cl, const float* __restrict__ cr,
+                               float* __restrict__ conf, float* __restrict__ num, float* __restrict__ den,
+                               float* __restrict__ ch, float* __restrict__ cv) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    size_t i = (size_t)y * w + x;
+    int j = x0 + x;
+    int l = dl[(size_t)y * W + j];
+    int ridx = j - (l >> 4);
+    float c = cl[i];
+    if (ridx >= 0 && ridx < w) {
+        int rr = dr[(size_t)y * W + ridx];
+        if (abs(l + rr) < thresh) c = fminf(c, cr[(size_t)y * w + ridx]);
+        else c = 0.f;
+    }
+    c = __fmul_rn(255.0f, c);
+    conf[i] = c;
+    num[i] = __fmul_rn(c, (float)l);
+    den[i] = c;
+    int g = guide[(size_t)y * W + j];
+    float wx = 0.f, wy = 0.f;
+    if (x < w - 1) { int d = g - (int)guide[(size_t)y * W + j + 1]; wx = lut[d * d]; }
+    if (y < h - 1) { int d = g - (int)guide[(size_t)(y + 1) * W + j]; wy = lut[d * d]; }
+    ch[i] = wx; cv[i] = wy;
+}
+
+// Thomas solve along rows; one thread per row, num and den share the elimination factors.
+__global__ void fgs_hpass_kernel(float* __restrict__ num, float* __restrict__ den, const float* __restrict__ ch,
+                                 float* __restrict__ interD, int w, int h, float lam) {
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    float* a = num + (size_t)y * w;
+    float* b = den + (size_t)y * w;
+    const float* c = ch + (size_t)y * w;
+    float* Dv = interD + (size_t)y * w;
+    float c0 = c[0];
+    float dn = __fsub_rn(1.0f, __fmul_rn(lam, c0));
+    float Dp = __fdiv_rn(__fmul_rn(lam, c0), dn);
+    float ap = __fdiv_rn(a[0], dn), bp = __fdiv_rn(b[0], dn);
+    Dv[0] = Dp; a[0] = ap; b[0] = bp;
+    float cm = c0;
+    for (int j = 1; j < w; j++) {
+        float cc = c[j];
+        float lcm = __fmul_rn(lam, cm);
+        dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cc))), __fmul_rn(lcm, Dp));
+        Dp = __fdiv_rn(__fmul_rn(lam, cc), dn);
+        ap = __fdiv_rn(__fsub_rn(a[j], __fmul_rn(lcm, ap)), dn);
+        bp = __fdiv_rn(__fsub_rn(b[j], __fmul_rn(lcm, bp)), dn);
+        Dv[j] = Dp; a[j] = ap; b[j] = bp;
+        cm = cc;
+    }
+    for (int j = w - 2; j >= 0; j--) {
+        float d = Dv[j];
+        ap = __fsub_rn(a[j], __fmul_rn(d, ap));
+        bp = __fsub_rn(b[j], __fmul_rn(d, bp));
+        a[j] = ap; b[j] = bp;
+    }
+}
+
+// Thomas solve along columns; one thread per column (coalesced rows).
+__global__ void fgs_vpass_kernel(float* __restrict__ num, float* __restrict__ den, const float* __restrict__ cv,
+                                 float* __restrict__ interD, int w, int h, float lam) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    float c0 = cv[x];
+    float dn = __fsub_rn(1.0f, __fmul_rn(lam, c0));
+    float Dp = __fdiv_rn(__fmul_rn(lam, c0), dn);
+    float ap = __fdiv_rn(num[x], dn), bp = __fdiv_rn(den[x], dn);
+    interD[x] = Dp; num[x] = ap; den[x] = bp;
+    float cm = c0;
+    for (int j = 1; j < h; j++) {
+        size_t i = (size_t)j * w + x;
+        float cc = cv[i];
+        float lcm = __fmul_rn(lam, cm);
+        dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cc))), __fmul_rn(lcm, Dp));
+        Dp = __fdiv_rn(__fmul_rn(lam, cc), dn);
+        ap = __fdiv_rn(__fsub_rn(num[i], __fmul_rn(lcm, ap)), dn);
+        bp = __fdiv_rn(__fsub_rn(den[i], __fmul_rn(lcm, bp)), dn);
+        interD[i] = Dp; num[i] = ap; den[i] = bp;
+        cm = cc;
+    }
+    for (int j = h - 2; j >= 0; j--) {
+        size_t i = (size_t)j * w + x;
+        float d = interD[i];
+        ap = __fsub_rn(num[i], __fmul_rn(d, ap));
+        bp = __fsub_rn(den[i], __fmul_rn(d, bp));
+        num[i] = ap; den[i] = bp;
+    }
+}
+
+__global__ void wls_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
+                                    const float* __restrict__ conf, int W, int H, int x0, int w, int outside,
+                                    int16_t* __restrict__ out, float* __restrict__ conf_out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    size_t o = (size_t)y * W + x;
+    if (x < x0) { out[o] = (int16_t)outside; if (conf_out) conf_out[o] = 0.f; return; }
+    size_t i = (size_t)y * w + (x - x0);
+    float v = __fmul_rn(num[i], __fdiv_rn(1.0f, __fadd_rn(den[i], 1e-43f)));
+    int q;
+    if (!(fabsf(v) < 2147483648.f)) q = -32768;  // NaN / |v| >= 2^31: cvRound gives INT_MIN
+    else if (v >= 32767.f) q = 32767;
+    else if (v <= -32768.f) q = -32768;
+    else q = __float2int_rn(v);
+    out[o] = (int16_t)q;
+    if (conf_out) conf_out[o] = conf[i];
+}
+
+// exp LUT for the guide weights: lut[k] = -exp(-sqrt(k)/sigma), k = squared grey difference
+static int wls_lut(Lane& L, double sigma, float** out) {
+    float* dev = L.get<float>(S_WLS_K, 65536);
+    if (L.wls_lut_sigma != sigma) {  // per-lane device copy, rebuilt only when sigma changes
+        std::vector<float> host(65536);
+        for (int i = 0; i < 65536; i++) host[i] = (float)(-exp(-sqrt((double)(float)i) / sigma));
+        L3D_CHECK(L, cudaMemcpyAsync(dev, host.data(), 65536 * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        L3D_CHECK(L, cudaStreamSynchronize(L.stream));
+        L.wls_lut_sigma = sigma;
+    }
+    *out = dev;
+    return L3D_OK;
+}
+
+int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* dr, const uint8_t* guide,
+            int W, int H, int16_t* out, float* conf_out) {
+    int x0 = std::max(0, p.min_disp + p.num_disp);
+    int w = W - x0, h = H;
+    int outside = 16 * (p.min_disp - 1);
+    if (w <= 0) {
+        // nothing inside the ROI: constant output
+        L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, nullptr, nullptr, nullptr, W, H, W, 0, outside, out, conf_out);
+        return L3D_OK;
+    }
+    L3D_ARG(L, p.dd_radius >= 0 && p.dd_radius < 64, "wls dd_radius");
+    size_t n = (size_t)w * h;
+    float *aL = L.get<float>(S_WLS_A, n), *bL = L.get<float>(S_WLS_B, n), *aR = L.get<float>(S_WLS_C, n), *bR = L.get<float>(S_WLS_D, n);
+    float *cl = L.get<float>(S_WLS_E, n), *cr = L.get<float>(S_WLS_F, n);
+    float *conf = L.get<float>(S_WLS_G, n), *ch = L.get<float>(S_WLS_H, n), *cv = L.get<float>(S_WLS_I, n);
+    float* interD = L.get<float>(S_WLS_J, n);
+    float* lut = nullptr;
+    int rc = wls_lut(L, p.sigma_color, &lut);
+    if (rc != L3D_OK) return rc;
+    dim3 g(cdiv(w, 128), h);
+    L.t_begin("wls");
+    L3D_LAUNCH(L, wls_hbox_kernel, g, 128, 0, dl, dr, W, x0, w, h, p.dd_radius, aL, bL, aR, bR);
+    L3D_LAUNCH(L, wls_vbox_conf_kernel, g, 128, 0, aL, bL, aR, bR, w, h, p.dd_radius, cl, cr);
+    // aL/bL are free now: reuse as num/den
+    float *num = aL, *den = bL;
+    L3D_LAUNCH(L, wls_lrc_kernel, g, 128, 0, dl, dr, guide, lut, W, x0, w, h, p.lrc_thresh, cl, cr, conf, num, den, ch, cv);
+    float lam = (float)p.lambda;
+    for (int it = 0; it < 3; it++) {
+        L3D_LAUNCH(L, fgs_hpass_kernel, cdiv(h, 32), 32, 0, num, den, ch, interD, w, h, lam);
+        L3D_LAUNCH(L, fgs_vpass_kernel, cdiv(w, 32), 32, 0, num, den, cv, interD, w, h, lam);
+        lam *= 0.25f;
+    }
+    L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, num, den, conf, W, H, x0, w, outside, out, conf_out);
+    L.t_end("wls");
+    return L3D_OK;
+}
+
+// ---- K5a: disparity -> depth (camera/single_usb_stereo_camera.py:335-357) -------------------
+struct QMat { double q[16]; };
+
+__global__ void depth_q_kernel(const int16_t* __restrict__ d16, int W, int H, QMat Q, float* __restrict__ depth) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    size_t i = (size_t)y * W + x;
+    float disp = __fdiv_rn((float)d16[i], 16.0f);
+    double d = (double)disp, fx = (double)x, fy = (double)y;
+    // cv2.reprojectImageTo3D: [X Y Z W]^T = Q [x y d 1]^T, Z/W evaluated in f64, stored as f32
+    double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q.q[8], fx), __dmul_rn(Q.q[9], fy)), __dmul_rn(Q.q[10], d)), Q.q[11]);
+    double Wh = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q.q[12], fx), __dmul_rn(Q.q[13], fy)), __dmul_rn(Q.q[14], d)), Q.q[15]);
+    float z = (float)__ddiv_rn(Z, Wh);
+    if (z < 0.f) z = 0.f;
+    if (z > 10.f) z = 0.f;
+    if (disp <= 0.f) z = 0.f;
+    depth[i] = z;
+}
+
+__global__ void depth_default_kernel(const int16_t* __restrict__ d16, size_t n, float* __restrict__ depth) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float disp = __fdiv_rn((float)d16[i], 16.0f);
+    float z = 0.f;
+    if (disp > 0.f) z = __fdiv_rn((float)(0.06 * 350), disp);
+    if (z > 10.f) z = 0.f;
+    depth[i] = z;
+}
+
+int dev_depth(Lane& L, const int16_t* disp16, int W, int H, const double* Q, float* depth) {
+    if (Q) {
+        QMat q;
+        memcpy(q.q, Q, sizeof(q.q));
+        L3D_LAUNCH(L, depth_q_kernel, dim3(cdiv(W, 128), H), 128, 0, disp16, W, H, q, depth);
+    } else {
+        size_t n = (size_t)W * H;
+        L3D_LAUNCH(L, depth_default_kernel, cdiv(n, 256), 256, 0, disp16, n, depth);
+    }
+    return L3D_OK;
+}
+
+}  // namespace l3d

@@ -1,0 +1,173 @@
+"""Batched, device-resident frame pipeline: LaserReconstructionSystem.process_frame
+(reference main.py:164-189) for many independent frames at once, and its frame-wise sharding over
+the GPUs of one box (no collective on the hot path; NCCL only gathers the point clouds).
+
+    rectify -> gray -> SGBM left/right -> WLS -> depth -> laser centre line -> 3D points
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as N
+
+
+def sgbm_params(num_disparities, block_size, mode, min_disparity=0, disp12=1, uniq=10, speckle=(100, 32),
+                pre_filter_cap=63):
+    """cv2.StereoSGBM_create arguments as the reference builds them
+    (camera/single_usb_stereo_camera.py:252-274): P1 = 8*3*bs^2, P2 = 32*3*bs^2."""
+    return N.SgbmParams(min_disparity, num_disparities, block_size, 8 * 3 * block_size ** 2,
+                        32 * 3 * block_size ** 2, disp12, pre_filter_cap, uniq, speckle[0], speckle[1], mode)
+
+
+def wls_mutate(p):
+    """cv2.ximgproc.createDisparityWLSFilter(left_matcher) mutates the matcher it is given."""
+    q = N.SgbmParams.from_buffer_copy(p)
+    q.disp12MaxDiff = 1000000
+    q.speckleWindowSize = 0
+    q.uniquenessRatio = 0
+    return q
+
+
+def right_matcher_params(p):
+    """cv2.ximgproc.createRightMatcher(left_matcher) for a StereoSGBM."""
+    return N.SgbmParams(-(p.minDisparity + p.numDisparities) + 1, p.numDisparities, p.blockSize, p.P1, p.P2,
+                        1000000, p.preFilterCap, 0, 0, 0, p.mode)
+
+
+def depth_config(num_disparities, block_size, mode, Q, use_wls=True, use_maps=True, lam=8000.0, sigma_color=1.5):
+    cfg = N.DepthConfig()
+    left = sgbm_params(num_disparities, block_size, mode)
+    if use_wls:
+        cfg.right = right_matcher_params(left)  # created before the mutation, but identical either way
+        left = wls_mutate(left)
+    cfg.left = left
+    cfg.wls = N.WlsParams(lam, sigma_color, left.minDisparity, left.numDisparities, int(math.ceil(0.5 * block_size)), 24)
+    cfg.use_wls = int(use_wls)
+    cfg.use_maps = int(use_maps)
+    cfg.use_Q = int(Q is not None)
+    if Q is not None:
+        cfg.Q[:] = [float(v) for v in np.asarray(Q, np.float64).reshape(16)]
+    return cfg
+
+
+def make_pipeline_config(W, H, num_disparities, block_size, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=2,
+                         max_points=20000, use_wls=True, use_maps=True, sigma=3.0, bright_thr=200, resp_thr=0.5,
+                         hsv_lo=(50, 100, 180), hsv_hi=(70, 255, 255), min_area=50.0):
+    cfg = N.PipelineConfig()
+    cfg.W, cfg.H = W, H
+    cfg.depth = depth_config(num_disparities, block_size, mode, Q, use_wls, use_maps)
+    cfg.extractor = extractor
+    cfg.steger = N.StegerParams(min(extractor, 3), sigma, bright_thr, resp_thr, (C.c_int * 4)(0, 0, 0, 0),
+                                (C.c_int * 3)(*hsv_lo), (C.c_int * 3)(*hsv_hi))
+    cfg.simple_hsv_lo[:] = list(hsv_lo)
+    cfg.simple_hsv_hi[:] = list(hsv_hi)
+    cfg.simple_bright_thr = bright_thr
+    cfg.simple_min_area = min_area
+    cfg.recon = N.ReconParams()
+    cfg.recon.kind = N.RECON_DEPTH  # main.py:176 calls reconstruct_from_depth
+    cfg.recon.K[:] = [float(v) for v in np.asarray(K, np.float64).reshape(9)]
+    cfg.recon.n_water = 1.33
+    cfg.max_points = max_points
+    cfg.lanes = lanes
+    return cfg
+
+
+class FramePipeline:
+    """Owns a Context and an l3d_pipeline; frames in, per-frame depth + point clouds out."""
+
+    def __init__(self, cfg, maps=None, device=0, ctx=None):
+        self.ctx = ctx or N.Context(device)
+        self.cfg = cfg
+        self.lib = self.ctx.lib
+        self.h = C.c_void_p()
+        self.ctx.check(self.lib.l3d_pipeline_create(self.ctx.h, C.byref(cfg), C.byref(self.h)), "l3d_pipeline_create")
+        if maps is not None:
+            mlx, mly, mrx, mry = [np.ascontiguousarray(m, np.float32) for m in maps]
+            self.ctx.check(self.lib.l3d_pipeline_set_maps(self.h, 0, N._ptr(mlx), N._ptr(mly)), "l3d_pipeline_set_maps")
+            self.ctx.check(self.lib.l3d_pipeline_set_maps(self.h, 1, N._ptr(mrx), N._ptr(mry)), "l3d_pipeline_set_maps")
+        self._dev = []
+
+    def close(self):
+        if self.h:
+            for p in self._dev:
+                self.lib.l3d_dev_free(self.ctx.h, p)
+            self._dev = []
+            self.lib.l3d_pipeline_destroy(self.h)
+            self.h = None
+
+    def upload(self, frames_u8):
+        """Stage a (nframes, H, W, 3) uint8 batch in HBM; returns the device pointer."""
+        a = np.ascontiguousarray(frames_u8, np.uint8)
+        p = self.lib.l3d_dev_alloc(self.ctx.h, a.nbytes)
+        if not p:
+            raise N.L3DError("device allocation of %d bytes failed" % a.nbytes)
+        self.ctx.check(self.lib.l3d_memcpy_h2d(self.ctx.h, p, a.ctypes.data, a.nbytes), "l3d_memcpy_h2d")
+        self._dev.append(p)
+        return p
+
+    def run_dev(self, left_dev, right_dev, nframes):
+        counts = (C.c_int * nframes)()
+        self.ctx.check(self.lib.l3d_pipeline_run_dev(self.h, C.c_void_p(left_dev), C.c_void_p(right_dev), nframes, counts),
+                       "l3d_pipeline_run_dev")
+        return np.frombuffer(counts, np.int32).copy()
+
+    def run_host(self, left, right, depth_out=None, xyz_out=None):
+        """left/right: (n,H,W,3) uint8 host arrays (pinned for full overlap)."""
+        n = left.shape[0]
+        counts = (C.c_int * n)()
+        self.ctx.check(self.lib.l3d_pipeline_run_host(self.h, C.c_void_p(left.ctypes.data), C.c_void_p(right.ctypes.data), n,
+                                                      C.c_void_p(depth_out.ctypes.data) if depth_out is not None else None,
+                                                      C.c_void_p(xyz_out.ctypes.data) if xyz_out is not None else None,
+                                                      counts), "l3d_pipeline_run_host")
+        return np.frombuffer(counts, np.int32).copy()
+
+    @property
+    def last_ms(self):
+        return float(self.lib.l3d_pipeline_last_ms(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.l3d_pipeline_launch_count(self.h))
+
+    def set_timing(self, on):
+        self.lib.l3d_pipeline_set_timing(self.h, int(on))
+
+    def kernel_time(self, name):
+        t, k = C.c_float(), C.c_int()
+        self.ctx.check(self.lib.l3d_pipeline_kernel_time(self.h, name.encode(), C.byref(t), C.byref(k)), "l3d_pipeline_kernel_time")
+        return t.value, k.value
+
+    def fetch(self, frame):
+        W, H, cap = self.cfg.W, self.cfg.H, self.cfg.max_points
+        rect = np.empty((H, W, 3), np.uint8)
+        depth = np.empty((H, W), np.float32)
+        disp = np.empty((H, W), np.int16)
+        xy = np.empty((cap, 2), np.float32)
+        xyz = np.empty((cap, 3), np.float64)
+        nxy, nxyz = C.c_int(), C.c_int()
+        self.ctx.check(self.lib.l3d_pipeline_fetch(self.h, int(frame), N._ptr(rect), N._ptr(depth), N._ptr(disp), N._ptr(xy),
+                                                   N._ptr(xyz), C.byref(nxy), C.byref(nxyz)), "l3d_pipeline_fetch")
+        return dict(left_rect=rect, depth=depth, disp16=disp, points_2d=xy[:min(nxy.value, cap)], points_3d=xyz[:nxyz.value])
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (l3d_host_alloc)."""
+    lib = N.load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = lib.l3d_host_alloc(max(nbytes, 1))
+    if not p:
+        raise N.L3DError("pinned allocation of %d bytes failed" % nbytes)
+    buf = (C.c_char * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED.append((p, buf))  # page-locked blocks live until process exit
+    return arr
+
+
+_PINNED = []
+
+
+def shard_frames(nframes, rank, world):
+    """Frame-wise sharding: rank r takes frames r::world."""
+    return list(range(rank, nframes, world))

@@ -218,9 +218,9 @@ void orc_sobel3_f32(const float* src, int W, int H, int dx, int dy, float* dst) 
 #define S(yy, xx) src[(long)(yy) * W + (xx)]
             float v;
             if (dx == 1 && dy == 0)
-                v = (S(ym, xp) - S(ym, xm)) + 2.0f * (S(y, xp) - S(y, xm)) + (S(yp, xp) - S(yp, xm));
-            else
-                v = (S(yp, xm) - S(ym, xm)) + 2.0f * (S(yp, x) - S(ym, x)) + (S(yp, xp) - S(ym, xp));
+                v = ((S(ym, xp) - S(ym, xm)) + (S(yp, xp) - S(yp, xm))) + 2.0f * (S(y, xp) - S(y, xm));
+            else /* cv2's symmetric [1,2,1] order: (a + c) + 2b, rows first */
+                v = ((S(yp, xm) + S(yp, xp)) + 2.0f * S(yp, x)) - ((S(ym, xm) + S(ym, xp)) + 2.0f * S(ym, x));
 #undef S
             dst[(long)y * W + x] = v;
         }

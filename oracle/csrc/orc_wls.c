@@ -158,7 +158,7 @@ void orc_wls_filter(const int16_t* dl, const int16_t* dr, const uint8_t* guide, 
         for (int x = 0; x < w; x++) {
             long i = (long)y * w + x;
             float v = num[i] * (1.0f / (den[i] + 1e-43f));
-            long q = (v == v) ? lrintf(v) : -32768; /* half-even, saturate; NaN -> INT_MIN saturated (x86 cvRound) */
+            long q = (fabsf(v) < 2147483648.0f) ? lrintf(v) : -32768; /* half-even, saturate; NaN or |v|>=2^31 -> INT_MIN saturated (x86 cvRound) */
             if (q > 32767) q = 32767; if (q < -32768) q = -32768;
             out[(long)y * W + x0 + x] = (int16_t)q;
             if (conf_out) conf_out[(long)y * W + x0 + x] = conf[i];
