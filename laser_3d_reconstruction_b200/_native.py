@@ -288,3 +288,16 @@ class Context:
         self.check(self.lib.l3d_reconstruct(self.h, C.byref(params), _ptr(xy), n, _ptr(img), W, H, _ptr(out),
                                             C.byref(n_out)), "l3d_reconstruct")
         return out[:n_out.value]
+
+
+# ---- per-process default contexts (one per device) ----------------------------------------
+_default = {}
+
+
+def default_context(device=0):
+    """The process-wide Context of `device` used by the reference-API classes.  Raises L3DError
+    when the CUDA library or a GPU is missing: there is no CPU fallback."""
+    ctx = _default.get(device)
+    if ctx is None or ctx.h is None:
+        ctx = _default[device] = Context(device)
+    return ctx

@@ -470,12 +470,12 @@ __global__ void sgbm_lrcheck_kernel(int16_t* __restrict__ raw, const unsigned* _
     bool c = true;
     if (0 <= _x && _x < W) {
         unsigned k = k2[_x];
-        int d2 = (k >> 16) ? (int)(k & 0xffffu) + minX1 - _x : minD - 1;
+        int d2 = (k >> 16) ? (int)(k & 0xffffu) + minX1 - _x : INVALID;  // unset entries hold the SCALED invalid value, as in OpenCV
         c = c && d2 >= minD && abs(d2 - _d) > d12;
     } else c = false;
     if (0 <= x_ && x_ < W) {
         unsigned k = k2[x_];
-        int d2 = (k >> 16) ? (int)(k & 0xffffu) + minX1 - x_ : minD - 1;
+        int d2 = (k >> 16) ? (int)(k & 0xffffu) + minX1 - x_ : INVALID;
         c = c && d2 >= minD && abs(d2 - d_) > d12;
     } else c = false;
     if (c) raw[(size_t)y * W + x] = (int16_t)INVALID;

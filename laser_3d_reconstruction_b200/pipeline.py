@@ -151,6 +151,19 @@ class FramePipeline:
         return dict(left_rect=rect, depth=depth, disp16=disp, points_2d=xy[:min(nxy.value, cap)], points_3d=xyz[:nxyz.value])
 
 
+def _fetch_points(self, frame, n_hint=None):
+    """Only the 3D points of frame slot `frame` of the last run (device -> host)."""
+    cap = self.cfg.max_points if n_hint is None else max(int(n_hint), 1)
+    xyz = np.empty((cap, 3), np.float64)
+    nxy, nxyz = C.c_int(), C.c_int()
+    self.ctx.check(self.lib.l3d_pipeline_fetch(self.h, int(frame), None, None, None, None, N._ptr(xyz),
+                                               C.byref(nxy), C.byref(nxyz)), "l3d_pipeline_fetch")
+    return xyz[:nxyz.value]
+
+
+FramePipeline.fetch_points = _fetch_points
+
+
 def pinned_empty(shape, dtype):
     """numpy array backed by page-locked host memory (l3d_host_alloc)."""
     lib = N.load()
@@ -168,6 +181,4 @@ def pinned_empty(shape, dtype):
 _PINNED = []
 
 
-def shard_frames(nframes, rank, world):
-    """Frame-wise sharding (SURVEY 8e): rank r takes frames r::world."""
-    return list(range(rank, nframes, world))
+from .sharding import shard_frames  # noqa: E402,F401  (frame-wise sharding)

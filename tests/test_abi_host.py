@@ -1,0 +1,125 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/l3d.h declares (no
+compute calls), ctypes struct layouts match the header, the host logic of the reference-API classes,
+and the loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from laser_3d_reconstruction_b200 import _native as N
+from laser_3d_reconstruction_b200 import pipeline, sharding, stereo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "l3d.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(l3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.load()
+    syms = header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), "libl3d.so does not export %s" % s
+    assert set(N.EXPORTS) == set(syms)
+    assert b"sm_100a" in lib.l3d_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes as the C compiler lays them out (ints 4, doubles 8, natural alignment)
+    assert C.sizeof(N.SgbmParams) == 11 * 4
+    assert C.sizeof(N.WlsParams) == 2 * 8 + 4 * 4
+    assert C.sizeof(N.DepthConfig) == 44 + 44 + 32 + 12 + 4 + 16 * 8
+    assert C.sizeof(N.StegerParams) == 8 + 8 + 8 + 8 + 16 + 12 + 12
+    assert N.ReconParams.K.offset == 8 and N.ReconParams.window.offset == 8 + 72 + 32 + 8 + 8 + 5 * 8
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(N.L3DError, match="no CPU fallback|no CUDA"):
+        N.Context(0)
+    from laser_3d_reconstruction_b200 import SimpleLaserExtractor
+    with pytest.raises(N.L3DError):
+        SimpleLaserExtractor(verbose=False).extract_centerline(np.zeros((8, 8, 3), np.uint8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "laser_3d_reconstruction_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dp, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "liborc" not in txt, f
+
+
+def test_wls_creation_mutates_left_matcher():
+    m = stereo.StereoSGBM(minDisparity=0, numDisparities=64, blockSize=5, P1=600, P2=2400, disp12MaxDiff=1,
+                          uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, preFilterCap=63, mode=2)
+    r = stereo.createRightMatcher(m)
+    assert (r.getMinDisparity(), r.getNumDisparities(), r.getUniquenessRatio(), r.getDisp12MaxDiff(),
+            r.getSpeckleWindowSize()) == (-63, 64, 0, 1000000, 0)
+    w = stereo.createDisparityWLSFilter(m)
+    assert (m.getUniquenessRatio(), m.getDisp12MaxDiff(), m.getSpeckleWindowSize()) == (0, 1000000, 0)
+    assert (w.getLambda(), w.getSigmaColor(), w.getLRCthresh(), w.getDepthDiscontinuityRadius()) == (8000.0, 1.0, 24, 3)
+    # pipeline.depth_config builds the same parameter sets
+    cfg = pipeline.depth_config(64, 5, 2, np.eye(4))
+    for f, _ in N.SgbmParams._fields_:
+        assert getattr(cfg.left, f) == getattr(m.params(), f), f
+        if f != "speckleRange":
+            assert getattr(cfg.right, f) == getattr(r.params(), f), f
+
+
+def test_camera_class_host_side(golden_real, tmp_path):
+    """Calibration loading / matcher selection of the camera class without touching the GPU."""
+    import json
+    from laser_3d_reconstruction_b200 import SingleUSBStereoCameraManager
+    g = golden_real
+    calib = {k: g[k].tolist() for k in ("R", "T")}
+    calib.update(camera_matrix_left=g["K_left"].tolist(), dist_coeffs_left=g["dist_left"].tolist(),
+                 camera_matrix_right=g["K_right"].tolist(), dist_coeffs_right=g["dist_right"].tolist())
+    path = tmp_path / "stereo_calibration.json"
+    path.write_text(json.dumps(calib))
+    cam = SingleUSBStereoCameraManager(camera_id=0, width=640, height=240, calibration_file=str(path), verbose=False)
+    assert (cam.single_width, cam.single_height) == (320, 240)
+    assert cam.initialize_offline()
+    assert np.array_equal(cam.Q, g["Q"])
+    assert np.array_equal(cam.map_left_x[::8, ::8], g["map_left_x"])
+    assert cam.roi_left is None and cam.roi_right is None
+    intr = cam.get_camera_intrinsics()
+    assert np.allclose([intr[k] for k in ("fx", "fy", "cx", "cy", "baseline")], g["intr"])
+    assert cam.stereo_matcher.getNumDisparities() == 64 and cam.stereo_matcher.getBlockSize() == 5
+    assert cam.stereo_matcher.getMode() == stereo.STEREO_SGBM_MODE_SGBM_3WAY
+    assert cam.stereo_matcher.getUniquenessRatio() == 0  # mutated by the WLS filter creation
+    assert cam.right_matcher.getMinDisparity() == -63
+    l, r = cam._split_frame(g["frame_a"])
+    assert l.shape == (240, 320, 3) and not r.flags["C_CONTIGUOUS"]
+    assert cam.get_frames() == (None, None)  # no capture device opened
+    big = SingleUSBStereoCameraManager(width=2560, height=720, calibration_file="/nonexistent", num_disparities=128,
+                                       block_size=9, sgbm_mode=1, verbose=False)
+    big.initialize_offline()
+    assert big.Q is None and big.map_left_x is None
+    assert (big.stereo_matcher.getNumDisparities(), big.stereo_matcher.getBlockSize(), big.stereo_matcher.getMode(),
+            big.stereo_matcher.getP2()) == (128, 9, 1, 7776)
+    assert SingleUSBStereoCameraManager(width=1280, height=720, verbose=False, calibration_file="/x").single_width == 640
+
+
+def test_shard_and_pack_roundtrip():
+    for world in (1, 2, 3, 8):
+        seen = sorted(sum((sharding.shard_frames(37, r, world) for r in range(world)), []))
+        assert seen == list(range(37))
+    with pytest.raises(ValueError):
+        sharding.shard_frames(4, 2, 2)
+    rng = np.random.default_rng(0)
+    clouds = [rng.random((n, 3)) for n in (0, 5, 1, 0, 7)]
+    tabs = [sharding.pack_clouds(sharding.shard_frames(5, r, 2), [clouds[f] for f in sharding.shard_frames(5, r, 2)])
+            for r in range(2)]
+    back = sharding.unpack_clouds(np.concatenate(tabs), 5)
+    assert all(np.array_equal(a, b) for a, b in zip(back, clouds))

@@ -1,0 +1,398 @@
+"""Parity of the sm_100a kernels (through the C ABI, via ctypes) against cv2 -- the library the
+reference calls -- and against the oracle restatement for intermediates cv2 never exposes.
+Bit-exact for integer stages; stated tolerances for WLS (unpinned), Steger centres and 3D points."""
+import ctypes as C
+
+import cv2
+import numpy as np
+import pytest
+
+from laser_3d_reconstruction_b200 import _native as N
+from laser_3d_reconstruction_b200 import pipeline, synth
+from oracle import cref, ref_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def gray_pair(W, H, D, seed, quant=0):
+    l, r = synth.stereo_pair(W, H, D, seed)
+    lg, rg = cv2.cvtColor(l, cv2.COLOR_BGR2GRAY), cv2.cvtColor(r, cv2.COLOR_BGR2GRAY)
+    if quant:
+        lg = (lg // quant * quant).astype(np.uint8)
+        rg = (rg // quant * quant).astype(np.uint8)
+    return lg, rg
+
+
+def eq(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    bad = np.argwhere(a != b)
+    assert len(bad) == 0, "%s: %d/%d differ, first %s got %s want %s" % (
+        what, len(bad), a.size, tuple(bad[0]), a[tuple(bad[0])], b[tuple(bad[0])])
+
+
+# ---- K1 remap + gray -----------------------------------------------------------------------
+@pytest.mark.parametrize("case", range(4))
+def test_remap_gray(ctx, case):
+    rng = np.random.default_rng(case)
+    H, W = (53, 97) if case == 0 else (240, 320)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mx = (rng.random((H, W)) * (W + 8) - 4).astype(np.float32)  # includes out-of-range taps (border 0)
+    my = (rng.random((H, W)) * (H + 8) - 4).astype(np.float32)
+    if case == 1:
+        mx = (np.round(mx * 64) / 64).astype(np.float32)
+        my = (np.round(my * 64) / 64).astype(np.float32)
+    if case == 3:
+        mx, my = synth.warp_maps(W, H, 2)
+    ctx.set_rectify_maps(0, mx, my)
+    rect, gray = ctx.remap_gray(0, src, (H, W))
+    want = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
+    eq(rect, want, "remap")
+    eq(gray, cv2.cvtColor(want, cv2.COLOR_BGR2GRAY), "gray")
+
+
+def test_remap_noncontiguous_view_and_real_pair(ctx, golden_real):
+    g = golden_real
+    size = (320, 240)
+    R1, R2, P1, P2, Q, _, _ = cv2.stereoRectify(g["K_left"], g["dist_left"], g["K_right"], g["dist_right"], size,
+                                                g["R"], g["T"], flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
+    mlx, mly = cv2.initUndistortRectifyMap(g["K_left"], g["dist_left"], R1, P1, size, cv2.CV_32FC1)
+    mrx, mry = cv2.initUndistortRectifyMap(g["K_right"], g["dist_right"], R2, P2, size, cv2.CV_32FC1)
+    ctx.set_rectify_maps(0, mlx, mly)
+    ctx.set_rectify_maps(1, mrx, mry)
+    for tag in ("a", "b"):
+        frame = g["frame_" + tag]
+        l, r = frame[:, :320], frame[:, 320:]  # _split_frame views
+        eq(ctx.remap_gray(0, l, (240, 320))[0], g["lrect_" + tag], "left rect")
+        eq(ctx.remap_gray(1, r, (240, 320))[0], g["rrect_" + tag], "right rect")
+
+
+def test_gray_exhaustive_slice(ctx):
+    v = np.unique(np.concatenate([np.arange(0, 256, 5), [254, 255]])).astype(np.uint8)
+    b, g, r = np.meshgrid(v, v, v, indexing="ij")
+    img = np.ascontiguousarray(np.stack([b, g, r], -1).reshape(len(v), -1, 3))
+    eq(ctx.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+# ---- K2 SGBM -------------------------------------------------------------------------------
+SMALL = [(96, 48, 16, 3), (130, 50, 32, 5), (200, 64, 64, 9), (300, 56, 128, 7), (400, 48, 256, 11), (180, 52, 96, 5),
+         (120, 50, 48, 3)]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", SMALL)
+def test_sgbm_small_all_roles(ctx, mode, shape):
+    W, H, D, bs = shape
+    for minD, swap in ((0, False), (-(D - 1), True), (3, False)):
+        for (uq, d12, sw) in [(10, 1, 100), (0, 1000000, 0), (15, 2, 0)]:
+            lg, rg = gray_pair(W, H, D, 3 + mode, quant=16 if bs == 5 else 0)
+            if swap:
+                lg, rg = rg, lg
+            kw = dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs,
+                      disp12MaxDiff=d12, preFilterCap=63, uniquenessRatio=uq, speckleWindowSize=sw, speckleRange=32,
+                      mode=mode)
+            tag = "m%d %s minD%d u%d" % (mode, shape, minD, uq)
+            want = cv2.StereoSGBM_create(**kw).compute(lg, rg)
+            p = N.SgbmParams(**kw)
+            if mode != 2:
+                disp, raw, Cg, Sg = ctx.sgbm_compute(p, lg, rg, want_raw=True, want_volumes=True)
+                _, oraw, oC, oS = cref.sgbm_compute(lg, rg, want_volumes=True, want_raw=True, **kw)
+                eq(Cg, oC, tag + " C volume")
+                eq(Sg, oS, tag + " S volume")
+            else:
+                disp, raw = ctx.sgbm_compute(p, lg, rg, want_raw=True)
+                _, oraw = cref.sgbm_compute(lg, rg, want_raw=True, **kw)
+            eq(raw, oraw, tag + " raw")
+            eq(disp, want, tag + " disp vs cv2")
+
+
+@pytest.mark.parametrize("mode", [2, 0, 1])
+def test_sgbm_c1_parameter_sets(ctx, mode):
+    lg, rg = gray_pair(320, 360, 64, 7)
+    base, mut, right = ref_ops.sgbm_param_sets(64, 5, mode)
+    eq(ctx.sgbm_compute(N.SgbmParams(**base), lg, rg), cv2.StereoSGBM_create(**base).compute(lg, rg), "as constructed")
+    eq(ctx.sgbm_compute(N.SgbmParams(**mut), lg, rg), cv2.StereoSGBM_create(**mut).compute(lg, rg), "wls-mutated")
+    eq(ctx.sgbm_compute(N.SgbmParams(**right), rg, lg), cv2.StereoSGBM_create(**right).compute(rg, lg), "right matcher")
+
+
+def test_sgbm_real_pairs(ctx, golden_real):
+    base, _, _ = ref_ops.sgbm_param_sets(64, 5, 2)
+    for tag in ("a", "b"):
+        lg = cv2.cvtColor(golden_real["lrect_" + tag], cv2.COLOR_BGR2GRAY)
+        rg = cv2.cvtColor(golden_real["rrect_" + tag], cv2.COLOR_BGR2GRAY)
+        eq(ctx.sgbm_compute(N.SgbmParams(**base), lg, rg), golden_real["disp16_" + tag], "real pair " + tag)
+
+
+@pytest.mark.parametrize("mode", [1, 0, 2])
+def test_sgbm_c3_full_size(ctx, mode):
+    """BASELINE config 3: 1280x720, 128 disparities, block 9."""
+    lg, rg = gray_pair(1280, 720, 128, 11)
+    base, mut, right = ref_ops.sgbm_param_sets(128, 9, mode)
+    eq(ctx.sgbm_compute(N.SgbmParams(**mut), lg, rg), cv2.StereoSGBM_create(**mut).compute(lg, rg), "c3 wls-mutated")
+    if mode == 1:
+        eq(ctx.sgbm_compute(N.SgbmParams(**right), rg, lg), cv2.StereoSGBM_create(**right).compute(rg, lg), "c3 right")
+        eq(ctx.sgbm_compute(N.SgbmParams(**base), lg, rg), cv2.StereoSGBM_create(**base).compute(lg, rg), "c3 base")
+
+
+def test_sgbm_c4_full_size(ctx):
+    """BASELINE config 4: 1920x1080, 256 disparities, block 11, MODE_HH."""
+    lg, rg = gray_pair(1920, 1080, 256, 5)
+    _, mut, _ = ref_ops.sgbm_param_sets(256, 11, 1)
+    eq(ctx.sgbm_compute(N.SgbmParams(**mut), lg, rg), cv2.StereoSGBM_create(**mut).compute(lg, rg), "c4")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_sgbm_noise_saturation(ctx, mode):
+    rng = np.random.default_rng(0)
+    ln = rng.integers(0, 256, (96, 400)).astype(np.uint8)
+    rn = rng.integers(0, 256, (96, 400)).astype(np.uint8)
+    kw = dict(minDisparity=0, numDisparities=256, blockSize=11, P1=2904, P2=11616, disp12MaxDiff=1000000,
+              preFilterCap=63, uniquenessRatio=0, speckleWindowSize=0, speckleRange=32, mode=mode)
+    eq(ctx.sgbm_compute(N.SgbmParams(**kw), ln, rn), cv2.StereoSGBM_create(**kw).compute(ln, rn))
+
+
+def test_sgbm_properties_full_size(ctx):
+    """Size-independent properties at c3: determinism, invalid border columns, and shift
+    equivariance (a frame made of two different halves stacked vertically far apart matches the
+    halves' own results away from the seam for the row-local 3WAY mode's horizontal structure)."""
+    lg, rg = gray_pair(1280, 720, 128, 3)
+    _, mut, _ = ref_ops.sgbm_param_sets(128, 9, 1)
+    p = N.SgbmParams(**mut)
+    a = ctx.sgbm_compute(p, lg, rg)
+    b = ctx.sgbm_compute(p, lg, rg)
+    eq(a, b, "determinism")
+    assert np.all(a[:, :128 - 1] == -16)  # columns < minX1 (minus the 3x3 median reach) invalid
+    valid = a[:, 140:] >= 0
+    assert valid.mean() > 0.9
+    truth = np.rint(synth.disparity_field(1280, 720, 128))[:, 140:]
+    err = np.abs(a[:, 140:] / 16.0 - truth)[valid]
+    assert np.median(err) < 0.6  # the matcher recovers the rendered disparity field
+
+
+def test_sgbm_rejects_unsupported(ctx):
+    lg, rg = gray_pair(96, 48, 16, 0)
+    with pytest.raises(N.L3DError):
+        ctx.sgbm_compute(N.SgbmParams(0, 24, 3, 72, 288, 1, 63, 10, 0, 0, 0), lg, rg)  # numDisparities % 16
+    with pytest.raises(N.L3DError):
+        ctx.sgbm_compute(N.SgbmParams(0, 16, 4, 72, 288, 1, 63, 10, 0, 0, 0), lg, rg)  # even block
+    with pytest.raises(ValueError):
+        ctx.sgbm_compute(N.SgbmParams(0, 16, 3, 72, 288, 1, 63, 10, 0, 0, 0), lg, rg[:, :-1])
+
+
+def test_median_speckles(ctx):
+    rng = np.random.default_rng(1)
+    for t in range(5):
+        H, W = (37, 61) if t < 2 else ((360, 320) if t < 4 else (720, 1280))
+        d = (rng.integers(-1, 40, (H, W)) * 16 + rng.integers(0, 16, (H, W))).astype(np.int16)
+        d[rng.random((H, W)) < 0.3] = -16
+        eq(ctx.median3_s16(d), cv2.medianBlur(d, 3), "median")
+        e = d.copy()
+        cv2.filterSpeckles(e, -16, 25, 32)
+        eq(ctx.filter_speckles(d, -16, 25, 32), e, "speckles")
+    # large smooth regions (components far bigger than maxSize) and a tiny island
+    d = np.full((200, 300), 160, np.int16)
+    d[50:53, 60:64] = 1600
+    e = d.copy()
+    cv2.filterSpeckles(e, -16, 100, 32)
+    eq(ctx.filter_speckles(d, -16, 100, 32), e, "island")
+
+
+# ---- K3 WLS (PARITY UNPINNED: oracle restatement only) + K5a depth ---------------------------
+@pytest.mark.parametrize("cfg", [(320, 360, 64, 5, 2), (1280, 720, 128, 9, 1)])
+def test_wls_and_depth(ctx, cfg):
+    W, H, D, bs, mode = cfg
+    lg, rg = gray_pair(W, H, D, 9)
+    base, mut, right = ref_ops.sgbm_param_sets(D, bs, mode)
+    dl = cv2.StereoSGBM_create(**mut).compute(lg, rg)
+    dr = cv2.StereoSGBM_create(**right).compute(rg, lg)
+    r = int(np.ceil(0.5 * bs))
+    want, wconf = cref.wls_filter(dl, dr, lg, 0, D, r, 8000.0, 1.5, want_conf=True)
+    got, conf = ctx.wls_filter(N.WlsParams(8000.0, 1.5, 0, D, r, 24), dl, dr, lg, want_conf=True)
+    # tolerance: <= 1 LSB of the int16 output on >= 99.9 % of the pixels (f32 tridiagonal solves)
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999, "wls: %.5f within 1 LSB, max %d" % ((diff <= 1).mean(), diff.max())
+    assert np.allclose(conf, wconf, rtol=0, atol=0.5)
+    Q = synth.camera_model(W, H)[1]
+    eq(ctx.disp_to_depth(want, Q), ref_ops.depth_from_disparity(want, Q), "depth with Q")
+    eq(ctx.disp_to_depth(want, None), ref_ops.depth_from_disparity(want, None), "depth default branch")
+
+
+# ---- K4 extractors -------------------------------------------------------------------------
+CFG = dict(hsv_lower=(50, 100, 180), hsv_upper=(70, 255, 255), brightness_threshold=200, min_area=50)
+
+
+def steger_params(variant, sigma=None, roi=(0, 0, 0, 0)):
+    return N.StegerParams(variant, (2.0 if variant == 3 else 3.0) if sigma is None else sigma, 200, 0.5,
+                          (C.c_int * 4)(*roi), (C.c_int * 3)(50, 100, 180), (C.c_int * 3)(70, 255, 255))
+
+
+def point_sets_agree(got, want, tol=0.01, frac=0.999):
+    got, want = np.asarray(got, np.float64).reshape(-1, 2), np.asarray(want, np.float64).reshape(-1, 2)
+    if len(want) == 0 or len(got) == 0:
+        return len(want) == len(got)
+    from scipy.spatial import cKDTree
+    d1 = cKDTree(want).query(got)[0]
+    d2 = cKDTree(got).query(want)[0]
+    return (d1 <= tol).mean() >= frac and (d2 <= tol).mean() >= frac
+
+
+@pytest.mark.parametrize("size", [(320, 360, 64), (1280, 720, 128)])
+def test_simple_extractor(ctx, size):
+    W, H, D = size
+    left, _ = synth.stereo_pair(W, H, D, 1)
+    wpts, wm1, wm2 = ref_ops.simple_extract(left, want_masks=True, **CFG)
+    pts, m1, m2 = ctx.simple_extract(left, CFG["hsv_lower"], CFG["hsv_upper"], 200, 50, want_masks=True)
+    eq(m1, wm1, "mask after morphology")
+    eq(m2, wm2, "final contour mask")
+    eq(pts, np.array(wpts).reshape(-1, 2), "centroids")  # exact: integer sums, one f64 divide
+    assert len(pts) == H
+
+
+def test_simple_extractor_blobs(ctx):
+    rng = np.random.default_rng(5)
+    for t in range(12):
+        m = (cv2.GaussianBlur(rng.random((90, 120)).astype(np.float32), (0, 0), 1.5 + 0.15 * t) > 0.5)
+        img = np.zeros((90, 120, 3), np.uint8)
+        img[m] = (140, 255, 140)
+        wpts, wm1, wm2 = ref_ops.simple_extract(img, want_masks=True, **dict(CFG, min_area=8 + t))
+        pts, m1, m2 = ctx.simple_extract(img, CFG["hsv_lower"], CFG["hsv_upper"], 200, 8 + t, want_masks=True)
+        eq(m1, wm1, "blob morph %d" % t)
+        eq(m2, wm2, "blob final %d" % t)
+        eq(pts, np.array(wpts, np.float64).reshape(-1, 2), "blob points %d" % t)
+
+
+@pytest.mark.parametrize("size", [(320, 360, 64), (1280, 720, 128)])
+def test_steger_variants(ctx, size):
+    W, H, D = size
+    left, _ = synth.stereo_pair(W, H, D, 1)
+    for variant, fn in ((0, ref_ops.fast_steger_extract), (1, ref_ops.improved_steger_extract),
+                        (2, ref_ops.improved_steger_extract_optimized), (3, ref_ops.hybrid_extract)):
+        got = ctx.steger_extract(steger_params(variant), left)
+        want = np.array(fn(left), np.float64).reshape(-1, 2)
+        assert len(want) > 100
+        assert point_sets_agree(got, want), "variant %d: %d vs %d points" % (variant, len(got), len(want))
+        if got.shape == want.shape:  # raster order preserved -> element-wise tolerance 0.01 px
+            assert np.abs(got - want).max() <= 0.01
+
+
+def test_extractors_on_golden(ctx, golden_synth):
+    """Against outputs of the REAL reference classes (tests/golden/make_golden.py)."""
+    g = golden_synth
+    left = g["left"]
+    eq(ctx.simple_extract(left, CFG["hsv_lower"], CFG["hsv_upper"], 200, 50), g["simple_cfg"], "simple cfg")
+    eq(ctx.simple_extract(left, (40, 50, 100), (80, 255, 255), 100, 50), g["simple_def"], "simple defaults")
+    for variant, key in ((0, "fast"), (1, "improved"), (2, "optimized"), (3, "hybrid")):
+        got = ctx.steger_extract(steger_params(variant), left)
+        assert got.shape == g[key].shape and np.abs(got - g[key]).max() <= 0.01, key
+    got = ctx.steger_extract(steger_params(0, roi=(100, 40, 150, 200)), left)
+    assert got.shape == g["fast_roi"].shape and np.abs(got - g["fast_roi"]).max() <= 0.01
+    gray = cv2.cvtColor(left, cv2.COLOR_BGR2GRAY)
+    got = ctx.steger_extract(steger_params(0), gray)
+    assert got.shape == g["fast_gray"].shape and np.abs(got - g["fast_gray"]).max() <= 0.01
+
+
+def test_extractors_empty_image(ctx):
+    dark = np.full((64, 96, 3), 40, np.uint8)
+    assert len(ctx.simple_extract(dark, CFG["hsv_lower"], CFG["hsv_upper"], 200, 50)) == 0
+    for v in range(4):
+        assert len(ctx.steger_extract(steger_params(v), dark)) == 0
+
+
+# ---- K5b reconstruction ----------------------------------------------------------------------
+def test_reconstruction_on_golden(ctx, golden_synth):
+    g = golden_synth
+    K, Q = g["K"], g["Q"]
+    sp = g["simple_cfg"]
+
+    def rp(kind, refr=0):
+        p = N.ReconParams()
+        p.kind = kind
+        p.K[:] = list(K.reshape(9))
+        p.plane[:] = list(synth.LASER_PLANE)
+        p.use_refraction = refr
+        p.n_water = 1.33
+        return p
+
+    for name, refr in (("rec_air", 0), ("rec_water", 1)):
+        got = ctx.reconstruct(rp(N.RECON_PLANE, refr), sp)
+        want = g[name + "_line"]
+        assert got.shape == want.shape and np.allclose(got, want, rtol=1e-9, atol=1e-12), name  # north_star: <= 1e-5 rel
+        eq(ctx.reconstruct(rp(N.RECON_DEPTH), sp, g["depth"]), g[name + "_depth"], name + " depth")
+    got = ctx.reconstruct(rp(N.RECON_DEPTH), g["fast"].astype(np.float64), g["depth"])
+    eq(got, g["rec_fast_depth"], "from_depth with float32 points")
+    disp = g["disp16_3way"].astype(np.float32) / 16.0
+    ir = ref_ops.ImprovedLaserReconstructorRef(Q)
+    for kind, key in ((N.RECON_DISPARITY, "irec_disp"), (N.RECON_DISPARITY_MEDIAN, "irec_interp")):
+        p = N.ReconParams()
+        p.kind = kind
+        p.fx, p.baseline, p.cx, p.cy = ir.fx, ir.baseline, ir.cx, ir.cy
+        p.min_disparity = 1.0
+        p.window = 3
+        eq(ctx.reconstruct(p, g["optimized"], disp).astype(np.float32), g[key], key)
+    assert ctx.reconstruct(rp(N.RECON_PLANE), np.zeros((0, 2))).shape == (0, 3)
+
+
+# ---- fused depth path + frame pipeline ---------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(320, 360, 64, 5, 2, True), (320, 360, 64, 5, 0, False), (1280, 720, 128, 9, 1, True)])
+def test_compute_depth_fused(ctx, cfg):
+    W, H, D, bs, mode, use_wls = cfg
+    left, right = synth.stereo_pair(W, H, D, 4)
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    ctx.set_rectify_maps(0, maps[0], maps[1])
+    ctx.set_rectify_maps(1, maps[2], maps[3])
+    dc = pipeline.depth_config(D, bs, mode, Q, use_wls=use_wls)
+    rect, depth, disp = ctx.compute_depth(dc, left, right, want_disp=True)
+    wrect, wdepth, aux = ref_ops.depth_path(left, right, maps, D, bs, mode, Q, use_wls=use_wls, want_all=True)
+    eq(rect, wrect, "rectified left")
+    if use_wls:
+        diff = np.abs(disp.astype(np.int32) - aux["df"].astype(np.int32))
+        assert (diff <= 1).mean() >= 0.999
+        ok = diff == 0
+        assert np.array_equal(depth[ok], wdepth[ok])
+    else:
+        eq(disp, aux["df"], "disparity")
+        eq(depth, wdepth, "depth")
+
+
+def test_pipeline_matches_stagewise_and_is_frame_independent(ctx):
+    W, H, D, bs = 320, 360, 64, 5
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, s) for s in range(5)]
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    results = {}
+    for lanes in (1, 3):
+        cfg = pipeline.make_pipeline_config(W, H, D, bs, 2, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=8000)
+        fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+        try:
+            dl, dr = fp.upload(L), fp.upload(R)
+            counts = fp.run_dev(dl, dr, len(frames))
+            results[lanes] = [fp.fetch(i) for i in range(len(frames))]
+            assert list(counts) == [len(r["points_3d"]) for r in results[lanes]]
+            # host-buffer entry point gives the same answer
+            depth = np.empty((len(frames), H, W), np.float32)
+            xyz = np.empty((len(frames), 8000, 3), np.float64)
+            counts2 = fp.run_host(L, R, depth, xyz)
+            assert list(counts2) == list(counts)
+            for i in range(len(frames)):
+                eq(depth[i], results[lanes][i]["depth"], "run_host depth")
+                eq(xyz[i, :counts[i]], results[lanes][i]["points_3d"], "run_host xyz")
+        finally:
+            fp.close()
+    for i in range(len(frames)):  # lanes (streams) do not change any bit
+        for k in ("left_rect", "depth", "disp16", "points_2d", "points_3d"):
+            eq(results[1][i][k], results[3][i][k], "lanes %s frame %d" % (k, i))
+    # frame 2 against the stage-wise reference path
+    wrect, wdepth, aux = ref_ops.depth_path(frames[2][0], frames[2][1], maps, D, bs, 2, Q, want_all=True)
+    got = results[1][2]
+    eq(got["left_rect"], wrect, "pipeline rect")
+    diff = np.abs(got["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999
+    wp = ref_ops.improved_steger_extract(wrect)
+    assert point_sets_agree(got["points_2d"], wp)
+    wxyz = ref_ops.ReconstructorRef(K, synth.LASER_PLANE, False).reconstruct_from_depth(
+        [tuple(p) for p in got["points_2d"].astype(np.float64)], got["depth"]).reshape(-1, 3)
+    assert got["points_3d"].shape == wxyz.shape
+    assert np.allclose(got["points_3d"], wxyz, rtol=1e-5, atol=1e-12)  # north_star: 3D points <= 1e-5 relative

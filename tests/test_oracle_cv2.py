@@ -1,0 +1,146 @@
+"""Pin the oracle's C restatement (oracle/csrc) against the installed cv2 binary -- the library the
+reference calls on its hot path.  Bit-exact for every integer stage."""
+import cv2
+import numpy as np
+import pytest
+
+from laser_3d_reconstruction_b200 import synth
+from oracle import cref, ref_ops
+
+
+def gray_pair(W, H, D, seed, quant=0):
+    l, r = synth.stereo_pair(W, H, D, seed)
+    lg, rg = cv2.cvtColor(l, cv2.COLOR_BGR2GRAY), cv2.cvtColor(r, cv2.COLOR_BGR2GRAY)
+    if quant:
+        lg = (lg // quant * quant).astype(np.uint8)
+        rg = (rg // quant * quant).astype(np.uint8)
+    return lg, rg
+
+
+def test_gray_hsv_colour_cube_slice():
+    # a dense slice of the 2^24 cube (every 3rd value per channel + the extremes)
+    v = np.unique(np.concatenate([np.arange(0, 256, 3), [254, 255]])).astype(np.uint8)
+    b, g, r = np.meshgrid(v, v, v, indexing="ij")
+    img = np.stack([b, g, r], -1).reshape(len(v), -1, 3)
+    assert np.array_equal(cref.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(cref.bgr2hsv(img), cv2.cvtColor(img, cv2.COLOR_BGR2HSV))
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_remap(case):
+    rng = np.random.default_rng(case)
+    H, W = (53, 97) if case < 2 else (120, 160)
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mx = (rng.random((H, W)) * (W + 8) - 4).astype(np.float32)
+    my = (rng.random((H, W)) * (H + 8) - 4).astype(np.float32)
+    if case == 1:  # exact half-way fixed-point roundings
+        mx = (np.round(mx * 64) / 64).astype(np.float32)
+        my = (np.round(my * 64) / 64).astype(np.float32)
+    if case == 3:
+        mx, my = synth.warp_maps(W, H, 1)
+    assert np.array_equal(cref.remap_bilinear(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+
+
+SGBM_CASES = [
+    # (W, H, D, bs, minD-kind, params-kind, quant)
+    (96, 48, 16, 3, "zero", "base", 0), (130, 50, 32, 5, "zero", "base", 16), (130, 50, 32, 5, "right", "mut", 16),
+    (200, 64, 64, 9, "zero", "mut", 0), (200, 64, 64, 9, "pos", "base", 0), (300, 56, 128, 7, "zero", "base", 0),
+    (300, 56, 128, 7, "right", "mut", 0), (400, 48, 256, 11, "zero", "mut", 0), (180, 52, 96, 5, "pos", "base", 8),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("case", SGBM_CASES)
+def test_sgbm_vs_cv2(mode, case):
+    W, H, D, bs, mk, pk, quant = case
+    lg, rg = gray_pair(W, H, D, 3 + mode, quant)
+    minD = {"zero": 0, "right": -(D - 1), "pos": 3}[mk]
+    if mk == "right":
+        lg, rg = rg, lg
+    uq, d12, sw = (10, 1, 100) if pk == "base" else (0, 1000000, 0)
+    kw = dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs, disp12MaxDiff=d12,
+              preFilterCap=63, uniquenessRatio=uq, speckleWindowSize=sw, speckleRange=32, mode=mode)
+    want = cv2.StereoSGBM_create(**kw).compute(lg, rg)
+    assert np.array_equal(cref.sgbm_compute(lg, rg, **kw), want)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_sgbm_c1_and_saturation(mode):
+    lg, rg = gray_pair(320, 360, 64, 7)
+    base, mut, right = ref_ops.sgbm_param_sets(64, 5, mode)
+    assert np.array_equal(cref.sgbm_compute(lg, rg, **base), cv2.StereoSGBM_create(**base).compute(lg, rg))
+    assert np.array_equal(cref.sgbm_compute(rg, lg, **right), cv2.StereoSGBM_create(**right).compute(rg, lg))
+    # pure noise at bs=11: S saturates at 32767 (all-saturated pixels stay invalid)
+    rng = np.random.default_rng(0)
+    ln = rng.integers(0, 256, (64, 400)).astype(np.uint8)
+    rn = rng.integers(0, 256, (64, 400)).astype(np.uint8)
+    kw = dict(minDisparity=0, numDisparities=256, blockSize=11, P1=2904, P2=11616, disp12MaxDiff=1000000,
+              preFilterCap=63, uniquenessRatio=0, speckleWindowSize=0, speckleRange=32, mode=mode)
+    assert np.array_equal(cref.sgbm_compute(ln, rn, **kw), cv2.StereoSGBM_create(**kw).compute(ln, rn))
+
+
+def test_sgbm_real_pair(golden_real):
+    """int16 disparity of the real 320x240 pair as the reference's camera class computed it."""
+    g = golden_real
+    base, _, _ = ref_ops.sgbm_param_sets(64, 5, 2)
+    for tag in ("a", "b"):
+        lg = cv2.cvtColor(g["lrect_" + tag], cv2.COLOR_BGR2GRAY)
+        rg = cv2.cvtColor(g["rrect_" + tag], cv2.COLOR_BGR2GRAY)
+        assert np.array_equal(cref.sgbm_compute(lg, rg, **base), g["disp16_" + tag])
+
+
+def test_median_speckles():
+    rng = np.random.default_rng(1)
+    for t in range(4):
+        H, W = (37, 61) if t < 2 else (240, 320)
+        d = (rng.integers(-1, 40, (H, W)) * 16 + rng.integers(0, 16, (H, W))).astype(np.int16)
+        d[rng.random((H, W)) < 0.3] = -16
+        assert np.array_equal(cref.median3_s16(d), cv2.medianBlur(d, 3))
+        e = d.copy()
+        cv2.filterSpeckles(e, -16, 25, 32)
+        assert np.array_equal(cref.filter_speckles(d, -16, 25, 32), e)
+
+
+def test_simple_masks_and_filters(golden_synth):
+    left = golden_synth["left"]
+    cfg = dict(hsv_lower=(50, 100, 180), hsv_upper=(70, 255, 255), brightness_threshold=200, min_area=50)
+    _, wm1, wm2 = ref_ops.simple_extract(left, want_masks=True, **cfg)
+    m1, m2 = cref.simple_masks(left, cfg["hsv_lower"], cfg["hsv_upper"], 200, 50)
+    assert np.array_equal(m1, wm1) and np.array_equal(m2, wm2)
+    rng = np.random.default_rng(5)
+    for t in range(20):  # random blobs: contour semantics (holes, thin bridges, border contact)
+        m = (cv2.GaussianBlur(rng.random((60, 80)).astype(np.float32), (0, 0), 1.5 + 0.1 * t) > 0.5).astype(np.uint8) * 255
+        img = np.zeros((60, 80, 3), np.uint8)
+        img[m > 0] = (140, 255, 140)
+        _, wm1, wm2 = ref_ops.simple_extract(img, want_masks=True, **dict(cfg, min_area=8 + t))
+        m1, m2 = cref.simple_masks(img, cfg["hsv_lower"], cfg["hsv_upper"], 200, 8 + t)
+        assert np.array_equal(m1, wm1) and np.array_equal(m2, wm2), t
+    f = cv2.cvtColor(left, cv2.COLOR_BGR2GRAY).astype(np.float32)
+    for sigma in (2.0, 3.0):
+        # f32 filters: cv2's SIMD summation order is not reproduced -> tolerance 4 ulp of the image range
+        assert np.allclose(cref.gaussian_blur_f32(f, sigma), cv2.GaussianBlur(f, (0, 0), sigma), rtol=0, atol=1.3e-4)
+    s = cv2.GaussianBlur(f, (0, 0), 3.0)
+    for dx, dy in ((1, 0), (0, 1)):
+        assert np.allclose(cref.sobel3_f32(s, dx, dy), cv2.Sobel(s, cv2.CV_32F, dx, dy, ksize=3), rtol=0, atol=2e-4)
+
+
+def test_depth_vs_cv2(golden_synth):
+    d16 = golden_synth["disp16_3way"]
+    Q = golden_synth["Q"]
+    assert np.array_equal(cref.disp_to_depth_q(d16, Q), ref_ops.depth_from_disparity(d16, Q))
+    assert np.array_equal(cref.disp_to_depth_q(d16, Q), golden_synth["depth"])
+    assert np.array_equal(cref.disp_to_depth_default(d16), ref_ops.depth_from_disparity(d16, None))
+
+
+def test_wls_restatement_properties():
+    """WLS: PARITY UNPINNED (cv2.ximgproc absent).  Check the restatement's invariants only:
+    outside-ROI fill, determinism, and that a constant, fully confident field is a fixed point."""
+    H, W, D = 40, 120, 32
+    guide = np.random.default_rng(0).integers(0, 256, (H, W)).astype(np.uint8)
+    dl = np.full((H, W), 10 * 16, np.int16)
+    dr = np.full((H, W), -10 * 16, np.int16)
+    out, conf = cref.wls_filter(dl, dr, guide, 0, D, 3, want_conf=True)
+    assert np.all(out[:, :D] == -16)
+    assert np.all(out[:, D + 12:] == 160)
+    assert conf.max() <= 255.0 + 1e-3
+    assert np.array_equal(out, cref.wls_filter(dl, dr, guide, 0, D, 3))
