@@ -331,7 +331,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- CPU baseline leg (rank 0, N = 1 only): bounded sample ----------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = CpuPath()
-        ns = max(cpu.cores, 4) if cpu.cores <= 8 else cpu.cores
+        ns = 8 * cpu.cores  # ~10-30 s of CPU work
         pairs = [(L[i % nfr], R[i % nfr]) for i in range(ns)]
         dt, ccounts = cpu.run(pairs)
         cpu.close()

@@ -93,68 +93,113 @@ __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __
     ch[i] = wx; cv[i] = wy;
 }
 
-// Thomas solve along rows; one thread per row, num and den share the elimination factors.
-__global__ void fgs_hpass_kernel(float* __restrict__ num, float* __restrict__ den, const float* __restrict__ ch,
-                                 float* __restrict__ interD, int w, int h, float lam) {
-    int y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= h) return;
-    float* a = num + (size_t)y * w;
-    float* b = den + (size_t)y * w;
-    const float* c = ch + (size_t)y * w;
-    float* Dv = interD + (size_t)y * w;
-    float c0 = c[0];
-    float dn = __fsub_rn(1.0f, __fmul_rn(lam, c0));
-    float Dp = __fdiv_rn(__fmul_rn(lam, c0), dn);
-    float ap = __fdiv_rn(a[0], dn), bp = __fdiv_rn(b[0], dn);
-    Dv[0] = Dp; a[0] = ap; b[0] = bp;
-    float cm = c0;
-    for (int j = 1; j < w; j++) {
-        float cc = c[j];
-        float lcm = __fmul_rn(lam, cm);
-        dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cc))), __fmul_rn(lcm, Dp));
-        Dp = __fdiv_rn(__fmul_rn(lam, cc), dn);
-        ap = __fdiv_rn(__fsub_rn(a[j], __fmul_rn(lcm, ap)), dn);
-        bp = __fdiv_rn(__fsub_rn(b[j], __fmul_rn(lcm, bp)), dn);
-        Dv[j] = Dp; a[j] = ap; b[j] = bp;
-        cm = cc;
+// Thomas solves of one FGS pass: forward elimination + back substitution of a group of lines with
+// the whole lines resident in shared memory.  HORIZ: lines are rows (CTA = `nl` consecutive rows),
+// else columns (CTA = `nl` consecutive columns).  All threads stage num/den/weights into smem with
+// coalesced loads; lane l of warp 0 then runs line l's two sweeps (a serial recurrence of
+// fmul-fsub-fdiv per element, identical op order to oracle/csrc/orc_wls.c), with the elimination
+// factors overwriting the weights in place; all threads store the result.  HBM traffic is the
+// minimum of the pass: 3 reads + 2 writes per pixel.
+constexpr int FGS_THREADS = 256;
+constexpr int FGS_UNROLL = 4;
+
+template <bool HORIZ>
+__global__ void __launch_bounds__(FGS_THREADS) fgs_lines_kernel(float* __restrict__ num, float* __restrict__ den,
+                                                                const float* __restrict__ wgt, int w, int h,
+                                                                float lam, int nl) {
+    extern __shared__ float fgs_sm[];
+    const int nlines = HORIZ ? h : w, len = HORIZ ? w : h;
+    const int l0 = blockIdx.x * nl;
+    const int cnt = min(nl, nlines - l0);
+    // smem element (line l, position j): HORIZ -> l*(len+1) + j (padded rows), else j*nl + l
+    const int ls = HORIZ ? len + 1 : 1, es = HORIZ ? 1 : nl;
+    const int plane = HORIZ ? nl * (len + 1) : len * nl;
+    float* A = fgs_sm;
+    float* B = fgs_sm + plane;
+    float* Cw = fgs_sm + 2 * plane;
+    const int total = cnt * len;
+    for (int idx = threadIdx.x; idx < total; idx += FGS_THREADS) {
+        int l, j;
+        if (HORIZ) { l = idx / len; j = idx - l * len; } else { j = idx / cnt; l = idx - j * cnt; }
+        size_t g = HORIZ ? (size_t)(l0 + l) * w + j : (size_t)j * w + l0 + l;
+        int s = l * ls + j * es;
+        A[s] = num[g]; B[s] = den[g]; Cw[s] = wgt[g];
     }
-    for (int j = w - 2; j >= 0; j--) {
-        float d = Dv[j];
-        ap = __fsub_rn(a[j], __fmul_rn(d, ap));
-        bp = __fsub_rn(b[j], __fmul_rn(d, bp));
-        a[j] = ap; b[j] = bp;
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+        float* a = A + threadIdx.x * ls;
+        float* b = B + threadIdx.x * ls;
+        float* c = Cw + threadIdx.x * ls;
+        float c0 = c[0];
+        float dn = __fsub_rn(1.0f, __fmul_rn(lam, c0));
+        float Dp = __fdiv_rn(__fmul_rn(lam, c0), dn);
+        float ap = __fdiv_rn(a[0], dn), bp = __fdiv_rn(b[0], dn);
+        c[0] = Dp; a[0] = ap; b[0] = bp;
+        float cm = c0;
+        int j = 1;
+        for (; j + FGS_UNROLL <= len; j += FGS_UNROLL) {
+            float cc[FGS_UNROLL], av[FGS_UNROLL], bv[FGS_UNROLL];
+#pragma unroll
+            for (int k = 0; k < FGS_UNROLL; k++) { cc[k] = c[(j + k) * es]; av[k] = a[(j + k) * es]; bv[k] = b[(j + k) * es]; }
+#pragma unroll
+            for (int k = 0; k < FGS_UNROLL; k++) {
+                float lcm = __fmul_rn(lam, cm);
+                dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cc[k]))), __fmul_rn(lcm, Dp));
+                Dp = __fdiv_rn(__fmul_rn(lam, cc[k]), dn);
+                ap = __fdiv_rn(__fsub_rn(av[k], __fmul_rn(lcm, ap)), dn);
+                bp = __fdiv_rn(__fsub_rn(bv[k], __fmul_rn(lcm, bp)), dn);
+                c[(j + k) * es] = Dp; a[(j + k) * es] = ap; b[(j + k) * es] = bp;
+                cm = cc[k];
+            }
+        }
+        for (; j < len; j++) {
+            float cck = c[j * es];
+            float lcm = __fmul_rn(lam, cm);
+            dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cck))), __fmul_rn(lcm, Dp));
+            Dp = __fdiv_rn(__fmul_rn(lam, cck), dn);
+            ap = __fdiv_rn(__fsub_rn(a[j * es], __fmul_rn(lcm, ap)), dn);
+            bp = __fdiv_rn(__fsub_rn(b[j * es], __fmul_rn(lcm, bp)), dn);
+            c[j * es] = Dp; a[j * es] = ap; b[j * es] = bp;
+            cm = cck;
+        }
+        j = len - 2;
+        for (; j - (FGS_UNROLL - 1) >= 0; j -= FGS_UNROLL) {
+            float dv[FGS_UNROLL], av[FGS_UNROLL], bv[FGS_UNROLL];
+#pragma unroll
+            for (int k = 0; k < FGS_UNROLL; k++) { dv[k] = c[(j - k) * es]; av[k] = a[(j - k) * es]; bv[k] = b[(j - k) * es]; }
+#pragma unroll
+            for (int k = 0; k < FGS_UNROLL; k++) {
+                ap = __fsub_rn(av[k], __fmul_rn(dv[k], ap));
+                bp = __fsub_rn(bv[k], __fmul_rn(dv[k], bp));
+                a[(j - k) * es] = ap; b[(j - k) * es] = bp;
+            }
+        }
+        for (; j >= 0; j--) {
+            float d = c[j * es];
+            ap = __fsub_rn(a[j * es], __fmul_rn(d, ap));
+            bp = __fsub_rn(b[j * es], __fmul_rn(d, bp));
+            a[j * es] = ap; b[j * es] = bp;
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < total; idx += FGS_THREADS) {
+        int l, j;
+        if (HORIZ) { l = idx / len; j = idx - l * len; } else { j = idx / cnt; l = idx - j * cnt; }
+        size_t g = HORIZ ? (size_t)(l0 + l) * w + j : (size_t)j * w + l0 + l;
+        int s = l * ls + j * es;
+        num[g] = A[s]; den[g] = B[s];
     }
 }
 
-// Thomas solve along columns; one thread per column (coalesced rows).
-__global__ void fgs_vpass_kernel(float* __restrict__ num, float* __restrict__ den, const float* __restrict__ cv,
-                                 float* __restrict__ interD, int w, int h, float lam) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
-    float c0 = cv[x];
-    float dn = __fsub_rn(1.0f, __fmul_rn(lam, c0));
-    float Dp = __fdiv_rn(__fmul_rn(lam, c0), dn);
-    float ap = __fdiv_rn(num[x], dn), bp = __fdiv_rn(den[x], dn);
-    interD[x] = Dp; num[x] = ap; den[x] = bp;
-    float cm = c0;
-    for (int j = 1; j < h; j++) {
-        size_t i = (size_t)j * w + x;
-        float cc = cv[i];
-        float lcm = __fmul_rn(lam, cm);
-        dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cc))), __fmul_rn(lcm, Dp));
-        Dp = __fdiv_rn(__fmul_rn(lam, cc), dn);
-        ap = __fdiv_rn(__fsub_rn(num[i], __fmul_rn(lcm, ap)), dn);
-        bp = __fdiv_rn(__fsub_rn(den[i], __fmul_rn(lcm, bp)), dn);
-        interD[i] = Dp; num[i] = ap; den[i] = bp;
-        cm = cc;
-    }
-    for (int j = h - 2; j >= 0; j--) {
-        size_t i = (size_t)j * w + x;
-        float d = interD[i];
-        ap = __fsub_rn(num[i], __fmul_rn(d, ap));
-        bp = __fsub_rn(den[i], __fmul_rn(d, bp));
-        num[i] = ap; den[i] = bp;
-    }
+// lines per CTA: spread the lines over ~one CTA per SM, within the shared-memory budget
+static int fgs_lines_per_cta(int nlines, int len, bool horiz, size_t* smem) {
+    const size_t budget = 200 * 1024;
+    size_t per_line = (size_t)3 * (len + (horiz ? 1 : 0)) * sizeof(float);
+    int cap = (int)std::min<size_t>(32, budget / per_line);
+    int nl = std::max(1, std::min(cap, cdiv(nlines, NUM_SMS)));
+    if (!horiz) nl = std::max(1, std::min(cap, std::max(nl, 8)));  // >= one 32 B sector per row segment
+    *smem = per_line * nl;
+    return nl;
 }
 
 __global__ void wls_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
@@ -205,7 +250,6 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     float *aL = L.get<float>(S_WLS_A, n), *bL = L.get<float>(S_WLS_B, n), *aR = L.get<float>(S_WLS_C, n), *bR = L.get<float>(S_WLS_D, n);
     float *cl = L.get<float>(S_WLS_E, n), *cr = L.get<float>(S_WLS_F, n);
     float *conf = L.get<float>(S_WLS_G, n), *ch = L.get<float>(S_WLS_H, n), *cv = L.get<float>(S_WLS_I, n);
-    float* interD = L.get<float>(S_WLS_J, n);
     float* lut = nullptr;
     int rc = wls_lut(L, p.sigma_color, &lut);
     if (rc != L3D_OK) return rc;
@@ -217,9 +261,14 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     float *num = aL, *den = bL;
     L3D_LAUNCH(L, wls_lrc_kernel, g, 128, 0, dl, dr, guide, lut, W, x0, w, h, p.lrc_thresh, cl, cr, conf, num, den, ch, cv);
     float lam = (float)p.lambda;
+    size_t smh = 0, smv = 0;
+    const int nlh = fgs_lines_per_cta(h, w, true, &smh), nlv = fgs_lines_per_cta(w, h, false, &smv);
+    L3D_ARG(L, smh <= 220 * 1024 && smv <= 220 * 1024, "wls: image too large for the line-resident FGS solver");
+    L3D_CHECK(L, cudaFuncSetAttribute(fgs_lines_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    L3D_CHECK(L, cudaFuncSetAttribute(fgs_lines_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     for (int it = 0; it < 3; it++) {
-        L3D_LAUNCH(L, fgs_hpass_kernel, cdiv(h, 32), 32, 0, num, den, ch, interD, w, h, lam);
-        L3D_LAUNCH(L, fgs_vpass_kernel, cdiv(w, 32), 32, 0, num, den, cv, interD, w, h, lam);
+        L3D_LAUNCH(L, fgs_lines_kernel<true>, cdiv(h, nlh), FGS_THREADS, smh, num, den, ch, w, h, lam, nlh);
+        L3D_LAUNCH(L, fgs_lines_kernel<false>, cdiv(w, nlv), FGS_THREADS, smv, num, den, cv, w, h, lam, nlv);
         lam *= 0.25f;
     }
     L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, num, den, conf, W, H, x0, w, outside, out, conf_out);
@@ -237,10 +286,11 @@ __global__ void depth_q_kernel(const int16_t* __restrict__ d16, int W, int H, QM
     size_t i = (size_t)y * W + x;
     float disp = __fdiv_rn((float)d16[i], 16.0f);
     double d = (double)disp, fx = (double)x, fy = (double)y;
-    // cv2.reprojectImageTo3D: [X Y Z W]^T = Q [x y d 1]^T, Z/W evaluated in f64, stored as f32
+    // cv2.reprojectImageTo3D (4.13, probed): [X Y Z W]^T = Q [x y d 1]^T in f64, the numerator is
+    // first stored as f32 (Vec3f), then divided by the f64 W and rounded to f32 again
     double Z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q.q[8], fx), __dmul_rn(Q.q[9], fy)), __dmul_rn(Q.q[10], d)), Q.q[11]);
     double Wh = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q.q[12], fx), __dmul_rn(Q.q[13], fy)), __dmul_rn(Q.q[14], d)), Q.q[15]);
-    float z = (float)__ddiv_rn(Z, Wh);
+    float z = (float)__ddiv_rn((double)(float)Z, Wh);
     if (z < 0.f) z = 0.f;
     if (z > 10.f) z = 0.f;
     if (disp <= 0.f) z = 0.f;

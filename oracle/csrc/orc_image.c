@@ -234,7 +234,8 @@ void orc_disp_to_depth_q(const int16_t* disp16, int W, int H, const double* Q, f
             double d = disp;
             double Z = Q[8] * x + Q[9] * y + Q[10] * d + Q[11];
             double Wh = Q[12] * x + Q[13] * y + Q[14] * d + Q[15];
-            float z = (float)(Z / Wh);
+            float zf = (float)Z; /* Vec3f store before the division (probed against cv2 4.13) */
+            float z = (float)((double)zf / Wh);
             if (z < 0) z = 0;
             if (z > 10) z = 0;
             if (disp <= 0) z = 0;

@@ -164,7 +164,10 @@ def test_sgbm_properties_full_size(ctx):
     assert np.all(a[:, :128 - 1] == -16)  # columns < minX1 (minus the 3x3 median reach) invalid
     valid = a[:, 140:] >= 0
     assert valid.mean() > 0.9
-    truth = np.rint(synth.disparity_field(1280, 720, 128))[:, 140:]
+    # right(x) = left(x + d(x)): the disparity seen at left pixel x is d evaluated at the matching right pixel
+    field = np.rint(synth.disparity_field(1280, 720, 128))
+    xs = np.arange(1280)[None, :] - np.rint(a / 16.0).astype(np.int64)
+    truth = np.take_along_axis(field, np.clip(xs, 0, 1279), axis=1)[:, 140:]
     err = np.abs(a[:, 140:] / 16.0 - truth)[valid]
     assert np.median(err) < 0.6  # the matcher recovers the rendered disparity field
 

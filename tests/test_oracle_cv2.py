@@ -124,6 +124,15 @@ def test_simple_masks_and_filters(golden_synth):
         assert np.allclose(cref.sobel3_f32(s, dx, dy), cv2.Sobel(s, cv2.CV_32F, dx, dy, ksize=3), rtol=0, atol=2e-4)
 
 
+def test_depth_vs_cv2_real_and_random_Q(golden_real):
+    for tag in ("a", "b"):
+        assert np.array_equal(cref.disp_to_depth_q(golden_real["disp16_" + tag], golden_real["Q"]), golden_real["depth_" + tag])
+    rng = np.random.default_rng(0)
+    d16 = rng.integers(-16, 2000, (100, 150)).astype(np.int16)
+    Q = np.array([[1, 0, 0, -150.3], [0, 1, 0, -99.7], [0.001, 0.002, 0.0003, 233.123], [0.0001, 0.0002, 16.3, -0.7]])
+    assert np.array_equal(cref.disp_to_depth_q(d16, Q), ref_ops.depth_from_disparity(d16, Q))
+
+
 def test_depth_vs_cv2(golden_synth):
     d16 = golden_synth["disp16_3way"]
     Q = golden_synth["Q"]
