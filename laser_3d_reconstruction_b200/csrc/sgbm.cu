@@ -29,7 +29,7 @@ namespace l3d {
 
 constexpr int MAXSEG = 4;
 constexpr int MAXBAND = 64;
-constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr uint32_t INF2 = 0x7fff7fffu;
 
 struct Geom {
@@ -92,7 +92,10 @@ int sgbm_volume_rows(const l3d_sgbm_params& p, int W, int H) {
 }
 
 // ------------------------------------------------------------------------------------------
-// prefilter: per pixel {c0.v, c0.lo, c0.hi, c1.v | c1.lo, c1.hi, 0, 0}
+// prefilter: per pixel and channel (0 = clipped x-Sobel, 1 = intensity) the Birchfield-Tomasi
+// operands as signed 16-bit values, ready for packed s16x2 DPX arithmetic:
+//   desc.x = v | (-v) << 16,  desc.y = lo | (-hi) << 16   (channel 0)      desc.z, desc.w (channel 1)
+// where lo / hi = min / max of v and its two half-pixel interpolants.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pre_pixel(const uint8_t* __restrict__ img, int W, int H, int y, int x,
                                           int ftzero, int& c0, int& c1) {
@@ -105,8 +108,10 @@ __device__ __forceinline__ void pre_pixel(const uint8_t* __restrict__ img, int W
     c1 = r[x];
 }
 
+__device__ __forceinline__ uint32_t pack_s16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
 __global__ void sgbm_prefilter_kernel(const uint8_t* __restrict__ img, int W, int H, int ftzero,
-                                      uint2* __restrict__ desc) {
+                                      uint4* __restrict__ desc) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= W) return;
@@ -123,95 +128,121 @@ __global__ void sgbm_prefilter_kernel(const uint8_t* __restrict__ img, int W, in
         int t0 = (b0 + c0) >> 1, t1 = (b1 + c1) >> 1;
         lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
     }
-    uint2 d;
-    d.x = (uint32_t)b0 | ((uint32_t)lo0 << 8) | ((uint32_t)hi0 << 16) | ((uint32_t)b1 << 24);
-    d.y = (uint32_t)lo1 | ((uint32_t)hi1 << 8);
-    desc[(size_t)y * W + x] = d;
+    desc[(size_t)y * W + x] = make_uint4(pack_s16(b0, -b0), pack_s16(lo0, -hi0), pack_s16(b1, -b1), pack_s16(lo1, -hi1));
 }
 
 // ------------------------------------------------------------------------------------------
-// cost volume
+// cost volume: C[y][x][d] = P2 + sum over the blockSize^2 window of the BT pixel cost
 // ------------------------------------------------------------------------------------------
+// A CTA owns TX output columns (TXH = TX + 2*SW2 computed columns) of a band of rows and walks the
+// band top to bottom.  Per image row:
+//   build   operand tables in smem: one uint4 per right pixel position holding the s16x2 pairs
+//           (v, -v, lo, -hi) of the two right pixels a disparity pair (d, d+1) looks at, and one per
+//           left column with the same operands broadcast to both halves
+//   phase A thread <-> (column, every (256/TXH)-th disparity pair): BT cost of both channels in
+//           10 VIADDMNMX/VIMNMX.S16x2 ops per two disparities -> pd[dp][col] (row stride TXH+1)
+//   phase B thread <-> (disparity pair, group of columns): running horizontal box sum along its
+//           columns, vertical running sum against a ring of the last blockSize row sums, C store
+//           (a warp writes 128 contiguous bytes per column)
+// All sums are wrap-around u16 like OpenCV's int16 arithmetic.
 struct CostArgs {
-    const uint2* Ldesc; const uint2* Rdesc; int16_t* C;
-    int W, minD, D, minX1, width1, SW2, bs, P2, TX;
+    const uint4* Ldesc; const uint4* Rdesc; int16_t* C;
+    int W, minD, D, minX1, width1, SW2, bs, P2, TX, TXH;
+    int nxg, cpg;  // phase B: column groups per CTA, columns per group
     int nbands;
     int band_vr0[MAXBAND], band_y0[MAXBAND], band_rows[MAXBAND], band_clo[MAXBAND], band_chi[MAXBAND];
 };
 
-__device__ __forceinline__ uint32_t bt_cost(uint2 l, uint2 r) {
-    int u = l.x & 255, u0 = (l.x >> 8) & 255, u1 = (l.x >> 16) & 255;
-    int v = r.x & 255, v0 = (r.x >> 8) & 255, v1 = (r.x >> 16) & 255;
-    int c0 = max(max(0, u - v1), v0 - u);
-    int c1 = max(max(0, v - u1), u0 - v);
-    int a = min(c0, c1);
-    u = l.x >> 24; u0 = l.y & 255; u1 = (l.y >> 8) & 255;
-    v = r.x >> 24; v0 = r.y & 255; v1 = (r.y >> 8) & 255;
-    c0 = max(max(0, u - v1), v0 - u);
-    c1 = max(max(0, v - u1), u0 - v);
-    return (uint32_t)(a + (min(c0, c1) >> 2));
-}
-
 constexpr int COST_THREADS = 256;
-constexpr int COST_NB = 8;  // phase-B items per thread (TX*D/2 <= 2048)
+constexpr int COST_MAXCPG = 16;
+
+__device__ __forceinline__ uint32_t bt_pair(uint32_t U, uint32_t nU, uint32_t U0, uint32_t nU1, const uint4& r) {
+    // r = (V, -V, V0, -V1) pairs; max(0, u - v1, v0 - u) and max(0, v - u1, u0 - v), then the smaller
+    uint32_t t = __viaddmax_s16x2(U, r.w, 0u);
+    t = __viaddmax_s16x2(r.z, nU, t);
+    uint32_t q = __viaddmax_s16x2(r.x, nU1, 0u);
+    q = __viaddmax_s16x2(r.y, U0, q);
+    return __vmins2(t, q);
+}
 
 __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int TX = a.TX, SW2 = a.SW2, bs = a.bs, D = a.D, D2 = D >> 1, TXH = TX + 2 * SW2;
+    const int TX = a.TX, TXH = a.TXH, SW2 = a.SW2, bs = a.bs, D = a.D, D2 = D >> 1;
     const int width1 = a.width1, W = a.W;
-    uint2* sL = (uint2*)smem_raw;
-    uint2* sR = sL + TXH;
-    uint32_t* pd = (uint32_t*)(sR + TXH + D);
-    uint32_t* ring = pd + TXH * D2;
     const int tid = threadIdx.x;
     const int b = blockIdx.y, x0 = blockIdx.x * TX;
     const int y0 = a.band_y0[b], rows = a.band_rows[b], clo = a.band_clo[b], chi = a.band_chi[b], vr0 = a.band_vr0[b];
     const int xa = min(max(x0 - SW2, 0), width1 - 1);
-    const int xb = min(max(x0 + TX - 1 + SW2, 0), width1 - 1);
-    const int xr_base = xa + a.minX1 - (a.minD + D - 1);
-    const int nR = (xb - xa) + D;
-    const int nitemsA = TXH * D2, nitemsB = TX * D2;
+    const int xb = min(max(x0 + TXH - 1 - SW2, 0), width1 - 1);
+    const int xr_base = xa + a.minX1 - (a.minD + D - 1);  // lowest right pixel any pair reads
+    const int nE = (xb - xa) + D - 1;                      // right operand entries (pair = pixels e+1, e)
+    const int PS = TXH + 1;                                // pd row stride (bank-conflict-free both ways)
+    // smem carve-up
+    uint4* R0 = (uint4*)smem_raw;              // [nEmax] channel 0
+    const int nEmax = TXH + D;
+    uint4* R1 = R0 + nEmax;                    // channel 1
+    uint4* L0 = R1 + nEmax;                    // [TXH]
+    uint4* L1 = L0 + TXH;
+    uint32_t* pd = (uint32_t*)(L1 + TXH);      // [D2][PS]
+    uint32_t* ring = pd + D2 * PS;             // [bs][TX][D2]
+    // phase A role
+    const int ca = tid % TXH, dpa0 = tid / TXH, dpa_step = COST_THREADS / TXH;
+    const int xca = min(max(x0 - SW2 + ca, 0), width1 - 1);
+    // phase B role
+    const int dpb = tid % D2, xg = tid / D2;
+    const bool roleB = xg < a.nxg;
+    const int cb0 = xg * a.cpg;                // first output column (tile coordinates)
+    const int ncb = roleB ? max(0, min(a.cpg, TX - cb0)) : 0;
     const uint32_t p2x2 = (uint32_t)a.P2 * 0x10001u;
-    uint32_t crun[COST_NB];
+    uint32_t crun[COST_MAXCPG];
 #pragma unroll
-    for (int j = 0; j < COST_NB; j++) crun[j] = p2x2;
+    for (int j = 0; j < COST_MAXCPG; j++) crun[j] = p2x2;
 
     for (int k = 0; k < rows + bs - 1; k++) {
         const int ky = min(max(y0 - SW2 + k, clo), chi);
-        const uint2* Lrow = a.Ldesc + (size_t)ky * W;
-        const uint2* Rrow = a.Rdesc + (size_t)ky * W;
-        for (int i = tid; i < TXH; i += COST_THREADS) {
-            int xc = min(max(x0 - SW2 + i, 0), width1 - 1);
-            sL[i] = Lrow[xc + a.minX1];
+        const uint4* Lrow = a.Ldesc + (size_t)ky * W;
+        const uint4* Rrow = a.Rdesc + (size_t)ky * W;
+        for (int e = tid; e < nE; e += COST_THREADS) {
+            const uint4 hi = Rrow[xr_base + e + 1], lo = Rrow[xr_base + e];  // disparities (d, d+1) -> pixels (e+1, e)
+            R0[e] = make_uint4(__byte_perm(hi.x, lo.x, 0x5410), __byte_perm(hi.x, lo.x, 0x7632),
+                               __byte_perm(hi.y, lo.y, 0x5410), __byte_perm(hi.y, lo.y, 0x7632));
+            R1[e] = make_uint4(__byte_perm(hi.z, lo.z, 0x5410), __byte_perm(hi.z, lo.z, 0x7632),
+                               __byte_perm(hi.w, lo.w, 0x5410), __byte_perm(hi.w, lo.w, 0x7632));
         }
-        for (int i = tid; i < nR; i += COST_THREADS) sR[i] = Rrow[xr_base + i];
-        __syncthreads();
-        for (int item = tid; item < nitemsA; item += COST_THREADS) {
-            int c = item / D2, dp = item - c * D2;
-            int xc = min(max(x0 - SW2 + c, 0), width1 - 1);
-            uint2 l = sL[c];
-            int ri = xc - xa + (D - 1) - 2 * dp;
-            pd[item] = bt_cost(l, sR[ri]) | (bt_cost(l, sR[ri - 1]) << 16);
+        if (tid < TXH) {
+            const uint4 l = Lrow[xca + a.minX1];
+            L0[tid] = make_uint4(__byte_perm(l.x, l.x, 0x1010), __byte_perm(l.x, l.x, 0x3232),
+                                 __byte_perm(l.y, l.y, 0x1010), __byte_perm(l.y, l.y, 0x3232));
+            L1[tid] = make_uint4(__byte_perm(l.z, l.z, 0x1010), __byte_perm(l.z, l.z, 0x3232),
+                                 __byte_perm(l.w, l.w, 0x1010), __byte_perm(l.w, l.w, 0x3232));
         }
         __syncthreads();
-        const int slot = k % bs;
+        {   // phase A
+            const uint4 l0 = L0[ca], l1 = L1[ca];
+            const int ebase = xca - xa + D - 2;
+            for (int dp = dpa0; dp < D2; dp += dpa_step) {
+                const int e = ebase - 2 * dp;
+                const uint32_t c0 = bt_pair(l0.x, l0.y, l0.z, l0.w, R0[e]);
+                const uint32_t c1 = bt_pair(l1.x, l1.y, l1.z, l1.w, R1[e]);
+                pd[dp * PS + ca] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+            }
+        }
+        __syncthreads();
+        if (ncb > 0) {  // phase B
+            const uint32_t* pp = pd + dpb * PS + cb0;  // pp[j + i] = pixel cost at output column cb0 + j, tap i
+            uint32_t h = 0;
+            for (int i = 0; i < bs; i++) h = __vadd2(h, pp[i]);
+            uint32_t* rp = ring + ((size_t)(k % bs) * TX + cb0) * D2 + dpb;
+            const int16_t* Cdst = a.C + ((size_t)(vr0 + k - (bs - 1)) * width1 + x0 + cb0) * D + 2 * dpb;
 #pragma unroll
-        for (int j = 0; j < COST_NB; j++) {
-            int item = tid + COST_THREADS * j;
-            if (item < nitemsB) {
-                int xx = item / D2, dp = item - xx * D2;
-                uint32_t h = 0;
-                const uint32_t* pp = pd + xx * D2 + dp;
-                for (int jj = 0; jj < bs; jj++) h = __vadd2(h, pp[jj * D2]);
-                uint32_t* rp = ring + (slot * TX + xx) * D2 + dp;
-                uint32_t c = __vadd2(crun[j], h);
-                if (k >= bs) c = __vsub2(c, *rp);
-                *rp = h;
-                crun[j] = c;
-                int x = x0 + xx;
-                if (k >= bs - 1 && x < width1) {
-                    size_t off = ((size_t)(vr0 + k - (bs - 1)) * width1 + x) * D + 2 * dp;
-                    *(uint32_t*)(a.C + off) = c;
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j < ncb) {
+                    if (j > 0) h = __vsub2(__vadd2(h, pp[j + bs - 1]), pp[j - 1]);
+                    uint32_t c = __vadd2(crun[j], h);
+                    if (k >= bs) c = __vsub2(c, rp[(size_t)j * D2]);
+                    rp[(size_t)j * D2] = h;
+                    crun[j] = c;
+                    if (k >= bs - 1 && x0 + cb0 + j < width1) *(uint32_t*)(Cdst + (size_t)j * D) = c;
                 }
             }
         }
@@ -228,6 +259,7 @@ struct ScanArgs {
     int kind;   // 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up, 6 up-left, 7 up-right
     int store;  // 1: S = L ; 0: S = min(S + L, 32767)
     int HV, nseg;
+    int lines_per_seg;  // kinds >= 2: lines per segment (columns, or diagonals)
     int seg_vr0[MAXSEG], seg_rows[MAXSEG];
 };
 
@@ -246,21 +278,22 @@ template <> __device__ __forceinline__ uint2 vec_pack<2>(const uint32_t (&o)[2])
 template <> __device__ __forceinline__ uint4 vec_pack<4>(const uint32_t (&o)[4]) { return make_uint4(o[0], o[1], o[2], o[3]); }
 
 constexpr int SCAN_WARPS = 4;
-constexpr int SCAN_DEPTH = 16;
 
-// one SGM step for the disparities held by this lane; returns the warp-wide min of the new L
-template <int NP>
+// one SGM step for the disparities held by this lane; returns the warp-wide min of the new L.
+// Inactive lanes (lane >= nact, only when D is not a multiple of 64*NP/2... i.e. !FULL) keep L = INF2
+// so that neither the neighbour exchange nor the min-reduction sees them.
+template <int NP, bool FULL>
 __device__ __forceinline__ int sgm_step(uint32_t (&L)[NP], int minL, const uint32_t (&Cv)[NP], uint32_t p1x2,
-                                        int P2, int lane, int nact) {
-    uint32_t up = __shfl_up_sync(FULL, L[NP - 1], 1);
-    uint32_t dn = __shfl_down_sync(FULL, L[0], 1);
+                                        int P2, int lane, bool active) {
+    uint32_t up = __shfl_up_sync(FULL_MASK, L[NP - 1], 1);
+    uint32_t dn = __shfl_down_sync(FULL_MASK, L[0], 1);
     if (lane == 0) up = INF2;
-    if (lane >= nact - 1) dn = INF2;
+    if (lane == 31) dn = INF2;
     const uint32_t delta = (uint32_t)(minL + P2) & 0xffffu;
     const uint32_t delta2 = delta * 0x10001u;
     const uint32_t ndelta2 = ((0x10000u - delta) & 0xffffu) * 0x10001u;
-    uint32_t Ln[NP];
     uint32_t mn = INF2;
+    uint32_t Ln[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) {
         uint32_t prev = k ? L[k - 1] : up;
@@ -271,94 +304,119 @@ __device__ __forceinline__ int sgm_step(uint32_t (&L)[NP], int minL, const uint3
         m = __viaddmin_u16x2(dm1, p1x2, m);
         m = __viaddmin_u16x2(dp1, p1x2, m);
         Ln[k] = __vadd2(__vadd2(Cv[k], m), ndelta2);
+        if (!FULL && !active) Ln[k] = INF2;
         mn = __vminu2(mn, Ln[k]);
     }
-    int m16 = (int)min(mn & 0xffffu, mn >> 16);
-    if (lane >= nact) m16 = 0x7fff;
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = Ln[k];
-    return __reduce_min_sync(FULL, m16);
+    int m16 = (int)min(mn & 0xffffu, mn >> 16);
+    return __reduce_min_sync(FULL_MASK, m16);
 }
 
-template <int NP>
+// Scan lines of one path direction.  kinds: 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up,
+// 6 up-left, 7 up-right (direction of travel; the predecessor is one step behind).  Horizontal
+// and vertical lines are rows / columns; the diagonal kinds run over true (anti-)diagonals of
+// varying length, so there is no wrap-around logic in the loop.
+struct ScanLine { int vr, x, n, dvr, dx; };
+
+__device__ __forceinline__ bool scan_decode(const ScanArgs& a, int line, ScanLine& o) {
+    const int width1 = a.width1, kind = a.kind;
+    if (kind <= 1) {
+        if (line >= a.HV) return false;
+        o.vr = line; o.n = width1; o.dvr = 0;
+        if (kind == 0) { o.x = 0; o.dx = 1; } else { o.x = width1 - 1; o.dx = -1; }
+        return true;
+    }
+    const int lps = a.lines_per_seg;
+    const int seg = line / lps, u = line - seg * lps;
+    if (seg >= a.nseg) return false;
+    const int rows = a.seg_rows[seg], top = a.seg_vr0[seg];
+    int y0, x0, n;
+    if (kind == 2 || kind == 5) {
+        if (u >= width1) return false;
+        y0 = 0; x0 = u; n = rows;
+        o.dx = 0;
+    } else if (kind == 3 || kind == 6) {  // diagonals x - y = u - (rows - 1)
+        const int uu = u - (rows - 1);
+        if (uu > width1 - 1) return false;
+        y0 = max(0, -uu); x0 = uu + y0; n = min(rows - y0, width1 - x0);
+        o.dx = 1;
+    } else {  // anti-diagonals x + y = u
+        if (u > width1 + rows - 2) return false;
+        y0 = max(0, u - (width1 - 1)); x0 = u - y0; n = min(rows - y0, x0 + 1);
+        o.dx = -1;
+    }
+    o.dvr = 1;
+    if (kind >= 5) {  // bottom-up: start from the other end of the same line
+        y0 += n - 1; x0 += o.dx * (n - 1);
+        o.dvr = -1; o.dx = -o.dx;
+    }
+    o.vr = top + y0; o.x = x0; o.n = n;
+    return n > 0;
+}
+
+template <int NP, bool STORE, bool FULL>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) sgbm_scan_kernel(const ScanArgs a) {
     typedef typename VecOf<NP>::T vec;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int U = NP == 4 ? 4 : 8;  // steps per register-prefetch batch
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    vec* ringC = (vec*)smem_raw + (size_t)warp * SCAN_DEPTH * 32;
-    vec* ringS = (vec*)smem_raw + (size_t)(SCAN_WARPS + warp) * SCAN_DEPTH * 32;
-    const int line = blockIdx.x * SCAN_WARPS + warp;
-    const int width1 = a.width1, kind = a.kind;
-    int n, vr, x, dvr, dx;
-    if (kind <= 1) {
-        if (line >= a.HV) return;
-        n = width1; vr = line; dvr = 0;
-        if (kind == 0) { x = 0; dx = 1; } else { x = width1 - 1; dx = -1; }
-    } else {
-        int seg = line / width1, xs = line - seg * width1;
-        if (seg >= a.nseg) return;
-        n = a.seg_rows[seg];
-        if (kind <= 4) { vr = a.seg_vr0[seg]; dvr = 1; } else { vr = a.seg_vr0[seg] + n - 1; dvr = -1; }
-        x = xs;
-        dx = (kind == 2 || kind == 5) ? 0 : ((kind == 3 || kind == 7) ? 1 : -1);
-    }
-    const bool active = lane < a.nact;
-    const bool store = a.store != 0;
-    const size_t lane_off = (size_t)lane * (NP * 2);  // int16 elements
-    const int D = a.D;
+    ScanLine ln;
+    if (!scan_decode(a, blockIdx.x * SCAN_WARPS + warp, ln)) return;
+    const int nact = a.nact, n = ln.n;
+    const bool active = FULL || lane < nact;
+    const vec* __restrict__ Cv = (const vec*)a.C;
+    vec* __restrict__ Sv = (vec*)a.S;
+    // element offsets in vec units (a pixel holds nact vecs); volumes stay below 2^32 vecs
+    const int stride = (ln.dvr * a.width1 + ln.dx) * nact;
+    unsigned lo = (unsigned)(ln.vr * a.width1 + ln.x) * (unsigned)nact + (unsigned)lane;  // next load
+    unsigned so = lo;                                                                      // next store
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const int P2 = a.P2;
 
-    // look-ahead iterator for the cp.async ring
-    int pvr = vr, px = x;
-    auto issue = [&](int stage) {
-        if (active) {
-            size_t off = ((size_t)pvr * width1 + px) * D + lane_off;
-            __pipeline_memcpy_async(&ringC[stage * 32 + lane], a.C + off, sizeof(vec));
-            if (!store) __pipeline_memcpy_async(&ringS[stage * 32 + lane], a.S + off, sizeof(vec));
-        }
-        pvr += dvr; px += dx;
-        if (px >= width1) px = 0;
-        if (px < 0) px = width1 - 1;
-    };
-    for (int s = 0; s < SCAN_DEPTH; s++) {
-        if (s < n) issue(s);
-        __pipeline_commit();
-    }
     uint32_t L[NP];
 #pragma unroll
-    for (int k = 0; k < NP; k++) L[k] = 0;
+    for (int k = 0; k < NP; k++) L[k] = active ? 0u : INF2;
     int minL = 0;
-    for (int i = 0; i < n; i++) {
-        const int stage = i % SCAN_DEPTH;
-        __pipeline_wait_prior(SCAN_DEPTH - 1);
-        uint32_t Cv[NP], Sv[NP];
-        if (active) {
-            vec_unpack<NP>(ringC[stage * 32 + lane], Cv);
-            if (!store) vec_unpack<NP>(ringS[stage * 32 + lane], Sv);
-        } else {
+
+    vec cA[U], cB[U], sA[U], sB[U];
+    auto load = [&](vec (&c)[U], vec (&s)[U], int base) {
 #pragma unroll
-            for (int k = 0; k < NP; k++) { Cv[k] = 0; Sv[k] = 0; }
+        for (int k = 0; k < U; k++) {
+            if (base + k < n && active) {
+                const unsigned o = lo + (unsigned)(k * stride);
+                c[k] = __ldg(Cv + o);
+                if (!STORE) s[k] = Sv[o];
+            }
         }
-        // diagonal lines wrap around the image; the predecessor of the re-entry pixel is outside
-        if (dx != 0 && dvr != 0 && i > 0 && ((dx > 0 && x == 0) || (dx < 0 && x == width1 - 1))) {
+        lo += (unsigned)(U * stride);
+    };
+    auto step = [&](const vec& c, const vec& s) {
+        uint32_t Cw[NP], Sw[NP];
+        vec_unpack<NP>(c, Cw);
+        if (!STORE) vec_unpack<NP>(s, Sw);
+        minL = sgm_step<NP, FULL>(L, minL, Cw, p1x2, P2, lane, active);
+        uint32_t out[NP];
 #pragma unroll
-            for (int k = 0; k < NP; k++) L[k] = 0;
-            minL = 0;
-        }
-        minL = sgm_step<NP>(L, minL, Cv, p1x2, P2, lane, a.nact);
-        if (active) {
-            uint32_t out[NP];
+        for (int q = 0; q < NP; q++) out[q] = STORE ? L[q] : __viaddmin_u16x2(Sw[q], L[q], INF2);
+        if (active) Sv[so] = vec_pack<NP>(out);
+        so += (unsigned)stride;
+    };
+    load(cA, sA, 0);
+    int i = 0;
+    for (; i + 2 * U <= n; i += 2 * U) {  // two full batches: no per-step checks
+        load(cB, sB, i + U);
 #pragma unroll
-            for (int k = 0; k < NP; k++) out[k] = store ? L[k] : __vminu2(__vadd2(Sv[k], L[k]), INF2);
-            size_t off = ((size_t)vr * width1 + x) * D + lane_off;
-            *(vec*)(a.S + off) = vec_pack<NP>(out);
-        }
-        if (i + SCAN_DEPTH < n) issue(stage);
-        __pipeline_commit();
-        vr += dvr; x += dx;
-        if (x >= width1) x = 0;
-        if (x < 0) x = width1 - 1;
+        for (int k = 0; k < U; k++) step(cA[k], sA[k]);
+        load(cA, sA, i + 2 * U);
+#pragma unroll
+        for (int k = 0; k < U; k++) step(cB[k], sB[k]);
+    }
+    if (i < n) {  // tail of fewer than 2U steps (warp-uniform bounds)
+        load(cB, sB, i + U);
+#pragma unroll
+        for (int k = 0; k < U; k++) if (i + k < n) step(cA[k], sA[k]);
+#pragma unroll
+        for (int k = 0; k < U; k++) if (i + U + k < n) step(cB[k], sB[k]);
     }
 }
 
@@ -402,7 +460,7 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_kernel(const WtaArgs 
         unsigned key = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < DPL; j++) key = min(key, ((unsigned)s[j] << 8) | (unsigned)((d0 + j) & 255));
-        key = __reduce_min_sync(FULL, key);
+        key = __reduce_min_sync(FULL_MASK, key);
         minS = (int)(key >> 8); best = (int)(key & 255);
         if (minS >= 32767) return;  // nothing beats MAX_COST: pixel stays invalid, disp2 untouched
         bool rej = false;
@@ -411,12 +469,12 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_kernel(const WtaArgs 
             int d = d0 + j;
             if (lane < a.nact && s[j] * (100 - a.uniq) < minS * 100 && abs(best - d) > 1) rej = true;
         }
-        if (__any_sync(FULL, rej)) return;
+        if (__any_sync(FULL_MASK, rej)) return;
     } else {
         int m = 32767;
 #pragma unroll
         for (int j = 0; j < DPL; j++) m = min(m, s[j]);
-        minS = __reduce_min_sync(FULL, m);
+        minS = __reduce_min_sync(FULL_MASK, m);
         best = 0x7fffffff;
         for (int c = 0; c < 8; c++) {
             int v = -1;
@@ -425,7 +483,7 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_kernel(const WtaArgs 
                 int d = d0 + j;
                 if (lane < a.nact && (d & 7) == c && s[j] == minS) v = max(v, d);
             }
-            v = __reduce_max_sync(FULL, v);
+            v = __reduce_max_sync(FULL_MASK, v);
             if (v >= 0) best = min(best, v);
         }
         if (a.uniq > 0) {
@@ -437,7 +495,7 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_kernel(const WtaArgs 
                 int d = d0 + j;
                 if (lane < a.nact && s[j] < tr && (d < best - 1 || d > best + 1)) rej = true;
             }
-            if (__any_sync(FULL, rej)) return;
+            if (__any_sync(FULL_MASK, rej)) return;
         }
     }
     if (lane == 0) {
@@ -452,6 +510,74 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_kernel(const WtaArgs 
             int denom2 = max(sm + sp - 2 * sc, 1);
             dd = d * 16 + ((sm - sp) * 16 + denom2) / (denom2 * 2);
         } else dd = d * 16;
+        a.raw[(size_t)y * a.W + x + a.minX1] = (int16_t)(dd + a.minD * 16);
+    }
+}
+
+// Lean WTA for modes SGBM / HH (single segment): a warp walks 32 consecutive pixels; for each it
+// loads the pixel's S vector (one coalesced 64..512 B access), reduces a packed (cost << 8 | d) key
+// with CREDUX (first minimum wins, as OpenCV's strict '<' scan) and parks the result in lane k.
+// The per-pixel tail (disp2 vote, sub-pixel interpolation with its integer division, store) then
+// runs once for 32 pixels in parallel instead of once per pixel on one lane.
+template <int NP, bool FULL>
+__global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_lean_kernel(const WtaArgs a) {
+    typedef typename VecOf<NP>::T vec;
+    constexpr int DPL = NP * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long npix = (long)a.HV * a.width1;
+    const long base = ((long)blockIdx.x * WTA_WARPS + warp) * 32;
+    if (base >= npix) return;
+    const int cnt = (int)min(32L, npix - base);
+    const int nact = a.nact;
+    const bool active = FULL || lane < nact;
+    const vec* __restrict__ Sv = (const vec*)a.S + (size_t)base * nact + lane;
+    const unsigned dkey = (unsigned)(lane * DPL);
+    const int uniq = a.uniq;
+    unsigned mykey = 0xffffffffu;
+    bool myok = false;
+    for (int k = 0; k < cnt; k++) {
+        uint32_t w[NP];
+        if (active) vec_unpack<NP>(__ldg(Sv + (size_t)k * nact), w);
+        else {
+#pragma unroll
+            for (int q = 0; q < NP; q++) w[q] = INF2;
+        }
+        unsigned key = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            key = min(key, ((w[q] << 8) & 0xffff00u) | (dkey + 2 * q));
+            key = min(key, ((w[q] >> 8) & 0xffff00u) | (dkey + 2 * q + 1));
+        }
+        key = __reduce_min_sync(FULL_MASK, key);
+        const int minS = (int)(key >> 8), best = (int)(key & 255u);
+        bool ok = minS < 32767;  // nothing beats MAX_COST: pixel stays invalid, disp2 untouched
+        if (uniq > 0 && ok) {
+            bool rej = false;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const int s0 = (int)(w[q] & 0xffffu), s1 = (int)(w[q] >> 16);
+                const int d0 = (int)dkey + 2 * q;
+                if (active && s0 * (100 - uniq) < minS * 100 && abs(best - d0) > 1) rej = true;
+                if (active && s1 * (100 - uniq) < minS * 100 && abs(best - d0 - 1) > 1) rej = true;
+            }
+            ok = !__any_sync(FULL_MASK, rej);
+        }
+        if (lane == k) { mykey = key; myok = ok; }
+    }
+    if (lane < cnt && myok) {
+        const long pix = base + lane;
+        const int y = (int)(pix / a.width1), x = (int)(pix - (long)y * a.width1);
+        const int minS = (int)(mykey >> 8), d = (int)(mykey & 255u);
+        const int x2 = x + a.minX1 - d - a.minD;
+        if (x2 >= 0 && x2 < a.W + 2)
+            atomicMax(a.disp2key + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
+        int dd = d * 16;
+        if (0 < d && d < a.D - 1) {
+            const int16_t* Sp = a.S + (size_t)pix * a.D;
+            const int sm = Sp[d - 1], sp = Sp[d + 1];
+            const int denom2 = max(sm + sp - 2 * minS, 1);
+            dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
+        }
         a.raw[(size_t)y * a.W + x + a.minX1] = (int16_t)(dd + a.minD * 16);
     }
 }
@@ -489,21 +615,21 @@ __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v) {
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
-template <int NP>
-static int launch_scan(Lane& L, const ScanArgs& sa, int lines) {
-    size_t smem = (size_t)2 * SCAN_WARPS * SCAN_DEPTH * 32 * sizeof(typename VecOf<NP>::T);
-    static bool attr_done = false;
-    if (!attr_done) {
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
-        attr_done = true;
-    }
-    L3D_LAUNCH(L, sgbm_scan_kernel<NP>, cdiv(lines, SCAN_WARPS), SCAN_WARPS * 32, smem, sa);
+template <int NP, bool STORE>
+static int launch_scan_t(Lane& L, const ScanArgs& sa, int lines) {
+    if (sa.nact == 32) L3D_LAUNCH(L, (sgbm_scan_kernel<NP, STORE, true>), cdiv(lines, SCAN_WARPS), SCAN_WARPS * 32, 0, sa);
+    else L3D_LAUNCH(L, (sgbm_scan_kernel<NP, STORE, false>), cdiv(lines, SCAN_WARPS), SCAN_WARPS * 32, 0, sa);
     return L3D_OK;
 }
 static int launch_scan_np(Lane& L, int NP, const ScanArgs& sa, int lines) {
-    if (NP == 1) return launch_scan<1>(L, sa, lines);
-    if (NP == 2) return launch_scan<2>(L, sa, lines);
-    return launch_scan<4>(L, sa, lines);
+    if (sa.store) {
+        if (NP == 1) return launch_scan_t<1, true>(L, sa, lines);
+        if (NP == 2) return launch_scan_t<2, true>(L, sa, lines);
+        return launch_scan_t<4, true>(L, sa, lines);
+    }
+    if (NP == 1) return launch_scan_t<1, false>(L, sa, lines);
+    if (NP == 2) return launch_scan_t<2, false>(L, sa, lines);
+    return launch_scan_t<4, false>(L, sa, lines);
 }
 
 int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W, int H,
@@ -517,8 +643,8 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
     L3D_LAUNCH(L, fill_s16_kernel, cdiv(npix, 256), 256, 0, raw, npix, INVALID);
     if (g.width1 > 0) {
         // --- descriptors
-        uint2* dL = L.get<uint2>(S_DESC_L, npix);
-        uint2* dR = L.get<uint2>(S_DESC_R, npix);
+        uint4* dL = L.get<uint4>(S_DESC_L, npix);
+        uint4* dR = L.get<uint4>(S_DESC_R, npix);
         dim3 pg(cdiv(W, 128), H);
         L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, 128, 0, left, W, H, g.ftzero, dL);
         L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, 128, 0, right, W, H, g.ftzero, dR);
@@ -530,16 +656,23 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         ca.Ldesc = dL; ca.Rdesc = dR; ca.C = C;
         ca.W = W; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
         ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
-        int TX = std::min(32, 4096 / g.D);
-        auto cost_smem = [&](int tx) {
-            int TXH = tx + 2 * g.SW2;
-            return (size_t)TXH * 8 + (size_t)(TXH + g.D) * 8 + (size_t)TXH * (g.D / 2) * 4 + (size_t)g.bs * tx * (g.D / 2) * 4;
+        const int D2 = g.D / 2;
+        auto cost_smem = [&](int txh) {
+            int tx = txh - 2 * g.SW2;
+            return (size_t)2 * (txh + g.D) * 16 + (size_t)2 * txh * 16 + (size_t)D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4;
         };
-        while (TX > 1 && cost_smem(TX) > 200 * 1024) TX /= 2;
-        ca.TX = TX;
-        // bands: split each segment so the grid fills the SMs about twice
-        int xtiles = cdiv(g.width1, TX);
-        int want = std::max(1, (2 * NUM_SMS * 2 + xtiles - 1) / xtiles);
+        ca.nxg = std::max(1, COST_THREADS / D2);
+        int TXH = 64;
+        while (TXH > 2 * g.SW2 + 1 &&
+               (cost_smem(TXH) > 200 * 1024 || cdiv(TXH - 2 * g.SW2, ca.nxg) > COST_MAXCPG)) TXH /= 2;
+        L3D_ARG(L, TXH > 2 * g.SW2 && COST_THREADS % TXH == 0 && cost_smem(TXH) <= 200 * 1024 &&
+                       cdiv(TXH - 2 * g.SW2, ca.nxg) <= COST_MAXCPG,
+                "sgbm: blockSize / numDisparities combination exceeds the cost kernel's shared-memory tile");
+        ca.TXH = TXH; ca.TX = TXH - 2 * g.SW2;
+        ca.cpg = cdiv(ca.TX, ca.nxg);
+        // bands: split each segment so that the grid is close to a multiple of the SM count
+        int xtiles = cdiv(g.width1, ca.TX);
+        int want = std::max(1, (2 * NUM_SMS) / xtiles);
         int per_seg = std::max(1, std::min(want / g.nseg, MAXBAND / g.nseg));
         ca.nbands = 0;
         for (int s = 0; s < g.nseg; s++) {
@@ -555,7 +688,7 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
                 ca.band_chi[i] = H - 1;
             }
         }
-        size_t smem = cost_smem(TX);
+        size_t smem = cost_smem(TXH);
         L3D_CHECK(L, cudaFuncSetAttribute(sgbm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         L.t_begin("sgbm_cost");
         L3D_LAUNCH(L, sgbm_cost_kernel, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);
@@ -571,7 +704,9 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
         for (int i = 0; i < nk; i++) {
             sa.kind = kinds[i]; sa.store = (i == 0);
-            int lines = kinds[i] <= 1 ? g.HV : g.nseg * g.width1;
+            const int k = kinds[i];
+            sa.lines_per_seg = (k == 2 || k == 5) ? g.width1 : g.width1 + g.H - 1;  // diagonals only with nseg == 1
+            int lines = k <= 1 ? g.HV : g.nseg * sa.lines_per_seg;
             L.t_begin("sgbm_scan");
             rc = launch_scan_np(L, g.NP, sa, lines);
             L.t_end("sgbm_scan");
@@ -587,11 +722,23 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         for (int s = 0; s < MAXSEG; s++) {
             wa.seg_vr0[s] = g.seg_vr0[s]; wa.seg_y0[s] = g.seg_y0[s]; wa.seg_rows[s] = g.seg_rows[s]; wa.seg_emit[s] = g.seg_emit[s];
         }
-        int wgrid = cdiv((long)g.HV * g.width1, WTA_WARPS);
         L.t_begin("sgbm_wta");
-        if (g.NP == 1) L3D_LAUNCH(L, sgbm_wta_kernel<1>, wgrid, WTA_WARPS * 32, 0, wa);
-        else if (g.NP == 2) L3D_LAUNCH(L, sgbm_wta_kernel<2>, wgrid, WTA_WARPS * 32, 0, wa);
-        else L3D_LAUNCH(L, sgbm_wta_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
+        if (g.mode != 2) {
+            const int wgrid = cdiv(cdiv((long)g.HV * g.width1, 32), WTA_WARPS);
+            const bool full = g.nact == 32;
+#define L3D_WTA(NPV)                                                                                         \
+    do {                                                                                                     \
+        if (full) L3D_LAUNCH(L, (sgbm_wta_lean_kernel<NPV, true>), wgrid, WTA_WARPS * 32, 0, wa);            \
+        else L3D_LAUNCH(L, (sgbm_wta_lean_kernel<NPV, false>), wgrid, WTA_WARPS * 32, 0, wa);                \
+    } while (0)
+            if (g.NP == 1) L3D_WTA(1); else if (g.NP == 2) L3D_WTA(2); else L3D_WTA(4);
+#undef L3D_WTA
+        } else {
+            const int wgrid = cdiv((long)g.HV * g.width1, WTA_WARPS);
+            if (g.NP == 1) L3D_LAUNCH(L, sgbm_wta_kernel<1>, wgrid, WTA_WARPS * 32, 0, wa);
+            else if (g.NP == 2) L3D_LAUNCH(L, sgbm_wta_kernel<2>, wgrid, WTA_WARPS * 32, 0, wa);
+            else L3D_LAUNCH(L, sgbm_wta_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
+        }
         L.t_end("sgbm_wta");
         L3D_LAUNCH(L, sgbm_lrcheck_kernel, dim3(cdiv(g.width1, 128), H), 128, 0, raw, d2, W, H, g.minX1, g.maxX1, g.minD, g.d12);
         if (dbg) {
