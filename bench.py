@@ -305,9 +305,15 @@ def run_gpu(args, rank, world, local_rank):
         fp1.set_timing(True)
         fp1.run_dev(dL, dR, nr)
         groups = {}
-        for g in ("sgbm_cost", "sgbm_scan", "sgbm_wta", "wls"):
+        scan_kinds = {}
+        for kk in range(8):  # per path direction: 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up, 6 up-left, 7 up-right
+            t, k = fp1.kernel_time("sgbm_scan_k%d" % kk)
+            if k:
+                scan_kinds["k%d" % kk] = t / k
+        for g in ("sgbm_cost", "sgbm_wta", "wls"):
             t, k = fp1.kernel_time(g)
             groups[g] = {"ms_total": t, "timed_regions": k}
+        groups["sgbm_scan"] = {"ms_total": sum(fp1.kernel_time("sgbm_scan_k%d" % kk)[0] for kk in range(8)), "timed_regions": 0}
         fp1.set_timing(False)
         runs = 2 * nr  # left + right matcher per frame
         sgbm_ms = (groups["sgbm_cost"]["ms_total"] + groups["sgbm_scan"]["ms_total"] + groups["sgbm_wta"]["ms_total"]) / runs
@@ -325,6 +331,7 @@ def run_gpu(args, rank, world, local_rank):
             "algorithmic_bytes_per_run": sgbm_algorithmic_bytes(), "ms_per_run": sgbm_ms, "traffic": None,
             "how": "CUDA events on the launching stream around each kernel group, lanes=1 (kernels alone), %d frames" % nr,
             "groups_ms_per_frame": {g: v["ms_total"] / nr for g, v in groups.items()},
+            "scan_ms_per_launch": scan_kinds,
         }
         fp1.close()
 

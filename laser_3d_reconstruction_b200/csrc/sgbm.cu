@@ -261,7 +261,11 @@ struct ScanArgs {
     int HV, nseg;
     int lines_per_seg;  // kinds >= 2: lines per segment (columns, or diagonals)
     int seg_vr0[MAXSEG], seg_rows[MAXSEG];
+    // SCAN_FINAL only: the winner-takes-all stage fused into the last path (modes SGBM / HH)
+    int16_t* raw; unsigned* disp2key;
+    int W, minD, minX1, uniq;
 };
+enum { SCAN_STORE = 0, SCAN_ACCUM = 1, SCAN_FINAL = 2 };  // S = L | S = sat(S + L) | sat(S + L) -> WTA, S not written
 
 template <int NP> struct VecOf;
 template <> struct VecOf<1> { typedef uint32_t T; };
@@ -355,69 +359,182 @@ __device__ __forceinline__ bool scan_decode(const ScanArgs& a, int line, ScanLin
     return n > 0;
 }
 
-template <int NP, bool STORE, bool FULL>
-__global__ void __launch_bounds__(SCAN_WARPS * 32) sgbm_scan_kernel(const ScanArgs a) {
+// ---- async copy helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// OpenCV's uniqueness test (modes SGBM / HH): reject when another disparity further than 1 from
+// the winner costs less than minS * 100 / (100 - uniq).  Kept out of line: only the as-constructed
+// parameter set (uniquenessRatio > 0) pays for it.
+template <int NP>
+__device__ __noinline__ bool wta_not_unique(const uint32_t (&w)[NP], unsigned key, int uniq, unsigned dkey, bool active) {
+    const int minS = (int)(key >> 8), best = (int)(key & 255u);
+    bool rej = false;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const int s0 = (int)(w[q] & 0xffffu), s1 = (int)(w[q] >> 16);
+        const int d0 = (int)dkey + 2 * q;
+        if (active && s0 * (100 - uniq) < minS * 100 && abs(best - d0) > 1) rej = true;
+        if (active && s1 * (100 - uniq) < minS * 100 && abs(best - d0 - 1) > 1) rej = true;
+    }
+    return __any_sync(FULL_MASK, rej) && minS < 32767;
+}
+
+constexpr int SCAN_CH = 16;   // steps per chunk
+constexpr int SCAN_NST = 3;   // chunks in flight per warp (two chunks = 32 steps of look-ahead)
+
+static size_t scan_smem_bytes(int D, int smode) {
+    return (size_t)SCAN_NST * SCAN_CH * (D * 2) * (smode == 0 ? 1 : 2) + (smode == 2 ? (size_t)32 * D * 2 : 0);
+}
+
+// One warp (= one CTA) per scan line.  The line's C (and, when accumulating, S) vectors are staged
+// through a shared-memory ring with 16-byte cp.async copies (LDGSTS.128: one instruction moves 512
+// contiguous ring bytes = two 128-disparity steps), 32 steps ahead of the consumer, so that the
+// HBM latency is off the recurrence's critical path; the recurrence itself lives in registers.
+template <int NP, int SMODE, bool FULL>
+__global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
     typedef typename VecOf<NP>::T vec;
-    constexpr int U = NP == 4 ? 4 : 8;  // steps per register-prefetch batch
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool STORE = SMODE == SCAN_STORE;
+    constexpr bool FINAL = SMODE == SCAN_FINAL;
+    constexpr int DPL = NP * 2;
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int lane = threadIdx.x;
     ScanLine ln;
-    if (!scan_decode(a, blockIdx.x * SCAN_WARPS + warp, ln)) return;
+    if (!scan_decode(a, blockIdx.x, ln)) return;
     const int nact = a.nact, n = ln.n;
     const bool active = FULL || lane < nact;
-    const vec* __restrict__ Cv = (const vec*)a.C;
+    const uint32_t B = (uint32_t)a.D * 2u;                      // bytes per pixel vector
+    const uint32_t stage_bytes = SCAN_CH * B * (STORE ? 1 : 2);
+    const uint32_t ring = smem_u32(scan_smem);
+    const long pstride = (long)ln.dvr * a.width1 + ln.dx;      // pixel-index step along the line
+    const long pix0 = (long)ln.vr * a.width1 + ln.x;
+    const char* __restrict__ Cb = (const char*)a.C;
+    const char* __restrict__ Sb = (const char*)a.S;
     vec* __restrict__ Sv = (vec*)a.S;
-    // element offsets in vec units (a pixel holds nact vecs); volumes stay below 2^32 vecs
-    const int stride = (ln.dvr * a.width1 + ln.dx) * nact;
-    unsigned lo = (unsigned)(ln.vr * a.width1 + ln.x) * (unsigned)nact + (unsigned)lane;  // next load
-    unsigned so = lo;                                                                      // next store
+    const int nchunks = (n + SCAN_CH - 1) / SCAN_CH;
+    // 16-byte pieces: ppv per pixel vector, SCAN_CH * ppv per chunk and array; piece p = it * 32 + lane
+    const int ppv = a.D >> 3;
+    const int pieces = SCAN_CH * ppv;
+    const int li0 = lane / ppv, lr0 = lane - li0 * ppv, di = 32 / ppv, dr = 32 - di * ppv;
+    auto issue = [&](int chunk) {
+        if (chunk < nchunks) {
+            const int first = chunk * SCAN_CH;
+            const int cnt = min(SCAN_CH, n - first);
+            uint32_t dst = ring + (chunk % SCAN_NST) * stage_bytes + lane * 16;
+            int i = li0, r = lr0;
+            for (int p = lane; p < pieces; p += 32) {
+                if (i < cnt) {
+                    const size_t off = (size_t)(pix0 + (long)(first + i) * pstride) * B + (size_t)r * 16;
+                    cp_async16(dst, Cb + off);
+                    if (!STORE) cp_async16(dst + SCAN_CH * B, Sb + off);
+                }
+                dst += 512; i += di; r += dr;
+                if (r >= ppv) { r -= ppv; i++; }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int c = 0; c < SCAN_NST; c++) issue(c);
+
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const int P2 = a.P2;
-
     uint32_t L[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = active ? 0u : INF2;
     int minL = 0;
+    const int vstride = (int)pstride * nact;                    // vec-index step
+    unsigned so = (unsigned)pix0 * (unsigned)nact + (unsigned)lane;
 
-    vec cA[U], cB[U], sA[U], sB[U];
-    auto load = [&](vec (&c)[U], vec (&s)[U], int base) {
-#pragma unroll
-        for (int k = 0; k < U; k++) {
-            if (base + k < n && active) {
-                const unsigned o = lo + (unsigned)(k * stride);
-                c[k] = __ldg(Cv + o);
-                if (!STORE) s[k] = Sv[o];
+    // SCAN_FINAL: the finished S vectors of the last (up to) 32 steps are stashed in shared memory and
+    // their arg-min keys parked one per lane; every 32 steps lane k finishes pixel k (disp2 vote,
+    // sub-pixel interpolation with its integer division, store) -- once per 32 pixels, in parallel.
+    unsigned wkey = 0xffffffffu;
+    bool wrej = false;
+    int nsteps = 0;  // steps done so far (warp-uniform)
+    const unsigned dkey = (unsigned)(lane * DPL);
+    unsigned char* stash = scan_smem + SCAN_NST * stage_bytes;  // [32][B]
+    auto wta_flush = [&](int first_step, int count) {
+        __syncwarp();
+        const int minS = (int)(wkey >> 8), d = (int)(wkey & 255u);
+        if (lane < count && minS < 32767 && !wrej) {  // minS == 32767: nothing beat MAX_COST, pixel stays invalid
+            const int j = first_step + lane;
+            const int y = ln.vr + ln.dvr * j, x = ln.x + ln.dx * j;
+            const int x2 = x + a.minX1 - d - a.minD;
+            if (x2 >= 0 && x2 < a.W + 2)
+                atomicMax(a.disp2key + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
+            int dd = d * 16;
+            if (0 < d && d < a.D - 1) {
+                const uint16_t* Sp = (const uint16_t*)(stash + (size_t)lane * B);
+                const int sm = Sp[d - 1], sp = Sp[d + 1];
+                const int denom2 = max(sm + sp - 2 * minS, 1);
+                dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
             }
+            a.raw[(size_t)y * a.W + x + a.minX1] = (int16_t)(dd + a.minD * 16);
         }
-        lo += (unsigned)(U * stride);
+        wrej = false;
+        __syncwarp();
     };
-    auto step = [&](const vec& c, const vec& s) {
+    auto step = [&](const vec* cs, const vec* ss, int i) {
         uint32_t Cw[NP], Sw[NP];
-        vec_unpack<NP>(c, Cw);
-        if (!STORE) vec_unpack<NP>(s, Sw);
+        if (active) {
+            vec_unpack<NP>(cs[i * nact + lane], Cw);
+            if (!STORE) vec_unpack<NP>(ss[i * nact + lane], Sw);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NP; q++) { Cw[q] = 0; Sw[q] = 0; }
+        }
         minL = sgm_step<NP, FULL>(L, minL, Cw, p1x2, P2, lane, active);
         uint32_t out[NP];
 #pragma unroll
         for (int q = 0; q < NP; q++) out[q] = STORE ? L[q] : __viaddmin_u16x2(Sw[q], L[q], INF2);
-        if (active) Sv[so] = vec_pack<NP>(out);
-        so += (unsigned)stride;
+        if (!FINAL) {
+            if (active) Sv[so] = vec_pack<NP>(out);
+            so += (unsigned)vstride;
+        } else {
+            // winner-takes-all on the finished S vector (first minimum wins, as OpenCV's strict '<')
+            if (!FULL && !active) {
+#pragma unroll
+                for (int q = 0; q < NP; q++) out[q] = INF2;
+            }
+            unsigned key = 0xffffffffu;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                key = min(key, ((out[q] << 8) & 0xffff00u) | (dkey + 2 * q));
+                key = min(key, ((out[q] >> 8) & 0xffff00u) | (dkey + 2 * q + 1));
+            }
+            key = __reduce_min_sync(FULL_MASK, key);
+            const int slot = nsteps & 31;
+            if (active) *(vec*)(stash + (size_t)slot * B + (size_t)lane * sizeof(vec)) = vec_pack<NP>(out);
+            bool rej = false;
+            if (a.uniq > 0) rej = wta_not_unique<NP>(out, key, a.uniq, dkey, active);
+            if (lane == slot) { wkey = key; wrej = rej; }
+            nsteps++;
+        }
     };
-    load(cA, sA, 0);
-    int i = 0;
-    for (; i + 2 * U <= n; i += 2 * U) {  // two full batches: no per-step checks
-        load(cB, sB, i + U);
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c % SCAN_NST;
+        cp_async_wait<SCAN_NST - 1>();
+        __syncwarp();
+        const vec* cs = (const vec*)(scan_smem + s * stage_bytes);
+        const vec* ss = (const vec*)(scan_smem + s * stage_bytes + SCAN_CH * B);
+        const int cnt = min(SCAN_CH, n - c * SCAN_CH);
+        if (cnt == SCAN_CH) {
 #pragma unroll
-        for (int k = 0; k < U; k++) step(cA[k], sA[k]);
-        load(cA, sA, i + 2 * U);
-#pragma unroll
-        for (int k = 0; k < U; k++) step(cB[k], sB[k]);
+            for (int i = 0; i < SCAN_CH; i++) step(cs, ss, i);
+        } else {
+            for (int i = 0; i < cnt; i++) step(cs, ss, i);
+        }
+        __syncwarp();  // every lane is done reading the slot before it is refilled
+        issue(c + SCAN_NST);
+        if (FINAL && (nsteps & 31) == 0) wta_flush(nsteps - 32, 32);  // SCAN_CH divides 32
     }
-    if (i < n) {  // tail of fewer than 2U steps (warp-uniform bounds)
-        load(cB, sB, i + U);
-#pragma unroll
-        for (int k = 0; k < U; k++) if (i + k < n) step(cA[k], sA[k]);
-#pragma unroll
-        for (int k = 0; k < U; k++) if (i + U + k < n) step(cB[k], sB[k]);
-    }
+    if (FINAL && (nsteps & 31)) wta_flush(nsteps & ~31, nsteps & 31);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -615,21 +732,28 @@ __global__ void fill_s16_kernel(int16_t* p, size_t n, int16_t v) {
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
-template <int NP, bool STORE>
+template <int NP, int SMODE>
 static int launch_scan_t(Lane& L, const ScanArgs& sa, int lines) {
-    if (sa.nact == 32) L3D_LAUNCH(L, (sgbm_scan_kernel<NP, STORE, true>), cdiv(lines, SCAN_WARPS), SCAN_WARPS * 32, 0, sa);
-    else L3D_LAUNCH(L, (sgbm_scan_kernel<NP, STORE, false>), cdiv(lines, SCAN_WARPS), SCAN_WARPS * 32, 0, sa);
+    const size_t smem = scan_smem_bytes(sa.D, SMODE);
+    if (sa.nact == 32) {
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_kernel<NP, SMODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        L3D_LAUNCH(L, (sgbm_scan_kernel<NP, SMODE, true>), lines, 32, smem, sa);
+    } else {
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_kernel<NP, SMODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        L3D_LAUNCH(L, (sgbm_scan_kernel<NP, SMODE, false>), lines, 32, smem, sa);
+    }
     return L3D_OK;
 }
-static int launch_scan_np(Lane& L, int NP, const ScanArgs& sa, int lines) {
-    if (sa.store) {
-        if (NP == 1) return launch_scan_t<1, true>(L, sa, lines);
-        if (NP == 2) return launch_scan_t<2, true>(L, sa, lines);
-        return launch_scan_t<4, true>(L, sa, lines);
-    }
-    if (NP == 1) return launch_scan_t<1, false>(L, sa, lines);
-    if (NP == 2) return launch_scan_t<2, false>(L, sa, lines);
-    return launch_scan_t<4, false>(L, sa, lines);
+template <int NP>
+static int launch_scan_m(Lane& L, int smode, const ScanArgs& sa, int lines) {
+    if (smode == SCAN_STORE) return launch_scan_t<NP, SCAN_STORE>(L, sa, lines);
+    if (smode == SCAN_ACCUM) return launch_scan_t<NP, SCAN_ACCUM>(L, sa, lines);
+    return launch_scan_t<NP, SCAN_FINAL>(L, sa, lines);
+}
+static int launch_scan_np(Lane& L, int NP, int smode, const ScanArgs& sa, int lines) {
+    if (NP == 1) return launch_scan_m<1>(L, smode, sa, lines);
+    if (NP == 2) return launch_scan_m<2>(L, smode, sa, lines);
+    return launch_scan_m<4>(L, smode, sa, lines);
 }
 
 int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W, int H,
@@ -698,23 +822,30 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         sa.C = C; sa.S = S; sa.width1 = g.width1; sa.D = g.D; sa.nact = g.nact; sa.P1 = g.P1; sa.P2 = g.P2;
         sa.HV = g.HV; sa.nseg = g.nseg;
         for (int s = 0; s < MAXSEG; s++) { sa.seg_vr0[s] = g.seg_vr0[s]; sa.seg_rows[s] = g.seg_rows[s]; }
+        unsigned* d2 = L.get<unsigned>(S_DISP2, (size_t)H * (W + 2));
+        L3D_CHECK(L, cudaMemsetAsync(d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
+        sa.raw = raw; sa.disp2key = d2; sa.W = W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
         int kinds[8], nk = 0;
         kinds[nk++] = 0; kinds[nk++] = 1; kinds[nk++] = 2;  // ->, <-, down: all modes
         if (g.mode != 2) { kinds[nk++] = 3; kinds[nk++] = 4; }
         if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
+        // modes SGBM / HH: the last path does the WTA on its finished S vectors and never writes them
+        // (unless the caller asked for the S volume)
+        const bool fuse_wta = g.mode != 2 && !(dbg && dbg->S);
         for (int i = 0; i < nk; i++) {
-            sa.kind = kinds[i]; sa.store = (i == 0);
             const int k = kinds[i];
+            sa.kind = k; sa.store = (i == 0);
+            const int smode = i == 0 ? SCAN_STORE : ((fuse_wta && i == nk - 1) ? SCAN_FINAL : SCAN_ACCUM);
             sa.lines_per_seg = (k == 2 || k == 5) ? g.width1 : g.width1 + g.H - 1;  // diagonals only with nseg == 1
             int lines = k <= 1 ? g.HV : g.nseg * sa.lines_per_seg;
-            L.t_begin("sgbm_scan");
-            rc = launch_scan_np(L, g.NP, sa, lines);
-            L.t_end("sgbm_scan");
+            static const char* kind_names[8] = {"sgbm_scan_k0", "sgbm_scan_k1", "sgbm_scan_k2", "sgbm_scan_k3",
+                                                "sgbm_scan_k4", "sgbm_scan_k5", "sgbm_scan_k6", "sgbm_scan_k7"};
+            L.t_begin(kind_names[k]);
+            rc = launch_scan_np(L, g.NP, smode, sa, lines);
+            L.t_end(kind_names[k]);
             if (rc != L3D_OK) return rc;
         }
-        // --- WTA, LR check
-        unsigned* d2 = L.get<unsigned>(S_DISP2, (size_t)H * (W + 2));
-        L3D_CHECK(L, cudaMemsetAsync(d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
+        // --- WTA (when not fused), LR check
         WtaArgs wa;
         wa.S = S; wa.raw = raw; wa.disp2key = d2; wa.W = W; wa.width1 = g.width1; wa.D = g.D; wa.nact = g.nact;
         wa.DPL = g.DPL; wa.minD = g.minD; wa.minX1 = g.minX1; wa.uniq = g.uniq; wa.mode = g.mode;
@@ -723,7 +854,8 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
             wa.seg_vr0[s] = g.seg_vr0[s]; wa.seg_y0[s] = g.seg_y0[s]; wa.seg_rows[s] = g.seg_rows[s]; wa.seg_emit[s] = g.seg_emit[s];
         }
         L.t_begin("sgbm_wta");
-        if (g.mode != 2) {
+        if (fuse_wta) {
+        } else if (g.mode != 2) {
             const int wgrid = cdiv(cdiv((long)g.HV * g.width1, 32), WTA_WARPS);
             const bool full = g.nact == 32;
 #define L3D_WTA(NPV)                                                                                         \

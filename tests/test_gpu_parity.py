@@ -104,6 +104,8 @@ def test_sgbm_small_all_roles(ctx, mode, shape):
                 _, oraw = cref.sgbm_compute(lg, rg, want_raw=True, **kw)
             eq(raw, oraw, tag + " raw")
             eq(disp, want, tag + " disp vs cv2")
+            # production path (WTA fused into the last aggregation path, no S volume written)
+            eq(ctx.sgbm_compute(p, lg, rg), want, tag + " fused-WTA disp vs cv2")
 
 
 @pytest.mark.parametrize("mode", [2, 0, 1])
