@@ -60,6 +60,11 @@ static int make_geom(const l3d_sgbm_params& p, int W, int H, Geom& g, std::strin
     if (g.P2 > 16000) { set_err(err, "sgbm: P2=%d exceeds the int16 value domain", g.P2); return L3D_ERR_UNSUPPORTED; }
     g.ftzero = std::max(p.preFilterCap, 15) | 1;
     if (g.ftzero > 127) { set_err(err, "sgbm: preFilterCap too large"); return L3D_ERR_UNSUPPORTED; }
+    // the cost kernel adds u16x2 pairs with plain 32-bit arithmetic: every C value must fit 16 bits
+    if (g.P2 + g.bs * g.bs * (2 * g.ftzero + 63) > 65535) {
+        set_err(err, "sgbm: P2=%d with blockSize=%d exceeds the 16-bit cost domain", g.P2, g.bs);
+        return L3D_ERR_UNSUPPORTED;
+    }
     g.minX1 = std::max(g.maxD, 0); g.maxX1 = W + std::min(g.minD, 0); g.width1 = g.maxX1 - g.minX1;
     g.DPL = g.D <= 64 ? 2 : (g.D <= 128 ? 4 : 8);
     g.NP = g.DPL / 2;
@@ -153,8 +158,8 @@ struct CostArgs {
     int band_vr0[MAXBAND], band_y0[MAXBAND], band_rows[MAXBAND], band_clo[MAXBAND], band_chi[MAXBAND];
 };
 
-constexpr int COST_THREADS = 256;
-constexpr int COST_MAXCPG = 16;
+constexpr int COST_THREADS = 512;
+constexpr int COST_MAXCPG = 8;
 
 __device__ __forceinline__ uint32_t bt_pair(uint32_t U, uint32_t nU, uint32_t U0, uint32_t nU1, const uint4& r) {
     // r = (V, -V, V0, -V1) pairs; max(0, u - v1, v0 - u) and max(0, v - u1, u0 - v), then the smaller
@@ -177,31 +182,32 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
     const int xr_base = xa + a.minX1 - (a.minD + D - 1);  // lowest right pixel any pair reads
     const int nE = (xb - xa) + D - 1;                      // right operand entries (pair = pixels e+1, e)
     const int PS = TXH + 1;                                // pd row stride (bank-conflict-free both ways)
-    // smem carve-up
-    uint4* R0 = (uint4*)smem_raw;              // [nEmax] channel 0
+    // smem carve-up: operand tables and pixel costs are double-buffered so that one barrier per row
+    // separates {build + phase A of row k+1, phase B of row k}
     const int nEmax = TXH + D;
-    uint4* R1 = R0 + nEmax;                    // channel 1
-    uint4* L0 = R1 + nEmax;                    // [TXH]
-    uint4* L1 = L0 + TXH;
-    uint32_t* pd = (uint32_t*)(L1 + TXH);      // [D2][PS]
-    uint32_t* ring = pd + D2 * PS;             // [bs][TX][D2]
+    const int tab_u4 = 2 * nEmax;                          // uint4 per operand table set
+    uint4* tabs = (uint4*)smem_raw;                        // [2][R0 | R1]
+    uint32_t* pdb = (uint32_t*)(tabs + 2 * tab_u4);        // [2][D2][PS]
+    uint32_t* ring = pdb + 2 * D2 * PS;                    // [bs][TX][D2]
     // phase A role
     const int ca = tid % TXH, dpa0 = tid / TXH, dpa_step = COST_THREADS / TXH;
     const int xca = min(max(x0 - SW2 + ca, 0), width1 - 1);
     // phase B role
     const int dpb = tid % D2, xg = tid / D2;
-    const bool roleB = xg < a.nxg;
-    const int cb0 = xg * a.cpg;                // first output column (tile coordinates)
-    const int ncb = roleB ? max(0, min(a.cpg, TX - cb0)) : 0;
+    const int cb0 = xg * a.cpg;                            // first output column (tile coordinates)
+    const int ncb = xg < a.nxg ? max(0, min(min(a.cpg, TX - cb0), width1 - (x0 + cb0))) : 0;
     const uint32_t p2x2 = (uint32_t)a.P2 * 0x10001u;
     uint32_t crun[COST_MAXCPG];
 #pragma unroll
     for (int j = 0; j < COST_MAXCPG; j++) crun[j] = p2x2;
+    const int nk = rows + bs - 1;
 
-    for (int k = 0; k < rows + bs - 1; k++) {
+    auto stage_a = [&](int k) {  // operand tables + pixel costs of band row k into buffer k & 1
         const int ky = min(max(y0 - SW2 + k, clo), chi);
         const uint4* Lrow = a.Ldesc + (size_t)ky * W;
         const uint4* Rrow = a.Rdesc + (size_t)ky * W;
+        uint4* R0 = tabs + (k & 1) * tab_u4;
+        uint4* R1 = R0 + nEmax;
         for (int e = tid; e < nE; e += COST_THREADS) {
             const uint4 hi = Rrow[xr_base + e + 1], lo = Rrow[xr_base + e];  // disparities (d, d+1) -> pixels (e+1, e)
             R0[e] = make_uint4(__byte_perm(hi.x, lo.x, 0x5410), __byte_perm(hi.x, lo.x, 0x7632),
@@ -209,44 +215,49 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
             R1[e] = make_uint4(__byte_perm(hi.z, lo.z, 0x5410), __byte_perm(hi.z, lo.z, 0x7632),
                                __byte_perm(hi.w, lo.w, 0x5410), __byte_perm(hi.w, lo.w, 0x7632));
         }
-        if (tid < TXH) {
-            const uint4 l = Lrow[xca + a.minX1];
-            L0[tid] = make_uint4(__byte_perm(l.x, l.x, 0x1010), __byte_perm(l.x, l.x, 0x3232),
-                                 __byte_perm(l.y, l.y, 0x1010), __byte_perm(l.y, l.y, 0x3232));
-            L1[tid] = make_uint4(__byte_perm(l.z, l.z, 0x1010), __byte_perm(l.z, l.z, 0x3232),
-                                 __byte_perm(l.w, l.w, 0x1010), __byte_perm(l.w, l.w, 0x3232));
+        // every thread builds its own column's left operands in registers (no table, no barrier)
+        const uint4 l = Lrow[xca + a.minX1];
+        const uint32_t u0 = __byte_perm(l.x, l.x, 0x1010), nu0 = __byte_perm(l.x, l.x, 0x3232);
+        const uint32_t ul0 = __byte_perm(l.y, l.y, 0x1010), nuh0 = __byte_perm(l.y, l.y, 0x3232);
+        const uint32_t u1 = __byte_perm(l.z, l.z, 0x1010), nu1 = __byte_perm(l.z, l.z, 0x3232);
+        const uint32_t ul1 = __byte_perm(l.w, l.w, 0x1010), nuh1 = __byte_perm(l.w, l.w, 0x3232);
+        __syncthreads();  // right operand table complete (also orders this row's pd writes after row k-2's reads)
+        uint32_t* pd = pdb + (k & 1) * D2 * PS;
+        const int ebase = xca - xa + D - 2;
+        for (int dp = dpa0; dp < D2; dp += dpa_step) {
+            const int e = ebase - 2 * dp;
+            const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, R0[e]);
+            const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, R1[e]);
+            pd[dp * PS + ca] = c0 + ((c1 >> 2) & 0x3fff3fffu);
         }
-        __syncthreads();
-        {   // phase A
-            const uint4 l0 = L0[ca], l1 = L1[ca];
-            const int ebase = xca - xa + D - 2;
-            for (int dp = dpa0; dp < D2; dp += dpa_step) {
-                const int e = ebase - 2 * dp;
-                const uint32_t c0 = bt_pair(l0.x, l0.y, l0.z, l0.w, R0[e]);
-                const uint32_t c1 = bt_pair(l1.x, l1.y, l1.z, l1.w, R1[e]);
-                pd[dp * PS + ca] = c0 + ((c1 >> 2) & 0x3fff3fffu);
-            }
-        }
-        __syncthreads();
-        if (ncb > 0) {  // phase B
-            const uint32_t* pp = pd + dpb * PS + cb0;  // pp[j + i] = pixel cost at output column cb0 + j, tap i
-            uint32_t h = 0;
-            for (int i = 0; i < bs; i++) h = __vadd2(h, pp[i]);
-            uint32_t* rp = ring + ((size_t)(k % bs) * TX + cb0) * D2 + dpb;
-            const int16_t* Cdst = a.C + ((size_t)(vr0 + k - (bs - 1)) * width1 + x0 + cb0) * D + 2 * dpb;
+    };
+    // Box sums.  Every packed half stays below 2^16 for the supported parameter range (checked on the
+    // host), so plain 32-bit adds on the u16x2 pairs are exact: no carry crosses the halves.
+    auto stage_b = [&](int k) {
+        if (ncb <= 0) return;
+        const uint32_t* pp = pdb + (k & 1) * D2 * PS + dpb * PS + cb0;  // pp[j + i]: output column cb0 + j, tap i
+        uint32_t h = 0;
+        for (int i = 0; i < bs; i++) h += pp[i];
+        uint32_t* rp = ring + ((size_t)(k % bs) * TX + cb0) * D2 + dpb;
+        uint32_t* Cdst = (uint32_t*)(a.C + ((size_t)(vr0 + k - (bs - 1)) * width1 + x0 + cb0) * D) + dpb;
+        const bool sub = k >= bs, emit = k >= bs - 1;
 #pragma unroll
-            for (int j = 0; j < COST_MAXCPG; j++) {
-                if (j < ncb) {
-                    if (j > 0) h = __vsub2(__vadd2(h, pp[j + bs - 1]), pp[j - 1]);
-                    uint32_t c = __vadd2(crun[j], h);
-                    if (k >= bs) c = __vsub2(c, rp[(size_t)j * D2]);
-                    rp[(size_t)j * D2] = h;
-                    crun[j] = c;
-                    if (k >= bs - 1 && x0 + cb0 + j < width1) *(uint32_t*)(Cdst + (size_t)j * D) = c;
-                }
+        for (int j = 0; j < COST_MAXCPG; j++) {
+            if (j < ncb) {
+                if (j > 0) h = h + pp[j + bs - 1] - pp[j - 1];
+                uint32_t c = crun[j] + h;
+                if (sub) c -= rp[j * D2];
+                rp[j * D2] = h;
+                crun[j] = c;
+                if (emit) Cdst[j * D2] = c;
             }
         }
-        __syncthreads();
+    };
+    stage_a(0);
+    for (int k = 0; k < nk; k++) {
+        __syncthreads();  // pd[k & 1] complete; pd[(k + 1) & 1] and its tables free again
+        if (k + 1 < nk) stage_a(k + 1);  // contains one barrier; the condition is CTA-uniform
+        stage_b(k);
     }
 }
 
@@ -388,6 +399,7 @@ __device__ __noinline__ bool wta_not_unique(const uint32_t (&w)[NP], unsigned ke
 constexpr int SCAN_CH = 16;   // steps per chunk
 constexpr int SCAN_NST = 3;   // chunks in flight per warp (two chunks = 32 steps of look-ahead)
 
+__device__ __forceinline__ size_t scan_smem_bytes_dev(int D) { return (size_t)SCAN_NST * SCAN_CH * (D * 2) * 2; }
 static size_t scan_smem_bytes(int D, int smode) {
     return (size_t)SCAN_NST * SCAN_CH * (D * 2) * (smode == 0 ? 1 : 2) + (smode == 2 ? (size_t)32 * D * 2 : 0);
 }
@@ -397,15 +409,12 @@ static size_t scan_smem_bytes(int D, int smode) {
 // contiguous ring bytes = two 128-disparity steps), 32 steps ahead of the consumer, so that the
 // HBM latency is off the recurrence's critical path; the recurrence itself lives in registers.
 template <int NP, int SMODE, bool FULL>
-__global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
+__device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, unsigned char* scan_smem,
+                                         uint32_t (&L)[NP], int& minL, const int lane) {
     typedef typename VecOf<NP>::T vec;
     constexpr bool STORE = SMODE == SCAN_STORE;
     constexpr bool FINAL = SMODE == SCAN_FINAL;
     constexpr int DPL = NP * 2;
-    extern __shared__ __align__(128) unsigned char scan_smem[];
-    const int lane = threadIdx.x;
-    ScanLine ln;
-    if (!scan_decode(a, blockIdx.x, ln)) return;
     const int nact = a.nact, n = ln.n;
     const bool active = FULL || lane < nact;
     const uint32_t B = (uint32_t)a.D * 2u;                      // bytes per pixel vector
@@ -444,10 +453,6 @@ __global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
 
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const int P2 = a.P2;
-    uint32_t L[NP];
-#pragma unroll
-    for (int k = 0; k < NP; k++) L[k] = active ? 0u : INF2;
-    int minL = 0;
     const int vstride = (int)pstride * nact;                    // vec-index step
     unsigned so = (unsigned)pix0 * (unsigned)nact + (unsigned)lane;
 
@@ -535,6 +540,42 @@ __global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
         if (FINAL && (nsteps & 31) == 0) wta_flush(nsteps - 32, 32);  // SCAN_CH divides 32
     }
     if (FINAL && (nsteps & 31)) wta_flush(nsteps & ~31, nsteps & 31);
+}
+
+template <int NP, int SMODE, bool FULL>
+__global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int lane = threadIdx.x;
+    ScanLine ln;
+    if (!scan_decode(a, blockIdx.x, ln)) return;
+    uint32_t L[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
+    int minL = 0;
+    scan_run<NP, SMODE, FULL>(a, ln, scan_smem, L, minL, lane);
+}
+
+// Both horizontal paths of one row in one CTA of two warps: warp 0 runs left-to-right, warp 1
+// right-to-left.  Each first covers its own half storing S = L, the CTA synchronises, and each
+// continues through the other half accumulating S = sat(S + L) -- every S vector is written once
+// and read-modified once, and the two serial recurrences of a row run concurrently.
+template <int NP, bool FULL>
+__global__ void __launch_bounds__(64) sgbm_scan_hpair_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* my_smem = scan_smem + (size_t)warp * scan_smem_bytes_dev(a.D);
+    const int vr = blockIdx.x, width1 = a.width1, mid = width1 / 2;
+    ScanLine s1, s2;
+    s1.vr = s2.vr = vr; s1.dvr = s2.dvr = 0;
+    if (warp == 0) { s1.x = 0; s1.n = mid; s1.dx = 1; s2.x = mid; s2.n = width1 - mid; s2.dx = 1; }
+    else { s1.x = width1 - 1; s1.n = width1 - mid; s1.dx = -1; s2.x = mid - 1; s2.n = mid; s2.dx = -1; }
+    uint32_t L[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
+    int minL = 0;
+    scan_run<NP, SCAN_STORE, FULL>(a, s1, my_smem, L, minL, lane);
+    __syncthreads();  // the other warp's S stores of its first half are visible before we accumulate onto them
+    scan_run<NP, SCAN_ACCUM, FULL>(a, s2, my_smem, L, minL, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -745,6 +786,18 @@ static int launch_scan_t(Lane& L, const ScanArgs& sa, int lines) {
     return L3D_OK;
 }
 template <int NP>
+static int launch_hpair(Lane& L, const ScanArgs& sa) {
+    const size_t smem = 2 * scan_smem_bytes(sa.D, SCAN_ACCUM);
+    if (sa.nact == 32) {
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, true>), sa.HV, 64, smem, sa);
+    } else {
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, false>), sa.HV, 64, smem, sa);
+    }
+    return L3D_OK;
+}
+template <int NP>
 static int launch_scan_m(Lane& L, int smode, const ScanArgs& sa, int lines) {
     if (smode == SCAN_STORE) return launch_scan_t<NP, SCAN_STORE>(L, sa, lines);
     if (smode == SCAN_ACCUM) return launch_scan_t<NP, SCAN_ACCUM>(L, sa, lines);
@@ -783,7 +836,7 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         const int D2 = g.D / 2;
         auto cost_smem = [&](int txh) {
             int tx = txh - 2 * g.SW2;
-            return (size_t)2 * (txh + g.D) * 16 + (size_t)2 * txh * 16 + (size_t)D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4;
+            return (size_t)2 * 2 * (txh + g.D) * 16 + (size_t)2 * D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4;
         };
         ca.nxg = std::max(1, COST_THREADS / D2);
         int TXH = 64;
@@ -832,9 +885,15 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         // modes SGBM / HH: the last path does the WTA on its finished S vectors and never writes them
         // (unless the caller asked for the S volume)
         const bool fuse_wta = g.mode != 2 && !(dbg && dbg->S);
-        for (int i = 0; i < nk; i++) {
+        // both horizontal paths in one launch (kinds 0 and 1 are always the first two)
+        sa.kind = 0; sa.store = 1;
+        L.t_begin("sgbm_scan_k0");
+        rc = g.NP == 1 ? launch_hpair<1>(L, sa) : (g.NP == 2 ? launch_hpair<2>(L, sa) : launch_hpair<4>(L, sa));
+        L.t_end("sgbm_scan_k0");
+        if (rc != L3D_OK) return rc;
+        for (int i = 2; i < nk; i++) {
             const int k = kinds[i];
-            sa.kind = k; sa.store = (i == 0);
+            sa.kind = k; sa.store = 0;
             const int smode = i == 0 ? SCAN_STORE : ((fuse_wta && i == nk - 1) ? SCAN_FINAL : SCAN_ACCUM);
             sa.lines_per_seg = (k == 2 || k == 5) ? g.width1 : g.width1 + g.H - 1;  // diagonals only with nseg == 1
             int lines = k <= 1 ? g.HV : g.nseg * sa.lines_per_seg;
