@@ -218,9 +218,9 @@ def run_gpu(args, rank, world, local_rank):
         """NCCL gather of the per-frame point clouds to rank 0 (the only exchange, off the hot path)."""
         if world == 1:
             return None
-        clouds = [fp.fetch_points(i, int(counts[i])) for i in range(nfr)]
-        table = sharding.pack_clouds(mine, clouds)
-        return sharding.gather_point_clouds(table, device=dev)
+        table = torch.empty((max(int(np.sum(counts)), 1), 4), dtype=torch.float64, device=dev)
+        rows = fp.pack_points_dev(mine, table.data_ptr())  # device-side pack; nothing goes through the host
+        return sharding.gather_point_clouds(table[:rows], device=dev)
 
     def step_dev():
         counts = fp.run_dev(dL, dR, nfr)

@@ -173,6 +173,12 @@ int l3d_pipeline_run_host(l3d_pipeline* p, const uint8_t* left, const uint8_t* r
 /* fetch results of the last run for frame slot i (device -> host); any pointer may be NULL */
 int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* depth, int16_t* disp,
                        float* xy, double* xyz, int* n_xy, int* n_xyz);
+/* Pack the 3D points of the first nframes frame slots of the last run into ONE device table of rows
+ * (frame_id, x, y, z) (f64), frames in slot order: the payload of the NCCL gather to rank 0.
+ * frame_ids[nframes] = global frame numbers; table_dev holds >= sum(counts) * 4 doubles (device
+ * pointer owned by the caller, e.g. a torch tensor); *total_rows = rows written.  Synchronises. */
+int l3d_pipeline_pack_points_dev(l3d_pipeline* p, int nframes, const int* frame_ids, double* table_dev,
+                                 long long* total_rows);
 long long l3d_pipeline_launch_count(l3d_pipeline* p);
 /* CUDA-event time (ms) of the whole last run (first enqueue -> last lane done) */
 float l3d_pipeline_last_ms(l3d_pipeline* p);

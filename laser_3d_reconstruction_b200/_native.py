@@ -64,7 +64,7 @@ EXPORTS = (
     "l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
     "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
-    "l3d_pipeline_launch_count l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
+    "l3d_pipeline_pack_points_dev l3d_pipeline_launch_count l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
     "l3d_host_alloc l3d_host_free l3d_dev_alloc l3d_dev_free l3d_memcpy_h2d l3d_memcpy_d2h"
 ).split()
 

@@ -563,7 +563,59 @@ static int pipe_frame(l3d_pipeline* p, Lane& L, const uint8_t* l, const uint8_t*
     return L3D_OK;
 }
 
+// rows (frame_id, x, y, z) of up to PACK_FRAMES frames per launch
+constexpr int PACK_FRAMES = 64;
+struct PackArgs {
+    const double* xyz[PACK_FRAMES];
+    long long off[PACK_FRAMES];
+    int cnt[PACK_FRAMES], fid[PACK_FRAMES];
+    int n;
+};
+__global__ void pack_points_kernel(const PackArgs a, double* __restrict__ table) {
+    const int f = blockIdx.y;
+    if (f >= a.n) return;
+    const double* src = a.xyz[f];
+    double* dst = table + a.off[f] * 4;
+    const double id = (double)a.fid[f];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.cnt[f]; i += gridDim.x * blockDim.x) {
+        dst[4 * (size_t)i] = id;
+        dst[4 * (size_t)i + 1] = src[3 * (size_t)i];
+        dst[4 * (size_t)i + 2] = src[3 * (size_t)i + 1];
+        dst[4 * (size_t)i + 3] = src[3 * (size_t)i + 2];
+    }
+}
+
 extern "C" {
+
+int l3d_pipeline_pack_points_dev(l3d_pipeline* p, int nframes, const int* frame_ids, double* table_dev,
+                                 long long* total_rows) {
+    if (!p) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    API_BEGIN(ctx)
+    NEED(ctx, nframes >= 0 && nframes <= p->last_frames && frame_ids && total_rows, "pack_points arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = p->lanes[0];
+    long long off = 0;
+    for (int f0 = 0; f0 < nframes; f0 += PACK_FRAMES) {
+        PackArgs a;
+        a.n = std::min(PACK_FRAMES, nframes - f0);
+        int maxc = 0;
+        for (int i = 0; i < a.n; i++) {
+            const int f = f0 + i;
+            a.xyz[i] = p->outs[f].xyz; a.cnt[i] = p->counts_host[2 * f + 1]; a.fid[i] = frame_ids[f]; a.off[i] = off;
+            off += a.cnt[i];
+            maxc = std::max(maxc, a.cnt[i]);
+        }
+        if (maxc > 0) {
+            NEED(ctx, table_dev, "pack_points table");
+            L3D_LAUNCH(L, pack_points_kernel, dim3(std::max(1, std::min(cdiv(maxc, 256), 64)), a.n), 256, 0, a, table_dev);
+        }
+    }
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    *total_rows = off;
+    return L3D_OK;
+    API_END(ctx)
+}
 
 int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeline** out) {
     API_BEGIN(ctx)

@@ -399,7 +399,8 @@ __device__ __noinline__ bool wta_not_unique(const uint32_t (&w)[NP], unsigned ke
 constexpr int SCAN_CH = 16;   // steps per chunk
 constexpr int SCAN_NST = 3;   // chunks in flight per warp (two chunks = 32 steps of look-ahead)
 
-__device__ __forceinline__ size_t scan_smem_bytes_dev(int D) { return (size_t)SCAN_NST * SCAN_CH * (D * 2) * 2; }
+constexpr int HPAIR_NST = 2;  // 1440 warps must be resident at once: a shallower ring keeps the launch to one wave
+__device__ __host__ __forceinline__ size_t scan_smem_bytes_dev(int D) { return (size_t)HPAIR_NST * SCAN_CH * (D * 2) * 2; }
 static size_t scan_smem_bytes(int D, int smode) {
     return (size_t)SCAN_NST * SCAN_CH * (D * 2) * (smode == 0 ? 1 : 2) + (smode == 2 ? (size_t)32 * D * 2 : 0);
 }
@@ -408,7 +409,7 @@ static size_t scan_smem_bytes(int D, int smode) {
 // through a shared-memory ring with 16-byte cp.async copies (LDGSTS.128: one instruction moves 512
 // contiguous ring bytes = two 128-disparity steps), 32 steps ahead of the consumer, so that the
 // HBM latency is off the recurrence's critical path; the recurrence itself lives in registers.
-template <int NP, int SMODE, bool FULL>
+template <int NP, int SMODE, bool FULL, int NST>
 __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, unsigned char* scan_smem,
                                          uint32_t (&L)[NP], int& minL, const int lane) {
     typedef typename VecOf<NP>::T vec;
@@ -430,26 +431,30 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
     const int ppv = a.D >> 3;
     const int pieces = SCAN_CH * ppv;
     const int li0 = lane / ppv, lr0 = lane - li0 * ppv, di = 32 / ppv, dr = 32 - di * ppv;
+    const long step_bytes = pstride * (long)B;                      // between consecutive steps of the line
+    const long it_bytes = (long)di * step_bytes + (long)dr * 16;    // piece p -> p + 32
+    const long wrap_bytes = step_bytes - (long)ppv * 16;            // extra when the piece index wraps into the next step
+    const long lane_off = pix0 * (long)B + (long)li0 * step_bytes + (long)lr0 * 16;
     auto issue = [&](int chunk) {
         if (chunk < nchunks) {
             const int first = chunk * SCAN_CH;
             const int cnt = min(SCAN_CH, n - first);
-            uint32_t dst = ring + (chunk % SCAN_NST) * stage_bytes + lane * 16;
+            uint32_t dst = ring + (chunk % NST) * stage_bytes + lane * 16;
+            long off = lane_off + (long)first * step_bytes;
             int i = li0, r = lr0;
             for (int p = lane; p < pieces; p += 32) {
                 if (i < cnt) {
-                    const size_t off = (size_t)(pix0 + (long)(first + i) * pstride) * B + (size_t)r * 16;
                     cp_async16(dst, Cb + off);
                     if (!STORE) cp_async16(dst + SCAN_CH * B, Sb + off);
                 }
-                dst += 512; i += di; r += dr;
-                if (r >= ppv) { r -= ppv; i++; }
+                dst += 512; i += di; r += dr; off += it_bytes;
+                if (r >= ppv) { r -= ppv; i++; off += wrap_bytes; }
             }
         }
         cp_async_commit();
     };
 #pragma unroll
-    for (int c = 0; c < SCAN_NST; c++) issue(c);
+    for (int c = 0; c < NST; c++) issue(c);
 
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const int P2 = a.P2;
@@ -463,7 +468,7 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
     bool wrej = false;
     int nsteps = 0;  // steps done so far (warp-uniform)
     const unsigned dkey = (unsigned)(lane * DPL);
-    unsigned char* stash = scan_smem + SCAN_NST * stage_bytes;  // [32][B]
+    unsigned char* stash = scan_smem + NST * stage_bytes;  // [32][B]
     auto wta_flush = [&](int first_step, int count) {
         __syncwarp();
         const int minS = (int)(wkey >> 8), d = (int)(wkey & 255u);
@@ -523,8 +528,8 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
         }
     };
     for (int c = 0; c < nchunks; c++) {
-        const int s = c % SCAN_NST;
-        cp_async_wait<SCAN_NST - 1>();
+        const int s = c % NST;
+        cp_async_wait<NST - 1>();
         __syncwarp();
         const vec* cs = (const vec*)(scan_smem + s * stage_bytes);
         const vec* ss = (const vec*)(scan_smem + s * stage_bytes + SCAN_CH * B);
@@ -536,7 +541,7 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
             for (int i = 0; i < cnt; i++) step(cs, ss, i);
         }
         __syncwarp();  // every lane is done reading the slot before it is refilled
-        issue(c + SCAN_NST);
+        issue(c + NST);
         if (FINAL && (nsteps & 31) == 0) wta_flush(nsteps - 32, 32);  // SCAN_CH divides 32
     }
     if (FINAL && (nsteps & 31)) wta_flush(nsteps & ~31, nsteps & 31);
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
     int minL = 0;
-    scan_run<NP, SMODE, FULL>(a, ln, scan_smem, L, minL, lane);
+    scan_run<NP, SMODE, FULL, SCAN_NST>(a, ln, scan_smem, L, minL, lane);
 }
 
 // Both horizontal paths of one row in one CTA of two warps: warp 0 runs left-to-right, warp 1
@@ -573,9 +578,9 @@ __global__ void __launch_bounds__(64) sgbm_scan_hpair_kernel(const ScanArgs a) {
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
     int minL = 0;
-    scan_run<NP, SCAN_STORE, FULL>(a, s1, my_smem, L, minL, lane);
+    scan_run<NP, SCAN_STORE, FULL, HPAIR_NST>(a, s1, my_smem, L, minL, lane);
     __syncthreads();  // the other warp's S stores of its first half are visible before we accumulate onto them
-    scan_run<NP, SCAN_ACCUM, FULL>(a, s2, my_smem, L, minL, lane);
+    scan_run<NP, SCAN_ACCUM, FULL, HPAIR_NST>(a, s2, my_smem, L, minL, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -787,7 +792,7 @@ static int launch_scan_t(Lane& L, const ScanArgs& sa, int lines) {
 }
 template <int NP>
 static int launch_hpair(Lane& L, const ScanArgs& sa) {
-    const size_t smem = 2 * scan_smem_bytes(sa.D, SCAN_ACCUM);
+    const size_t smem = 2 * scan_smem_bytes_dev(sa.D);
     if (sa.nact == 32) {
         L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, true>), sa.HV, 64, smem, sa);

@@ -164,6 +164,20 @@ def _fetch_points(self, frame, n_hint=None):
 FramePipeline.fetch_points = _fetch_points
 
 
+def _pack_points_dev(self, frame_ids, table_ptr):
+    """Pack the last run's point clouds into the caller's device table (rows frame_id,x,y,z; f64).
+    table_ptr: device pointer with room for sum(counts)*4 doubles.  Returns the number of rows."""
+    n = len(frame_ids)
+    ids = (C.c_int * n)(*[int(f) for f in frame_ids])
+    total = C.c_longlong(0)
+    self.ctx.check(self.lib.l3d_pipeline_pack_points_dev(self.h, n, ids, C.c_void_p(table_ptr), C.byref(total)),
+                   "l3d_pipeline_pack_points_dev")
+    return int(total.value)
+
+
+FramePipeline.pack_points_dev = _pack_points_dev
+
+
 def pinned_empty(shape, dtype):
     """numpy array backed by page-locked host memory (l3d_host_alloc)."""
     lib = N.load()

@@ -42,11 +42,16 @@ def gather_point_clouds(table, device=None, group=None, dst=0):
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        if isinstance(table, torch.Tensor):
+            return table.detach().cpu().numpy().reshape(-1, 4)
         return np.asarray(table, np.float64).reshape(-1, 4)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = torch.device(device) if device is not None else torch.device("cpu")
-    t = torch.from_numpy(np.ascontiguousarray(table, np.float64).reshape(-1, 4)).to(dev)
+    if isinstance(table, torch.Tensor):  # already resident on the backend's device (packed by the C ABI)
+        t = table.reshape(-1, 4)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(table, np.float64).reshape(-1, 4)).to(dev)
     n = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n, group=group)

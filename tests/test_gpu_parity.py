@@ -376,6 +376,18 @@ def test_pipeline_matches_stagewise_and_is_frame_independent(ctx):
             counts = fp.run_dev(dl, dr, len(frames))
             results[lanes] = [fp.fetch(i) for i in range(len(frames))]
             assert list(counts) == [len(r["points_3d"]) for r in results[lanes]]
+            # device-side packing of the point clouds (payload of the NCCL gather to rank 0)
+            ids = [100 + 7 * i for i in range(len(frames))]
+            nrows = int(np.sum(counts))
+            buf = ctx.lib.l3d_dev_alloc(ctx.h, max(nrows, 1) * 32)
+            assert fp.pack_points_dev(ids, buf) == nrows
+            table = np.empty((nrows, 4), np.float64)
+            ctx.check(ctx.lib.l3d_memcpy_d2h(ctx.h, table.ctypes.data, buf, table.nbytes), "d2h")
+            ctx.lib.l3d_dev_free(ctx.h, buf)
+            from laser_3d_reconstruction_b200 import sharding
+            back = sharding.unpack_clouds(np.concatenate([table[:, :1] - 100, table[:, 1:]], axis=1) / [7, 1, 1, 1], len(frames))
+            for i in range(len(frames)):
+                eq(back[i], results[lanes][i]["points_3d"], "packed points frame %d" % i)
             # host-buffer entry point gives the same answer
             depth = np.empty((len(frames), H, W), np.float32)
             xyz = np.empty((len(frames), 8000, 3), np.float64)
