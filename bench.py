@@ -141,7 +141,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -250,9 +250,12 @@ def run_gpu(args, rank, world, local_rank):
     # a step's duration = CUDA-event time of the batch (first enqueue -> last lane done) + the gather's wall time
     # for N > 1; the wall clock over the K steps bounds it from above, so use the wall clock when gathering.
     el = torch.tensor([wall_ms if world > 1 else dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    nl = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
     elapsed_ms, wall_max = float(el[0]), float(el[1])
+    launches = int(nl[0])  # kernels of libl3d.so launched inside the timed region, summed over ranks
 
     # ---- end-to-end arm (host buffers through the C ABI) ----------------------------------------
     for _ in range(2):
@@ -324,11 +327,16 @@ def run_gpu(args, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = sgbm_algorithmic_bytes() / (sgbm_ms * 1e-3) / 1e9
+        traffic = None  # DRAM bytes of the same kernels from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sgbm_run_dram_bytes"]
+        except (OSError, ValueError, KeyError):
+            pass
         out["roofline"] = {
             "bound": "hbm", "kernel": "sgbm matcher run = cost-volume + path-aggregation + WTA kernels",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-            "algorithmic_bytes_per_run": sgbm_algorithmic_bytes(), "ms_per_run": sgbm_ms, "traffic": None,
+            "algorithmic_bytes_per_run": sgbm_algorithmic_bytes(), "ms_per_run": sgbm_ms, "traffic": traffic,
             "how": "CUDA events on the launching stream around each kernel group, lanes=1 (kernels alone), %d frames" % nr,
             "groups_ms_per_frame": {g: v["ms_total"] / nr for g, v in groups.items()},
             "scan_ms_per_launch": scan_kinds,
