@@ -294,19 +294,25 @@ template <> __device__ __forceinline__ uint4 vec_pack<4>(const uint32_t (&o)[4])
 
 constexpr int SCAN_WARPS = 4;
 
-// one SGM step for the disparities held by this lane; returns the warp-wide min of the new L.
-// Inactive lanes (lane >= nact, only when D is not a multiple of 64*NP/2... i.e. !FULL) keep L = INF2
-// so that neither the neighbour exchange nor the min-reduction sees them.
+// One SGM step for the disparities held by this lane.  State: L (u16x2 words) and minL2 = the
+// warp-wide minimum of L replicated in both halves.  With delta = minL + P2,
+//     L'[d] = C[d] + min(L[d] - delta, L[d-1] + P1 - delta, L[d+1] + P1 - delta, 0)
+// which is OpenCV's  C + min(L[d], L[d+-1] + P1, delta) - delta  with the subtraction folded into
+// the operands: three VIADDMNMX.S16x2 and one VIADD.16x2 per word.  -delta and P1 - delta are taken
+// modulo 2^16; every true intermediate lies in [-P2, 32767], so the wrapped s16 arithmetic is exact.
+// k2 = (0x10000 - P2) * 0x10001, p1x2 = P1 * 0x10001; neither k2 - minL2 nor (k2 - minL2) + p1x2 can
+// carry between the halves (minL <= 32767, P1 < P2 <= 16000).
+// Inactive lanes (lane >= nact, only when !FULL) keep L = INF2 so that neither the neighbour
+// exchange nor the min-reduction sees them.
 template <int NP, bool FULL>
-__device__ __forceinline__ int sgm_step(uint32_t (&L)[NP], int minL, const uint32_t (&Cv)[NP], uint32_t p1x2,
-                                        int P2, int lane, bool active) {
+__device__ __forceinline__ uint32_t sgm_step(uint32_t (&L)[NP], uint32_t minL2, const uint32_t (&Cv)[NP],
+                                             uint32_t p1x2, uint32_t k2, int lane, bool active) {
     uint32_t up = __shfl_up_sync(FULL_MASK, L[NP - 1], 1);
     uint32_t dn = __shfl_down_sync(FULL_MASK, L[0], 1);
     if (lane == 0) up = INF2;
     if (lane == 31) dn = INF2;
-    const uint32_t delta = (uint32_t)(minL + P2) & 0xffffu;
-    const uint32_t delta2 = delta * 0x10001u;
-    const uint32_t ndelta2 = ((0x10000u - delta) & 0xffffu) * 0x10001u;
+    const uint32_t nd2 = k2 - minL2;   // -(minL + P2) mod 2^16, both halves
+    const uint32_t pm2 = nd2 + p1x2;   // P1 - (minL + P2) mod 2^16
     uint32_t mn = INF2;
     uint32_t Ln[NP];
 #pragma unroll
@@ -315,17 +321,17 @@ __device__ __forceinline__ int sgm_step(uint32_t (&L)[NP], int minL, const uint3
         uint32_t next = (k < NP - 1) ? L[k + 1] : dn;
         uint32_t dm1 = __byte_perm(prev, L[k], 0x5432);
         uint32_t dp1 = __byte_perm(L[k], next, 0x5432);
-        uint32_t m = __vminu2(L[k], delta2);
-        m = __viaddmin_u16x2(dm1, p1x2, m);
-        m = __viaddmin_u16x2(dp1, p1x2, m);
-        Ln[k] = __vadd2(__vadd2(Cv[k], m), ndelta2);
+        uint32_t t = __viaddmin_s16x2(L[k], nd2, 0u);
+        t = __viaddmin_s16x2(dm1, pm2, t);
+        t = __viaddmin_s16x2(dp1, pm2, t);
+        Ln[k] = __vadd2(Cv[k], t);
         if (!FULL && !active) Ln[k] = INF2;
         mn = __vminu2(mn, Ln[k]);
     }
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = Ln[k];
-    int m16 = (int)min(mn & 0xffffu, mn >> 16);
-    return __reduce_min_sync(FULL_MASK, m16);
+    mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));  // both halves = min of the two
+    return __reduce_min_sync(FULL_MASK, mn);          // packed halves are equal, so the u32 min is the packed min
 }
 
 // Scan lines of one path direction.  kinds: 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up,
@@ -411,7 +417,7 @@ static size_t scan_smem_bytes(int D, int smode) {
 // HBM latency is off the recurrence's critical path; the recurrence itself lives in registers.
 template <int NP, int SMODE, bool FULL, int NST>
 __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, unsigned char* scan_smem,
-                                         uint32_t (&L)[NP], int& minL, const int lane) {
+                                         uint32_t (&L)[NP], uint32_t& minL, const int lane) {
     typedef typename VecOf<NP>::T vec;
     constexpr bool STORE = SMODE == SCAN_STORE;
     constexpr bool FINAL = SMODE == SCAN_FINAL;
@@ -457,7 +463,7 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
     for (int c = 0; c < NST; c++) issue(c);
 
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
-    const int P2 = a.P2;
+    const uint32_t k2 = (0x10000u - (uint32_t)a.P2) * 0x10001u;
     const int vstride = (int)pstride * nact;                    // vec-index step
     unsigned so = (unsigned)pix0 * (unsigned)nact + (unsigned)lane;
 
@@ -499,7 +505,7 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
 #pragma unroll
             for (int q = 0; q < NP; q++) { Cw[q] = 0; Sw[q] = 0; }
         }
-        minL = sgm_step<NP, FULL>(L, minL, Cw, p1x2, P2, lane, active);
+        minL = sgm_step<NP, FULL>(L, minL, Cw, p1x2, k2, lane, active);
         uint32_t out[NP];
 #pragma unroll
         for (int q = 0; q < NP; q++) out[q] = STORE ? L[q] : __viaddmin_u16x2(Sw[q], L[q], INF2);
@@ -556,7 +562,7 @@ __global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
     uint32_t L[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
-    int minL = 0;
+    uint32_t minL = 0;  // packed: warp-wide min of L in both halves
     scan_run<NP, SMODE, FULL, SCAN_NST>(a, ln, scan_smem, L, minL, lane);
 }
 
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(64) sgbm_scan_hpair_kernel(const ScanArgs a) {
     uint32_t L[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
-    int minL = 0;
+    uint32_t minL = 0;
     scan_run<NP, SCAN_STORE, FULL, HPAIR_NST>(a, s1, my_smem, L, minL, lane);
     __syncthreads();  // the other warp's S stores of its first half are visible before we accumulate onto them
     scan_run<NP, SCAN_ACCUM, FULL, HPAIR_NST>(a, s2, my_smem, L, minL, lane);
