@@ -114,6 +114,10 @@ struct SgbmDebug {
 int sgbm_volume_rows(const l3d_sgbm_params& p, int W, int H);
 int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W,
              int H, int16_t* disp, SgbmDebug* dbg);
+// cluster-fused aggregation of the three previous-row paths of one pass (sgbm_vgroup.cu)
+bool vgroup_supported(int width1, int H, int D);
+int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
+                    int P2, int dir);
 int dev_median3(Lane& L, const int16_t* src, int W, int H, int16_t* dst);
 int dev_speckles(Lane& L, int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff);
 

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "ccl.cuh"
 #include "remap.cu"
+#include "sgbm_vgroup.cu"
 #include "sgbm.cu"
 #include "post.cu"
 #include "wls.cu"

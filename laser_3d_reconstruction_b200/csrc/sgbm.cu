@@ -895,13 +895,31 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
         if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
         // modes SGBM / HH: the last path does the WTA on its finished S vectors and never writes them
         // (unless the caller asked for the S volume)
-        const bool fuse_wta = g.mode != 2 && !(dbg && dbg->S);
+        // L3D_VGROUP=1: aggregate the previous-row paths with the cluster-fused kernel (sgbm_vgroup.cu)
+        static const bool use_vgroup = getenv("L3D_VGROUP") && atoi(getenv("L3D_VGROUP")) > 0;
+        const bool vgroup = use_vgroup && g.mode != 2 && vgroup_supported(g.width1, g.HV, g.D);
+        const bool fuse_wta = g.mode != 2 && !(dbg && dbg->S) && !vgroup;
         // both horizontal paths in one launch (kinds 0 and 1 are always the first two)
         sa.kind = 0; sa.store = 1;
         L.t_begin("sgbm_scan_k0");
         rc = g.NP == 1 ? launch_hpair<1>(L, sa) : (g.NP == 2 ? launch_hpair<2>(L, sa) : launch_hpair<4>(L, sa));
         L.t_end("sgbm_scan_k0");
         if (rc != L3D_OK) return rc;
+        if (vgroup) {
+            const int16_t* Cj[1] = {C};
+            int16_t* Sj[1] = {S};
+            L.t_begin("sgbm_scan_k2");
+            rc = dev_sgbm_vgroup(L, Cj, Sj, 1, g.width1, g.HV, g.D, g.P1, g.P2, +1);
+            L.t_end("sgbm_scan_k2");
+            if (rc != L3D_OK) return rc;
+            if (g.mode == 1) {
+                L.t_begin("sgbm_scan_k5");
+                rc = dev_sgbm_vgroup(L, Cj, Sj, 1, g.width1, g.HV, g.D, g.P1, g.P2, -1);
+                L.t_end("sgbm_scan_k5");
+                if (rc != L3D_OK) return rc;
+            }
+            nk = 2;  // nothing left for the direction-split kernels
+        }
         for (int i = 2; i < nk; i++) {
             const int k = kinds[i];
             sa.kind = k; sa.store = 0;

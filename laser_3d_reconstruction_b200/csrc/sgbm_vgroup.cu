@@ -1,0 +1,341 @@
+// sgbm_vgroup.cu -- the three "from the previous row" SGM paths of one pass, fused, in row lock-step
+// on a thread-block cluster (modes SGBM / HH of cv2.StereoSGBM, camera/single_usb_stereo_camera.py:324-325).
+//
+// Pass 1 (top-down):  r1 from (x-1, y-1), r2 from (x, y-1), r3 from (x+1, y-1)
+// Pass 2 (bottom-up): r1 from (x+1, y+1), r2 from (x, y+1), r3 from (x-1, y+1)   (MODE_HH only)
+// Processing rows in travel order, all three predecessors live in the previously processed row, so a
+// row of the cost volume is read ONCE and the row of S is read-modified-written ONCE for three paths
+// (the direction-split kernels in sgbm.cu read C three times and read-modify-write S three times).
+//
+// One cluster of VG_CLUSTER CTAs owns one matcher run ("job"); the grid is (VG_CLUSTER, jobs), so the
+// kernel wants many jobs per launch (frames x {left, right} matcher) to fill the GPU.  CTA r of a
+// cluster owns a strip of VG_WARPS * cpw columns; warp w owns cpw adjacent columns whose path state
+// (3 paths x cpw vectors + their minima) lives in registers for the whole pass.  A diagonal path's
+// state moves one column per row: inside a warp that is a register rename done by updating in place in
+// the right order; between warps of a CTA it goes through a double-buffered shared-memory slot; between
+// CTAs the edge warps write the slot in the NEIGHBOUR's shared memory (DSMEM), and a split cluster
+// barrier (arrive after the export, wait before the next row's import) orders both.
+// Per row the C strip and the S strip (contiguous wc * 2D bytes each) arrive by one bulk async copy
+// each (TMA, mbarrier completion), two rows ahead; the updated S strip leaves by one bulk store.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace l3d {
+namespace cg = cooperative_groups;
+
+constexpr int VG_CLUSTER = 8;
+constexpr int VG_WARPS = 16;
+constexpr int VG_THREADS = VG_WARPS * 32;
+constexpr int VG_MAXCPW = 9;     // columns per warp: the cluster spans 8 * 16 * 9 = 1152 columns
+constexpr int VG_MAXJOBS = 64;
+
+struct VGroupArgs {
+    const int16_t* C[VG_MAXJOBS];
+    int16_t* S[VG_MAXJOBS];
+    int width1, H, D, P1, P2, cpw, dir;  // dir = +1 top-down (pass 1), -1 bottom-up (pass 2)
+};
+
+static size_t vgroup_smem_bytes(int D, int cpw) {
+    const size_t strip = (size_t)VG_WARPS * cpw * D * 2;
+    const size_t halo = (size_t)2 * 2 * VG_WARPS * (D * 2 + 16);
+    return 2 * 2 * strip + halo + 64;
+}
+
+__device__ __forceinline__ void vg_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vg_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "VG_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra VG_DONE_%=;\n\t"
+        "bra VG_WAIT_%=;\n\t"
+        "VG_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void vg_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void vg_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// the SGM step of sgbm.cu (sgm_step<NP, true>): L'[d] = C[d] + min(L[d]-delta, L[d+-1]+P1-delta, 0)
+template <int NP>
+__device__ __forceinline__ uint32_t vg_step(uint32_t (&L)[NP], uint32_t minL2, const uint32_t (&Cv)[NP],
+                                            uint32_t p1x2, uint32_t k2, int lane) {
+    constexpr uint32_t INF = 0x7fff7fffu;
+    uint32_t up = __shfl_up_sync(0xffffffffu, L[NP - 1], 1);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    if (lane == 0) up = INF;
+    if (lane == 31) dn = INF;
+    const uint32_t nd2 = k2 - minL2;
+    const uint32_t pm2 = nd2 + p1x2;
+    uint32_t mn = INF;
+    uint32_t Ln[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const uint32_t prev = k ? L[k - 1] : up;
+        const uint32_t next = (k < NP - 1) ? L[k + 1] : dn;
+        const uint32_t dm1 = __byte_perm(prev, L[k], 0x5432);
+        const uint32_t dp1 = __byte_perm(L[k], next, 0x5432);
+        uint32_t t = __viaddmin_s16x2(L[k], nd2, 0u);
+        t = __viaddmin_s16x2(dm1, pm2, t);
+        t = __viaddmin_s16x2(dp1, pm2, t);
+        Ln[k] = __vadd2(Cv[k], t);
+        mn = __vminu2(mn, Ln[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) L[k] = Ln[k];
+    mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
+    return __reduce_min_sync(0xffffffffu, mn);
+}
+
+template <int NP> struct VgVec;
+template <> struct VgVec<1> { typedef uint32_t T; };
+template <> struct VgVec<2> { typedef uint2 T; };
+template <> struct VgVec<4> { typedef uint4 T; };
+template <int NP> __device__ __forceinline__ void vg_unpack(const typename VgVec<NP>::T& v, uint32_t (&o)[NP]);
+template <> __device__ __forceinline__ void vg_unpack<1>(const uint32_t& v, uint32_t (&o)[1]) { o[0] = v; }
+template <> __device__ __forceinline__ void vg_unpack<2>(const uint2& v, uint32_t (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+template <> __device__ __forceinline__ void vg_unpack<4>(const uint4& v, uint32_t (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+template <int NP> __device__ __forceinline__ typename VgVec<NP>::T vg_pack(const uint32_t (&o)[NP]);
+template <> __device__ __forceinline__ uint32_t vg_pack<1>(const uint32_t (&o)[1]) { return o[0]; }
+template <> __device__ __forceinline__ uint2 vg_pack<2>(const uint32_t (&o)[2]) { return make_uint2(o[0], o[1]); }
+template <> __device__ __forceinline__ uint4 vg_pack<4>(const uint32_t (&o)[4]) { return make_uint4(o[0], o[1], o[2], o[3]); }
+
+// NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities)
+template <int NP>
+__global__ void __cluster_dims__(VG_CLUSTER, 1, 1) __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroupArgs a) {
+    typedef typename VgVec<NP>::T vec;
+    constexpr uint32_t INF = 0x7fff7fffu;
+    extern __shared__ __align__(128) unsigned char vg_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int job = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpw = a.cpw, width1 = a.width1, H = a.H;
+    const uint32_t B = (uint32_t)a.D * 2u;                       // bytes per pixel vector
+    const int wstrip = VG_WARPS * cpw;                           // columns per CTA
+    const int x0 = rank * wstrip;                                // first column of this CTA
+    const int wc = max(0, min(wstrip, width1 - x0));             // valid columns of this CTA
+    const uint32_t strip_bytes = (uint32_t)wstrip * B;
+    // smem: Cbuf[2] | Sbuf[2] | haloA[2][VG_WARPS] | haloB[2][VG_WARPS] | mbarriers[2]
+    unsigned char* Cbuf = vg_smem;
+    unsigned char* Sbuf = vg_smem + 2 * strip_bytes;
+    const uint32_t slot = B + 16;                                // vector + packed minimum
+    unsigned char* haloA = Sbuf + 2 * strip_bytes;               // state entering a warp from its LEFT neighbour
+    unsigned char* haloB = haloA + 2 * VG_WARPS * slot;          // state entering a warp from its RIGHT neighbour
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(haloB + 2 * VG_WARPS * slot);
+    const char* Cg = (const char*)a.C[job];
+    char* Sg = (char*)a.S[job];
+    const int dir = a.dir;
+
+    // zero both parities of every halo slot: "no predecessor" = (L = 0, min = 0), OpenCV's out-of-image rule
+    for (int i = threadIdx.x; i < (int)(4 * VG_WARPS * slot / 4); i += VG_THREADS) ((uint32_t*)haloA)[i] = 0u;
+    if (threadIdx.x == 0) {
+        vg_mbar_init(bars, 1);
+        vg_mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto load_row = [&](int it) {  // thread 0: C and S strips of the it-th processed row into stage it & 1
+        const int row = dir > 0 ? it : H - 1 - it;
+        const uint32_t bytes = (uint32_t)wc * B;
+        const uint32_t bar = bars + 8 * (it & 1);
+        const size_t off = ((size_t)row * width1 + x0) * B;
+        vg_mbar_expect_tx(bar, 2 * bytes);
+        vg_bulk_g2s((uint32_t)__cvta_generic_to_shared(Cbuf + (it & 1) * strip_bytes), Cg + off, bytes, bar);
+        vg_bulk_g2s((uint32_t)__cvta_generic_to_shared(Sbuf + (it & 1) * strip_bytes), Sg + off, bytes, bar);
+    };
+    if (threadIdx.x == 0 && wc > 0) {
+        load_row(0);
+        if (H > 1) load_row(1);
+    }
+    cluster.sync();  // halo zeroing of every CTA is complete before any neighbour writes into it
+
+    // path state: A = diagonal fed from the left neighbour column, V = vertical, Bp = diagonal fed from the right
+    uint32_t LA[VG_MAXCPW][NP], LV[VG_MAXCPW][NP], LB[VG_MAXCPW][NP];
+    uint32_t mA[VG_MAXCPW], mV[VG_MAXCPW], mB[VG_MAXCPW];
+#pragma unroll
+    for (int j = 0; j < VG_MAXCPW; j++) {
+#pragma unroll
+        for (int k = 0; k < NP; k++) { LA[j][k] = 0; LV[j][k] = 0; LB[j][k] = 0; }
+        mA[j] = 0; mV[j] = 0; mB[j] = 0;
+    }
+    const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
+    const uint32_t k2 = (0x10000u - (uint32_t)a.P2) * 0x10001u;
+    const int c0 = warp * cpw;  // first column of this warp inside the strip
+    // where this warp's exports go: A state leaves to the right (warp + 1 or the next CTA's warp 0),
+    // B state leaves to the left (warp - 1 or the previous CTA's last warp)
+    unsigned char* expA = nullptr;
+    unsigned char* expB = nullptr;
+    if (warp < VG_WARPS - 1) expA = haloA + (size_t)(warp + 1) * slot;
+    else if (rank < VG_CLUSTER - 1) expA = (unsigned char*)cluster.map_shared_rank((void*)haloA, rank + 1);
+    if (warp > 0) expB = haloB + (size_t)(warp - 1) * slot;
+    else if (rank > 0) expB = (unsigned char*)cluster.map_shared_rank((void*)(haloB + (size_t)(VG_WARPS - 1) * slot), rank - 1);
+    const uint32_t par_stride = VG_WARPS * slot;  // second parity of a halo array
+
+    for (int it = 0; it < H; it++) {
+        const int st = it & 1, par = it & 1;
+        if (wc > 0) vg_mbar_wait(bars + 8 * st, (uint32_t)((it >> 1) & 1));
+        if (it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // row it-1 exports visible
+        // ---- import the diagonal states entering this warp (exported during row it-1 into parity (it-1)&1)
+        uint32_t inA[NP], inB[NP], inAm, inBm;
+        {
+            const unsigned char* pa = haloA + (size_t)(par ^ 1) * par_stride + (size_t)warp * slot;
+            const unsigned char* pb = haloB + (size_t)(par ^ 1) * par_stride + (size_t)warp * slot;
+            vg_unpack<NP>(*(const vec*)(pa + lane * sizeof(vec)), inA);
+            vg_unpack<NP>(*(const vec*)(pb + lane * sizeof(vec)), inB);
+            inAm = *(const uint32_t*)(pa + B);
+            inBm = *(const uint32_t*)(pb + B);
+        }
+        // ---- export this warp's edge states of row it-1 (still in registers) for row it+1's import ... no:
+        // the state a neighbour needs in row it+1 is the one computed in row it, exported after the update below.
+        const vec* cs = (const vec*)(Cbuf + st * strip_bytes);
+        vec* ss = (vec*)(Sbuf + st * strip_bytes);
+        // ---- diagonal A (fed from the left): in place, right to left
+        uint32_t sum[VG_MAXCPW][NP];
+#pragma unroll
+        for (int jj = 0; jj < VG_MAXCPW; jj++) {
+            const int j = VG_MAXCPW - 1 - jj;
+            if (j < cpw) {
+                uint32_t Cw[NP];
+                vg_unpack<NP>(cs[(size_t)(c0 + j) * 32 + lane], Cw);
+                uint32_t T[NP], tm;
+                if (j > 0) {
+#pragma unroll
+                    for (int k = 0; k < NP; k++) T[k] = LA[j - 1][k];
+                    tm = mA[j - 1];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NP; k++) T[k] = inA[k];
+                    tm = inAm;
+                }
+                mA[j] = vg_step<NP>(T, tm, Cw, p1x2, k2, lane);
+#pragma unroll
+                for (int k = 0; k < NP; k++) { LA[j][k] = T[k]; sum[j][k] = T[k]; }
+            }
+        }
+        // ---- diagonal B (fed from the right): in place, left to right; beyond the image edge the predecessor is 0
+#pragma unroll
+        for (int j = 0; j < VG_MAXCPW; j++) {
+            if (j < cpw) {
+                uint32_t Cw[NP];
+                vg_unpack<NP>(cs[(size_t)(c0 + j) * 32 + lane], Cw);
+                uint32_t T[NP], tm;
+                if (j + 1 < cpw) {
+#pragma unroll
+                    for (int k = 0; k < NP; k++) T[k] = LB[(j + 1 < VG_MAXCPW) ? j + 1 : j][k];
+                    tm = mB[(j + 1 < VG_MAXCPW) ? j + 1 : j];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NP; k++) T[k] = inB[k];
+                    tm = inBm;
+                }
+                if (x0 + c0 + j + 1 >= width1) {  // right neighbour column is outside the image
+#pragma unroll
+                    for (int k = 0; k < NP; k++) T[k] = 0;
+                    tm = 0;
+                }
+                mB[j] = vg_step<NP>(T, tm, Cw, p1x2, k2, lane);
+#pragma unroll
+                for (int k = 0; k < NP; k++) { LB[j][k] = T[k]; sum[j][k] = __viaddmin_u16x2(sum[j][k], T[k], INF); }
+            }
+        }
+        // ---- export the new edge states (parity of this row) and let the cluster know
+        if (expA) {
+            const int je = cpw - 1;
+            uint32_t E[NP];
+#pragma unroll
+            for (int j = 0; j < VG_MAXCPW; j++) if (j == je) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) E[k] = LA[j][k];
+            }
+            uint32_t em = 0;
+#pragma unroll
+            for (int j = 0; j < VG_MAXCPW; j++) if (j == je) em = mA[j];
+            unsigned char* q = expA + (size_t)par * par_stride;
+            *(vec*)(q + lane * sizeof(vec)) = vg_pack<NP>(E);
+            if (lane == 0) *(uint32_t*)(q + B) = em;
+        }
+        if (expB) {
+            unsigned char* q = expB + (size_t)par * par_stride;
+            *(vec*)(q + lane * sizeof(vec)) = vg_pack<NP>(LB[0]);
+            if (lane == 0) *(uint32_t*)(q + B) = mB[0];
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        // ---- vertical path + S update (the cluster barrier's latency hides behind this)
+#pragma unroll
+        for (int j = 0; j < VG_MAXCPW; j++) {
+            if (j < cpw) {
+                uint32_t Cw[NP], Sw[NP];
+                vg_unpack<NP>(cs[(size_t)(c0 + j) * 32 + lane], Cw);
+                mV[j] = vg_step<NP>(LV[j], mV[j], Cw, p1x2, k2, lane);
+                vg_unpack<NP>(ss[(size_t)(c0 + j) * 32 + lane], Sw);
+#pragma unroll
+                for (int k = 0; k < NP; k++) {
+                    const uint32_t s3 = __viaddmin_u16x2(sum[j][k], LV[j][k], INF);
+                    Sw[k] = __viaddmin_u16x2(Sw[k], s3, INF);
+                }
+                ss[(size_t)(c0 + j) * 32 + lane] = vg_pack<NP>(Sw);
+            }
+        }
+        // ---- S strip back to HBM, next-but-one row in
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0 && wc > 0) {
+            const int row = dir > 0 ? it : H - 1 - it;
+            vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
+                        (uint32_t)wc * B);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+            if (it + 2 < H) load_row(it + 2);
+        }
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pair the last arrive
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    cluster.sync();  // no CTA exits while a neighbour may still write into its shared memory
+}
+
+// Host entry: aggregate the three previous-row paths of pass `dir` for `njobs` volumes at once.
+// Returns L3D_ERR_UNSUPPORTED when the geometry does not fit (caller falls back to the scan kernels).
+bool vgroup_supported(int width1, int H, int D) {
+    if (!(D == 64 || D == 128 || D == 256)) return false;
+    const int cpw = cdiv(width1, VG_CLUSTER * VG_WARPS);
+    if (cpw < 1 || cpw > VG_MAXCPW) return false;
+    if (D == 256 && cpw > 4) return false;  // register budget of the NP = 4 instantiation
+    return vgroup_smem_bytes(D, cpw) <= 220 * 1024 && H >= 1;
+}
+
+int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
+                    int P2, int dir) {
+    L3D_ARG(L, vgroup_supported(width1, H, D), "vgroup geometry");
+    for (int j0 = 0; j0 < njobs; j0 += VG_MAXJOBS) {
+        VGroupArgs a;
+        const int nj = std::min(VG_MAXJOBS, njobs - j0);
+        for (int j = 0; j < nj; j++) { a.C[j] = C[j0 + j]; a.S[j] = S[j0 + j]; }
+        a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir;
+        a.cpw = cdiv(width1, VG_CLUSTER * VG_WARPS);
+        const size_t smem = vgroup_smem_bytes(D, a.cpw);
+        dim3 grid(VG_CLUSTER, nj);
+        if (D == 64) {
+            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            L3D_LAUNCH(L, sgbm_vgroup_kernel<1>, grid, VG_THREADS, smem, a);
+        } else if (D == 128) {
+            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            L3D_LAUNCH(L, sgbm_vgroup_kernel<2>, grid, VG_THREADS, smem, a);
+        } else {
+            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            L3D_LAUNCH(L, sgbm_vgroup_kernel<4>, grid, VG_THREADS, smem, a);
+        }
+    }
+    return L3D_OK;
+}
+
+}  // namespace l3d
