@@ -252,6 +252,50 @@ int l3d_sgbm_compute(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left
     return l3d_sgbm_debug(ctx, p, left, right, W, H, disp, nullptr, nullptr, nullptr);
 }
 
+__global__ void fill_pattern_kernel(uint32_t* p, size_t n, uint32_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) {
+        uint32_t h = (uint32_t)i * 2654435761u + seed;
+        h ^= h >> 15;
+        p[i] = ((h & 0x3ffu) + 8000u) | ((((h >> 10) & 0x3ffu) + 8000u) << 16);  // plausible cost values
+    }
+}
+
+int l3d_sgbm_vgroup_time(l3d_ctx* ctx, int width1, int H, int D, int P1, int P2, int njobs, int dir, int reps,
+                         float* ms_per_launch) {
+    API_BEGIN(ctx)
+    NEED(ctx, ms_per_launch && njobs >= 1 && njobs <= 64 && reps >= 1, "vgroup_time arguments");
+    NEED(ctx, vgroup_supported(width1, H, D), "geometry not supported by the cluster kernel");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    const size_t nvol = (size_t)width1 * H * D;
+    int16_t* Cs = nullptr;
+    int16_t* Ss = nullptr;
+    CK(ctx, cudaMalloc(&Cs, nvol * 2 * njobs));
+    if (cudaMalloc(&Ss, nvol * 2 * njobs) != cudaSuccess) { cudaFree(Cs); set_err(&ctx->err, "out of memory"); return L3D_ERR_CUDA; }
+    fill_pattern_kernel<<<1024, 256, 0, L.stream>>>((uint32_t*)Cs, nvol * njobs / 2, 1u);
+    cudaMemsetAsync(Ss, 0, nvol * 2 * njobs, L.stream);
+    std::vector<const int16_t*> Cp(njobs);
+    std::vector<int16_t*> Sp(njobs);
+    for (int j = 0; j < njobs; j++) { Cp[j] = Cs + nvol * j; Sp[j] = Ss + nvol * j; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), njobs, width1, H, D, P1, P2, dir);  // warm-up
+    cudaEventRecord(e0, L.stream);
+    for (int r = 0; r < reps && rc == L3D_OK; r++) rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), njobs, width1, H, D, P1, P2, dir);
+    cudaEventRecord(e1, L.stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(Cs); cudaFree(Ss);
+    if (rc != L3D_OK) return rc;
+    if (e != cudaSuccess) { set_err(&ctx->err, "vgroup_time: %s", cudaGetErrorString(e)); return L3D_ERR_CUDA; }
+    *ms_per_launch = ms / reps;
+    return L3D_OK;
+    API_END(ctx)
+}
+
 int l3d_median3_s16(l3d_ctx* ctx, const int16_t* src, int W, int H, int16_t* dst) {
     API_BEGIN(ctx)
     NEED(ctx, src && dst && W > 0 && H > 0, "image");

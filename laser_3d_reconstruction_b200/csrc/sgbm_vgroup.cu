@@ -24,9 +24,9 @@
 namespace l3d {
 namespace cg = cooperative_groups;
 
-constexpr int VG_CLUSTER = 8;
+constexpr int VG_CLUSTER_MAX = 16;  // cluster sizes used: 8 (portable) and 16 (non-portable)
 constexpr int VG_WARPS = 16;
-constexpr int VG_THREADS = VG_WARPS * 32;
+constexpr int VG_THREADS = (VG_WARPS + 1) * 32;  // + one producer warp that owns all bulk copies
 constexpr int VG_MAXCPW = 9;     // columns per warp: the cluster spans 8 * 16 * 9 = 1152 columns
 constexpr int VG_MAXJOBS = 64;
 
@@ -34,12 +34,13 @@ struct VGroupArgs {
     const int16_t* C[VG_MAXJOBS];
     int16_t* S[VG_MAXJOBS];
     int width1, H, D, P1, P2, cpw, dir;  // dir = +1 top-down (pass 1), -1 bottom-up (pass 2)
+    int cluster;                         // CTAs per cluster (= per job)
 };
 
 static size_t vgroup_smem_bytes(int D, int cpw) {
     const size_t strip = (size_t)VG_WARPS * cpw * D * 2;
     const size_t halo = (size_t)2 * 2 * VG_WARPS * (D * 2 + 16);
-    return 2 * 2 * strip + halo + 64;
+    return 2 * 2 * strip + halo + 64;  // + 4 mbarriers
 }
 
 __device__ __forceinline__ void vg_mbar_init(uint32_t bar, int count) {
@@ -65,33 +66,34 @@ __device__ __forceinline__ void vg_bulk_s2g(void* dst, uint32_t src, uint32_t by
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-// the SGM step of sgbm.cu (sgm_step<NP, true>): L'[d] = C[d] + min(L[d]-delta, L[d+-1]+P1-delta, 0)
+// the SGM step of sgbm.cu (sgm_step<NP, true>): O[d] = C[d] + min(I[d]-delta, I[d+-1]+P1-delta, 0), delta = minI + P2.
+// In and out may be the same registers (every output word is computed before any is stored).
 template <int NP>
-__device__ __forceinline__ uint32_t vg_step(uint32_t (&L)[NP], uint32_t minL2, const uint32_t (&Cv)[NP],
-                                            uint32_t p1x2, uint32_t k2, int lane) {
+__device__ __forceinline__ uint32_t vg_step(uint32_t (&O)[NP], const uint32_t (&I)[NP], uint32_t minI2,
+                                            const uint32_t (&Cv)[NP], uint32_t p1x2, uint32_t k2, int lane) {
     constexpr uint32_t INF = 0x7fff7fffu;
-    uint32_t up = __shfl_up_sync(0xffffffffu, L[NP - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    uint32_t up = __shfl_up_sync(0xffffffffu, I[NP - 1], 1);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, I[0], 1);
     if (lane == 0) up = INF;
     if (lane == 31) dn = INF;
-    const uint32_t nd2 = k2 - minL2;
+    const uint32_t nd2 = k2 - minI2;
     const uint32_t pm2 = nd2 + p1x2;
     uint32_t mn = INF;
     uint32_t Ln[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) {
-        const uint32_t prev = k ? L[k - 1] : up;
-        const uint32_t next = (k < NP - 1) ? L[k + 1] : dn;
-        const uint32_t dm1 = __byte_perm(prev, L[k], 0x5432);
-        const uint32_t dp1 = __byte_perm(L[k], next, 0x5432);
-        uint32_t t = __viaddmin_s16x2(L[k], nd2, 0u);
+        const uint32_t prev = k ? I[k - 1] : up;
+        const uint32_t next = (k < NP - 1) ? I[k + 1] : dn;
+        const uint32_t dm1 = __byte_perm(prev, I[k], 0x5432);
+        const uint32_t dp1 = __byte_perm(I[k], next, 0x5432);
+        uint32_t t = __viaddmin_s16x2(I[k], nd2, 0u);
         t = __viaddmin_s16x2(dm1, pm2, t);
         t = __viaddmin_s16x2(dp1, pm2, t);
         Ln[k] = __vadd2(Cv[k], t);
         mn = __vminu2(mn, Ln[k]);
     }
 #pragma unroll
-    for (int k = 0; k < NP; k++) L[k] = Ln[k];
+    for (int k = 0; k < NP; k++) O[k] = Ln[k];
     mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
     return __reduce_min_sync(0xffffffffu, mn);
 }
@@ -109,17 +111,19 @@ template <> __device__ __forceinline__ uint32_t vg_pack<1>(const uint32_t (&o)[1
 template <> __device__ __forceinline__ uint2 vg_pack<2>(const uint32_t (&o)[2]) { return make_uint2(o[0], o[1]); }
 template <> __device__ __forceinline__ uint4 vg_pack<4>(const uint32_t (&o)[4]) { return make_uint4(o[0], o[1], o[2], o[3]); }
 
-// NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities)
-template <int NP>
-__global__ void __cluster_dims__(VG_CLUSTER, 1, 1) __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroupArgs a) {
+// NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities); CPW = columns per warp
+template <int NP, int CPW>
+__global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroupArgs a) {
     typedef typename VgVec<NP>::T vec;
     constexpr uint32_t INF = 0x7fff7fffu;
     extern __shared__ __align__(128) unsigned char vg_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
+    const int VG_CLUSTER = a.cluster;
     const int job = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cpw = a.cpw, width1 = a.width1, H = a.H;
+    constexpr int cpw = CPW;
+    const int width1 = a.width1, H = a.H;
     const uint32_t B = (uint32_t)a.D * 2u;                       // bytes per pixel vector
     const int wstrip = VG_WARPS * cpw;                           // columns per CTA
     const int x0 = rank * wstrip;                                // first column of this CTA
@@ -138,9 +142,13 @@ __global__ void __cluster_dims__(VG_CLUSTER, 1, 1) __launch_bounds__(VG_THREADS,
 
     // zero both parities of every halo slot: "no predecessor" = (L = 0, min = 0), OpenCV's out-of-image rule
     for (int i = threadIdx.x; i < (int)(4 * VG_WARPS * slot / 4); i += VG_THREADS) ((uint32_t*)haloA)[i] = 0u;
+    // bars[0..1]: row stage full (producer's expect_tx + the two bulk loads); bars[2..3]: S strip of the stage
+    // rewritten by all compute warps (one arrive per warp)
     if (threadIdx.x == 0) {
         vg_mbar_init(bars, 1);
         vg_mbar_init(bars + 8, 1);
+        vg_mbar_init(bars + 16, VG_WARPS);
+        vg_mbar_init(bars + 24, VG_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -153,17 +161,41 @@ __global__ void __cluster_dims__(VG_CLUSTER, 1, 1) __launch_bounds__(VG_THREADS,
         vg_bulk_g2s((uint32_t)__cvta_generic_to_shared(Cbuf + (it & 1) * strip_bytes), Cg + off, bytes, bar);
         vg_bulk_g2s((uint32_t)__cvta_generic_to_shared(Sbuf + (it & 1) * strip_bytes), Sg + off, bytes, bar);
     };
-    if (threadIdx.x == 0 && wc > 0) {
+    if (threadIdx.x == VG_WARPS * 32 && wc > 0) {
         load_row(0);
         if (H > 1) load_row(1);
     }
     cluster.sync();  // halo zeroing of every CTA is complete before any neighbour writes into it
 
+    if (warp == VG_WARPS) {
+        // ===== producer warp: every bulk copy of the CTA.  It takes part in the per-row cluster barrier
+        // (arriving at once: it exports nothing) so that the compute warps never wait for a copy it issues.
+        for (int it = 0; it < H; it++) {
+            if (it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            if (lane == 0 && wc > 0) {
+                const int st = it & 1;
+                vg_mbar_wait(bars + 16 + 8 * st, (uint32_t)((it >> 1) & 1));  // all compute warps rewrote the S strip
+                const int row = dir > 0 ? it : H - 1 - it;
+                vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B,
+                            (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes), (uint32_t)wc * B);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+                if (it + 2 < H) load_row(it + 2);
+            }
+            __syncwarp();
+        }
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pair the last arrive
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        cluster.sync();
+        return;
+    }
+
     // path state: A = diagonal fed from the left neighbour column, V = vertical, Bp = diagonal fed from the right
-    uint32_t LA[VG_MAXCPW][NP], LV[VG_MAXCPW][NP], LB[VG_MAXCPW][NP];
-    uint32_t mA[VG_MAXCPW], mV[VG_MAXCPW], mB[VG_MAXCPW];
+    uint32_t LA[CPW][NP], LV[CPW][NP], LB[CPW][NP];
+    uint32_t mA[CPW], mV[CPW], mB[CPW];
 #pragma unroll
-    for (int j = 0; j < VG_MAXCPW; j++) {
+    for (int j = 0; j < CPW; j++) {
 #pragma unroll
         for (int k = 0; k < NP; k++) { LA[j][k] = 0; LV[j][k] = 0; LB[j][k] = 0; }
         mA[j] = 0; mV[j] = 0; mB[j] = 0;
@@ -195,74 +227,41 @@ __global__ void __cluster_dims__(VG_CLUSTER, 1, 1) __launch_bounds__(VG_THREADS,
             inAm = *(const uint32_t*)(pa + B);
             inBm = *(const uint32_t*)(pb + B);
         }
-        // ---- export this warp's edge states of row it-1 (still in registers) for row it+1's import ... no:
-        // the state a neighbour needs in row it+1 is the one computed in row it, exported after the update below.
-        const vec* cs = (const vec*)(Cbuf + st * strip_bytes);
-        vec* ss = (vec*)(Sbuf + st * strip_bytes);
-        // ---- diagonal A (fed from the left): in place, right to left
-        uint32_t sum[VG_MAXCPW][NP];
+        const vec* cs = (const vec*)(Cbuf + st * strip_bytes) + (size_t)c0 * 32 + lane;  // cs[j * 32]: column j of this warp
+        vec* ss = (vec*)(Sbuf + st * strip_bytes) + (size_t)c0 * 32 + lane;
+        uint32_t Cw[NP];
+        // ---- diagonal A (fed from the left): in place, right to left (column j reads column j-1's old state)
 #pragma unroll
-        for (int jj = 0; jj < VG_MAXCPW; jj++) {
-            const int j = VG_MAXCPW - 1 - jj;
-            if (j < cpw) {
-                uint32_t Cw[NP];
-                vg_unpack<NP>(cs[(size_t)(c0 + j) * 32 + lane], Cw);
-                uint32_t T[NP], tm;
-                if (j > 0) {
-#pragma unroll
-                    for (int k = 0; k < NP; k++) T[k] = LA[j - 1][k];
-                    tm = mA[j - 1];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NP; k++) T[k] = inA[k];
-                    tm = inAm;
-                }
-                mA[j] = vg_step<NP>(T, tm, Cw, p1x2, k2, lane);
-#pragma unroll
-                for (int k = 0; k < NP; k++) { LA[j][k] = T[k]; sum[j][k] = T[k]; }
-            }
+        for (int j = CPW - 1; j >= 1; j--) {
+            vg_unpack<NP>(cs[j * 32], Cw);
+            mA[j] = vg_step<NP>(LA[j], LA[j - 1], mA[j - 1], Cw, p1x2, k2, lane);
         }
-        // ---- diagonal B (fed from the right): in place, left to right; beyond the image edge the predecessor is 0
+        vg_unpack<NP>(cs[0], Cw);
+        mA[0] = vg_step<NP>(LA[0], inA, inAm, Cw, p1x2, k2, lane);
+        // ---- diagonal B (fed from the right): in place, left to right
 #pragma unroll
-        for (int j = 0; j < VG_MAXCPW; j++) {
-            if (j < cpw) {
-                uint32_t Cw[NP];
-                vg_unpack<NP>(cs[(size_t)(c0 + j) * 32 + lane], Cw);
-                uint32_t T[NP], tm;
-                if (j + 1 < cpw) {
+        for (int j = 0; j < CPW - 1; j++) {
+            vg_unpack<NP>(cs[j * 32], Cw);
+            mB[j] = vg_step<NP>(LB[j], LB[j + 1], mB[j + 1], Cw, p1x2, k2, lane);
+        }
+        vg_unpack<NP>(cs[(CPW - 1) * 32], Cw);
+        mB[CPW - 1] = vg_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, lane);
+        if (x0 + c0 + CPW > width1) {
+            // columns outside the image: their state must read as "no predecessor" (0) for the last valid column
 #pragma unroll
-                    for (int k = 0; k < NP; k++) T[k] = LB[(j + 1 < VG_MAXCPW) ? j + 1 : j][k];
-                    tm = mB[(j + 1 < VG_MAXCPW) ? j + 1 : j];
-                } else {
+            for (int j = 0; j < CPW; j++) {
+                if (x0 + c0 + j >= width1) {
 #pragma unroll
-                    for (int k = 0; k < NP; k++) T[k] = inB[k];
-                    tm = inBm;
+                    for (int k = 0; k < NP; k++) LB[j][k] = 0;
+                    mB[j] = 0;
                 }
-                if (x0 + c0 + j + 1 >= width1) {  // right neighbour column is outside the image
-#pragma unroll
-                    for (int k = 0; k < NP; k++) T[k] = 0;
-                    tm = 0;
-                }
-                mB[j] = vg_step<NP>(T, tm, Cw, p1x2, k2, lane);
-#pragma unroll
-                for (int k = 0; k < NP; k++) { LB[j][k] = T[k]; sum[j][k] = __viaddmin_u16x2(sum[j][k], T[k], INF); }
             }
         }
         // ---- export the new edge states (parity of this row) and let the cluster know
         if (expA) {
-            const int je = cpw - 1;
-            uint32_t E[NP];
-#pragma unroll
-            for (int j = 0; j < VG_MAXCPW; j++) if (j == je) {
-#pragma unroll
-                for (int k = 0; k < NP; k++) E[k] = LA[j][k];
-            }
-            uint32_t em = 0;
-#pragma unroll
-            for (int j = 0; j < VG_MAXCPW; j++) if (j == je) em = mA[j];
             unsigned char* q = expA + (size_t)par * par_stride;
-            *(vec*)(q + lane * sizeof(vec)) = vg_pack<NP>(E);
-            if (lane == 0) *(uint32_t*)(q + B) = em;
+            *(vec*)(q + lane * sizeof(vec)) = vg_pack<NP>(LA[CPW - 1]);
+            if (lane == 0) *(uint32_t*)(q + B) = mA[CPW - 1];
         }
         if (expB) {
             unsigned char* q = expB + (size_t)par * par_stride;
@@ -272,45 +271,43 @@ __global__ void __cluster_dims__(VG_CLUSTER, 1, 1) __launch_bounds__(VG_THREADS,
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         // ---- vertical path + S update (the cluster barrier's latency hides behind this)
 #pragma unroll
-        for (int j = 0; j < VG_MAXCPW; j++) {
-            if (j < cpw) {
-                uint32_t Cw[NP], Sw[NP];
-                vg_unpack<NP>(cs[(size_t)(c0 + j) * 32 + lane], Cw);
-                mV[j] = vg_step<NP>(LV[j], mV[j], Cw, p1x2, k2, lane);
-                vg_unpack<NP>(ss[(size_t)(c0 + j) * 32 + lane], Sw);
+        for (int j = 0; j < CPW; j++) {
+            vg_unpack<NP>(cs[j * 32], Cw);
+            mV[j] = vg_step<NP>(LV[j], LV[j], mV[j], Cw, p1x2, k2, lane);
+            uint32_t Sw[NP];
+            vg_unpack<NP>(ss[j * 32], Sw);
 #pragma unroll
-                for (int k = 0; k < NP; k++) {
-                    const uint32_t s3 = __viaddmin_u16x2(sum[j][k], LV[j][k], INF);
-                    Sw[k] = __viaddmin_u16x2(Sw[k], s3, INF);
-                }
-                ss[(size_t)(c0 + j) * 32 + lane] = vg_pack<NP>(Sw);
+            for (int k = 0; k < NP; k++) {
+                uint32_t s3 = __viaddmin_u16x2(LA[j][k], LB[j][k], INF);
+                s3 = __viaddmin_u16x2(s3, LV[j][k], INF);
+                Sw[k] = __viaddmin_u16x2(Sw[k], s3, INF);
             }
+            ss[j * 32] = vg_pack<NP>(Sw);
         }
-        // ---- S strip back to HBM, next-but-one row in
+        // ---- hand the rewritten S strip to the producer warp (it stores it and refills the stage)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0 && wc > 0) {
-            const int row = dir > 0 ? it : H - 1 - it;
-            vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
-                        (uint32_t)wc * B);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
-            if (it + 2 < H) load_row(it + 2);
-        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 16 + 8 * st) : "memory");
     }
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pair the last arrive
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     cluster.sync();  // no CTA exits while a neighbour may still write into its shared memory
 }
 
 // Host entry: aggregate the three previous-row paths of pass `dir` for `njobs` volumes at once.
 // Returns L3D_ERR_UNSUPPORTED when the geometry does not fit (caller falls back to the scan kernels).
+static int vgroup_cluster_size(int width1, int D) {
+    // 16 CTAs per job when the state then still fits (more SMs per job, more jobs resident per GPC pair)
+    const int maxcpw = D == 256 ? 4 : VG_MAXCPW;
+    if (cdiv(width1, 16 * VG_WARPS) >= 1 && cdiv(width1, 16 * VG_WARPS) <= maxcpw && width1 > 8 * VG_WARPS) return 16;
+    if (cdiv(width1, 8 * VG_WARPS) <= maxcpw) return 8;
+    return 0;
+}
+
 bool vgroup_supported(int width1, int H, int D) {
-    if (!(D == 64 || D == 128 || D == 256)) return false;
-    const int cpw = cdiv(width1, VG_CLUSTER * VG_WARPS);
-    if (cpw < 1 || cpw > VG_MAXCPW) return false;
-    if (D == 256 && cpw > 4) return false;  // register budget of the NP = 4 instantiation
-    return vgroup_smem_bytes(D, cpw) <= 220 * 1024 && H >= 1;
+    if (!(D == 64 || D == 128 || D == 256) || width1 < 1 || H < 1) return false;
+    const int cl = vgroup_cluster_size(width1, D);
+    if (!cl) return false;
+    return vgroup_smem_bytes(D, cdiv(width1, cl * VG_WARPS)) <= 220 * 1024;
 }
 
 int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
@@ -321,19 +318,35 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
         const int nj = std::min(VG_MAXJOBS, njobs - j0);
         for (int j = 0; j < nj; j++) { a.C[j] = C[j0 + j]; a.S[j] = S[j0 + j]; }
         a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir;
-        a.cpw = cdiv(width1, VG_CLUSTER * VG_WARPS);
+        a.cluster = vgroup_cluster_size(width1, D);
+        a.cpw = cdiv(width1, a.cluster * VG_WARPS);
         const size_t smem = vgroup_smem_bytes(D, a.cpw);
-        dim3 grid(VG_CLUSTER, nj);
-        if (D == 64) {
-            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            L3D_LAUNCH(L, sgbm_vgroup_kernel<1>, grid, VG_THREADS, smem, a);
-        } else if (D == 128) {
-            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            L3D_LAUNCH(L, sgbm_vgroup_kernel<2>, grid, VG_THREADS, smem, a);
-        } else {
-            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            L3D_LAUNCH(L, sgbm_vgroup_kernel<4>, grid, VG_THREADS, smem, a);
-        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(a.cluster, nj);
+        cfg.blockDim = dim3(VG_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = L.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = a.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int rc = L3D_ERR_UNSUPPORTED;
+#define VG_CASE(NPV, CPWV)                                                                                            \
+    if (D == 64 * NPV && a.cpw == CPWV) {                                                                             \
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<NPV, CPWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                                \
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<NPV, CPWV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+        L3D_CHECK(L, cudaLaunchKernelEx(&cfg, sgbm_vgroup_kernel<NPV, CPWV>, a));                                     \
+        L.launches++;                                                                                                 \
+        rc = L3D_OK;                                                                                                  \
+    }
+#define VG_NP(NPV) VG_CASE(NPV, 1) VG_CASE(NPV, 2) VG_CASE(NPV, 3) VG_CASE(NPV, 4) VG_CASE(NPV, 5) VG_CASE(NPV, 6) \
+                   VG_CASE(NPV, 7) VG_CASE(NPV, 8) VG_CASE(NPV, 9)
+        VG_NP(1) VG_NP(2)
+        VG_CASE(4, 1) VG_CASE(4, 2) VG_CASE(4, 3) VG_CASE(4, 4)
+#undef VG_NP
+#undef VG_CASE
+        if (rc != L3D_OK) return rc;
     }
     return L3D_OK;
 }

@@ -1,0 +1,9 @@
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from laser_3d_reconstruction_b200 import _native as N
+ctx = N.Context(0)
+ms = C.c_float()
+nj = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+ctx.check(ctx.lib.l3d_sgbm_vgroup_time(ctx.h, 1152, 720, 128, 1944, 7776, nj, 1, 1, C.byref(ms)), "vgroup_time")
+print("njobs", nj, ms.value, "ms")
