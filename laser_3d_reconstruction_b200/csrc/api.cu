@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of include/l3d.h: context, host<->device marshalling, frame pipeline.
+#include <chrono>
 #include <stdexcept>
 
 #include "common.cuh"
@@ -396,6 +397,56 @@ static int depth_path(Lane& L, const l3d_depth_config& cfg, const RectMap* maps,
     return L3D_OK;
 }
 
+// The same path split around the cluster-fused aggregation, for the grouped frame pipeline:
+// front = rectify + gray + BT operands + both matchers' cost volumes and horizontal paths;
+// back  = WTA / LR check / median / speckles of both matchers + WLS + depth.
+struct DepthRuns {
+    SgbmRun left, right;
+    bool has_right = false;
+};
+static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps, const uint8_t* lsrc,
+                       const uint8_t* rsrc, int W, int H, long stride, uint8_t* rectL, DepthRuns& dr) {
+    size_t n = (size_t)W * H;
+    uint8_t* gl = L.get<uint8_t>(S_GRAY_L, n);
+    uint8_t* gr = L.get<uint8_t>(S_GRAY_R, n);
+    if (cfg.use_maps) {
+        L3D_ARG(L, maps[0].map && maps[1].map, "rectification maps not set");
+        L3D_ARG(L, maps[0].W == W && maps[0].H == H && maps[1].W == W && maps[1].H == H, "map size != image size");
+        RC(dev_remap_gray(L, maps[0], lsrc, W, H, stride, rectL, gl));
+        RC(dev_remap_gray(L, maps[1], rsrc, W, H, stride, nullptr, gr));
+    } else {
+        RC(dev_copy_gray(L, lsrc, W, H, stride, rectL, gl));
+        RC(dev_copy_gray(L, rsrc, W, H, stride, nullptr, gr));
+    }
+    uint4* dL = L.get<uint4>(S_DESC_L, n);
+    uint4* dR = L.get<uint4>(S_DESC_R, n);
+    RC(sgbm_front(L, cfg.left, gl, gr, W, H, 0, dL, dR, true, dr.left));
+    dr.has_right = cfg.use_wls != 0;
+    // the right matcher sees the views swapped: same BT operands, roles exchanged
+    if (dr.has_right) {
+        L3D_ARG(L, cfg.right.preFilterCap == cfg.left.preFilterCap, "left/right matcher preFilterCap differ");
+        RC(sgbm_front(L, cfg.right, gr, gl, W, H, 1, dR, dL, false, dr.right));
+    }
+    return L3D_OK;
+}
+static int depth_back(Lane& L, const l3d_depth_config& cfg, DepthRuns& dr, int W, int H, float* depth, int16_t* disp_f) {
+    size_t n = (size_t)W * H;
+    const uint8_t* gl = L.get<uint8_t>(S_GRAY_L, n);
+    int16_t* dl = L.get<int16_t>(S_DISP_L, n);
+    RC(sgbm_back(L, dr.left, dl, nullptr));
+    const int16_t* df = dl;
+    if (dr.has_right) {
+        int16_t* drr = L.get<int16_t>(S_DISP_R, n);
+        RC(sgbm_back(L, dr.right, drr, nullptr));
+        RC(dev_wls(L, cfg.wls, dl, drr, gl, W, H, disp_f, nullptr));
+        df = disp_f;
+    } else {
+        L3D_CHECK(L, cudaMemcpyAsync(disp_f, dl, n * 2, cudaMemcpyDeviceToDevice, L.stream));
+    }
+    RC(dev_depth(L, df, W, H, cfg.use_Q ? cfg.Q : nullptr, depth));
+    return L3D_OK;
+}
+
 int l3d_compute_depth(l3d_ctx* ctx, const l3d_depth_config* cfg, const uint8_t* left_bgr, const uint8_t* right_bgr,
                       int W, int H, long stride, uint8_t* left_rect, float* depth, int16_t* disp_out) {
     API_BEGIN(ctx)
@@ -541,6 +592,15 @@ struct l3d_pipeline {
     cudaStream_t main = nullptr;
     float last_ms = 0.f;
     int last_frames = 0;
+    // grouped mode: the frames of a lane set run their SGBM fronts on their lanes, ONE cluster-fused
+    // aggregation launch per pass over all their volumes on the set's middle stream, then their backs
+    static constexpr int MAXSETS = 4;
+    Lane mid[MAXSETS];
+    cudaEvent_t ev_mid[MAXSETS] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> lane_front;
+    std::vector<DepthRuns> runs;  // per lane
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dbg_events;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -584,10 +644,16 @@ static int pipe_prepare(l3d_pipeline* p, int nframes) {
 }
 
 // enqueue one frame on lane L (all device pointers)
+static int pipe_extract(l3d_pipeline* p, Lane& L, FrameOut& o);
 static int pipe_frame(l3d_pipeline* p, Lane& L, const uint8_t* l, const uint8_t* r, FrameOut& o) {
     const l3d_pipeline_config& c = p->cfg;
+    RC(depth_path(L, c.depth, p->maps, l, r, c.W, c.H, 3L * c.W, o.rect, o.depth, o.disp));
+    return pipe_extract(p, L, o);
+}
+// laser centre line on the rectified left image + 3D points (main.py:172-178)
+static int pipe_extract(l3d_pipeline* p, Lane& L, FrameOut& o) {
+    const l3d_pipeline_config& c = p->cfg;
     const int W = c.W, H = c.H;
-    RC(depth_path(L, c.depth, p->maps, l, r, W, H, 3L * W, o.rect, o.depth, o.disp));
     if (c.extractor < 0) {
         L3D_CHECK(L, cudaMemsetAsync(o.n_xy, 0, sizeof(int), L.stream));
         L3D_CHECK(L, cudaMemsetAsync(o.n_xyz, 0, sizeof(int), L.stream));
@@ -680,6 +746,14 @@ int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeli
     CK(ctx, cudaEventCreate(&p->ev1));
     p->lane_done.resize(cfg->lanes);
     for (auto& e : p->lane_done) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->lane_front.resize(cfg->lanes);
+    for (auto& e : p->lane_front) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->runs.resize(cfg->lanes);
+    for (int i = 0; i < l3d_pipeline::MAXSETS; i++) {
+        p->mid[i].err = &ctx->err;
+        CK(ctx, cudaStreamCreateWithFlags(&p->mid[i].stream, cudaStreamNonBlocking));
+        CK(ctx, cudaEventCreateWithFlags(&p->ev_mid[i], cudaEventDisableTiming));
+    }
     *out = p;
     return L3D_OK;
     API_END(ctx)
@@ -689,6 +763,8 @@ void l3d_pipeline_destroy(l3d_pipeline* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     for (auto& L : p->lanes) L.release();
+    for (int i = 0; i < l3d_pipeline::MAXSETS; i++) { p->mid[i].release(); if (p->ev_mid[i]) cudaEventDestroy(p->ev_mid[i]); }
+    for (auto e : p->lane_front) cudaEventDestroy(e);
     for (auto& m : p->maps) if (m.map) cudaFree(m.map);
     if (p->arena) cudaFree(p->arena);
     if (p->counts_host) cudaFreeHost(p->counts_host);
@@ -709,6 +785,87 @@ int l3d_pipeline_set_maps(l3d_pipeline* p, int eye, const float* mapx, const flo
     API_END(ctx)
 }
 
+// Grouped mode: one aggregation launch should carry close to (but not more than) one wave of clusters --
+// 15 clusters of 8 CTAs are resident on a B200 (cudaOccupancyMaxActiveClusters) -- so a lane set is
+// 7 frames with WLS (14 volumes) or 15 without; up to 4 sets alternate to overlap fronts/backs with
+// another set's aggregation.
+constexpr int VG_WAVE = 15;
+static int pipe_group_size(const l3d_pipeline* p) {
+    const int jobs_per_frame = p->cfg.depth.use_wls ? 2 : 1;
+    return std::min((int)p->lanes.size(), std::max(1, VG_WAVE / jobs_per_frame));
+}
+static bool pipe_grouped(const l3d_pipeline* p) {
+    static const bool off = getenv("L3D_NO_VGROUP") && atoi(getenv("L3D_NO_VGROUP")) > 0;
+    if (off) return false;
+    const l3d_pipeline_config& c = p->cfg;
+    const int jobs_per_frame = c.depth.use_wls ? 2 : 1;
+    if (pipe_group_size(p) * jobs_per_frame < 8 || c.depth.left.mode == 2) return false;
+    const l3d_sgbm_params& q = c.depth.left;
+    const int width1 = (c.W + std::min(q.minDisparity, 0)) - std::max(q.minDisparity + q.numDisparities, 0);
+    return width1 > 0 && vgroup_supported(width1, c.H, q.numDisparities);
+}
+
+static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, bool host_in, int nframes,
+                            float* depth_h, double* xyz_h) {
+    l3d_ctx* ctx = p->ctx;
+    const l3d_pipeline_config& c = p->cfg;
+    const int W = c.W, H = c.H, cap = c.max_points;
+    const size_t nb = (size_t)W * H * 3, n = (size_t)W * H;
+    const int nl = (int)p->lanes.size();
+    const int gsz = pipe_group_size(p);
+    const int nsets = p->timing ? 1 : std::max(1, std::min(l3d_pipeline::MAXSETS, nl / gsz));  // lane sets alternate
+    for (int i = 0; i < l3d_pipeline::MAXSETS; i++) {
+        p->mid[i].t_reset(); p->mid[i].timing = p->timing;
+        CK(ctx, cudaStreamWaitEvent(p->mid[i].stream, p->ev0, 0));
+    }
+    int chunk = 0;
+    for (int f0 = 0; f0 < nframes; f0 += gsz, chunk++) {
+        const int set = chunk % nsets, ng = std::min(gsz, nframes - f0);
+        Lane& M = p->mid[set];
+        std::vector<SgbmRun*> list;
+        for (int i = 0; i < ng; i++) {
+            const int li = set * gsz + i, f = f0 + i;
+            Lane& L = p->lanes[li];
+            const uint8_t *l = left + nb * f, *r = right + nb * f;
+            if (p->timing && i > 0) CK(ctx, cudaStreamWaitEvent(L.stream, p->lane_front[li - 1], 0));  // kernels alone
+            if (host_in) {
+                uint8_t* sl = L.get<uint8_t>(S_SRC_L, nb);
+                uint8_t* sr = L.get<uint8_t>(S_SRC_R, nb);
+                L3D_CHECK(L, cudaMemcpyAsync(sl, l, nb, cudaMemcpyHostToDevice, L.stream));
+                L3D_CHECK(L, cudaMemcpyAsync(sr, r, nb, cudaMemcpyHostToDevice, L.stream));
+                l = sl; r = sr;
+            }
+            DepthRuns& dr = p->runs[li];
+            RC(depth_front(L, c.depth, p->maps, l, r, W, H, 3L * W, p->outs[f].rect, dr));
+            CK(ctx, cudaEventRecord(p->lane_front[li], L.stream));
+            CK(ctx, cudaStreamWaitEvent(M.stream, p->lane_front[li], 0));
+            list.push_back(&dr.left);
+            if (dr.has_right) list.push_back(&dr.right);
+        }
+        static const bool dbg_phases = getenv("L3D_DEBUG_PHASES") != nullptr;
+        cudaEvent_t d0 = nullptr, d1 = nullptr;
+        if (dbg_phases) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, M.stream); }
+        RC(sgbm_middle_vgroup(M, list.data(), (int)list.size()));
+        if (dbg_phases) { cudaEventRecord(d1, M.stream); p->dbg_events.push_back({d0, d1}); }
+        CK(ctx, cudaEventRecord(p->ev_mid[set], M.stream));
+        for (int i = 0; i < ng; i++) {
+            const int li = set * gsz + i, f = f0 + i;
+            Lane& L = p->lanes[li];
+            FrameOut& o = p->outs[f];
+            CK(ctx, cudaStreamWaitEvent(L.stream, p->ev_mid[set], 0));
+            if (p->timing && i > 0) CK(ctx, cudaStreamWaitEvent(L.stream, p->lane_done[li - 1], 0));
+            RC(depth_back(L, c.depth, p->runs[li], W, H, o.depth, o.disp));
+            RC(pipe_extract(p, L, o));
+            L3D_CHECK(L, cudaMemcpyAsync(p->counts_host + 2 * f, o.n_xy, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+            L3D_CHECK(L, cudaMemcpyAsync(p->counts_host + 2 * f + 1, o.n_xyz, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+            if (depth_h) L3D_CHECK(L, cudaMemcpyAsync(depth_h + n * f, o.depth, n * 4, cudaMemcpyDeviceToHost, L.stream));
+            if (xyz_h) L3D_CHECK(L, cudaMemcpyAsync(xyz_h + (size_t)cap * 3 * f, o.xyz, (size_t)cap * 24, cudaMemcpyDeviceToHost, L.stream));
+            if (p->timing) CK(ctx, cudaEventRecord(p->lane_done[li], L.stream));
+        }
+    }
+    return L3D_OK;
+}
+
 static int pipe_run(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, bool host_in, int nframes,
                     float* depth_h, double* xyz_h, int* counts) {
     l3d_ctx* ctx = p->ctx;
@@ -718,9 +875,12 @@ static int pipe_run(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, 
     const size_t nb = (size_t)W * H * 3, n = (size_t)W * H;
     const int nl = (int)p->lanes.size();
     for (auto& L : p->lanes) L.t_reset();
+    auto t_enq0 = std::chrono::steady_clock::now();
     CK(ctx, cudaEventRecord(p->ev0, p->main));
     for (auto& L : p->lanes) CK(ctx, cudaStreamWaitEvent(L.stream, p->ev0, 0));
-    for (int f = 0; f < nframes; f++) {
+    const bool grouped = pipe_grouped(p);
+    if (grouped) RC(pipe_run_grouped(p, left, right, host_in, nframes, depth_h, xyz_h));
+    for (int f = 0; f < nframes && !grouped; f++) {
         Lane& L = p->lanes[f % nl];
         FrameOut& o = p->outs[f];
         const uint8_t *l = left + nb * f, *r = right + nb * f;
@@ -742,8 +902,20 @@ static int pipe_run(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, 
         CK(ctx, cudaStreamWaitEvent(p->main, p->lane_done[i], 0));
     }
     CK(ctx, cudaEventRecord(p->ev1, p->main));
+    if (getenv("L3D_DEBUG_ENQUEUE")) {
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[l3d] enqueue of %d frames took %.3f ms host time\n", nframes,
+                std::chrono::duration<double, std::milli>(t1 - t_enq0).count());
+    }
     CK(ctx, cudaEventSynchronize(p->ev1));
     CK(ctx, cudaEventElapsedTime(&p->last_ms, p->ev0, p->ev1));
+    for (auto& e : p->dbg_events) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, p->ev0, e.first); cudaEventElapsedTime(&b, p->ev0, e.second);
+        fprintf(stderr, "[l3d] aggregation launch pair: start %.2f ms, end %.2f ms (total run %.2f ms)\n", a, b, p->last_ms);
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    p->dbg_events.clear();
     p->last_frames = nframes;
     if (counts) for (int f = 0; f < nframes; f++) counts[f] = p->counts_host[2 * f + 1];
     return L3D_OK;
@@ -798,13 +970,17 @@ int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* de
 
 long long l3d_pipeline_launch_count(l3d_pipeline* p) {
     long long s = 0;
-    if (p) for (auto& L : p->lanes) s += L.launches;
+    if (p) {
+        for (auto& L : p->lanes) s += L.launches;
+        for (int i = 0; i < l3d_pipeline::MAXSETS; i++) s += p->mid[i].launches;
+    }
     return s;
 }
 
 int l3d_pipeline_set_timing(l3d_pipeline* p, int on) {
     if (!p) return L3D_ERR_ARG;
     for (auto& L : p->lanes) L.timing = on != 0;
+    p->timing = on != 0;  // grouped mode: lanes are chained so that every timed kernel runs alone
     return L3D_OK;
 }
 
@@ -814,7 +990,11 @@ int l3d_pipeline_kernel_time(l3d_pipeline* p, const char* which, float* ms, int*
     if (!p || !which || !ms || !launches) return L3D_ERR_ARG;
     l3d_ctx* ctx = p->ctx;
     float tot = 0.f; int cnt = 0;
-    for (auto& L : p->lanes) {
+    std::vector<Lane*> all;
+    for (auto& L : p->lanes) all.push_back(&L);
+    for (int i = 0; i < l3d_pipeline::MAXSETS; i++) all.push_back(&p->mid[i]);
+    for (Lane* Lp : all) {
+        Lane& L = *Lp;
         auto it = L.timers.find(which);
         if (it == L.timers.end()) continue;
         for (auto& r : it->second) {

@@ -24,7 +24,7 @@ struct DevBuf {
 // scratch slots (per lane)
 enum Slot {
     S_SRC_L, S_SRC_R, S_RECT_L, S_RECT_R, S_GRAY_L, S_GRAY_R,
-    S_DESC_L, S_DESC_R, S_COST, S_AGGR, S_DISP2, S_RAW, S_DISP_L, S_DISP_R, S_DISP_F, S_MED,
+    S_DESC_L, S_DESC_R, S_COST, S_AGGR, S_DISP2, S_RAW, S_COST2, S_AGGR2, S_DISP22, S_RAW2, S_DISP_L, S_DISP_R, S_DISP_F, S_MED,
     S_LABEL, S_CNT, S_DEPTH,
     S_WLS_A, S_WLS_B, S_WLS_C, S_WLS_D, S_WLS_E, S_WLS_F, S_WLS_G, S_WLS_H, S_WLS_I, S_WLS_J, S_WLS_K,
     S_ST_GRAY, S_ST_TMP, S_ST_SM, S_ST_ROW, S_ST_CNT, S_ST_XY, S_ST_N,

@@ -820,129 +820,157 @@ static int launch_scan_np(Lane& L, int NP, int smode, const ScanArgs& sa, int li
     return launch_scan_m<4>(L, smode, sa, lines);
 }
 
-int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W, int H,
-             int16_t* disp, SgbmDebug* dbg) {
+// ------------------------------------------------------------------------------------------
+// host driver.  One matcher run = front (descriptors, cost volume, both horizontal paths)
+//                               + middle (the previous-row paths: cluster-fused or direction-split)
+//                               + back (WTA if not fused, LR check, median, speckles).
+// The frame pipeline runs the fronts of a group of frames on their lanes, ONE cluster-fused middle
+// launch per pass over all the group's volumes, and the backs on the lanes again (api.cu).
+// ------------------------------------------------------------------------------------------
+struct SgbmRun {
+    l3d_sgbm_params p;
     Geom g;
+    int W = 0, H = 0;
+    int16_t* C = nullptr;
+    int16_t* S = nullptr;
+    int16_t* raw = nullptr;
+    unsigned* d2 = nullptr;
+    bool wta_done = false;
+};
+
+static void scan_args_of(const SgbmRun& r, ScanArgs& sa) {
+    const Geom& g = r.g;
+    sa.C = r.C; sa.S = r.S; sa.width1 = g.width1; sa.D = g.D; sa.nact = g.nact; sa.P1 = g.P1; sa.P2 = g.P2;
+    sa.HV = g.HV; sa.nseg = g.nseg;
+    for (int s = 0; s < MAXSEG; s++) { sa.seg_vr0[s] = g.seg_vr0[s]; sa.seg_rows[s] = g.seg_rows[s]; }
+    sa.raw = r.raw; sa.disp2key = r.d2; sa.W = r.W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
+    sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0;
+}
+
+// set: 0 / 1 selects the scratch slots (the pipeline keeps the left and the right matcher's volumes alive
+// together); descL/descR: BT operands of this run's left / right image, computed here when `make_desc`.
+int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W, int H, int set,
+               uint4* dL, uint4* dR, bool make_desc, SgbmRun& r) {
+    r.p = p; r.W = W; r.H = H; r.wta_done = false;
+    Geom& g = r.g;
     int rc = make_geom(p, W, H, g, L.err);
     if (rc != L3D_OK) return rc;
     const size_t npix = (size_t)W * H;
     const int16_t INVALID = (int16_t)((g.minD - 1) * 16);
-    int16_t* raw = L.get<int16_t>(S_RAW, npix);
-    L3D_LAUNCH(L, fill_s16_kernel, cdiv(npix, 256), 256, 0, raw, npix, INVALID);
-    if (g.width1 > 0) {
-        // --- descriptors
-        uint4* dL = L.get<uint4>(S_DESC_L, npix);
-        uint4* dR = L.get<uint4>(S_DESC_R, npix);
+    r.raw = L.get<int16_t>(set ? S_RAW2 : S_RAW, npix);
+    L3D_LAUNCH(L, fill_s16_kernel, cdiv(npix, 256), 256, 0, r.raw, npix, INVALID);
+    if (g.width1 <= 0) return L3D_OK;
+    if (make_desc) {
         dim3 pg(cdiv(W, 128), H);
         L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, 128, 0, left, W, H, g.ftzero, dL);
         L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, 128, 0, right, W, H, g.ftzero, dR);
-        // --- cost volume
-        const size_t nvol = (size_t)g.HV * g.width1 * g.D;
-        int16_t* C = L.get<int16_t>(S_COST, nvol);
-        int16_t* S = L.get<int16_t>(S_AGGR, nvol);
-        CostArgs ca;
-        ca.Ldesc = dL; ca.Rdesc = dR; ca.C = C;
-        ca.W = W; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
-        ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
-        const int D2 = g.D / 2;
-        auto cost_smem = [&](int txh) {
-            int tx = txh - 2 * g.SW2;
-            return (size_t)2 * 2 * (txh + g.D) * 16 + (size_t)2 * D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4;
-        };
-        ca.nxg = std::max(1, COST_THREADS / D2);
-        int TXH = 64;
-        while (TXH > 2 * g.SW2 + 1 &&
-               (cost_smem(TXH) > 200 * 1024 || cdiv(TXH - 2 * g.SW2, ca.nxg) > COST_MAXCPG)) TXH /= 2;
-        L3D_ARG(L, TXH > 2 * g.SW2 && COST_THREADS % TXH == 0 && cost_smem(TXH) <= 200 * 1024 &&
-                       cdiv(TXH - 2 * g.SW2, ca.nxg) <= COST_MAXCPG,
-                "sgbm: blockSize / numDisparities combination exceeds the cost kernel's shared-memory tile");
-        ca.TXH = TXH; ca.TX = TXH - 2 * g.SW2;
-        ca.cpg = cdiv(ca.TX, ca.nxg);
-        // bands: split each segment so that the grid is close to a multiple of the SM count
-        int xtiles = cdiv(g.width1, ca.TX);
-        int want = std::max(1, (2 * NUM_SMS) / xtiles);
-        int per_seg = std::max(1, std::min(want / g.nseg, MAXBAND / g.nseg));
-        ca.nbands = 0;
-        for (int s = 0; s < g.nseg; s++) {
-            int rows = g.seg_rows[s];
-            int nb = std::max(1, std::min(per_seg, rows / (2 * g.bs) > 0 ? rows / (2 * g.bs) : 1));
-            int br = cdiv(rows, nb);
-            for (int r0 = 0; r0 < rows; r0 += br) {
-                int i = ca.nbands++;
-                ca.band_vr0[i] = g.seg_vr0[s] + r0;
-                ca.band_y0[i] = g.seg_y0[s] + r0;
-                ca.band_rows[i] = std::min(br, rows - r0);
-                ca.band_clo[i] = g.seg_y0[s];  // the vertical box sum restarts at the segment top
-                ca.band_chi[i] = H - 1;
-            }
+    }
+    // --- cost volume
+    const size_t nvol = (size_t)g.HV * g.width1 * g.D;
+    r.C = L.get<int16_t>(set ? S_COST2 : S_COST, nvol);
+    r.S = L.get<int16_t>(set ? S_AGGR2 : S_AGGR, nvol);
+    CostArgs ca;
+    ca.Ldesc = dL; ca.Rdesc = dR; ca.C = r.C;
+    ca.W = W; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
+    ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
+    const int D2 = g.D / 2;
+    auto cost_smem = [&](int txh) {
+        int tx = txh - 2 * g.SW2;
+        return (size_t)2 * 2 * (txh + g.D) * 16 + (size_t)2 * D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4;
+    };
+    ca.nxg = std::max(1, COST_THREADS / D2);
+    int TXH = 64;
+    while (TXH > 2 * g.SW2 + 1 &&
+           (cost_smem(TXH) > 200 * 1024 || cdiv(TXH - 2 * g.SW2, ca.nxg) > COST_MAXCPG)) TXH /= 2;
+    L3D_ARG(L, TXH > 2 * g.SW2 && COST_THREADS % TXH == 0 && cost_smem(TXH) <= 200 * 1024 &&
+                   cdiv(TXH - 2 * g.SW2, ca.nxg) <= COST_MAXCPG,
+            "sgbm: blockSize / numDisparities combination exceeds the cost kernel's shared-memory tile");
+    ca.TXH = TXH; ca.TX = TXH - 2 * g.SW2;
+    ca.cpg = cdiv(ca.TX, ca.nxg);
+    // bands: split each segment so that the grid is close to a multiple of the SM count
+    int xtiles = cdiv(g.width1, ca.TX);
+    int want = std::max(1, (2 * NUM_SMS) / xtiles);
+    int per_seg = std::max(1, std::min(want / g.nseg, MAXBAND / g.nseg));
+    ca.nbands = 0;
+    for (int s = 0; s < g.nseg; s++) {
+        int rows = g.seg_rows[s];
+        int nb = std::max(1, std::min(per_seg, rows / (2 * g.bs) > 0 ? rows / (2 * g.bs) : 1));
+        int br = cdiv(rows, nb);
+        for (int r0 = 0; r0 < rows; r0 += br) {
+            int i = ca.nbands++;
+            ca.band_vr0[i] = g.seg_vr0[s] + r0;
+            ca.band_y0[i] = g.seg_y0[s] + r0;
+            ca.band_rows[i] = std::min(br, rows - r0);
+            ca.band_clo[i] = g.seg_y0[s];  // the vertical box sum restarts at the segment top
+            ca.band_chi[i] = H - 1;
         }
-        size_t smem = cost_smem(TXH);
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        L.t_begin("sgbm_cost");
-        L3D_LAUNCH(L, sgbm_cost_kernel, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);
-        L.t_end("sgbm_cost");
-        // --- aggregation
-        ScanArgs sa;
-        sa.C = C; sa.S = S; sa.width1 = g.width1; sa.D = g.D; sa.nact = g.nact; sa.P1 = g.P1; sa.P2 = g.P2;
-        sa.HV = g.HV; sa.nseg = g.nseg;
-        for (int s = 0; s < MAXSEG; s++) { sa.seg_vr0[s] = g.seg_vr0[s]; sa.seg_rows[s] = g.seg_rows[s]; }
-        unsigned* d2 = L.get<unsigned>(S_DISP2, (size_t)H * (W + 2));
-        L3D_CHECK(L, cudaMemsetAsync(d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
-        sa.raw = raw; sa.disp2key = d2; sa.W = W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
-        int kinds[8], nk = 0;
-        kinds[nk++] = 0; kinds[nk++] = 1; kinds[nk++] = 2;  // ->, <-, down: all modes
-        if (g.mode != 2) { kinds[nk++] = 3; kinds[nk++] = 4; }
-        if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
-        // modes SGBM / HH: the last path does the WTA on its finished S vectors and never writes them
-        // (unless the caller asked for the S volume)
-        // L3D_VGROUP=1: aggregate the previous-row paths with the cluster-fused kernel (sgbm_vgroup.cu)
-        static const bool use_vgroup = getenv("L3D_VGROUP") && atoi(getenv("L3D_VGROUP")) > 0;
-        const bool vgroup = use_vgroup && g.mode != 2 && vgroup_supported(g.width1, g.HV, g.D);
-        const bool fuse_wta = g.mode != 2 && !(dbg && dbg->S) && !vgroup;
-        // both horizontal paths in one launch (kinds 0 and 1 are always the first two)
-        sa.kind = 0; sa.store = 1;
-        L.t_begin("sgbm_scan_k0");
-        rc = g.NP == 1 ? launch_hpair<1>(L, sa) : (g.NP == 2 ? launch_hpair<2>(L, sa) : launch_hpair<4>(L, sa));
-        L.t_end("sgbm_scan_k0");
+    }
+    size_t smem = cost_smem(TXH);
+    L3D_CHECK(L, cudaFuncSetAttribute(sgbm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    L.t_begin("sgbm_cost");
+    L3D_LAUNCH(L, sgbm_cost_kernel, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);
+    L.t_end("sgbm_cost");
+    r.d2 = L.get<unsigned>(set ? S_DISP22 : S_DISP2, (size_t)H * (W + 2));
+    L3D_CHECK(L, cudaMemsetAsync(r.d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
+    // --- both horizontal paths in one launch
+    ScanArgs sa;
+    scan_args_of(r, sa);
+    L.t_begin("sgbm_scan_k0");
+    rc = g.NP == 1 ? launch_hpair<1>(L, sa) : (g.NP == 2 ? launch_hpair<2>(L, sa) : launch_hpair<4>(L, sa));
+    L.t_end("sgbm_scan_k0");
+    return rc;
+}
+
+// can the previous-row paths of this run go through the cluster-fused kernel?
+bool sgbm_vgroup_ok(const SgbmRun& r) {
+    return r.g.width1 > 0 && r.g.mode != 2 && vgroup_supported(r.g.width1, r.g.HV, r.g.D);
+}
+
+// the previous-row paths with the direction-split scan kernels (any geometry and mode); the last path fuses
+// the WTA unless the caller needs the finished S volume
+int sgbm_middle_split(Lane& L, SgbmRun& r, bool keep_S) {
+    const Geom& g = r.g;
+    if (g.width1 <= 0) return L3D_OK;
+    ScanArgs sa;
+    scan_args_of(r, sa);
+    int kinds[6], nk = 0;
+    kinds[nk++] = 2;  // down: all modes
+    if (g.mode != 2) { kinds[nk++] = 3; kinds[nk++] = 4; }
+    if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
+    const bool fuse_wta = g.mode != 2 && !keep_S;
+    for (int i = 0; i < nk; i++) {
+        const int k = kinds[i];
+        sa.kind = k; sa.store = 0;
+        const int smode = (fuse_wta && i == nk - 1) ? SCAN_FINAL : SCAN_ACCUM;
+        sa.lines_per_seg = (k == 2 || k == 5) ? g.width1 : g.width1 + g.H - 1;  // diagonals only with nseg == 1
+        const int lines = g.nseg * sa.lines_per_seg;
+        static const char* kind_names[8] = {"sgbm_scan_k0", "sgbm_scan_k1", "sgbm_scan_k2", "sgbm_scan_k3",
+                                            "sgbm_scan_k4", "sgbm_scan_k5", "sgbm_scan_k6", "sgbm_scan_k7"};
+        L.t_begin(kind_names[k]);
+        int rc = launch_scan_np(L, g.NP, smode, sa, lines);
+        L.t_end(kind_names[k]);
         if (rc != L3D_OK) return rc;
-        if (vgroup) {
-            const int16_t* Cj[1] = {C};
-            int16_t* Sj[1] = {S};
-            L.t_begin("sgbm_scan_k2");
-            rc = dev_sgbm_vgroup(L, Cj, Sj, 1, g.width1, g.HV, g.D, g.P1, g.P2, +1);
-            L.t_end("sgbm_scan_k2");
-            if (rc != L3D_OK) return rc;
-            if (g.mode == 1) {
-                L.t_begin("sgbm_scan_k5");
-                rc = dev_sgbm_vgroup(L, Cj, Sj, 1, g.width1, g.HV, g.D, g.P1, g.P2, -1);
-                L.t_end("sgbm_scan_k5");
-                if (rc != L3D_OK) return rc;
-            }
-            nk = 2;  // nothing left for the direction-split kernels
-        }
-        for (int i = 2; i < nk; i++) {
-            const int k = kinds[i];
-            sa.kind = k; sa.store = 0;
-            const int smode = i == 0 ? SCAN_STORE : ((fuse_wta && i == nk - 1) ? SCAN_FINAL : SCAN_ACCUM);
-            sa.lines_per_seg = (k == 2 || k == 5) ? g.width1 : g.width1 + g.H - 1;  // diagonals only with nseg == 1
-            int lines = k <= 1 ? g.HV : g.nseg * sa.lines_per_seg;
-            static const char* kind_names[8] = {"sgbm_scan_k0", "sgbm_scan_k1", "sgbm_scan_k2", "sgbm_scan_k3",
-                                                "sgbm_scan_k4", "sgbm_scan_k5", "sgbm_scan_k6", "sgbm_scan_k7"};
-            L.t_begin(kind_names[k]);
-            rc = launch_scan_np(L, g.NP, smode, sa, lines);
-            L.t_end(kind_names[k]);
-            if (rc != L3D_OK) return rc;
-        }
-        // --- WTA (when not fused), LR check
+    }
+    r.wta_done = fuse_wta;
+    return L3D_OK;
+}
+
+// WTA (unless the last path did it), LR check, medianBlur(3), filterSpeckles -> disp
+int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg) {
+    const Geom& g = r.g;
+    const int W = r.W, H = r.H;
+    const size_t npix = (size_t)W * H;
+    const int16_t INVALID = (int16_t)((g.minD - 1) * 16);
+    if (g.width1 > 0) {
         WtaArgs wa;
-        wa.S = S; wa.raw = raw; wa.disp2key = d2; wa.W = W; wa.width1 = g.width1; wa.D = g.D; wa.nact = g.nact;
+        wa.S = r.S; wa.raw = r.raw; wa.disp2key = r.d2; wa.W = W; wa.width1 = g.width1; wa.D = g.D; wa.nact = g.nact;
         wa.DPL = g.DPL; wa.minD = g.minD; wa.minX1 = g.minX1; wa.uniq = g.uniq; wa.mode = g.mode;
         wa.HV = g.HV; wa.nseg = g.nseg;
         for (int s = 0; s < MAXSEG; s++) {
             wa.seg_vr0[s] = g.seg_vr0[s]; wa.seg_y0[s] = g.seg_y0[s]; wa.seg_rows[s] = g.seg_rows[s]; wa.seg_emit[s] = g.seg_emit[s];
         }
         L.t_begin("sgbm_wta");
-        if (fuse_wta) {
+        if (r.wta_done) {
         } else if (g.mode != 2) {
             const int wgrid = cdiv(cdiv((long)g.HV * g.width1, 32), WTA_WARPS);
             const bool full = g.nact == 32;
@@ -960,18 +988,65 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
             else L3D_LAUNCH(L, sgbm_wta_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
         }
         L.t_end("sgbm_wta");
-        L3D_LAUNCH(L, sgbm_lrcheck_kernel, dim3(cdiv(g.width1, 128), H), 128, 0, raw, d2, W, H, g.minX1, g.maxX1, g.minD, g.d12);
+        L3D_LAUNCH(L, sgbm_lrcheck_kernel, dim3(cdiv(g.width1, 128), H), 128, 0, r.raw, r.d2, W, H, g.minX1, g.maxX1, g.minD, g.d12);
         if (dbg) {
-            if (dbg->C) L3D_CHECK(L, cudaMemcpyAsync(dbg->C, C, nvol * 2, cudaMemcpyDeviceToDevice, L.stream));
-            if (dbg->S) L3D_CHECK(L, cudaMemcpyAsync(dbg->S, S, nvol * 2, cudaMemcpyDeviceToDevice, L.stream));
+            const size_t nvol = (size_t)g.HV * g.width1 * g.D;
+            if (dbg->C) L3D_CHECK(L, cudaMemcpyAsync(dbg->C, r.C, nvol * 2, cudaMemcpyDeviceToDevice, L.stream));
+            if (dbg->S) L3D_CHECK(L, cudaMemcpyAsync(dbg->S, r.S, nvol * 2, cudaMemcpyDeviceToDevice, L.stream));
         }
     }
-    if (dbg && dbg->raw) L3D_CHECK(L, cudaMemcpyAsync(dbg->raw, raw, npix * 2, cudaMemcpyDeviceToDevice, L.stream));
+    if (dbg && dbg->raw) L3D_CHECK(L, cudaMemcpyAsync(dbg->raw, r.raw, npix * 2, cudaMemcpyDeviceToDevice, L.stream));
     // --- medianBlur(3) then filterSpeckles, as StereoSGBM::compute does
-    rc = dev_median3(L, raw, W, H, disp);
+    int rc = dev_median3(L, r.raw, W, H, disp);
     if (rc != L3D_OK) return rc;
-    if (p.speckleWindowSize > 0) rc = dev_speckles(L, disp, W, H, INVALID, p.speckleWindowSize, 16 * p.speckleRange);
+    if (r.p.speckleWindowSize > 0) rc = dev_speckles(L, disp, W, H, INVALID, r.p.speckleWindowSize, 16 * r.p.speckleRange);
     return rc;
+}
+
+// the cluster-fused middle of a set of runs that share one geometry (one launch per pass)
+int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns) {
+    if (nruns <= 0) return L3D_OK;
+    const Geom& g = runs[0]->g;
+    std::vector<const int16_t*> Cp(nruns);
+    std::vector<int16_t*> Sp(nruns);
+    for (int i = 0; i < nruns; i++) {
+        const Geom& h = runs[i]->g;
+        L3D_ARG(L, h.width1 == g.width1 && h.HV == g.HV && h.D == g.D && h.P1 == g.P1 && h.P2 == g.P2 && h.mode == g.mode,
+                "vgroup: runs of one launch must share geometry and penalties");
+        Cp[i] = runs[i]->C; Sp[i] = runs[i]->S;
+        runs[i]->wta_done = false;
+    }
+    L.t_begin("sgbm_vgroup_down");
+    int rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, +1);
+    L.t_end("sgbm_vgroup_down");
+    if (rc != L3D_OK) return rc;
+    if (g.mode == 1) {
+        L.t_begin("sgbm_vgroup_up");
+        rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, -1);
+        L.t_end("sgbm_vgroup_up");
+    }
+    return rc;
+}
+
+int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W, int H,
+             int16_t* disp, SgbmDebug* dbg) {
+    const size_t npix = (size_t)W * H;
+    uint4* dL = L.get<uint4>(S_DESC_L, npix);
+    uint4* dR = L.get<uint4>(S_DESC_R, npix);
+    SgbmRun r;
+    int rc = sgbm_front(L, p, left, right, W, H, 0, dL, dR, true, r);
+    if (rc != L3D_OK) return rc;
+    // L3D_VGROUP=1 forces the cluster-fused kernel even for a single run (tests); by default a lone run uses
+    // the direction-split kernels, which spread one volume over all SMs
+    static const bool force_vgroup = getenv("L3D_VGROUP") && atoi(getenv("L3D_VGROUP")) > 0;
+    if (force_vgroup && sgbm_vgroup_ok(r)) {
+        SgbmRun* one[1] = {&r};
+        rc = sgbm_middle_vgroup(L, one, 1);
+    } else {
+        rc = sgbm_middle_split(L, r, dbg && dbg->S);
+    }
+    if (rc != L3D_OK) return rc;
+    return sgbm_back(L, r, disp, dbg);
 }
 
 }  // namespace l3d

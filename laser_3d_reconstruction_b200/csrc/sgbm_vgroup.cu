@@ -26,7 +26,7 @@ namespace cg = cooperative_groups;
 
 constexpr int VG_CLUSTER_MAX = 16;  // cluster sizes used: 8 (portable) and 16 (non-portable)
 constexpr int VG_WARPS = 16;
-constexpr int VG_THREADS = (VG_WARPS + 1) * 32;  // + one producer warp that owns all bulk copies
+constexpr int VG_THREADS = VG_WARPS * 32;
 constexpr int VG_MAXCPW = 9;     // columns per warp: the cluster spans 8 * 16 * 9 = 1152 columns
 constexpr int VG_MAXJOBS = 64;
 
@@ -142,13 +142,10 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
 
     // zero both parities of every halo slot: "no predecessor" = (L = 0, min = 0), OpenCV's out-of-image rule
     for (int i = threadIdx.x; i < (int)(4 * VG_WARPS * slot / 4); i += VG_THREADS) ((uint32_t*)haloA)[i] = 0u;
-    // bars[0..1]: row stage full (producer's expect_tx + the two bulk loads); bars[2..3]: S strip of the stage
-    // rewritten by all compute warps (one arrive per warp)
+    // bars[0..1]: row stage full (expect_tx + the two bulk loads)
     if (threadIdx.x == 0) {
         vg_mbar_init(bars, 1);
         vg_mbar_init(bars + 8, 1);
-        vg_mbar_init(bars + 16, VG_WARPS);
-        vg_mbar_init(bars + 24, VG_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -161,35 +158,11 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
         vg_bulk_g2s((uint32_t)__cvta_generic_to_shared(Cbuf + (it & 1) * strip_bytes), Cg + off, bytes, bar);
         vg_bulk_g2s((uint32_t)__cvta_generic_to_shared(Sbuf + (it & 1) * strip_bytes), Sg + off, bytes, bar);
     };
-    if (threadIdx.x == VG_WARPS * 32 && wc > 0) {
+    if (threadIdx.x == 0 && wc > 0) {
         load_row(0);
         if (H > 1) load_row(1);
     }
     cluster.sync();  // halo zeroing of every CTA is complete before any neighbour writes into it
-
-    if (warp == VG_WARPS) {
-        // ===== producer warp: every bulk copy of the CTA.  It takes part in the per-row cluster barrier
-        // (arriving at once: it exports nothing) so that the compute warps never wait for a copy it issues.
-        for (int it = 0; it < H; it++) {
-            if (it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            if (lane == 0 && wc > 0) {
-                const int st = it & 1;
-                vg_mbar_wait(bars + 16 + 8 * st, (uint32_t)((it >> 1) & 1));  // all compute warps rewrote the S strip
-                const int row = dir > 0 ? it : H - 1 - it;
-                vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B,
-                            (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes), (uint32_t)wc * B);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
-                if (it + 2 < H) load_row(it + 2);
-            }
-            __syncwarp();
-        }
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pair the last arrive
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        cluster.sync();
-        return;
-    }
 
     // path state: A = diagonal fed from the left neighbour column, V = vertical, Bp = diagonal fed from the right
     uint32_t LA[CPW][NP], LV[CPW][NP], LB[CPW][NP];
@@ -284,11 +257,20 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
             }
             ss[j * 32] = vg_pack<NP>(Sw);
         }
-        // ---- hand the rewritten S strip to the producer warp (it stores it and refills the stage)
+        // ---- S strip back to HBM, next-but-one row in (thread 0 owns the bulk copies: a 17th producer warp was
+        // tried and lost more to the tighter register budget of a 544-thread CTA than it gained)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 16 + 8 * st) : "memory");
+        __syncthreads();
+        if (threadIdx.x == 0 && wc > 0) {
+            const int row = dir > 0 ? it : H - 1 - it;
+            vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
+                        (uint32_t)wc * B);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+            if (it + 2 < H) load_row(it + 2);
+        }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pair the last arrive
     cluster.sync();  // no CTA exits while a neighbour may still write into its shared memory
 }
@@ -296,10 +278,11 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
 // Host entry: aggregate the three previous-row paths of pass `dir` for `njobs` volumes at once.
 // Returns L3D_ERR_UNSUPPORTED when the geometry does not fit (caller falls back to the scan kernels).
 static int vgroup_cluster_size(int width1, int D) {
-    // 16 CTAs per job when the state then still fits (more SMs per job, more jobs resident per GPC pair)
+    // 8 CTAs per job when the per-warp state fits (measured: more jobs resident, better throughput than 16);
+    // 16 (non-portable) only for volumes wider than 8 * 16 * cpw_max columns
     const int maxcpw = D == 256 ? 4 : VG_MAXCPW;
-    if (cdiv(width1, 16 * VG_WARPS) >= 1 && cdiv(width1, 16 * VG_WARPS) <= maxcpw && width1 > 8 * VG_WARPS) return 16;
     if (cdiv(width1, 8 * VG_WARPS) <= maxcpw) return 8;
+    if (cdiv(width1, 16 * VG_WARPS) <= maxcpw) return 16;
     return 0;
 }
 
@@ -336,6 +319,11 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
         L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<NPV, CPWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                                \
         L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<NPV, CPWV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+        if (getenv("L3D_DEBUG_CLUSTERS")) {                                                                           \
+            int ncl = -1;                                                                                             \
+            cudaOccupancyMaxActiveClusters(&ncl, sgbm_vgroup_kernel<NPV, CPWV>, &cfg);                                \
+            fprintf(stderr, "[l3d] vgroup<%d,%d> cluster %d: max active clusters %d\n", NPV, CPWV, a.cluster, ncl); \
+        }                                                                                                             \
         L3D_CHECK(L, cudaLaunchKernelEx(&cfg, sgbm_vgroup_kernel<NPV, CPWV>, a));                                     \
         L.launches++;                                                                                                 \
         rc = L3D_OK;                                                                                                  \
