@@ -281,9 +281,9 @@ int l3d_sgbm_vgroup_time(l3d_ctx* ctx, int width1, int H, int D, int P1, int P2,
     for (int j = 0; j < njobs; j++) { Cp[j] = Cs + nvol * j; Sp[j] = Ss + nvol * j; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    int rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), njobs, width1, H, D, P1, P2, dir);  // warm-up
+    int rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), njobs, width1, H, D, P1, P2, dir, nullptr);  // warm-up
     cudaEventRecord(e0, L.stream);
-    for (int r = 0; r < reps && rc == L3D_OK; r++) rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), njobs, width1, H, D, P1, P2, dir);
+    for (int r = 0; r < reps && rc == L3D_OK; r++) rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), njobs, width1, H, D, P1, P2, dir, nullptr);
     cudaEventRecord(e1, L.stream);
     cudaError_t e = cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -845,7 +845,7 @@ static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t*
         static const bool dbg_phases = getenv("L3D_DEBUG_PHASES") != nullptr;
         cudaEvent_t d0 = nullptr, d1 = nullptr;
         if (dbg_phases) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, M.stream); }
-        RC(sgbm_middle_vgroup(M, list.data(), (int)list.size()));
+        RC(sgbm_middle_vgroup(M, list.data(), (int)list.size(), false));
         if (dbg_phases) { cudaEventRecord(d1, M.stream); p->dbg_events.push_back({d0, d1}); }
         CK(ctx, cudaEventRecord(p->ev_mid[set], M.stream));
         for (int i = 0; i < ng; i++) {

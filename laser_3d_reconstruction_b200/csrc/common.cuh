@@ -116,8 +116,10 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
              int H, int16_t* disp, SgbmDebug* dbg);
 // cluster-fused aggregation of the three previous-row paths of one pass (sgbm_vgroup.cu)
 bool vgroup_supported(int width1, int H, int D);
+// per-job WTA outputs when a pass is the last one (nullptr array: S is written back instead)
+struct VGroupWta { int16_t* raw; unsigned* d2; int W, minD, minX1, uniq; };
 int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
-                    int P2, int dir);
+                    int P2, int dir, const VGroupWta* wta);
 int dev_median3(Lane& L, const int16_t* src, int W, int H, int16_t* dst);
 int dev_speckles(Lane& L, int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff);
 

@@ -1003,26 +1003,31 @@ int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg) {
     return rc;
 }
 
-// the cluster-fused middle of a set of runs that share one geometry (one launch per pass)
-int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns) {
+// the cluster-fused middle of a set of runs that share one geometry (one launch per pass); the last pass
+// also does the WTA unless the caller needs the finished S volumes
+int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns, bool keep_S) {
     if (nruns <= 0) return L3D_OK;
     const Geom& g = runs[0]->g;
     std::vector<const int16_t*> Cp(nruns);
     std::vector<int16_t*> Sp(nruns);
+    std::vector<VGroupWta> wta(nruns);
     for (int i = 0; i < nruns; i++) {
         const Geom& h = runs[i]->g;
-        L3D_ARG(L, h.width1 == g.width1 && h.HV == g.HV && h.D == g.D && h.P1 == g.P1 && h.P2 == g.P2 && h.mode == g.mode,
+        L3D_ARG(L, h.width1 == g.width1 && h.HV == g.HV && h.D == g.D && h.P1 == g.P1 && h.P2 == g.P2 && h.mode == g.mode &&
+                       runs[i]->W == runs[0]->W,
                 "vgroup: runs of one launch must share geometry and penalties");
         Cp[i] = runs[i]->C; Sp[i] = runs[i]->S;
-        runs[i]->wta_done = false;
+        wta[i] = VGroupWta{runs[i]->raw, runs[i]->d2, runs[i]->W, h.minD, h.minX1, h.uniq};
+        runs[i]->wta_done = !keep_S;
     }
+    const VGroupWta* last = keep_S ? nullptr : wta.data();
     L.t_begin("sgbm_vgroup_down");
-    int rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, +1);
+    int rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, +1, g.mode == 1 ? nullptr : last);
     L.t_end("sgbm_vgroup_down");
     if (rc != L3D_OK) return rc;
     if (g.mode == 1) {
         L.t_begin("sgbm_vgroup_up");
-        rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, -1);
+        rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, -1, last);
         L.t_end("sgbm_vgroup_up");
     }
     return rc;
@@ -1041,7 +1046,7 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
     static const bool force_vgroup = getenv("L3D_VGROUP") && atoi(getenv("L3D_VGROUP")) > 0;
     if (force_vgroup && sgbm_vgroup_ok(r)) {
         SgbmRun* one[1] = {&r};
-        rc = sgbm_middle_vgroup(L, one, 1);
+        rc = sgbm_middle_vgroup(L, one, 1, dbg && dbg->S);
     } else {
         rc = sgbm_middle_split(L, r, dbg && dbg->S);
     }

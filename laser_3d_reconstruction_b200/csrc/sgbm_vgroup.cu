@@ -35,6 +35,13 @@ struct VGroupArgs {
     int16_t* S[VG_MAXJOBS];
     int width1, H, D, P1, P2, cpw, dir;  // dir = +1 top-down (pass 1), -1 bottom-up (pass 2)
     int cluster;                         // CTAs per cluster (= per job)
+    // final != 0: this is the last pass -- the winner-takes-all stage runs on the finished S rows while they
+    // are still in shared memory and S is NOT written back (per job: raw disparity image, disp2 vote buffer,
+    // minDisparity, minX1, uniquenessRatio; W = image width)
+    int final, W;
+    int16_t* raw[VG_MAXJOBS];
+    unsigned* d2[VG_MAXJOBS];
+    int minD[VG_MAXJOBS], minX1[VG_MAXJOBS], uniq[VG_MAXJOBS];
 };
 
 static size_t vgroup_smem_bytes(int D, int cpw) {
@@ -111,6 +118,21 @@ template <> __device__ __forceinline__ uint32_t vg_pack<1>(const uint32_t (&o)[1
 template <> __device__ __forceinline__ uint2 vg_pack<2>(const uint32_t (&o)[2]) { return make_uint2(o[0], o[1]); }
 template <> __device__ __forceinline__ uint4 vg_pack<4>(const uint32_t (&o)[4]) { return make_uint4(o[0], o[1], o[2], o[3]); }
 
+// OpenCV's uniqueness test (modes SGBM / HH), see wta_not_unique in sgbm.cu; out of line, uniquenessRatio > 0 only
+template <int NP>
+__device__ __noinline__ bool vg_not_unique(const uint32_t (&w)[NP], unsigned key, int uniq, unsigned dkey) {
+    const int minS = (int)(key >> 8), best = (int)(key & 255u);
+    bool rej = false;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const int s0 = (int)(w[q] & 0xffffu), s1 = (int)(w[q] >> 16);
+        const int d0 = (int)dkey + 2 * q;
+        if (s0 * (100 - uniq) < minS * 100 && abs(best - d0) > 1) rej = true;
+        if (s1 * (100 - uniq) < minS * 100 && abs(best - d0 - 1) > 1) rej = true;
+    }
+    return __any_sync(0xffffffffu, rej) && minS < 32767;
+}
+
 // NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities); CPW = columns per warp
 template <int NP, int CPW>
 __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroupArgs a) {
@@ -139,6 +161,10 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
     const char* Cg = (const char*)a.C[job];
     char* Sg = (char*)a.S[job];
     const int dir = a.dir;
+    const int final = a.final, uniq = a.uniq[job], minD = a.minD[job], minX1 = a.minX1[job];
+    int16_t* rawg = a.raw[job];
+    unsigned* d2g = a.d2[job];
+    const unsigned dkey = (unsigned)(lane * 2 * NP);
 
     // zero both parities of every halo slot: "no predecessor" = (L = 0, min = 0), OpenCV's out-of-image rule
     for (int i = threadIdx.x; i < (int)(4 * VG_WARPS * slot / 4); i += VG_THREADS) ((uint32_t*)haloA)[i] = 0u;
@@ -243,6 +269,8 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
         }
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         // ---- vertical path + S update (the cluster barrier's latency hides behind this)
+        unsigned wkey = 0xffffffffu;  // final pass: arg-min key of column `lane` of this warp
+        bool wrej = false;
 #pragma unroll
         for (int j = 0; j < CPW; j++) {
             vg_unpack<NP>(cs[j * 32], Cw);
@@ -256,17 +284,52 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
                 Sw[k] = __viaddmin_u16x2(Sw[k], s3, INF);
             }
             ss[j * 32] = vg_pack<NP>(Sw);
+            if (final) {  // first minimum wins (OpenCV's strict '<' scan over d): packed (cost << 8 | d) key
+                unsigned key = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < NP; k++) {
+                    key = min(key, ((Sw[k] << 8) & 0xffff00u) | (dkey + 2 * k));
+                    key = min(key, ((Sw[k] >> 8) & 0xffff00u) | (dkey + 2 * k + 1));
+                }
+                key = __reduce_min_sync(0xffffffffu, key);
+                bool rej = false;
+                if (uniq > 0) rej = vg_not_unique<NP>(Sw, key, uniq, dkey);
+                if (lane == j) { wkey = key; wrej = rej; }
+            }
+        }
+        if (final) {
+            // lane j finishes pixel j of this warp: disp2 vote, sub-pixel interpolation (neighbour costs from
+            // the S row still in shared memory), store -- once per row for CPW pixels in parallel
+            __syncwarp();
+            const int x = x0 + c0 + lane;
+            const int minS = (int)(wkey >> 8), d = (int)(wkey & 255u);
+            if (lane < CPW && x < width1 && minS < 32767 && !wrej) {
+                const int y = dir > 0 ? it : H - 1 - it;
+                const int x2 = x + minX1 - d - minD;
+                if (x2 >= 0 && x2 < a.W + 2)
+                    atomicMax(d2g + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
+                int dd = d * 16;
+                if (0 < d && d < a.D - 1) {
+                    const uint16_t* Sp = (const uint16_t*)(Sbuf + st * strip_bytes + (size_t)(c0 + lane) * B);
+                    const int sm = Sp[d - 1], sp = Sp[d + 1];
+                    const int denom2 = max(sm + sp - 2 * minS, 1);
+                    dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
+                }
+                rawg[(size_t)y * a.W + x + minX1] = (int16_t)(dd + minD * 16);
+            }
         }
         // ---- S strip back to HBM, next-but-one row in (thread 0 owns the bulk copies: a 17th producer warp was
         // tried and lost more to the tighter register budget of a 544-thread CTA than it gained)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0 && wc > 0) {
-            const int row = dir > 0 ? it : H - 1 - it;
-            vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
-                        (uint32_t)wc * B);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+            if (!final) {
+                const int row = dir > 0 ? it : H - 1 - it;
+                vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
+                            (uint32_t)wc * B);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+            }
             if (it + 2 < H) load_row(it + 2);
         }
     }
@@ -294,12 +357,20 @@ bool vgroup_supported(int width1, int H, int D) {
 }
 
 int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
-                    int P2, int dir) {
+                    int P2, int dir, const VGroupWta* wta) {
     L3D_ARG(L, vgroup_supported(width1, H, D), "vgroup geometry");
     for (int j0 = 0; j0 < njobs; j0 += VG_MAXJOBS) {
         VGroupArgs a;
         const int nj = std::min(VG_MAXJOBS, njobs - j0);
-        for (int j = 0; j < nj; j++) { a.C[j] = C[j0 + j]; a.S[j] = S[j0 + j]; }
+        for (int j = 0; j < nj; j++) {
+            a.C[j] = C[j0 + j]; a.S[j] = S[j0 + j];
+            a.raw[j] = nullptr; a.d2[j] = nullptr; a.minD[j] = 0; a.minX1[j] = 0; a.uniq[j] = 0;
+            if (wta) {
+                a.raw[j] = wta[j0 + j].raw; a.d2[j] = wta[j0 + j].d2; a.minD[j] = wta[j0 + j].minD;
+                a.minX1[j] = wta[j0 + j].minX1; a.uniq[j] = wta[j0 + j].uniq;
+            }
+        }
+        a.final = wta ? 1 : 0; a.W = wta ? wta[0].W : 0;
         a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir;
         a.cluster = vgroup_cluster_size(width1, D);
         a.cpw = cdiv(width1, a.cluster * VG_WARPS);

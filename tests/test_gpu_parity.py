@@ -413,3 +413,34 @@ def test_pipeline_matches_stagewise_and_is_frame_independent(ctx):
         [tuple(p) for p in got["points_2d"].astype(np.float64)], got["depth"]).reshape(-1, 3)
     assert got["points_3d"].shape == wxyz.shape
     assert np.allclose(got["points_3d"], wxyz, rtol=1e-5, atol=1e-12)  # north_star: 3D points <= 1e-5 relative
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_grouped_pipeline_cluster_aggregation(ctx, mode):
+    """lanes >= 7 switches the frame pipeline to grouped mode: SGBM fronts per lane, ONE cluster-fused
+    aggregation launch per pass over all volumes of a lane set (sgbm_vgroup.cu), backs per lane.  Every bit
+    must equal the lane-per-frame pipeline (direction-split scan kernels) and cv2."""
+    W, H, D, bs = 320, 360, 64, 5
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, 10 + s) for s in range(9)]  # 9 frames: one full lane set of 7 + a ragged one
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    results = {}
+    for lanes in (2, 14):
+        cfg = pipeline.make_pipeline_config(W, H, D, bs, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=8000)
+        fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+        try:
+            dl, dr = fp.upload(L), fp.upload(R)
+            fp.run_dev(dl, dr, len(frames))
+            fp.run_dev(dl, dr, len(frames))  # steady state: scratch reuse across runs
+            results[lanes] = [fp.fetch(i) for i in range(len(frames))]
+        finally:
+            fp.close()
+    for i in range(len(frames)):
+        for k in ("left_rect", "depth", "disp16", "points_2d", "points_3d"):
+            eq(results[2][i][k], results[14][i][k], "grouped vs per-lane %s frame %d" % (k, i))
+    # and the two matcher runs feeding WLS equal cv2 on one frame
+    wrect, wdepth, aux = ref_ops.depth_path(frames[8][0], frames[8][1], maps, D, bs, mode, Q, want_all=True)
+    diff = np.abs(results[14][8]["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999
