@@ -447,14 +447,38 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
             const int cnt = min(SCAN_CH, n - first);
             uint32_t dst = ring + (chunk % NST) * stage_bytes + lane * 16;
             long off = lane_off + (long)first * step_bytes;
-            int i = li0, r = lr0;
-            for (int p = lane; p < pieces; p += 32) {
-                if (i < cnt) {
-                    cp_async16(dst, Cb + off);
-                    if (!STORE) cp_async16(dst + SCAN_CH * B, Sb + off);
+            if (FULL) {
+                // D = 64 * NP: a pixel vector is 8 * NP pieces, which divides 32 -- no piece straddles two
+                // steps' boundaries differently per iteration, every constant folds
+                constexpr int PPV = 8 * NP, DI = 32 / PPV, ITERS = SCAN_CH * PPV / 32;
+                const long it_b = (long)DI * step_bytes;
+                if (cnt == SCAN_CH) {
+#pragma unroll
+                    for (int it = 0; it < ITERS; it++) {
+                        cp_async16(dst + it * 512, Cb + off);
+                        if (!STORE) cp_async16(dst + it * 512 + SCAN_CH * B, Sb + off);
+                        off += it_b;
+                    }
+                } else {
+#pragma unroll
+                    for (int it = 0; it < ITERS; it++) {
+                        if (li0 + it * DI < cnt) {
+                            cp_async16(dst + it * 512, Cb + off);
+                            if (!STORE) cp_async16(dst + it * 512 + SCAN_CH * B, Sb + off);
+                        }
+                        off += it_b;
+                    }
                 }
-                dst += 512; i += di; r += dr; off += it_bytes;
-                if (r >= ppv) { r -= ppv; i++; off += wrap_bytes; }
+            } else {
+                int i = li0, r = lr0;
+                for (int p = lane; p < pieces; p += 32) {
+                    if (i < cnt) {
+                        cp_async16(dst, Cb + off);
+                        if (!STORE) cp_async16(dst + SCAN_CH * B, Sb + off);
+                    }
+                    dst += 512; i += di; r += dr; off += it_bytes;
+                    if (r >= ppv) { r -= ppv; i++; off += wrap_bytes; }
+                }
             }
         }
         cp_async_commit();
