@@ -162,11 +162,10 @@ constexpr int COST_THREADS = 512;
 constexpr int COST_MAXCPG = 8;
 
 __device__ __forceinline__ uint32_t bt_pair(uint32_t U, uint32_t nU, uint32_t U0, uint32_t nU1, const uint4& r) {
-    // r = (V, -V, V0, -V1) pairs; max(0, u - v1, v0 - u) and max(0, v - u1, u0 - v), then the smaller
-    uint32_t t = __viaddmax_s16x2(U, r.w, 0u);
-    t = __viaddmax_s16x2(r.z, nU, t);
-    uint32_t q = __viaddmax_s16x2(r.x, nU1, 0u);
-    q = __viaddmax_s16x2(r.y, U0, q);
+    // r = (V, -V, V0, -V1) pairs; max(0, u - v1, v0 - u) and max(0, v - u1, u0 - v), then the smaller.
+    // One VIADD.16x2 + one VIADDMNMX.S16x2.RELU per term: no zero operand to materialise.
+    const uint32_t t = __viaddmax_s16x2_relu(r.z, nU, __vadd2(U, r.w));
+    const uint32_t q = __viaddmax_s16x2_relu(r.y, U0, __vadd2(r.x, nU1));
     return __vmins2(t, q);
 }
 
@@ -201,6 +200,8 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
 #pragma unroll
     for (int j = 0; j < COST_MAXCPG; j++) crun[j] = p2x2;
     const int nk = rows + bs - 1;
+    const int nitA = dpa0 < D2 ? (D2 - dpa0 + dpa_step - 1) / dpa_step : 0;  // phase A items of this thread
+    int slot = 0;                                                            // ring slot of row k (k % bs without the division)
 
     auto stage_a = [&](int k) {  // operand tables + pixel costs of band row k into buffer k & 1
         const int ky = min(max(y0 - SW2 + k, clo), chi);
@@ -222,13 +223,17 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
         const uint32_t u1 = __byte_perm(l.z, l.z, 0x1010), nu1 = __byte_perm(l.z, l.z, 0x3232);
         const uint32_t ul1 = __byte_perm(l.w, l.w, 0x1010), nuh1 = __byte_perm(l.w, l.w, 0x3232);
         __syncthreads();  // right operand table complete (also orders this row's pd writes after row k-2's reads)
-        uint32_t* pd = pdb + (k & 1) * D2 * PS;
-        const int ebase = xca - xa + D - 2;
-        for (int dp = dpa0; dp < D2; dp += dpa_step) {
-            const int e = ebase - 2 * dp;
-            const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, R0[e]);
-            const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, R1[e]);
-            pd[dp * PS + ca] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+        // this thread's disparity pairs dpa0, dpa0 + dpa_step, ...: table entry and pd slot move by constant strides
+        const uint4* r0p = R0 + (xca - xa + D - 2 - 2 * dpa0);
+        const uint4* r1p = r0p + nEmax;
+        uint32_t* pdp = pdb + (k & 1) * D2 * PS + dpa0 * PS + ca;
+        const int rstep = 2 * dpa_step, pstep = dpa_step * PS;
+#pragma unroll 4
+        for (int i = 0; i < nitA; i++) {
+            const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, *r0p);
+            const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, *r1p);
+            *pdp = c0 + ((c1 >> 2) & 0x3fff3fffu);
+            r0p -= rstep; r1p -= rstep; pdp += pstep;
         }
     };
     // Box sums.  Every packed half stays below 2^16 for the supported parameter range (checked on the
@@ -237,8 +242,9 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
         if (ncb <= 0) return;
         const uint32_t* pp = pdb + (k & 1) * D2 * PS + dpb * PS + cb0;  // pp[j + i]: output column cb0 + j, tap i
         uint32_t h = 0;
+#pragma unroll 3
         for (int i = 0; i < bs; i++) h += pp[i];
-        uint32_t* rp = ring + ((size_t)(k % bs) * TX + cb0) * D2 + dpb;
+        uint32_t* rp = ring + ((size_t)slot * TX + cb0) * D2 + dpb;
         uint32_t* Cdst = (uint32_t*)(a.C + ((size_t)(vr0 + k - (bs - 1)) * width1 + x0 + cb0) * D) + dpb;
         const bool sub = k >= bs, emit = k >= bs - 1;
 #pragma unroll
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
         __syncthreads();  // pd[k & 1] complete; pd[(k + 1) & 1] and its tables free again
         if (k + 1 < nk) stage_a(k + 1);  // contains one barrier; the condition is CTA-uniform
         stage_b(k);
+        slot = slot + 1 == bs ? 0 : slot + 1;
     }
 }
 
