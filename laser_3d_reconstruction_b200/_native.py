@@ -82,6 +82,8 @@ def load():
         if not os.path.exists(_LIB_PATH):
             from . import build as _b
             _b.build()
+        # one hardware work queue per pipeline stream (read by the driver when the CUDA context is created)
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         lib = C.CDLL(_LIB_PATH)
         for name in EXPORTS:
             if not hasattr(lib, name):

@@ -44,6 +44,8 @@ void Lane::release() {
     for (auto e : ev_pool) cudaEventDestroy(e);
     ev_pool.clear(); timers.clear(); ev_used = 0;
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    if (back_stream) { cudaStreamSynchronize(back_stream); cudaStreamDestroy(back_stream); back_stream = nullptr; }
+    if (back_done) { cudaEventDestroy(back_done); back_done = nullptr; }
 }
 
 cudaEvent_t Lane::new_event() {
@@ -93,7 +95,13 @@ extern "C" {
 
 const char* l3d_version(void) { return "laser3d-b200 0.1 (sm_100a)"; }
 
+// The frame pipeline keeps 14+ streams busy; with the default of 8 hardware work queues streams share queues
+// and serialise falsely.  Must be in the environment before the process creates its CUDA context (a host
+// application that initialises CUDA first has to export it itself); never overrides the user's value.
+static void want_hw_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 int l3d_device_count(void) {
+    want_hw_queues();
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
@@ -102,6 +110,7 @@ int l3d_device_count(void) {
 int l3d_ctx_create(int device, l3d_ctx** out) {
     if (!out) return L3D_ERR_ARG;
     *out = nullptr;
+    want_hw_queues();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -418,8 +427,8 @@ static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps
         RC(dev_copy_gray(L, lsrc, W, H, stride, rectL, gl));
         RC(dev_copy_gray(L, rsrc, W, H, stride, nullptr, gr));
     }
-    uint4* dL = L.get<uint4>(S_DESC_L, n);
-    uint4* dR = L.get<uint4>(S_DESC_R, n);
+    uint4* dL = L.get<uint4>(S_DESC_L, 2 * n);  // two operand planes per view (sgbm_prefilter_kernel)
+    uint4* dR = L.get<uint4>(S_DESC_R, 2 * n);
     RC(sgbm_front(L, cfg.left, gl, gr, W, H, 0, dL, dR, true, dr.left));
     dr.has_right = cfg.use_wls != 0;
     // the right matcher sees the views swapped: same BT operands, roles exchanged
@@ -601,6 +610,12 @@ struct l3d_pipeline {
     std::vector<DepthRuns> runs;  // per lane
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dbg_events;
+    // L3D_DEBUG_PHASES: tagged timeline marks (tag, frame, event) printed relative to the run's first enqueue
+    struct Mark { const char* tag; int frame; cudaEvent_t ev; };
+    std::vector<Mark> dbg_marks;
+    void mark(const char* tag, int frame, cudaStream_t s) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); dbg_marks.push_back({tag, frame, e});
+    }
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -737,9 +752,19 @@ int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeli
     l3d_pipeline* p = new l3d_pipeline();
     p->ctx = ctx; p->cfg = *cfg;
     p->lanes.resize(cfg->lanes);
+    // Stream priorities.  The cluster-fused aggregation needs 8 completely free SMs of one GPC per volume, so its
+    // launches go first whenever they are ready (any resident CTA of another kernel blocks a cluster CTA: it takes
+    // the whole register file); the short back-half kernels come next, the wide front kernels fill the rest.
+    int prio_lo = 0, prio_hi = 0;
+    CK(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    int prio[3] = {prio_hi, prio_lo, std::max(prio_hi, prio_lo - 2)};  // aggregation, front, back
+    if (const char* e = getenv("L3D_PRIO")) sscanf(e, "%d,%d,%d", &prio[0], &prio[1], &prio[2]);
+    for (int& q : prio) q = std::min(prio_lo, std::max(prio_hi, q));
     for (auto& L : p->lanes) {
         L.err = &ctx->err;
-        CK(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CK(ctx, cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio[1]));
+        CK(ctx, cudaStreamCreateWithPriority(&L.back_stream, cudaStreamNonBlocking, prio[2]));
+        CK(ctx, cudaEventCreateWithFlags(&L.back_done, cudaEventDisableTiming));
     }
     CK(ctx, cudaStreamCreateWithFlags(&p->main, cudaStreamNonBlocking));
     CK(ctx, cudaEventCreate(&p->ev0));
@@ -751,7 +776,7 @@ int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeli
     p->runs.resize(cfg->lanes);
     for (int i = 0; i < l3d_pipeline::MAXSETS; i++) {
         p->mid[i].err = &ctx->err;
-        CK(ctx, cudaStreamCreateWithFlags(&p->mid[i].stream, cudaStreamNonBlocking));
+        CK(ctx, cudaStreamCreateWithPriority(&p->mid[i].stream, cudaStreamNonBlocking, prio[0]));
         CK(ctx, cudaEventCreateWithFlags(&p->ev_mid[i], cudaEventDisableTiming));
     }
     *out = p;
@@ -836,7 +861,10 @@ static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t*
                 l = sl; r = sr;
             }
             DepthRuns& dr = p->runs[li];
+            static const bool dbg_marks_on = getenv("L3D_DEBUG_PHASES") != nullptr;
+            if (dbg_marks_on) p->mark("front0", f, L.stream);
             RC(depth_front(L, c.depth, p->maps, l, r, W, H, 3L * W, p->outs[f].rect, dr));
+            if (dbg_marks_on) p->mark("front1", f, L.stream);
             CK(ctx, cudaEventRecord(p->lane_front[li], L.stream));
             CK(ctx, cudaStreamWaitEvent(M.stream, p->lane_front[li], 0));
             list.push_back(&dr.left);
@@ -852,15 +880,29 @@ static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t*
             const int li = set * gsz + i, f = f0 + i;
             Lane& L = p->lanes[li];
             FrameOut& o = p->outs[f];
+            // the back half runs on the lane's second stream (own priority); the lane's main stream rejoins below
+            cudaStream_t front_stream = L.stream;
+            if (!p->timing) {
+                CK(ctx, cudaStreamWaitEvent(L.back_stream, p->lane_front[li], 0));
+                L.stream = L.back_stream;
+            }
+            struct Restore { Lane& l; cudaStream_t s; ~Restore() { l.stream = s; } } restore{L, front_stream};
             CK(ctx, cudaStreamWaitEvent(L.stream, p->ev_mid[set], 0));
             if (p->timing && i > 0) CK(ctx, cudaStreamWaitEvent(L.stream, p->lane_done[li - 1], 0));
+            if (dbg_phases) p->mark("back0", f, L.stream);
             RC(depth_back(L, c.depth, p->runs[li], W, H, o.depth, o.disp));
+            if (dbg_phases) p->mark("back1", f, L.stream);
             RC(pipe_extract(p, L, o));
+            if (dbg_phases) p->mark("extr1", f, L.stream);
             L3D_CHECK(L, cudaMemcpyAsync(p->counts_host + 2 * f, o.n_xy, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
             L3D_CHECK(L, cudaMemcpyAsync(p->counts_host + 2 * f + 1, o.n_xyz, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
             if (depth_h) L3D_CHECK(L, cudaMemcpyAsync(depth_h + n * f, o.depth, n * 4, cudaMemcpyDeviceToHost, L.stream));
             if (xyz_h) L3D_CHECK(L, cudaMemcpyAsync(xyz_h + (size_t)cap * 3 * f, o.xyz, (size_t)cap * 24, cudaMemcpyDeviceToHost, L.stream));
             if (p->timing) CK(ctx, cudaEventRecord(p->lane_done[li], L.stream));
+            if (!p->timing) {
+                CK(ctx, cudaEventRecord(L.back_done, L.back_stream));
+                CK(ctx, cudaStreamWaitEvent(front_stream, L.back_done, 0));
+            }
         }
     }
     return L3D_OK;
@@ -916,6 +958,13 @@ static int pipe_run(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, 
         cudaEventDestroy(e.first); cudaEventDestroy(e.second);
     }
     p->dbg_events.clear();
+    for (auto& m : p->dbg_marks) {
+        float a = 0.f;
+        cudaEventElapsedTime(&a, p->ev0, m.ev);
+        fprintf(stderr, "[l3d] mark %-7s frame %3d at %8.3f ms\n", m.tag, m.frame, a);
+        cudaEventDestroy(m.ev);
+    }
+    p->dbg_marks.clear();
     p->last_frames = nframes;
     if (counts) for (int f = 0; f < nframes; f++) counts[f] = p->counts_host[2 * f + 1];
     return L3D_OK;

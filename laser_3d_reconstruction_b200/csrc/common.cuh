@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -40,6 +41,8 @@ struct TimerRec {
 // One stream with its own scratch: the unit of frame-level concurrency.
 struct Lane {
     cudaStream_t stream = nullptr;
+    cudaStream_t back_stream = nullptr;  // grouped frame pipeline: the frame's back half runs here (own priority)
+    cudaEvent_t back_done = nullptr;
     DevBuf bufs[S_NUM];
     long long launches = 0;
     std::string* err = nullptr;
@@ -72,8 +75,29 @@ void set_err(std::string* err, const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// L3D_DEBUG_SKIP="fgs_lines,sgbm_cost,...": launches whose kernel name contains one of the comma-separated
+// substrings are skipped (results are then garbage) -- measures a kernel's marginal cost in the frame pipeline
+inline bool dbg_skip(const char* kern) {
+    static const char* env = getenv("L3D_DEBUG_SKIP");
+    if (!env) return false;
+    const char* p = env;
+    while (*p) {
+        const char* q = strchr(p, ',');
+        size_t n = q ? (size_t)(q - p) : strlen(p);
+        if (n > 0 && n < 64) {
+            char tok[64];
+            memcpy(tok, p, n); tok[n] = 0;
+            if (strstr(kern, tok)) return true;
+        }
+        if (!q) break;
+        p = q + 1;
+    }
+    return false;
+}
+
 #define L3D_LAUNCH(lane, kern, grid, block, smem, ...)                                     \
     do {                                                                                   \
+        if (l3d::dbg_skip(#kern)) break;                                                   \
         kern<<<(grid), (block), (smem), (lane).stream>>>(__VA_ARGS__);                     \
         (lane).launches++;                                                                 \
         cudaError_t e__ = cudaGetLastError();                                              \

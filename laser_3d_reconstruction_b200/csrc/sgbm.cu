@@ -115,25 +115,44 @@ __device__ __forceinline__ void pre_pixel(const uint8_t* __restrict__ img, int W
 
 __device__ __forceinline__ uint32_t pack_s16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
-__global__ void sgbm_prefilter_kernel(const uint8_t* __restrict__ img, int W, int H, int ftzero,
-                                      uint4* __restrict__ desc) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
+// Output: two planes of W*H uint4 (plane c = channel c).  Entry x of a row holds the operands of the pixel PAIR
+// (x+1, x) -- low halves pixel x+1, high halves pixel x -- exactly the layout the cost kernel's packed
+// arithmetic wants for the disparity pair (d, d+1) of a left pixel (x - d = x_pair + 1):
+//   .x = v | v' << 16,  .y = -v | -v' << 16,  .z = lo | lo' << 16,  .w = -hi | -hi' << 16     (' = pixel x)
+// so a CTA's per-row operand table is a contiguous run of entries that one bulk async copy (TMA) moves
+// into shared memory with no register staging; the left pixel's own operands are the high halves.
+constexpr int PRE_THREADS = 128;
+__global__ void __launch_bounds__(PRE_THREADS) sgbm_prefilter_kernel(const uint8_t* __restrict__ img, int W, int H,
+                                                                     int ftzero, uint4* __restrict__ desc) {
+    __shared__ int sv[6][PRE_THREADS + 1];
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * PRE_THREADS, y = blockIdx.y;
+    auto vals = [&](int x, int slot) {
+        int a0, a1, b0, b1, c0, c1;
+        pre_pixel(img, W, H, y, x, ftzero, b0, b1);
+        int lo0 = b0, hi0 = b0, lo1 = b1, hi1 = b1;
+        if (x > 0) {
+            pre_pixel(img, W, H, y, x - 1, ftzero, a0, a1);
+            int t0 = (b0 + a0) >> 1, t1 = (b1 + a1) >> 1;
+            lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
+        }
+        if (x < W - 1) {
+            pre_pixel(img, W, H, y, x + 1, ftzero, c0, c1);
+            int t0 = (b0 + c0) >> 1, t1 = (b1 + c1) >> 1;
+            lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
+        }
+        sv[0][slot] = b0; sv[1][slot] = lo0; sv[2][slot] = hi0; sv[3][slot] = b1; sv[4][slot] = lo1; sv[5][slot] = hi1;
+    };
+    vals(min(x0 + t, W - 1), t);
+    if (t == PRE_THREADS - 1) vals(min(x0 + PRE_THREADS, W - 1), PRE_THREADS);  // pixel right of the block (clamped: pad)
+    __syncthreads();
+    const int x = x0 + t;
     if (x >= W) return;
-    int a0, a1, b0, b1, c0, c1;
-    pre_pixel(img, W, H, y, x, ftzero, b0, b1);
-    int lo0 = b0, hi0 = b0, lo1 = b1, hi1 = b1;
-    if (x > 0) {
-        pre_pixel(img, W, H, y, x - 1, ftzero, a0, a1);
-        int t0 = (b0 + a0) >> 1, t1 = (b1 + a1) >> 1;
-        lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
-    }
-    if (x < W - 1) {
-        pre_pixel(img, W, H, y, x + 1, ftzero, c0, c1);
-        int t0 = (b0 + c0) >> 1, t1 = (b1 + c1) >> 1;
-        lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
-    }
-    desc[(size_t)y * W + x] = make_uint4(pack_s16(b0, -b0), pack_s16(lo0, -hi0), pack_s16(b1, -b1), pack_s16(lo1, -hi1));
+    const size_t i = (size_t)y * W + x, plane = (size_t)W * H;
+    desc[i] = make_uint4(pack_s16(sv[0][t + 1], sv[0][t]), pack_s16(-sv[0][t + 1], -sv[0][t]),
+                         pack_s16(sv[1][t + 1], sv[1][t]), pack_s16(-sv[2][t + 1], -sv[2][t]));
+    desc[plane + i] = make_uint4(pack_s16(sv[3][t + 1], sv[3][t]), pack_s16(-sv[3][t + 1], -sv[3][t]),
+                                 pack_s16(sv[4][t + 1], sv[4][t]), pack_s16(-sv[5][t + 1], -sv[5][t]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -141,18 +160,19 @@ __global__ void sgbm_prefilter_kernel(const uint8_t* __restrict__ img, int W, in
 // ------------------------------------------------------------------------------------------
 // A CTA owns TX output columns (TXH = TX + 2*SW2 computed columns) of a band of rows and walks the
 // band top to bottom.  Per image row:
-//   build   operand tables in smem: one uint4 per right pixel position holding the s16x2 pairs
-//           (v, -v, lo, -hi) of the two right pixels a disparity pair (d, d+1) looks at, and one per
-//           left column with the same operands broadcast to both halves
+//   tables  thread 0 issues two bulk async copies (cp.async.bulk, mbarrier completion) that bring the row's
+//           right-image operand entries (prefilter layout above) into shared memory TWO rows ahead
 //   phase A thread <-> (column, every (256/TXH)-th disparity pair): BT cost of both channels in
-//           10 VIADDMNMX/VIMNMX.S16x2 ops per two disparities -> pd[dp][col] (row stride TXH+1)
+//           10 VIADD/VIADDMNMX/VIMNMX.S16x2 ops per two disparities -> pd[dp][col] (row stride TXH+1);
+//           the thread's left operands sit in registers (loaded one row ahead)
 //   phase B thread <-> (disparity pair, group of columns): running horizontal box sum along its
 //           columns, vertical running sum against a ring of the last blockSize row sums, C store
 //           (a warp writes 128 contiguous bytes per column)
-// All sums are wrap-around u16 like OpenCV's int16 arithmetic.
+// pd is double-buffered, so ONE block barrier per row separates {phase A of row k+1, phase B of row k}
+// from the next pair.  All sums are wrap-around u16 like OpenCV's int16 arithmetic.
 struct CostArgs {
-    const uint4* Ldesc; const uint4* Rdesc; int16_t* C;
-    int W, minD, D, minX1, width1, SW2, bs, P2, TX, TXH;
+    const uint4* Ldesc; const uint4* Rdesc; int16_t* C;  // two planes each (channel 0, channel 1)
+    int W, H, minD, D, minX1, width1, SW2, bs, P2, TX, TXH;
     int nxg, cpg;  // phase B: column groups per CTA, columns per group
     int nbands;
     int band_vr0[MAXBAND], band_y0[MAXBAND], band_rows[MAXBAND], band_clo[MAXBAND], band_chi[MAXBAND];
@@ -169,8 +189,30 @@ __device__ __forceinline__ uint32_t bt_pair(uint32_t U, uint32_t nU, uint32_t U0
     return __vmins2(t, q);
 }
 
-__global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void cost_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cost_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cost_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "COST_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra COST_DONE_%=;\n\t"
+        "bra COST_WAIT_%=;\n\t"
+        "COST_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cost_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// NIT: phase A items (disparity pairs) per thread and row when known at compile time (D/2 / (512/TXH)), 0 = generic
+template <int NIT>
+__global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int TX = a.TX, TXH = a.TXH, SW2 = a.SW2, bs = a.bs, D = a.D, D2 = D >> 1;
     const int width1 = a.width1, W = a.W;
     const int tid = threadIdx.x;
@@ -181,13 +223,14 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
     const int xr_base = xa + a.minX1 - (a.minD + D - 1);  // lowest right pixel any pair reads
     const int nE = (xb - xa) + D - 1;                      // right operand entries (pair = pixels e+1, e)
     const int PS = TXH + 1;                                // pd row stride (bank-conflict-free both ways)
-    // smem carve-up: operand tables and pixel costs are double-buffered so that one barrier per row
-    // separates {build + phase A of row k+1, phase B of row k}
+    const size_t plane = (size_t)W * a.H;
+    // smem carve-up: operand tables [2 stages][R0 | R1][nEmax], pixel costs [2][D2][PS], ring [bs][TX][D2], 2 mbarriers
     const int nEmax = TXH + D;
-    const int tab_u4 = 2 * nEmax;                          // uint4 per operand table set
-    uint4* tabs = (uint4*)smem_raw;                        // [2][R0 | R1]
-    uint32_t* pdb = (uint32_t*)(tabs + 2 * tab_u4);        // [2][D2][PS]
-    uint32_t* ring = pdb + 2 * D2 * PS;                    // [bs][TX][D2]
+    const int tab_u4 = 2 * nEmax;                          // uint4 per operand table stage
+    uint4* tabs = (uint4*)smem_raw;
+    uint32_t* pdb = (uint32_t*)(tabs + 2 * tab_u4);
+    uint32_t* ring = pdb + 2 * D2 * PS;
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(ring + (size_t)bs * TX * D2);
     // phase A role
     const int ca = tid % TXH, dpa0 = tid / TXH, dpa_step = COST_THREADS / TXH;
     const int xca = min(max(x0 - SW2 + ca, 0), width1 - 1);
@@ -200,71 +243,99 @@ __global__ void __launch_bounds__(COST_THREADS) sgbm_cost_kernel(const CostArgs 
 #pragma unroll
     for (int j = 0; j < COST_MAXCPG; j++) crun[j] = p2x2;
     const int nk = rows + bs - 1;
-    const int nitA = dpa0 < D2 ? (D2 - dpa0 + dpa_step - 1) / dpa_step : 0;  // phase A items of this thread
-    int slot = 0;                                                            // ring slot of row k (k % bs without the division)
+    const int nitA = NIT ? NIT : (dpa0 < D2 ? (D2 - dpa0 + dpa_step - 1) / dpa_step : 0);  // phase A items of this thread
 
-    auto stage_a = [&](int k) {  // operand tables + pixel costs of band row k into buffer k & 1
-        const int ky = min(max(y0 - SW2 + k, clo), chi);
-        const uint4* Lrow = a.Ldesc + (size_t)ky * W;
-        const uint4* Rrow = a.Rdesc + (size_t)ky * W;
-        uint4* R0 = tabs + (k & 1) * tab_u4;
-        uint4* R1 = R0 + nEmax;
-        for (int e = tid; e < nE; e += COST_THREADS) {
-            const uint4 hi = Rrow[xr_base + e + 1], lo = Rrow[xr_base + e];  // disparities (d, d+1) -> pixels (e+1, e)
-            R0[e] = make_uint4(__byte_perm(hi.x, lo.x, 0x5410), __byte_perm(hi.x, lo.x, 0x7632),
-                               __byte_perm(hi.y, lo.y, 0x5410), __byte_perm(hi.y, lo.y, 0x7632));
-            R1[e] = make_uint4(__byte_perm(hi.z, lo.z, 0x5410), __byte_perm(hi.z, lo.z, 0x7632),
-                               __byte_perm(hi.w, lo.w, 0x5410), __byte_perm(hi.w, lo.w, 0x7632));
+    auto row_of = [&](int k) { return min(max(y0 - SW2 + k, clo), chi); };
+    auto issue_tables = [&](int k) {  // thread 0: both channels' operand entries of band row k -> stage k & 1
+        const uint32_t bar = bars + 8 * (k & 1);
+        const uint32_t bytes = (uint32_t)nE * 16u;
+        const uint4* src = a.Rdesc + (size_t)row_of(k) * W + xr_base;
+        uint4* dst = tabs + (k & 1) * tab_u4;
+        cost_mbar_expect_tx(bar, 2 * bytes);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), src, bytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + nEmax), src + plane, bytes, bar);
+    };
+    if (tid == 0) {
+        cost_mbar_init(bars, 1);
+        cost_mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue_tables(0);
+        if (nk > 1) issue_tables(1);
+    }
+    // left operands of this thread's column: entry of pixel xca + minX1, loaded one row ahead
+    const uint4* Lcol = a.Ldesc + xca + a.minX1;
+    uint4 l0 = Lcol[(size_t)row_of(0) * W], l1 = Lcol[plane + (size_t)row_of(0) * W];
+    __syncthreads();  // mbarrier init visible to every waiter
+
+    auto phase_a = [&](int k) {  // pixel costs of band row k into pd[k & 1]
+        // broadcast the left pixel's operands (high halves of its entry) to both halves
+        const uint32_t u0 = __byte_perm(l0.x, l0.x, 0x3232), nu0 = __byte_perm(l0.y, l0.y, 0x3232);
+        const uint32_t ul0 = __byte_perm(l0.z, l0.z, 0x3232), nuh0 = __byte_perm(l0.w, l0.w, 0x3232);
+        const uint32_t u1 = __byte_perm(l1.x, l1.x, 0x3232), nu1 = __byte_perm(l1.y, l1.y, 0x3232);
+        const uint32_t ul1 = __byte_perm(l1.z, l1.z, 0x3232), nuh1 = __byte_perm(l1.w, l1.w, 0x3232);
+        if (k + 1 < nk) {  // next row's left operands: in flight during this row's arithmetic
+            const size_t ro = (size_t)row_of(k + 1) * W;
+            l0 = Lcol[ro]; l1 = Lcol[plane + ro];
         }
-        // every thread builds its own column's left operands in registers (no table, no barrier)
-        const uint4 l = Lrow[xca + a.minX1];
-        const uint32_t u0 = __byte_perm(l.x, l.x, 0x1010), nu0 = __byte_perm(l.x, l.x, 0x3232);
-        const uint32_t ul0 = __byte_perm(l.y, l.y, 0x1010), nuh0 = __byte_perm(l.y, l.y, 0x3232);
-        const uint32_t u1 = __byte_perm(l.z, l.z, 0x1010), nu1 = __byte_perm(l.z, l.z, 0x3232);
-        const uint32_t ul1 = __byte_perm(l.w, l.w, 0x1010), nuh1 = __byte_perm(l.w, l.w, 0x3232);
-        __syncthreads();  // right operand table complete (also orders this row's pd writes after row k-2's reads)
+        cost_mbar_wait(bars + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
         // this thread's disparity pairs dpa0, dpa0 + dpa_step, ...: table entry and pd slot move by constant strides
-        const uint4* r0p = R0 + (xca - xa + D - 2 - 2 * dpa0);
+        const uint4* r0p = tabs + (k & 1) * tab_u4 + (xca - xa + D - 2 - 2 * dpa0);
         const uint4* r1p = r0p + nEmax;
         uint32_t* pdp = pdb + (k & 1) * D2 * PS + dpa0 * PS + ca;
         const int rstep = 2 * dpa_step, pstep = dpa_step * PS;
+        if (NIT) {
+#pragma unroll
+            for (int i = 0; i < (NIT ? NIT : 1); i++) {
+                const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, r0p[-i * rstep]);
+                const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, r1p[-i * rstep]);
+                pdp[i * pstep] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+            }
+        } else {
 #pragma unroll 4
-        for (int i = 0; i < nitA; i++) {
-            const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, *r0p);
-            const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, *r1p);
-            *pdp = c0 + ((c1 >> 2) & 0x3fff3fffu);
-            r0p -= rstep; r1p -= rstep; pdp += pstep;
+            for (int i = 0; i < nitA; i++) {
+                const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, *r0p);
+                const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, *r1p);
+                *pdp = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                r0p -= rstep; r1p -= rstep; pdp += pstep;
+            }
         }
     };
     // Box sums.  Every packed half stays below 2^16 for the supported parameter range (checked on the
     // host), so plain 32-bit adds on the u16x2 pairs are exact: no carry crosses the halves.
-    auto stage_b = [&](int k) {
-        if (ncb <= 0) return;
-        const uint32_t* pp = pdb + (k & 1) * D2 * PS + dpb * PS + cb0;  // pp[j + i]: output column cb0 + j, tap i
-        uint32_t h = 0;
+    const uint32_t* ppb = pdb + dpb * PS + cb0;                 // + (k & 1) * D2 * PS per row
+    uint32_t* rpb = ring + (size_t)cb0 * D2 + dpb;              // + slot * TX * D2 per row
+    uint32_t* Cdst = (uint32_t*)(a.C + ((ptrdiff_t)(vr0 - (bs - 1)) * width1 + x0 + cb0) * D) + dpb;  // row k: + k * width1 * D2
+    const size_t crow = (size_t)width1 * D2;
+    int slot = 0;                                               // ring slot of row k (k % bs without the division)
+    auto phase_b = [&](int k) {
+        if (ncb > 0) {
+            const uint32_t* pp = ppb + (k & 1) * D2 * PS;       // pp[j + i]: output column cb0 + j, tap i
+            uint32_t h = 0;
 #pragma unroll 3
-        for (int i = 0; i < bs; i++) h += pp[i];
-        uint32_t* rp = ring + ((size_t)slot * TX + cb0) * D2 + dpb;
-        uint32_t* Cdst = (uint32_t*)(a.C + ((size_t)(vr0 + k - (bs - 1)) * width1 + x0 + cb0) * D) + dpb;
-        const bool sub = k >= bs, emit = k >= bs - 1;
+            for (int i = 0; i < bs; i++) h += pp[i];
+            uint32_t* rp = rpb + (size_t)slot * TX * D2;
+            const bool sub = k >= bs, emit = k >= bs - 1;
 #pragma unroll
-        for (int j = 0; j < COST_MAXCPG; j++) {
-            if (j < ncb) {
-                if (j > 0) h = h + pp[j + bs - 1] - pp[j - 1];
-                uint32_t c = crun[j] + h;
-                if (sub) c -= rp[j * D2];
-                rp[j * D2] = h;
-                crun[j] = c;
-                if (emit) Cdst[j * D2] = c;
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j < ncb) {
+                    if (j > 0) h = h + pp[j + bs - 1] - pp[j - 1];
+                    uint32_t c = crun[j] + h;
+                    if (sub) c -= rp[j * D2];
+                    rp[j * D2] = h;
+                    crun[j] = c;
+                    if (emit) Cdst[j * D2] = c;
+                }
             }
         }
-    };
-    stage_a(0);
-    for (int k = 0; k < nk; k++) {
-        __syncthreads();  // pd[k & 1] complete; pd[(k + 1) & 1] and its tables free again
-        if (k + 1 < nk) stage_a(k + 1);  // contains one barrier; the condition is CTA-uniform
-        stage_b(k);
+        Cdst += crow;
         slot = slot + 1 == bs ? 0 : slot + 1;
+    };
+    phase_a(0);
+    for (int k = 0; k < nk; k++) {
+        __syncthreads();  // pd[k & 1] complete; stage k & 1 of the tables and pd[(k + 1) & 1] are free again
+        if (tid == 0 && k + 2 < nk) issue_tables(k + 2);
+        if (k + 1 < nk) phase_a(k + 1);
+        phase_b(k);
     }
 }
 
@@ -892,9 +963,9 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
     L3D_LAUNCH(L, fill_s16_kernel, cdiv(npix, 256), 256, 0, r.raw, npix, INVALID);
     if (g.width1 <= 0) return L3D_OK;
     if (make_desc) {
-        dim3 pg(cdiv(W, 128), H);
-        L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, 128, 0, left, W, H, g.ftzero, dL);
-        L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, 128, 0, right, W, H, g.ftzero, dR);
+        dim3 pg(cdiv(W, PRE_THREADS), H);
+        L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, PRE_THREADS, 0, left, W, H, g.ftzero, dL);
+        L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, PRE_THREADS, 0, right, W, H, g.ftzero, dR);
     }
     // --- cost volume
     const size_t nvol = (size_t)g.HV * g.width1 * g.D;
@@ -902,12 +973,12 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
     r.S = L.get<int16_t>(set ? S_AGGR2 : S_AGGR, nvol);
     CostArgs ca;
     ca.Ldesc = dL; ca.Rdesc = dR; ca.C = r.C;
-    ca.W = W; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
+    ca.W = W; ca.H = H; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
     ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
     const int D2 = g.D / 2;
     auto cost_smem = [&](int txh) {
         int tx = txh - 2 * g.SW2;
-        return (size_t)2 * 2 * (txh + g.D) * 16 + (size_t)2 * D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4;
+        return (size_t)2 * 2 * (txh + g.D) * 16 + (size_t)2 * D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4 + 16;
     };
     ca.nxg = std::max(1, COST_THREADS / D2);
     int TXH = 64;
@@ -937,9 +1008,16 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
         }
     }
     size_t smem = cost_smem(TXH);
-    L3D_CHECK(L, cudaFuncSetAttribute(sgbm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const int dpa_step = COST_THREADS / TXH;
+    const int nit = (D2 % dpa_step == 0) ? D2 / dpa_step : 0;
     L.t_begin("sgbm_cost");
-    L3D_LAUNCH(L, sgbm_cost_kernel, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);
+#define COST_CASE(NITV)                                                                                                   \
+    {                                                                                                                     \
+        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_cost_kernel<NITV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+        L3D_LAUNCH(L, sgbm_cost_kernel<NITV>, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);                           \
+    }
+    if (nit == 8) COST_CASE(8) else if (nit == 4) COST_CASE(4) else COST_CASE(0)
+#undef COST_CASE
     L.t_end("sgbm_cost");
     r.d2 = L.get<unsigned>(set ? S_DISP22 : S_DISP2, (size_t)H * (W + 2));
     L3D_CHECK(L, cudaMemsetAsync(r.d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
@@ -1067,8 +1145,8 @@ int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns, bool keep_S) {
 int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8_t* right, int W, int H,
              int16_t* disp, SgbmDebug* dbg) {
     const size_t npix = (size_t)W * H;
-    uint4* dL = L.get<uint4>(S_DESC_L, npix);
-    uint4* dR = L.get<uint4>(S_DESC_R, npix);
+    uint4* dL = L.get<uint4>(S_DESC_L, 2 * npix);  // two operand planes per view (sgbm_prefilter_kernel)
+    uint4* dR = L.get<uint4>(S_DESC_R, 2 * npix);
     SgbmRun r;
     int rc = sgbm_front(L, p, left, right, W, H, 0, dL, dR, true, r);
     if (rc != L3D_OK) return rc;

@@ -395,7 +395,8 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
             cudaOccupancyMaxActiveClusters(&ncl, sgbm_vgroup_kernel<NPV, CPWV>, &cfg);                                \
             fprintf(stderr, "[l3d] vgroup<%d,%d> cluster %d: max active clusters %d\n", NPV, CPWV, a.cluster, ncl); \
         }                                                                                                             \
-        L3D_CHECK(L, cudaLaunchKernelEx(&cfg, sgbm_vgroup_kernel<NPV, CPWV>, a));                                     \
+        if (!dbg_skip("sgbm_vgroup_kernel"))                                                                          \
+            L3D_CHECK(L, cudaLaunchKernelEx(&cfg, sgbm_vgroup_kernel<NPV, CPWV>, a));                                 \
         L.launches++;                                                                                                 \
         rc = L3D_OK;                                                                                                  \
     }

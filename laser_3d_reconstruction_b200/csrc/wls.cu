@@ -93,113 +93,96 @@ __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __
     ch[i] = wx; cv[i] = wy;
 }
 
-// Thomas solves of one FGS pass: forward elimination + back substitution of a group of lines with
-// the whole lines resident in shared memory.  HORIZ: lines are rows (CTA = `nl` consecutive rows),
-// else columns (CTA = `nl` consecutive columns).  All threads stage num/den/weights into smem with
-// coalesced loads; lane l of warp 0 then runs line l's two sweeps (a serial recurrence of
-// fmul-fsub-fdiv per element, identical op order to oracle/csrc/orc_wls.c), with the elimination
-// factors overwriting the weights in place; all threads store the result.  HBM traffic is the
-// minimum of the pass: 3 reads + 2 writes per pixel.
-constexpr int FGS_THREADS = 256;
-constexpr int FGS_UNROLL = 4;
+// Thomas solves of one FGS pass (forward elimination + back substitution of every line), identical
+// op order to oracle/csrc/orc_wls.c, as THREE lock-step lanes per line:
+//   role 0  elimination factors  dn_j = (1 - lam (c_{j-1} + c_j)) - (lam c_{j-1}) D_{j-1},  D_j = (lam c_j) / dn_j
+//   role 1  numerator plane      a_j  = (a_j - (lam c_{j-1}) a_{j-1}) / dn_j
+//   role 2  denominator plane    the same on den
+// Roles 1/2 run one element behind role 0 and receive (dn, lam c_{j-1}) of their element by warp shuffle, so
+// a step costs the warp ONE IEEE division sequence for all three quotients and the serial chain per
+// element is fmul -> fsub -> fdiv.  The zero initial state reproduces the oracle's special-cased first
+// element bit for bit (x + 0, x - 0 and 0 * 0 are exact).  A warp carries FGS_LPW lines and streams
+// straight from/to global memory (L1 turns the per-row 4-byte accesses of the horizontal pass into one
+// sector fetch per 8 steps; the vertical pass is coalesced): no shared memory, 72-116 one-warp CTAs per
+// pass, so the solver leaves every SM free for the matcher kernels of the other frames in flight.
+// D goes to a scratch plane for the back substitution (role 0 reloads it, shuffles it to roles 1/2).
+constexpr int FGS_LPW = 10;   // lines per warp: lanes [0,10) role 0, [10,20) role 1, [20,30) role 2
+constexpr int FGS_BLK = 8;    // elements per register block (the next block is prefetched during the current one)
 
 template <bool HORIZ>
-__global__ void __launch_bounds__(FGS_THREADS) fgs_lines_kernel(float* __restrict__ num, float* __restrict__ den,
-                                                                const float* __restrict__ wgt, int w, int h,
-                                                                float lam, int nl) {
-    extern __shared__ float fgs_sm[];
+__global__ void __launch_bounds__(32) fgs_lines_kernel(float* num, float* den, const float* __restrict__ wgt,
+                                                       float* Dscr, int w, int h, float lam) {
     const int nlines = HORIZ ? h : w, len = HORIZ ? w : h;
-    const int l0 = blockIdx.x * nl;
-    const int cnt = min(nl, nlines - l0);
-    // smem element (line l, position j): HORIZ -> l*(len+1) + j (padded rows), else j*nl + l
-    const int ls = HORIZ ? len + 1 : 1, es = HORIZ ? 1 : nl;
-    const int plane = HORIZ ? nl * (len + 1) : len * nl;
-    float* A = fgs_sm;
-    float* B = fgs_sm + plane;
-    float* Cw = fgs_sm + 2 * plane;
-    const int total = cnt * len;
-    for (int idx = threadIdx.x; idx < total; idx += FGS_THREADS) {
-        int l, j;
-        if (HORIZ) { l = idx / len; j = idx - l * len; } else { j = idx / cnt; l = idx - j * cnt; }
-        size_t g = HORIZ ? (size_t)(l0 + l) * w + j : (size_t)j * w + l0 + l;
-        int s = l * ls + j * es;
-        A[s] = num[g]; B[s] = den[g]; Cw[s] = wgt[g];
+    const int lane = threadIdx.x;
+    const int role = lane / FGS_LPW, li = lane - role * FGS_LPW;
+    const int line = min(blockIdx.x * FGS_LPW + li, nlines - 1);
+    const bool active = role < 3 && blockIdx.x * FGS_LPW + li < nlines;
+    const int src = li;                                   // role-0 lane of this lane's line
+    const size_t ls = HORIZ ? (size_t)w : 1, es = HORIZ ? 1 : (size_t)w;
+    const float* in = role == 0 ? wgt : (role == 1 ? num : den);
+    float* out = role == 0 ? Dscr : (role == 1 ? num : den);
+    in += (size_t)line * ls; out += (size_t)line * ls;
+    const int lag = role == 0 ? 0 : 1;
+    const bool r0 = role == 0;
+    // ---- forward elimination: steps j = 0 .. len (roles 1/2 finish element len-1 in step len)
+    float p = 0.f, cm = 0.f;              // previous quotient (D or a), previous weight (role 0)
+    float dn_pub = 1.f, lcm_pub = 0.f;    // role 0: dn and lam*c_{j-1} of the element it processed last
+    float xs[FGS_BLK], xn[FGS_BLK];
+    auto load_blk = [&](float (&dst)[FGS_BLK], int j0) {
+#pragma unroll
+        for (int k = 0; k < FGS_BLK; k++) {
+            const int e = j0 + k - lag;
+            dst[k] = (e >= 0 && e < len) ? in[(size_t)e * es] : 0.f;
+        }
+    };
+    load_blk(xs, 0);
+    for (int j0 = 0; j0 <= len; j0 += FGS_BLK) {
+        if (j0 + FGS_BLK <= len) load_blk(xn, j0 + FGS_BLK);
+#pragma unroll
+        for (int k = 0; k < FGS_BLK; k++) {
+            const int e = j0 + k - lag;
+            const float x = xs[k];
+            const float dn_s = __shfl_sync(0xffffffffu, dn_pub, src);
+            const float lcm_s = __shfl_sync(0xffffffffu, lcm_pub, src);
+            const float t = r0 ? __fmul_rn(lam, cm) : lcm_s;
+            const float prod = __fmul_rn(t, p);
+            const float dn0 = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, x))), prod);
+            const float numer = r0 ? __fmul_rn(lam, x) : __fsub_rn(x, prod);
+            const float denom = r0 ? dn0 : dn_s;
+            p = __fdiv_rn(numer, denom);
+            if (active && e >= 0 && e < len) out[(size_t)e * es] = p;
+            dn_pub = denom; lcm_pub = t; cm = x;
+        }
+#pragma unroll
+        for (int k = 0; k < FGS_BLK; k++) xs[k] = xn[k];
     }
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-        float* a = A + threadIdx.x * ls;
-        float* b = B + threadIdx.x * ls;
-        float* c = Cw + threadIdx.x * ls;
-        float c0 = c[0];
-        float dn = __fsub_rn(1.0f, __fmul_rn(lam, c0));
-        float Dp = __fdiv_rn(__fmul_rn(lam, c0), dn);
-        float ap = __fdiv_rn(a[0], dn), bp = __fdiv_rn(b[0], dn);
-        c[0] = Dp; a[0] = ap; b[0] = bp;
-        float cm = c0;
-        int j = 1;
-        for (; j + FGS_UNROLL <= len; j += FGS_UNROLL) {
-            float cc[FGS_UNROLL], av[FGS_UNROLL], bv[FGS_UNROLL];
+    // ---- back substitution: r_j = r_j - D_j r_{j+1}, j = len-2 .. 0 (p holds r_{len-1} for roles 1/2)
+    // roles 1/2 processed element len-1 in the step with e == len-1; later steps of the last block ran on
+    // zero inputs with stale (dn, lcm): restore p from memory instead of tracking it through the tail
+    if (len >= 1) p = out[(size_t)(len - 1) * es];
+    auto load_rev = [&](float (&dst)[FGS_BLK], int j0) {  // elements j0, j0-1, ...
 #pragma unroll
-            for (int k = 0; k < FGS_UNROLL; k++) { cc[k] = c[(j + k) * es]; av[k] = a[(j + k) * es]; bv[k] = b[(j + k) * es]; }
+        for (int k = 0; k < FGS_BLK; k++) {
+            const int e = j0 - k;
+            dst[k] = e >= 0 ? out[(size_t)e * es] : 0.f;
+        }
+    };
+    load_rev(xs, len - 2);
+    for (int j0 = len - 2; j0 >= 0; j0 -= FGS_BLK) {
+        if (j0 - FGS_BLK >= 0) load_rev(xn, j0 - FGS_BLK);
 #pragma unroll
-            for (int k = 0; k < FGS_UNROLL; k++) {
-                float lcm = __fmul_rn(lam, cm);
-                dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cc[k]))), __fmul_rn(lcm, Dp));
-                Dp = __fdiv_rn(__fmul_rn(lam, cc[k]), dn);
-                ap = __fdiv_rn(__fsub_rn(av[k], __fmul_rn(lcm, ap)), dn);
-                bp = __fdiv_rn(__fsub_rn(bv[k], __fmul_rn(lcm, bp)), dn);
-                c[(j + k) * es] = Dp; a[(j + k) * es] = ap; b[(j + k) * es] = bp;
-                cm = cc[k];
+        for (int k = 0; k < FGS_BLK; k++) {
+            const int e = j0 - k;
+            const float Dj = __shfl_sync(0xffffffffu, xs[k], src);
+            const float r = __fsub_rn(xs[k], __fmul_rn(Dj, p));
+            if (e >= 0 && !r0) {
+                p = r;
+                if (active) out[(size_t)e * es] = r;
             }
         }
-        for (; j < len; j++) {
-            float cck = c[j * es];
-            float lcm = __fmul_rn(lam, cm);
-            dn = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, cck))), __fmul_rn(lcm, Dp));
-            Dp = __fdiv_rn(__fmul_rn(lam, cck), dn);
-            ap = __fdiv_rn(__fsub_rn(a[j * es], __fmul_rn(lcm, ap)), dn);
-            bp = __fdiv_rn(__fsub_rn(b[j * es], __fmul_rn(lcm, bp)), dn);
-            c[j * es] = Dp; a[j * es] = ap; b[j * es] = bp;
-            cm = cck;
-        }
-        j = len - 2;
-        for (; j - (FGS_UNROLL - 1) >= 0; j -= FGS_UNROLL) {
-            float dv[FGS_UNROLL], av[FGS_UNROLL], bv[FGS_UNROLL];
 #pragma unroll
-            for (int k = 0; k < FGS_UNROLL; k++) { dv[k] = c[(j - k) * es]; av[k] = a[(j - k) * es]; bv[k] = b[(j - k) * es]; }
-#pragma unroll
-            for (int k = 0; k < FGS_UNROLL; k++) {
-                ap = __fsub_rn(av[k], __fmul_rn(dv[k], ap));
-                bp = __fsub_rn(bv[k], __fmul_rn(dv[k], bp));
-                a[(j - k) * es] = ap; b[(j - k) * es] = bp;
-            }
-        }
-        for (; j >= 0; j--) {
-            float d = c[j * es];
-            ap = __fsub_rn(a[j * es], __fmul_rn(d, ap));
-            bp = __fsub_rn(b[j * es], __fmul_rn(d, bp));
-            a[j * es] = ap; b[j * es] = bp;
-        }
+        for (int k = 0; k < FGS_BLK; k++) xs[k] = xn[k];
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < total; idx += FGS_THREADS) {
-        int l, j;
-        if (HORIZ) { l = idx / len; j = idx - l * len; } else { j = idx / cnt; l = idx - j * cnt; }
-        size_t g = HORIZ ? (size_t)(l0 + l) * w + j : (size_t)j * w + l0 + l;
-        int s = l * ls + j * es;
-        num[g] = A[s]; den[g] = B[s];
-    }
-}
-
-// lines per CTA: spread the lines over ~one CTA per SM, within the shared-memory budget
-static int fgs_lines_per_cta(int nlines, int len, bool horiz, size_t* smem) {
-    const size_t budget = 200 * 1024;
-    size_t per_line = (size_t)3 * (len + (horiz ? 1 : 0)) * sizeof(float);
-    int cap = (int)std::min<size_t>(32, budget / per_line);
-    int nl = std::max(1, std::min(cap, cdiv(nlines, NUM_SMS)));
-    if (!horiz) nl = std::max(1, std::min(cap, std::max(nl, 8)));  // >= one 32 B sector per row segment
-    *smem = per_line * nl;
-    return nl;
 }
 
 __global__ void wls_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
@@ -261,14 +244,10 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     float *num = aL, *den = bL;
     L3D_LAUNCH(L, wls_lrc_kernel, g, 128, 0, dl, dr, guide, lut, W, x0, w, h, p.lrc_thresh, cl, cr, conf, num, den, ch, cv);
     float lam = (float)p.lambda;
-    size_t smh = 0, smv = 0;
-    const int nlh = fgs_lines_per_cta(h, w, true, &smh), nlv = fgs_lines_per_cta(w, h, false, &smv);
-    L3D_ARG(L, smh <= 220 * 1024 && smv <= 220 * 1024, "wls: image too large for the line-resident FGS solver");
-    L3D_CHECK(L, cudaFuncSetAttribute(fgs_lines_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    L3D_CHECK(L, cudaFuncSetAttribute(fgs_lines_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    float* Dscr = aR;  // aR/bR are free as well: elimination factors of the current pass
     for (int it = 0; it < 3; it++) {
-        L3D_LAUNCH(L, fgs_lines_kernel<true>, cdiv(h, nlh), FGS_THREADS, smh, num, den, ch, w, h, lam, nlh);
-        L3D_LAUNCH(L, fgs_lines_kernel<false>, cdiv(w, nlv), FGS_THREADS, smv, num, den, cv, w, h, lam, nlv);
+        L3D_LAUNCH(L, fgs_lines_kernel<true>, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
+        L3D_LAUNCH(L, fgs_lines_kernel<false>, cdiv(w, FGS_LPW), 32, 0, num, den, cv, Dscr, w, h, lam);
         lam *= 0.25f;
     }
     L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, num, den, conf, W, H, x0, w, outside, out, conf_out);
