@@ -385,10 +385,11 @@ constexpr int SCAN_WARPS = 4;
 template <int NP, bool FULL>
 __device__ __forceinline__ uint32_t sgm_step(uint32_t (&L)[NP], uint32_t minL2, const uint32_t (&Cv)[NP],
                                              uint32_t p1x2, uint32_t k2, int lane, bool active) {
-    uint32_t up = __shfl_up_sync(FULL_MASK, L[NP - 1], 1);
-    uint32_t dn = __shfl_down_sync(FULL_MASK, L[0], 1);
-    if (lane == 0) up = INF2;
-    if (lane == 31) dn = INF2;
+    const uint32_t up = __shfl_up_sync(FULL_MASK, L[NP - 1], 1);
+    const uint32_t dn = __shfl_down_sync(FULL_MASK, L[0], 1);
+    // lane 0 has no d-1 and lane 31 no d+1 neighbour: their byte-permute selectors (loop-invariant per-lane
+    // constants) put the word's own value into the missing slot -- L[d] + P1 - delta >= L[d] - delta never wins
+    const uint32_t selA = lane == 0 ? 0x5454u : 0x5432u, selB = lane == 31 ? 0x3232u : 0x5432u;
     const uint32_t nd2 = k2 - minL2;   // -(minL + P2) mod 2^16, both halves
     const uint32_t pm2 = nd2 + p1x2;   // P1 - (minL + P2) mod 2^16
     uint32_t mn = INF2;
@@ -397,8 +398,8 @@ __device__ __forceinline__ uint32_t sgm_step(uint32_t (&L)[NP], uint32_t minL2, 
     for (int k = 0; k < NP; k++) {
         uint32_t prev = k ? L[k - 1] : up;
         uint32_t next = (k < NP - 1) ? L[k + 1] : dn;
-        uint32_t dm1 = __byte_perm(prev, L[k], 0x5432);
-        uint32_t dp1 = __byte_perm(L[k], next, 0x5432);
+        uint32_t dm1 = k ? __byte_perm(prev, L[k], 0x5432) : __byte_perm(prev, L[k], selA);
+        uint32_t dp1 = (k < NP - 1) ? __byte_perm(L[k], next, 0x5432) : __byte_perm(L[k], next, selB);
         uint32_t t = __viaddmin_s16x2(L[k], nd2, 0u);
         t = __viaddmin_s16x2(dm1, pm2, t);
         t = __viaddmin_s16x2(dp1, pm2, t);
@@ -991,7 +992,8 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
     ca.cpg = cdiv(ca.TX, ca.nxg);
     // bands: split each segment so that the grid is close to a multiple of the SM count
     int xtiles = cdiv(g.width1, ca.TX);
-    int want = std::max(1, (2 * NUM_SMS) / xtiles);
+    static const int waves = getenv("L3D_COST_WAVES") ? atoi(getenv("L3D_COST_WAVES")) : 1;
+    int want = std::max(1, (waves * NUM_SMS) / xtiles);
     int per_seg = std::max(1, std::min(want / g.nseg, MAXBAND / g.nseg));
     ca.nbands = 0;
     for (int s = 0; s < g.nseg; s++) {

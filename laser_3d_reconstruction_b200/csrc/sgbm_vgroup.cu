@@ -75,14 +75,16 @@ __device__ __forceinline__ void vg_bulk_s2g(void* dst, uint32_t src, uint32_t by
 
 // the SGM step of sgbm.cu (sgm_step<NP, true>): O[d] = C[d] + min(I[d]-delta, I[d+-1]+P1-delta, 0), delta = minI + P2.
 // In and out may be the same registers (every output word is computed before any is stored).
+// Lane 0 has no d-1 neighbour and lane 31 no d+1 neighbour.  Instead of substituting "infinity" after the shuffles
+// (two SELs per step) the byte-permute selectors of those two lanes (selA / selB, per-lane constants) feed the
+// word's own value into the missing slot: L[d] + P1 - delta >= L[d] - delta, so that term never wins.
 template <int NP>
 __device__ __forceinline__ uint32_t vg_step(uint32_t (&O)[NP], const uint32_t (&I)[NP], uint32_t minI2,
-                                            const uint32_t (&Cv)[NP], uint32_t p1x2, uint32_t k2, int lane) {
+                                            const uint32_t (&Cv)[NP], uint32_t p1x2, uint32_t k2, uint32_t selA,
+                                            uint32_t selB) {
     constexpr uint32_t INF = 0x7fff7fffu;
-    uint32_t up = __shfl_up_sync(0xffffffffu, I[NP - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, I[0], 1);
-    if (lane == 0) up = INF;
-    if (lane == 31) dn = INF;
+    const uint32_t up = __shfl_up_sync(0xffffffffu, I[NP - 1], 1);
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, I[0], 1);
     const uint32_t nd2 = k2 - minI2;
     const uint32_t pm2 = nd2 + p1x2;
     uint32_t mn = INF;
@@ -91,8 +93,8 @@ __device__ __forceinline__ uint32_t vg_step(uint32_t (&O)[NP], const uint32_t (&
     for (int k = 0; k < NP; k++) {
         const uint32_t prev = k ? I[k - 1] : up;
         const uint32_t next = (k < NP - 1) ? I[k + 1] : dn;
-        const uint32_t dm1 = __byte_perm(prev, I[k], 0x5432);
-        const uint32_t dp1 = __byte_perm(I[k], next, 0x5432);
+        const uint32_t dm1 = k ? __byte_perm(prev, I[k], 0x5432) : __byte_perm(prev, I[k], selA);
+        const uint32_t dp1 = (k < NP - 1) ? __byte_perm(I[k], next, 0x5432) : __byte_perm(I[k], next, selB);
         uint32_t t = __viaddmin_s16x2(I[k], nd2, 0u);
         t = __viaddmin_s16x2(dm1, pm2, t);
         t = __viaddmin_s16x2(dp1, pm2, t);
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
     const int rank = (int)cluster.block_rank();
     const int VG_CLUSTER = a.cluster;
     const int job = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     constexpr int cpw = CPW;
     const int width1 = a.width1, H = a.H;
     const uint32_t B = (uint32_t)a.D * 2u;                       // bytes per pixel vector
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
     }
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const uint32_t k2 = (0x10000u - (uint32_t)a.P2) * 0x10001u;
+    const uint32_t selA = lane == 0 ? 0x5454u : 0x5432u, selB = lane == 31 ? 0x3232u : 0x5432u;
     const int c0 = warp * cpw;  // first column of this warp inside the strip
     // where this warp's exports go: A state leaves to the right (warp + 1 or the next CTA's warp 0),
     // B state leaves to the left (warp - 1 or the previous CTA's last warp)
@@ -233,18 +237,18 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
 #pragma unroll
         for (int j = CPW - 1; j >= 1; j--) {
             vg_unpack<NP>(cs[j * 32], Cw);
-            mA[j] = vg_step<NP>(LA[j], LA[j - 1], mA[j - 1], Cw, p1x2, k2, lane);
+            mA[j] = vg_step<NP>(LA[j], LA[j - 1], mA[j - 1], Cw, p1x2, k2, selA, selB);
         }
         vg_unpack<NP>(cs[0], Cw);
-        mA[0] = vg_step<NP>(LA[0], inA, inAm, Cw, p1x2, k2, lane);
+        mA[0] = vg_step<NP>(LA[0], inA, inAm, Cw, p1x2, k2, selA, selB);
         // ---- diagonal B (fed from the right): in place, left to right
 #pragma unroll
         for (int j = 0; j < CPW - 1; j++) {
             vg_unpack<NP>(cs[j * 32], Cw);
-            mB[j] = vg_step<NP>(LB[j], LB[j + 1], mB[j + 1], Cw, p1x2, k2, lane);
+            mB[j] = vg_step<NP>(LB[j], LB[j + 1], mB[j + 1], Cw, p1x2, k2, selA, selB);
         }
         vg_unpack<NP>(cs[(CPW - 1) * 32], Cw);
-        mB[CPW - 1] = vg_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, lane);
+        mB[CPW - 1] = vg_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, selA, selB);
         if (x0 + c0 + CPW > width1) {
             // columns outside the image: their state must read as "no predecessor" (0) for the last valid column
 #pragma unroll
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
 #pragma unroll
         for (int j = 0; j < CPW; j++) {
             vg_unpack<NP>(cs[j * 32], Cw);
-            mV[j] = vg_step<NP>(LV[j], LV[j], mV[j], Cw, p1x2, k2, lane);
+            mV[j] = vg_step<NP>(LV[j], LV[j], mV[j], Cw, p1x2, k2, selA, selB);
             uint32_t Sw[NP];
             vg_unpack<NP>(ss[j * 32], Sw);
 #pragma unroll
@@ -318,22 +322,32 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
                 rawg[(size_t)y * a.W + x + minX1] = (int16_t)(dd + minD * 16);
             }
         }
-        // ---- S strip back to HBM, next-but-one row in (thread 0 owns the bulk copies: a 17th producer warp was
-        // tried and lost more to the tighter register budget of a 544-thread CTA than it gained)
+        // ---- S strip back to HBM, next-but-one row in.  The bulk copies of row `it` are owned by warp it % 16
+        // (a 17th producer warp was tried and lost more to the tighter register budget of a 544-thread CTA than
+        // it gained).  Split named barrier: the other 15 warps only ARRIVE ("my reads and writes of this stage are
+        // done") and run on into the next row; the owner waits for them, then stores / reloads the stage.  Its
+        // lateness (the wait for the store's shared-memory read) is absorbed by the slack before the next cluster
+        // barrier wait, and rotating the role keeps any one warp from falling behind row after row.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0 && wc > 0) {
-            if (!final) {
-                const int row = dir > 0 ? it : H - 1 - it;
-                vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
-                            (uint32_t)wc * B);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+        const uint32_t bar_id = 1u + (uint32_t)(it & 1);
+        if (warp == (it & (VG_WARPS - 1))) {
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(VG_THREADS) : "memory");
+            if (lane == 0 && wc > 0) {
+                if (!final) {
+                    const int row = dir > 0 ? it : H - 1 - it;
+                    vg_bulk_s2g(Sg + ((size_t)row * width1 + x0) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + st * strip_bytes),
+                                (uint32_t)wc * B);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's smem may be overwritten
+                }
+                if (it + 2 < H) load_row(it + 2);
             }
-            if (it + 2 < H) load_row(it + 2);
+            __syncwarp();
+        } else {
+            asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "r"(VG_THREADS) : "memory");
         }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every warp owned some rows' stores
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // pair the last arrive
     cluster.sync();  // no CTA exits while a neighbour may still write into its shared memory
 }
