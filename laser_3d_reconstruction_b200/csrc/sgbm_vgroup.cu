@@ -47,7 +47,7 @@ struct VGroupArgs {
 static size_t vgroup_smem_bytes(int D, int cpw) {
     const size_t strip = (size_t)VG_WARPS * cpw * D * 2;
     const size_t halo = (size_t)2 * 2 * VG_WARPS * (D * 2 + 16);
-    return 2 * 2 * strip + halo + 64;  // + 4 mbarriers
+    return 2 * 2 * strip + halo + 64;  // + 6 mbarriers (2 row stages, 2 x 2 remote-halo parities)
 }
 
 __device__ __forceinline__ void vg_mbar_init(uint32_t bar, int count) {
@@ -71,6 +71,30 @@ __device__ __forceinline__ void vg_bulk_g2s(uint32_t dst, const void* src, uint3
 }
 __device__ __forceinline__ void vg_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// asynchronous store into a NEIGHBOUR CTA's shared memory that signals the neighbour's mbarrier (DSMEM hand-off
+// without any fence on the producer side)
+__device__ __forceinline__ uint32_t vg_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void vg_st_async(uint32_t raddr, uint32_t v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+template <int NP> __device__ __forceinline__ void vg_st_async_vec(uint32_t raddr, const uint32_t (&v)[NP], uint32_t rbar);
+template <> __device__ __forceinline__ void vg_st_async_vec<1>(uint32_t raddr, const uint32_t (&v)[1], uint32_t rbar) {
+    vg_st_async(raddr, v[0], rbar);
+}
+template <> __device__ __forceinline__ void vg_st_async_vec<2>(uint32_t raddr, const uint32_t (&v)[2], uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(raddr), "r"(v[0]), "r"(v[1]), "r"(rbar) : "memory");
+}
+template <> __device__ __forceinline__ void vg_st_async_vec<4>(uint32_t raddr, const uint32_t (&v)[4], uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(raddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(rbar) : "memory");
 }
 
 // the SGM step of sgbm.cu (sgm_step<NP, true>): O[d] = C[d] + min(I[d]-delta, I[d+-1]+P1-delta, 0), delta = minI + P2.
@@ -122,7 +146,9 @@ template <> __device__ __forceinline__ uint4 vg_pack<4>(const uint32_t (&o)[4]) 
 
 // OpenCV's uniqueness test (modes SGBM / HH), see wta_not_unique in sgbm.cu; out of line, uniquenessRatio > 0 only
 template <int NP>
-__device__ __noinline__ bool vg_not_unique(const uint32_t (&w)[NP], unsigned key, int uniq, unsigned dkey) {
+__device__ __noinline__ bool vg_not_unique(typename VgVec<NP>::T wv, unsigned key, int uniq, unsigned dkey) {
+    uint32_t w[NP];  // by value: a by-reference array would force the caller's S words through local memory every column
+    vg_unpack<NP>(wv, w);
     const int minS = (int)(key >> 8), best = (int)(key & 255u);
     bool rej = false;
 #pragma unroll
@@ -172,9 +198,9 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
     // zero both parities of every halo slot: "no predecessor" = (L = 0, min = 0), OpenCV's out-of-image rule
     for (int i = threadIdx.x; i < (int)(4 * VG_WARPS * slot / 4); i += VG_THREADS) ((uint32_t*)haloA)[i] = 0u;
     // bars[0..1]: row stage full (expect_tx + the two bulk loads)
+    // bars[2..3]: A state arrived from the left neighbour CTA (parity of the exporting row), bars[4..5]: B state from the right
     if (threadIdx.x == 0) {
-        vg_mbar_init(bars, 1);
-        vg_mbar_init(bars + 8, 1);
+        for (int i = 0; i < 6; i++) vg_mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -208,19 +234,34 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
     const int c0 = warp * cpw;  // first column of this warp inside the strip
     // where this warp's exports go: A state leaves to the right (warp + 1 or the next CTA's warp 0),
     // B state leaves to the left (warp - 1 or the previous CTA's last warp)
-    unsigned char* expA = nullptr;
+    unsigned char* expA = nullptr;   // local slot (same CTA)
     unsigned char* expB = nullptr;
+    uint32_t rexpA = 0, rexpB = 0, rbarA = 0, rbarB = 0;  // remote slot + the neighbour's mbarrier (shared::cluster addresses)
     if (warp < VG_WARPS - 1) expA = haloA + (size_t)(warp + 1) * slot;
-    else if (rank < VG_CLUSTER - 1) expA = (unsigned char*)cluster.map_shared_rank((void*)haloA, rank + 1);
+    else if (rank < VG_CLUSTER - 1) {
+        rexpA = vg_mapa((uint32_t)__cvta_generic_to_shared(haloA), (uint32_t)(rank + 1));
+        rbarA = vg_mapa(bars + 16, (uint32_t)(rank + 1));
+    }
     if (warp > 0) expB = haloB + (size_t)(warp - 1) * slot;
-    else if (rank > 0) expB = (unsigned char*)cluster.map_shared_rank((void*)(haloB + (size_t)(VG_WARPS - 1) * slot), rank - 1);
+    else if (rank > 0) {
+        rexpB = vg_mapa((uint32_t)__cvta_generic_to_shared(haloB + (size_t)(VG_WARPS - 1) * slot), (uint32_t)(rank - 1));
+        rbarB = vg_mapa(bars + 32, (uint32_t)(rank - 1));
+    }
+    const bool remote_inA = warp == 0 && rank > 0, remote_inB = warp == VG_WARPS - 1 && rank < VG_CLUSTER - 1;
     const uint32_t par_stride = VG_WARPS * slot;  // second parity of a halo array
 
     for (int it = 0; it < H; it++) {
         const int st = it & 1, par = it & 1;
         if (wc > 0) vg_mbar_wait(bars + 8 * st, (uint32_t)((it >> 1) & 1));
         if (it > 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // row it-1 exports visible
-        // ---- import the diagonal states entering this warp (exported during row it-1 into parity (it-1)&1)
+        // ---- import the diagonal states entering this warp (exported during row it-1 into parity (it-1)&1).
+        // State from a neighbour CTA arrives by st.async and completes this CTA's mbarrier for that parity.
+        if (it > 0 && (remote_inA || remote_inB)) {
+            const uint32_t hb = bars + (remote_inA ? 16u : 32u) + 8u * (uint32_t)(par ^ 1);
+            if (lane == 0) vg_mbar_expect_tx(hb, B + 4u);
+            __syncwarp();
+            vg_mbar_wait(hb, (uint32_t)(((it - 1) >> 1) & 1));
+        }
         uint32_t inA[NP], inB[NP], inAm, inBm;
         {
             const unsigned char* pa = haloA + (size_t)(par ^ 1) * par_stride + (size_t)warp * slot;
@@ -260,18 +301,30 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
                 }
             }
         }
-        // ---- export the new edge states (parity of this row) and let the cluster know
+        // ---- export the new edge states (parity of this row).  Inside the CTA: plain shared-memory stores, made
+        // visible by a CTA-scope fence before the (relaxed) cluster-barrier arrive -- the barrier then only orders
+        // the reuse of the slots.  To a neighbour CTA: st.async + the neighbour's mbarrier, no fence at all.  (An
+        // arrive.release would cost every warp a GPU-scope MEMBAR + ERRBAR per row: 18 % of the stall samples.)
         if (expA) {
             unsigned char* q = expA + (size_t)par * par_stride;
             *(vec*)(q + lane * sizeof(vec)) = vg_pack<NP>(LA[CPW - 1]);
             if (lane == 0) *(uint32_t*)(q + B) = mA[CPW - 1];
+        } else if (rexpA && it + 1 < H) {
+            const uint32_t q = rexpA + (uint32_t)par * par_stride, rb = rbarA + 8u * (uint32_t)par;
+            vg_st_async_vec<NP>(q + lane * (uint32_t)sizeof(vec), LA[CPW - 1], rb);
+            if (lane == 0) vg_st_async(q + B, mA[CPW - 1], rb);
         }
         if (expB) {
             unsigned char* q = expB + (size_t)par * par_stride;
             *(vec*)(q + lane * sizeof(vec)) = vg_pack<NP>(LB[0]);
             if (lane == 0) *(uint32_t*)(q + B) = mB[0];
+        } else if (rexpB && it + 1 < H) {
+            const uint32_t q = rexpB + (uint32_t)par * par_stride, rb = rbarB + 8u * (uint32_t)par;
+            vg_st_async_vec<NP>(q + lane * (uint32_t)sizeof(vec), LB[0], rb);
+            if (lane == 0) vg_st_async(q + B, mB[0], rb);
         }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
         // ---- vertical path + S update (the cluster barrier's latency hides behind this)
         unsigned wkey = 0xffffffffu;  // final pass: arg-min key of column `lane` of this warp
         bool wrej = false;
@@ -297,7 +350,7 @@ __global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroup
                 }
                 key = __reduce_min_sync(0xffffffffu, key);
                 bool rej = false;
-                if (uniq > 0) rej = vg_not_unique<NP>(Sw, key, uniq, dkey);
+                if (uniq > 0) rej = vg_not_unique<NP>(vg_pack<NP>(Sw), key, uniq, dkey);
                 if (lane == j) { wkey = key; wrej = rej; }
             }
         }
