@@ -372,9 +372,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=56, help="frames per step per GPU (a multiple of the 7-frame lane set)")
+    ap.add_argument("--frames", type=int, default=112, help="frames per step per GPU (a multiple of the 7-frame lane set)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames rendered per rank")
-    ap.add_argument("--lanes", type=int, default=14, help="frames in flight per GPU (streams): two lane sets of 7 frames")
+    ap.add_argument("--lanes", type=int, default=28, help="frames in flight per GPU (streams): four lane sets of 7 frames")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

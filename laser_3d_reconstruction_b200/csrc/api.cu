@@ -603,9 +603,9 @@ struct l3d_pipeline {
     int last_frames = 0;
     // grouped mode: the frames of a lane set run their SGBM fronts on their lanes, ONE cluster-fused
     // aggregation launch per pass over all their volumes on the set's middle stream, then their backs
-    static constexpr int MAXSETS = 4;
+    static constexpr int MAXSETS = 8;
     Lane mid[MAXSETS];
-    cudaEvent_t ev_mid[MAXSETS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_mid[MAXSETS] = {};
     std::vector<cudaEvent_t> lane_front;
     std::vector<DepthRuns> runs;  // per lane
     bool timing = false;

@@ -29,6 +29,9 @@ constexpr int VG_WARPS = 16;
 constexpr int VG_THREADS = VG_WARPS * 32;
 constexpr int VG_MAXCPW = 9;     // columns per warp: the cluster spans 8 * 16 * 9 = 1152 columns
 constexpr int VG_MAXJOBS = 64;
+// 16 warps x 120 registers leave 4096 registers of the SM free: the one-warp CTAs of the back-half kernels (FGS
+// solver, ...) can then share an SM with an aggregation CTA instead of blocking a whole cluster from launching
+#define VG_MAXREG 120
 
 struct VGroupArgs {
     const int16_t* C[VG_MAXJOBS];
@@ -163,7 +166,7 @@ __device__ __noinline__ bool vg_not_unique(typename VgVec<NP>::T wv, unsigned ke
 
 // NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities); CPW = columns per warp
 template <int NP, int CPW>
-__global__ void __launch_bounds__(VG_THREADS, 1) sgbm_vgroup_kernel(const VGroupArgs a) {
+__global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
     typedef typename VgVec<NP>::T vec;
     constexpr uint32_t INF = 0x7fff7fffu;
     extern __shared__ __align__(128) unsigned char vg_smem[];

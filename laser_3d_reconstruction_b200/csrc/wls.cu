@@ -185,6 +185,124 @@ __global__ void __launch_bounds__(32) fgs_lines_kernel(float* num, float* den, c
     }
 }
 
+// Horizontal pass of the same solver.  Ten rows per warp would read and write 4 scattered bytes per lane
+// and step (one 32-byte sector per useful float, every step of every frame in flight -- measured: a tenth of
+// the whole pipeline's throughput), so the rows move through shared memory in 32-column tiles: 30 coalesced
+// 128-byte cp.async requests bring the next tile of the 3 x 10 row segments in while the current one is being
+// eliminated, results overwrite their inputs in the ring and leave as coalesced 128-byte stores one tile later.
+constexpr int FGS_T = 32;               // tile columns
+constexpr int FGS_RING = 3 * FGS_T;     // ring of three tiles per row segment (processing / prefetch / draining)
+constexpr int FGS_RS = FGS_RING + 1;    // padded segment stride: the 30 lanes of a step hit 30 different banks
+constexpr int FGS_NSEG = 3 * FGS_LPW;
+
+__global__ void __launch_bounds__(32) fgs_rows_kernel(float* num, float* den, const float* __restrict__ wgt,
+                                                      float* Dscr, int w, int h, float lam) {
+    __shared__ float ring[FGS_NSEG * FGS_RS];
+    const int lane = threadIdx.x;
+    const int role = lane / FGS_LPW, li = lane - role * FGS_LPW;
+    const int row0 = blockIdx.x * FGS_LPW;
+    const int nrows = min(FGS_LPW, h - row0);
+    const bool active = role < 3 && li < nrows;
+    const bool r0 = role == 0;
+    const int lag = r0 ? 0 : 1;
+    const int src = li;
+    const int seg = min(role, 2) * FGS_LPW + li;  // lanes 30/31 shadow a real segment (reads only)
+    float* const myring = ring + seg * FGS_RS;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const int ntiles = (w + FGS_T - 1) / FGS_T;
+    auto seg_ptr = [&](int i, bool out) -> float* {  // row segment i = plane i / 10, row i % 10 (clamped: duplicates are never stored)
+        const int pr = i / FGS_LPW, r = row0 + min(i - pr * FGS_LPW, nrows - 1);
+        float* base = pr == 0 ? (out ? Dscr : const_cast<float*>(wgt)) : (pr == 1 ? num : den);
+        return base + (size_t)r * w;
+    };
+    auto load_tile = [&](int T, bool fwd) {  // fwd: weights + num + den; backward: D + num + den
+        const int col = T * FGS_T + lane;
+        if (col < w) {
+#pragma unroll
+            for (int i = 0; i < FGS_NSEG; i++) {
+                const float* g = seg_ptr(i, !fwd) + col;
+                const uint32_t d = ring_s + (uint32_t)(i * FGS_RS + (T % 3) * FGS_T + lane) * 4u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto flush_tile = [&](int T, int first_plane) {
+        const int col = T * FGS_T + lane;
+        if (col < w) {
+#pragma unroll
+            for (int i = 0; i < FGS_NSEG; i++) {
+                if (i < first_plane * FGS_LPW || i - (i / FGS_LPW) * FGS_LPW >= nrows) continue;
+                seg_ptr(i, true)[col] = ring[i * FGS_RS + (T % 3) * FGS_T + lane];
+            }
+        }
+    };
+    // ---- forward elimination: steps j = 0 .. w, roles 1/2 one element behind role 0 (see fgs_lines_kernel)
+    float p = 0.f, cm = 0.f, dn_pub = 1.f, lcm_pub = 0.f;
+    const int nsteps_t = (w + 1 + FGS_T - 1) / FGS_T;
+    load_tile(0, true);
+    for (int T = 0; T < nsteps_t; T++) {
+        if (T + 1 < ntiles) {
+            load_tile(T + 1, true);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int k = 0; k < FGS_T; k++) {
+            const int e = T * FGS_T + k - lag;
+            const bool ok = e >= 0 && e < w;
+            const int slot = ok ? e % FGS_RING : 0;
+            const float x = ok ? myring[slot] : 0.f;
+            const float dn_s = __shfl_sync(0xffffffffu, dn_pub, src);
+            const float lcm_s = __shfl_sync(0xffffffffu, lcm_pub, src);
+            const float t = r0 ? __fmul_rn(lam, cm) : lcm_s;
+            const float prod = __fmul_rn(t, p);
+            const float dn0 = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(lam, __fadd_rn(cm, x))), prod);
+            const float numer = r0 ? __fmul_rn(lam, x) : __fsub_rn(x, prod);
+            const float denom = r0 ? dn0 : dn_s;
+            p = __fdiv_rn(numer, denom);
+            if (active && ok) myring[slot] = p;
+            dn_pub = denom; lcm_pub = t; cm = x;
+        }
+        __syncwarp();
+        if (T >= 1) flush_tile(T - 1, 0);
+        __syncwarp();  // the drained slot is the next iteration's prefetch target
+    }
+    for (int T = nsteps_t - 1; T < ntiles; T++) flush_tile(T, 0);
+    __syncwarp();
+    // ---- back substitution: r_e = r_e - D_e r_{e+1}, e = w-2 .. 0; role 0 lanes supply D by shuffle
+    if (w >= 1) p = myring[(w - 1) % FGS_RING];
+    __syncwarp();
+    load_tile(ntiles - 1, false);
+    for (int T = ntiles - 1; T >= 0; T--) {
+        if (T >= 1) {
+            load_tile(T - 1, false);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int k = FGS_T - 1; k >= 0; k--) {
+            const int e = T * FGS_T + k;
+            const bool ok = e <= w - 2;
+            const int slot = e % FGS_RING;
+            const float x = ok ? myring[slot] : 0.f;
+            const float Dj = __shfl_sync(0xffffffffu, x, src);
+            const float r = __fsub_rn(x, __fmul_rn(Dj, p));
+            if (ok && !r0) {
+                p = r;
+                if (active) myring[slot] = r;
+            }
+        }
+        __syncwarp();
+        flush_tile(T, 1);
+        __syncwarp();
+    }
+}
+
 __global__ void wls_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
                                     const float* __restrict__ conf, int W, int H, int x0, int w, int outside,
                                     int16_t* __restrict__ out, float* __restrict__ conf_out) {
@@ -246,7 +364,7 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     float lam = (float)p.lambda;
     float* Dscr = aR;  // aR/bR are free as well: elimination factors of the current pass
     for (int it = 0; it < 3; it++) {
-        L3D_LAUNCH(L, fgs_lines_kernel<true>, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
+        L3D_LAUNCH(L, fgs_rows_kernel, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
         L3D_LAUNCH(L, fgs_lines_kernel<false>, cdiv(w, FGS_LPW), 32, 0, num, den, cv, Dscr, w, h, lam);
         lam *= 0.25f;
     }
