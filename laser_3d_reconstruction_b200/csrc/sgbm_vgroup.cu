@@ -165,7 +165,7 @@ __device__ __noinline__ bool vg_not_unique(typename VgVec<NP>::T wv, unsigned ke
 }
 
 // NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities); CPW = columns per warp
-template <int NP, int CPW>
+template <int NP, int CPW, bool FINAL>
 __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
     typedef typename VgVec<NP>::T vec;
     constexpr uint32_t INF = 0x7fff7fffu;
@@ -193,10 +193,12 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
     const char* Cg = (const char*)a.C[job];
     char* Sg = (char*)a.S[job];
     const int dir = a.dir;
-    const int final = a.final, uniq = a.uniq[job], minD = a.minD[job], minX1 = a.minX1[job];
+    constexpr bool final = FINAL;  // last pass: WTA on the finished S rows, S not written back
+    const int uniq = a.uniq[job], minD = a.minD[job], minX1 = a.minX1[job];
     int16_t* rawg = a.raw[job];
     unsigned* d2g = a.d2[job];
     const unsigned dkey = (unsigned)(lane * 2 * NP);
+    const unsigned dpair = dkey | ((dkey + 1u) << 8);
 
     // zero both parities of every halo slot: "no predecessor" = (L = 0, min = 0), OpenCV's out-of-image rule
     for (int i = threadIdx.x; i < (int)(4 * VG_WARPS * slot / 4); i += VG_THREADS) ((uint32_t*)haloA)[i] = 0u;
@@ -345,11 +347,13 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
             }
             ss[j * 32] = vg_pack<NP>(Sw);
             if (final) {  // first minimum wins (OpenCV's strict '<' scan over d): packed (cost << 8 | d) key
+                // key = cost << 8 | d: one PRMT per disparity (cost bytes from the S word, d byte and the zero top byte
+                // from a per-lane constant), the minima pair up into 3-input VIMNMX
                 unsigned key = 0xffffffffu;
 #pragma unroll
                 for (int k = 0; k < NP; k++) {
-                    key = min(key, ((Sw[k] << 8) & 0xffff00u) | (dkey + 2 * k));
-                    key = min(key, ((Sw[k] >> 8) & 0xffff00u) | (dkey + 2 * k + 1));
+                    const unsigned dk = dpair + 0x0202u * (unsigned)k;  // byte 0 = d, byte 1 = d + 1, bytes 2-3 = 0
+                    key = min(key, min(__byte_perm(Sw[k], dk, 0x7104), __byte_perm(Sw[k], dk, 0x7325)));
                 }
                 key = __reduce_min_sync(0xffffffffu, key);
                 bool rej = false;
@@ -455,20 +459,23 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
         attr[0].val.clusterDim.x = a.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int rc = L3D_ERR_UNSUPPORTED;
-#define VG_CASE(NPV, CPWV)                                                                                            \
-    if (D == 64 * NPV && a.cpw == CPWV) {                                                                             \
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<NPV, CPWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                                \
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_vgroup_kernel<NPV, CPWV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+#define VG_LAUNCH(KERN)                                                                                               \
+    {                                                                                                                 \
+        L3D_CHECK(L, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        L3D_CHECK(L, cudaFuncSetAttribute(KERN, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));                  \
         if (getenv("L3D_DEBUG_CLUSTERS")) {                                                                           \
             int ncl = -1;                                                                                             \
-            cudaOccupancyMaxActiveClusters(&ncl, sgbm_vgroup_kernel<NPV, CPWV>, &cfg);                                \
-            fprintf(stderr, "[l3d] vgroup<%d,%d> cluster %d: max active clusters %d\n", NPV, CPWV, a.cluster, ncl); \
+            cudaOccupancyMaxActiveClusters(&ncl, KERN, &cfg);                                                         \
+            fprintf(stderr, "[l3d] %s cluster %d: max active clusters %d\n", #KERN, a.cluster, ncl);                 \
         }                                                                                                             \
-        if (!dbg_skip("sgbm_vgroup_kernel"))                                                                          \
-            L3D_CHECK(L, cudaLaunchKernelEx(&cfg, sgbm_vgroup_kernel<NPV, CPWV>, a));                                 \
+        if (!dbg_skip("sgbm_vgroup_kernel")) L3D_CHECK(L, cudaLaunchKernelEx(&cfg, KERN, a));                         \
         L.launches++;                                                                                                 \
         rc = L3D_OK;                                                                                                  \
+    }
+#define VG_CASE(NPV, CPWV)                                                                                            \
+    if (D == 64 * NPV && a.cpw == CPWV) {                                                                             \
+        if (a.final) VG_LAUNCH((sgbm_vgroup_kernel<NPV, CPWV, true>))                                                 \
+        else VG_LAUNCH((sgbm_vgroup_kernel<NPV, CPWV, false>))                                                        \
     }
 #define VG_NP(NPV) VG_CASE(NPV, 1) VG_CASE(NPV, 2) VG_CASE(NPV, 3) VG_CASE(NPV, 4) VG_CASE(NPV, 5) VG_CASE(NPV, 6) \
                    VG_CASE(NPV, 7) VG_CASE(NPV, 8) VG_CASE(NPV, 9)
@@ -476,6 +483,7 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
         VG_CASE(4, 1) VG_CASE(4, 2) VG_CASE(4, 3) VG_CASE(4, 4)
 #undef VG_NP
 #undef VG_CASE
+#undef VG_LAUNCH
         if (rc != L3D_OK) return rc;
     }
     return L3D_OK;
