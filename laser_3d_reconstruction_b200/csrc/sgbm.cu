@@ -210,10 +210,13 @@ __device__ __forceinline__ void cost_bulk_g2s(uint32_t dst, const void* src, uin
 }
 
 // NIT: phase A items (disparity pairs) per thread and row when known at compile time (D/2 / (512/TXH)), 0 = generic
-template <int NIT>
+// BS:  blockSize when known at compile time (phase B then keeps its window in registers), 0 = generic
+// DD:  numDisparities, TXHT: tile width incl. halo when known at compile time (all strides become immediates), 0 = generic
+template <int NIT, int BS, int DD, int TXHT>
 __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int TX = a.TX, TXH = a.TXH, SW2 = a.SW2, bs = a.bs, D = a.D, D2 = D >> 1;
+    const int bs = BS ? BS : a.bs, SW2 = BS ? BS / 2 : a.SW2, D = DD ? DD : a.D, D2 = D >> 1;
+    const int TXH = TXHT ? TXHT : a.TXH, TX = TXH - 2 * SW2;
     const int width1 = a.width1, W = a.W;
     const int tid = threadIdx.x;
     const int b = blockIdx.y, x0 = blockIdx.x * TX;
@@ -284,11 +287,23 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
         uint32_t* pdp = pdb + (k & 1) * D2 * PS + dpa0 * PS + ca;
         const int rstep = 2 * dpa_step, pstep = dpa_step * PS;
         if (NIT) {
+            // batches of 4 items: all table loads first (the compiler cannot hoist them over the pd stores itself,
+            // both are shared-memory accesses), then the arithmetic, then the stores
+            constexpr int NB = 4;
 #pragma unroll
-            for (int i = 0; i < (NIT ? NIT : 1); i++) {
-                const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, r0p[-i * rstep]);
-                const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, r1p[-i * rstep]);
-                pdp[i * pstep] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+            for (int i0 = 0; i0 < (NIT ? NIT : 1); i0 += NB) {
+                uint4 e0[NB], e1[NB];
+#pragma unroll
+                for (int i = 0; i < NB; i++) { e0[i] = r0p[-(i0 + i) * rstep]; e1[i] = r1p[-(i0 + i) * rstep]; }
+                uint32_t c[NB];
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
+                    const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
+                    c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                }
+#pragma unroll
+                for (int i = 0; i < NB; i++) pdp[(i0 + i) * pstep] = c[i];
             }
         } else {
 #pragma unroll 4
@@ -308,7 +323,35 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
     const size_t crow = (size_t)width1 * D2;
     int slot = 0;                                               // ring slot of row k (k % bs without the division)
     auto phase_b = [&](int k) {
-        if (ncb > 0) {
+        if (BS && ncb > 0) {
+            // all shared-memory loads first (window taps, ring entries that drop out), then the sums, then the stores:
+            // the compiler cannot move a load over the ring stores by itself
+            const uint32_t* pp = ppb + (k & 1) * D2 * PS;       // pp[j + i]: output column cb0 + j, tap i
+            uint32_t* rp = rpb + (size_t)slot * TX * D2;
+            const bool sub = k >= bs, emit = k >= bs - 1;
+            constexpr int NV = COST_MAXCPG + (BS ? BS : 1) - 1;
+            uint32_t pv[NV], old[COST_MAXCPG], hs[COST_MAXCPG];
+#pragma unroll
+            for (int i = 0; i < NV; i++) pv[i] = pp[i];         // taps beyond this group's columns are never used
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) old[j] = (sub && j < ncb) ? rp[j * D2] : 0u;
+            uint32_t h = 0;
+#pragma unroll
+            for (int i = 0; i < (BS ? BS : 1); i++) h += pv[i];
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j > 0) h = h + pv[j + (BS ? BS : 1) - 1] - pv[j - 1];
+                hs[j] = h;
+                crun[j] = crun[j] + h - old[j];
+            }
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j < ncb) {
+                    rp[j * D2] = hs[j];
+                    if (emit) Cdst[j * D2] = crun[j];
+                }
+            }
+        } else if (ncb > 0) {
             const uint32_t* pp = ppb + (k & 1) * D2 * PS;       // pp[j + i]: output column cb0 + j, tap i
             uint32_t h = 0;
 #pragma unroll 3
@@ -1013,12 +1056,16 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
     const int dpa_step = COST_THREADS / TXH;
     const int nit = (D2 % dpa_step == 0) ? D2 / dpa_step : 0;
     L.t_begin("sgbm_cost");
-#define COST_CASE(NITV)                                                                                                   \
-    {                                                                                                                     \
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_cost_kernel<NITV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
-        L3D_LAUNCH(L, sgbm_cost_kernel<NITV>, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);                           \
+#define COST_CASE(KERN)                                                                                          \
+    {                                                                                                            \
+        L3D_CHECK(L, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));       \
+        L3D_LAUNCH(L, KERN, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);                                    \
     }
-    if (nit == 8) COST_CASE(8) else if (nit == 4) COST_CASE(4) else COST_CASE(0)
+    // specialised for the configurations of BASELINE.json (c3: D 128 / block 9, c1-c2: D 64 / block 5, c4: D 256 / block 11)
+    if (nit == 8 && g.bs == 9 && g.D == 128 && TXH == 64) COST_CASE((sgbm_cost_kernel<8, 9, 128, 64>))
+    else if (nit == 4 && g.bs == 5 && g.D == 64 && TXH == 64) COST_CASE((sgbm_cost_kernel<4, 5, 64, 64>))
+    else if (nit == 8 && g.bs == 11 && g.D == 256 && TXH == 32) COST_CASE((sgbm_cost_kernel<8, 11, 256, 32>))
+    else COST_CASE((sgbm_cost_kernel<0, 0, 0, 0>))
 #undef COST_CASE
     L.t_end("sgbm_cost");
     r.d2 = L.get<unsigned>(set ? S_DISP22 : S_DISP2, (size_t)H * (W + 2));
