@@ -383,6 +383,169 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
 }
 
 // ------------------------------------------------------------------------------------------
+// cost volume, warp-decoupled form (numDisparities 64 / 128, 64-column tiles)
+// ------------------------------------------------------------------------------------------
+// Same tile / band decomposition and the same arithmetic as sgbm_cost_kernel, but the disparity pairs are split
+// over the 16 warps (DPW = D/32 pairs each) and BOTH phases of a pair stay in one warp: the warp computes the pixel
+// costs of its pairs for all 64 tile columns (lane <-> columns lane and lane + 32), writes them to a private strip
+// of shared memory, and sums them itself (lane <-> pair x group of columns) against a private ring of row sums.
+// There is no block-wide barrier in the row loop: warps only meet at the mbarriers of the operand-table ring
+// (full: TMA bulk copies landed; empty: all 16 warps are done reading a stage) and drift apart by up to
+// CW_NS - 1 rows, so one warp's shared-memory latency is covered by another warp's arithmetic.  The left operands
+// come in with the same bulk copies (contiguous run of the tile's columns; replicate-clamped tile edges index the
+// run with a clamped column).  A warp stores DPW * 4 contiguous bytes per pixel; the 16 warps' pieces of a pixel's
+// vector meet in L2 before they reach HBM.
+constexpr int CW_NS = 4;        // operand-table stages
+constexpr int CW_TXH = 64;      // tile width incl. halo
+constexpr int CW_PDS = 88;      // pixel-cost strip stride per pair (== 24 mod 32: phase B's 32 lanes hit 32 banks)
+
+static size_t cost_warp_smem(int D, int bs) {
+    const int D2 = D / 2, TX = CW_TXH - (bs - 1);
+    return (size_t)CW_NS * (2 * (CW_TXH + D) + 2 * CW_TXH) * 16 + (size_t)D2 * CW_PDS * 4 + (size_t)bs * D2 * TX * 4 + 64;
+}
+
+template <int BS, int DD>
+__global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const CostArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int D = DD, D2 = DD / 2, SW2 = BS / 2, TXH = CW_TXH, TX = TXH - 2 * SW2;
+    constexpr int NW = COST_THREADS / 32, DPW = D2 / NW, NG = 32 / DPW, CPG = (TX + NG - 1) / NG;
+    constexpr int NEMAX = TXH + D;                      // right-operand entries per channel and stage
+    constexpr int STAGE_U4 = 2 * NEMAX + 2 * TXH;       // [R0 | R1 | L0 | L1]
+    static_assert(DPW >= 1 && 32 % DPW == 0 && CPG <= COST_MAXCPG, "tile geometry");
+    const int width1 = a.width1, W = a.W;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int b = blockIdx.y, x0 = blockIdx.x * TX;
+    const int y0 = a.band_y0[b], rows = a.band_rows[b], clo = a.band_clo[b], chi = a.band_chi[b], vr0 = a.band_vr0[b];
+    const int xa = min(max(x0 - SW2, 0), width1 - 1);
+    const int xb = min(max(x0 + TXH - 1 - SW2, 0), width1 - 1);
+    const int xr_base = xa + a.minX1 - (a.minD + D - 1);
+    const int nE = (xb - xa) + D - 1;
+    const size_t plane = (size_t)W * a.H;
+    // contiguous run of left columns this tile reads: tile columns [lc0, lc1) hold image columns x0 - SW2 + c unclamped
+    const int lc0 = max(0, SW2 - x0), lc1 = min(TXH, width1 - (x0 - SW2));
+    uint4* tabs = (uint4*)smem_raw;                                          // [CW_NS][STAGE_U4]
+    uint32_t* pdw = (uint32_t*)(tabs + CW_NS * STAGE_U4) + warp * DPW * CW_PDS;  // this warp's pixel-cost strip [DPW][CW_PDS]
+    uint32_t* ringw = (uint32_t*)(tabs + CW_NS * STAGE_U4) + D2 * CW_PDS + (size_t)warp * BS * DPW * TX;  // [BS][DPW][TX]
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared((uint32_t*)(tabs + CW_NS * STAGE_U4) + D2 * CW_PDS + (size_t)BS * D2 * TX);
+    // bars + 8 s: full[s], bars + 8 (CW_NS + s): empty[s]
+    const int nk = rows + BS - 1;
+    auto row_of = [&](int k) { return min(max(y0 - SW2 + k, clo), chi); };
+    auto issue_tables = [&](int k) {  // one thread: operand entries of band row k -> stage k % CW_NS
+        const int s = k % CW_NS;
+        const uint32_t bar = bars + 8 * s;
+        const uint32_t rbytes = (uint32_t)nE * 16u, lbytes = (uint32_t)(lc1 - lc0) * 16u;
+        const size_t ro = (size_t)row_of(k) * W;
+        const uint4* rsrc = a.Rdesc + ro + xr_base;
+        const uint4* lsrc = a.Ldesc + ro + (x0 - SW2 + lc0) + a.minX1;
+        uint4* dst = tabs + s * STAGE_U4;
+        cost_mbar_expect_tx(bar, 2 * rbytes + 2 * lbytes);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), rsrc, rbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + NEMAX), rsrc + plane, rbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + 2 * NEMAX + lc0), lsrc, lbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + 2 * NEMAX + TXH + lc0), lsrc + plane, lbytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CW_NS; s++) { cost_mbar_init(bars + 8 * s, 1); cost_mbar_init(bars + 8 * (CW_NS + s), NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < CW_NS - 1 && k < nk; k++) issue_tables(k);
+    }
+    __syncthreads();  // barrier init visible; the only block-wide barrier of the kernel
+
+    // phase A role: tile columns lane and lane + 32, pairs dp0 .. dp0 + DPW - 1
+    const int dp0 = warp * DPW;
+    int eoff[2], lcol[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+        const int c = lane + 32 * hh;
+        const int xc = min(max(x0 - SW2 + c, 0), width1 - 1);
+        eoff[hh] = xc - xa + D - 2 - 2 * dp0;               // entry of pair dp0; pair dp0 + i is 2 i entries lower
+        lcol[hh] = min(max(c, lc0), lc1 - 1);               // replicate clamp inside the staged run
+    }
+    // phase B role
+    const int dpi = lane % DPW, g = lane / DPW;
+    const int cb0 = g * CPG;
+    const int ncb = max(0, min(min(CPG, TX - cb0), width1 - (x0 + cb0)));
+    const uint32_t p2x2 = (uint32_t)a.P2 * 0x10001u;
+    uint32_t crun[CPG];
+#pragma unroll
+    for (int j = 0; j < CPG; j++) crun[j] = p2x2;
+    uint32_t* Cdst = (uint32_t*)(a.C + ((ptrdiff_t)(vr0 - (BS - 1)) * width1 + x0 + cb0) * D) + dp0 + dpi;
+    const size_t crow = (size_t)width1 * D2;
+    const uint32_t* ppb = pdw + dpi * CW_PDS + cb0;
+    uint32_t* rpb = ringw + dpi * TX + cb0;
+    int slot = 0;
+
+    for (int k = 0; k < nk; k++) {
+        const int s = k % CW_NS;
+        // refill duty: rows' tables are issued CW_NS - 1 rows ahead by the warp whose turn it is
+        if (warp == (k & (NW - 1)) && k + CW_NS - 1 < nk) {
+            if (lane == 0) {
+                const int kk = k + CW_NS - 1, sk = kk % CW_NS;  // stage last read for row k - 1
+                if (k >= 1) cost_mbar_wait(bars + 8 * (CW_NS + sk), (uint32_t)(((k - 1) / CW_NS) & 1));
+                issue_tables(kk);
+            }
+            __syncwarp();
+        }
+        cost_mbar_wait(bars + 8 * s, (uint32_t)((k / CW_NS) & 1));
+        const uint4* T0 = tabs + s * STAGE_U4;
+        // ---- phase A
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const uint4 l0 = T0[2 * NEMAX + lcol[hh]], l1 = T0[2 * NEMAX + TXH + lcol[hh]];
+            const uint32_t u0 = __byte_perm(l0.x, l0.x, 0x3232), nu0 = __byte_perm(l0.y, l0.y, 0x3232);
+            const uint32_t ul0 = __byte_perm(l0.z, l0.z, 0x3232), nuh0 = __byte_perm(l0.w, l0.w, 0x3232);
+            const uint32_t u1 = __byte_perm(l1.x, l1.x, 0x3232), nu1 = __byte_perm(l1.y, l1.y, 0x3232);
+            const uint32_t ul1 = __byte_perm(l1.z, l1.z, 0x3232), nuh1 = __byte_perm(l1.w, l1.w, 0x3232);
+            uint4 e0[DPW], e1[DPW];
+#pragma unroll
+            for (int i = 0; i < DPW; i++) { e0[i] = T0[eoff[hh] - 2 * i]; e1[i] = T0[NEMAX + eoff[hh] - 2 * i]; }
+            uint32_t c[DPW];
+#pragma unroll
+            for (int i = 0; i < DPW; i++) {
+                const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
+                const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
+                c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+            }
+#pragma unroll
+            for (int i = 0; i < DPW; i++) pdw[i * CW_PDS + lane + 32 * hh] = c[i];
+        }
+        __syncwarp();  // strip complete; every lane's table reads have returned
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (CW_NS + s)) : "memory");
+        // ---- phase B
+        if (ncb > 0) {
+            uint32_t* rp = rpb + (size_t)slot * DPW * TX;
+            const bool sub = k >= BS, emit = k >= BS - 1;
+            constexpr int NV = CPG + BS - 1;
+            uint32_t pv[NV], old[CPG], hs[CPG];
+#pragma unroll
+            for (int i = 0; i < NV; i++) pv[i] = ppb[i];
+#pragma unroll
+            for (int j = 0; j < CPG; j++) old[j] = (sub && j < ncb) ? rp[j] : 0u;
+            uint32_t h = 0;
+#pragma unroll
+            for (int i = 0; i < BS; i++) h += pv[i];
+#pragma unroll
+            for (int j = 0; j < CPG; j++) {
+                if (j > 0) h = h + pv[j + BS - 1] - pv[j - 1];
+                hs[j] = h;
+                crun[j] = crun[j] + h - old[j];
+            }
+#pragma unroll
+            for (int j = 0; j < CPG; j++) {
+                if (j < ncb) {
+                    rp[j] = hs[j];
+                    if (emit) Cdst[(size_t)j * D2] = crun[j];
+                }
+            }
+        }
+        __syncwarp();  // the strip is rewritten by the next row's phase A
+        Cdst += crow;
+        slot = slot + 1 == BS ? 0 : slot + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // directional aggregation scan
 // ------------------------------------------------------------------------------------------
 struct ScanArgs {
@@ -1053,6 +1216,14 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
         }
     }
     size_t smem = cost_smem(TXH);
+    static const bool no_warp_cost = getenv("L3D_COST_CLASSIC") != nullptr;
+    const bool warp_form = !no_warp_cost && ((g.D == 128 && g.bs == 9) || (g.D == 64 && g.bs == 5));
+    if (warp_form) {
+        // warp-decoupled form: 64-column tiles; band split as above
+        ca.TXH = CW_TXH; ca.TX = CW_TXH - 2 * g.SW2;
+        xtiles = cdiv(g.width1, ca.TX);
+        smem = cost_warp_smem(g.D, g.bs);
+    }
     const int dpa_step = COST_THREADS / TXH;
     const int nit = (D2 % dpa_step == 0) ? D2 / dpa_step : 0;
     L.t_begin("sgbm_cost");
@@ -1062,7 +1233,9 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
         L3D_LAUNCH(L, KERN, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);                                    \
     }
     // specialised for the configurations of BASELINE.json (c3: D 128 / block 9, c1-c2: D 64 / block 5, c4: D 256 / block 11)
-    if (nit == 8 && g.bs == 9 && g.D == 128 && TXH == 64) COST_CASE((sgbm_cost_kernel<8, 9, 128, 64>))
+    if (warp_form && g.D == 128) COST_CASE((sgbm_cost_warp_kernel<9, 128>))
+    else if (warp_form) COST_CASE((sgbm_cost_warp_kernel<5, 64>))
+    else if (nit == 8 && g.bs == 9 && g.D == 128 && TXH == 64) COST_CASE((sgbm_cost_kernel<8, 9, 128, 64>))
     else if (nit == 4 && g.bs == 5 && g.D == 64 && TXH == 64) COST_CASE((sgbm_cost_kernel<4, 5, 64, 64>))
     else if (nit == 8 && g.bs == 11 && g.D == 256 && TXH == 32) COST_CASE((sgbm_cost_kernel<8, 11, 256, 32>))
     else COST_CASE((sgbm_cost_kernel<0, 0, 0, 0>))
