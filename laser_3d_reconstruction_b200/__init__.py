@@ -9,8 +9,9 @@ from .core.laser_extractor import FastStegerExtractor, SimpleLaserExtractor
 from .core.reconstruction import Reconstructor
 from .improved_reconstruction import ImprovedLaserReconstructor, fix_roi_alignment
 from .improved_steger import HybridLaserExtractor, ImprovedStegerExtractor, StegerLaserExtractor
+from .system import LaserReconstructionSystem
 
 __version__ = "0.1.0"
 __all__ = ["SingleUSBStereoCameraManager", "SimpleLaserExtractor", "FastStegerExtractor", "ImprovedStegerExtractor",
            "StegerLaserExtractor", "HybridLaserExtractor", "Reconstructor", "ImprovedLaserReconstructor",
-           "fix_roi_alignment", "Config"]
+           "fix_roi_alignment", "Config", "LaserReconstructionSystem"]

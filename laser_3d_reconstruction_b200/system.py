@@ -1,0 +1,171 @@
+"""LaserReconstructionSystem -- the immediate caller of the hot path (reference main.py:40-189).
+
+`initialize` / `process_frame` keep the reference's names, flow, prints-and-False error behaviour and
+the accumulation rule (rows with a NaN are dropped, main.py:181-184).  `process_frames` is the
+batched, device-resident form of the same loop: many already captured stereo pairs go through
+`l3d_pipeline_*` (rectify -> SGBM x2 -> WLS -> depth -> extractor -> reconstruct_from_depth without a
+host round trip between the stages) and produce exactly what calling `process_frame` once per pair
+produces.  The point-cloud sink (`utils/point_cloud.py`, Open3D) stays out of scope: the
+system only accumulates the points.
+"""
+import numpy as np
+
+from . import _native as N
+from . import pipeline as _pl
+from .camera.single_usb_stereo_camera import SingleUSBStereoCameraManager
+from .config import Config
+from .core.laser_extractor import FastStegerExtractor, SimpleLaserExtractor
+from .core.reconstruction import Reconstructor
+
+
+class LaserReconstructionSystem:
+    """reference main.py:40-56 (attributes), :58-162 (initialize), :164-189 (process_frame)."""
+
+    def __init__(self, config=None, verbose=True):
+        self.config = config or Config()
+        self.camera = None
+        self.laser_extractor = None
+        self.reconstructor = None
+        self.point_cloud_processor = None  # Open3D sink: out of scope, kept as an attribute for drop-in code
+        self.point_cloud = []
+        self.frame_count = 0
+        self.start_time = None
+        self.show_depth = True
+        self.verbose = verbose
+        self._pipe = None
+        self._pipe_key = None
+
+    def _say(self, *a):
+        if self.verbose:
+            print(*a)
+
+    # ---- reference :58-162 ------------------------------------------------------------------
+    def initialize(self, camera_id=None, width=None, height=None, camera=None):
+        """`camera`: an already initialised SingleUSBStereoCameraManager (offline / batch use); otherwise the
+        capture device is opened like the reference does (returns False without one)."""
+        cfg = self.config
+        camera_id = camera_id if camera_id is not None else cfg.SINGLE_USB_CAMERA_ID
+        width = width or cfg.CAMERA_WIDTH
+        height = height or cfg.CAMERA_HEIGHT
+        try:
+            if camera is not None:
+                self.camera = camera
+            else:
+                self.camera = SingleUSBStereoCameraManager(camera_id=camera_id, width=width, height=height,
+                                                           fps=cfg.CAMERA_FPS, split_mode=cfg.SPLIT_MODE,
+                                                           calibration_file=cfg.STEREO_CALIBRATION_FILE,
+                                                           verbose=self.verbose)
+                if not self.camera.initialize():
+                    print("❌ 相机初始化失败")
+                    return False
+        except Exception as e:  # the reference reports and returns False
+            print(f"❌ 相机初始化错误: {e}")
+            return False
+        try:
+            if cfg.LASER_EXTRACTOR_TYPE == 'simple':
+                self.laser_extractor = SimpleLaserExtractor(hsv_lower=cfg.SIMPLE_LASER_HSV_LOWER,
+                                                            hsv_upper=cfg.SIMPLE_LASER_HSV_UPPER,
+                                                            brightness_threshold=cfg.SIMPLE_LASER_BRIGHTNESS_THRESHOLD,
+                                                            min_area=cfg.SIMPLE_LASER_MIN_AREA)
+            else:
+                self.laser_extractor = FastStegerExtractor(sigma=cfg.STEGER_SIGMA,
+                                                           brightness_threshold=cfg.STEGER_BRIGHTNESS_THRESHOLD,
+                                                           use_lut=cfg.STEGER_USE_LUT)
+        except Exception as e:
+            print(f"❌ 激光提取器初始化错误: {e}")
+            return False
+        try:
+            intr = self.camera.get_camera_intrinsics()
+            if intr is None:
+                print("❌ 无法获取相机内参")
+                return False
+            K = np.array([[intr['fx'], 0, intr['cx']], [0, intr['fy'], intr['cy']], [0, 0, 1]], dtype=np.float64)
+            self.reconstructor = Reconstructor(camera_intrinsic=K, laser_plane=cfg.LASER_PLANE_COEFFICIENTS,
+                                               use_refraction_correction=cfg.USE_REFRACTION_CORRECTION)
+        except Exception as e:
+            print(f"❌ 重建器初始化错误: {e}")
+            return False
+        self._say("✅ 系统初始化完成!")
+        return True
+
+    # ---- reference :164-189 -----------------------------------------------------------------
+    def process_frame(self):
+        color_image, depth_image = self.camera.get_frames()
+        if color_image is None:
+            return None, None, None
+        laser_points = self.laser_extractor.extract_centerline(color_image)
+        self._accumulate(laser_points, depth_image)
+        self.frame_count += 1
+        return color_image, depth_image, laser_points
+
+    def _accumulate(self, laser_points, depth_image):
+        if len(laser_points) > 0 and depth_image is not None:
+            points_3d = self.reconstructor.reconstruct_from_depth(laser_points, depth_image)
+            if len(points_3d) > 0:
+                valid_mask = ~np.isnan(points_3d).any(axis=1)
+                points_3d = points_3d[valid_mask]
+                self.point_cloud.extend(points_3d.tolist())
+
+    # ---- batched, device-resident form ---------------------------------------------------------
+    def _pipeline(self, lanes):
+        cam = self.camera
+        W, H = cam.single_width, cam.single_height
+        dcfg = cam._depth_config()
+        simple = isinstance(self.laser_extractor, SimpleLaserExtractor)
+        ex = self.laser_extractor
+        key = (W, H, lanes, simple, bytes(dcfg))
+        if self._pipe is not None and self._pipe_key == key:
+            return self._pipe
+        if self._pipe is not None:
+            self._pipe.close()
+        cap = max(H, 20000)
+        if simple:
+            pc = _pl.make_pipeline_config(W, H, dcfg.left.numDisparities, dcfg.left.blockSize, dcfg.left.mode, None,
+                                          self.reconstructor.K, extractor=N.EXTRACT_SIMPLE, lanes=lanes, max_points=cap,
+                                          bright_thr=int(ex.brightness_threshold), hsv_lo=tuple(int(v) for v in ex.hsv_lower),
+                                          hsv_hi=tuple(int(v) for v in ex.hsv_upper), min_area=float(ex.min_area))
+        else:
+            pc = _pl.make_pipeline_config(W, H, dcfg.left.numDisparities, dcfg.left.blockSize, dcfg.left.mode, None,
+                                          self.reconstructor.K, extractor=N.STEGER_FAST, lanes=lanes, max_points=cap,
+                                          sigma=float(ex.sigma), bright_thr=int(ex.brightness_threshold))
+        pc.depth = dcfg  # exactly the camera's matcher / WLS / Q configuration
+        maps = None
+        if dcfg.use_maps:
+            maps = (cam.map_left_x, cam.map_left_y, cam.map_right_x, cam.map_right_y)
+        self._pipe = _pl.FramePipeline(pc, maps=maps, device=cam.device)
+        self._pipe_key = key
+        return self._pipe
+
+    def process_frames(self, frames=None, lefts=None, rights=None, lanes=8, want_images=True):
+        """Batched `process_frame`: `frames` = side-by-side captures (n, H, 2W, 3) as `cap.read()` delivers them, or
+        `lefts` / `rights` = already split views (n, H, W, 3).  Returns a list of (color_image, depth_image,
+        laser_points) per frame (images omitted when `want_images` is False) and accumulates the valid 3D points in
+        `self.point_cloud` in frame order, exactly as n calls of `process_frame` would."""
+        if frames is not None:
+            pairs = [self.camera._split_frame(f) for f in frames]
+            lefts = np.stack([np.ascontiguousarray(p[0]) for p in pairs])
+            rights = np.stack([np.ascontiguousarray(p[1]) for p in pairs])
+        lefts = np.ascontiguousarray(lefts, np.uint8)
+        rights = np.ascontiguousarray(rights, np.uint8)
+        n = lefts.shape[0]
+        fp = self._pipeline(lanes)
+        fp.run_host(lefts, rights)
+        out = []
+        for i in range(n):
+            got = fp.fetch(i)
+            pts2 = [(np.float64(x), np.float64(y)) for x, y in got["points_2d"]] if isinstance(
+                self.laser_extractor, SimpleLaserExtractor) else [(x, y) for x, y in got["points_2d"]]
+            p3 = got["points_3d"]
+            if len(p3) > 0:
+                p3 = p3[~np.isnan(p3).any(axis=1)]
+                self.point_cloud.extend(p3.tolist())
+            self.frame_count += 1
+            out.append((got["left_rect"], got["depth"], pts2) if want_images else (None, None, pts2))
+        return out
+
+    def stop(self):
+        if self._pipe is not None:
+            self._pipe.close()
+            self._pipe = None
+        if self.camera is not None:
+            self.camera.stop()
