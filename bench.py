@@ -222,7 +222,7 @@ def run_gpu(args, rank, world, local_rank):
             return None
         table = torch.empty((max(int(np.sum(counts)), 1), 4), dtype=torch.float64, device=dev)
         rows = fp.pack_points_dev(mine, table.data_ptr())  # device-side pack; nothing goes through the host
-        return sharding.gather_point_clouds(table[:rows], device=dev)
+        return sharding.gather_point_clouds(table[:rows], device=dev, to_host=False)  # stays on rank 0's GPU
 
     def step_dev():
         counts = fp.run_dev(dL, dR, nfr)

@@ -34,10 +34,12 @@ def unpack_clouds(table, nframes):
     return [table[bounds[f]:bounds[f + 1], 1:] for f in range(nframes)]
 
 
-def gather_point_clouds(table, device=None, group=None, dst=0):
+def gather_point_clouds(table, device=None, group=None, dst=0, to_host=True):
     """Gather each rank's packed (N_r x 4) table to rank `dst`.  Returns the concatenated table on
     dst and None elsewhere.  Works with any initialised torch.distributed backend; `device` is the
-    torch device the backend needs its tensors on (cuda:<local_rank> for nccl, cpu for gloo)."""
+    torch device the backend needs its tensors on (cuda:<local_rank> for nccl, cpu for gloo).
+    `to_host=False` leaves the gathered table on dst's device (a torch tensor): the exchange then costs the
+    collective only, no device-to-host copy of the whole job's point clouds per step."""
     import torch
     import torch.distributed as dist
 
@@ -57,11 +59,14 @@ def gather_point_clouds(table, device=None, group=None, dst=0):
     dist.all_gather(counts, n, group=group)
     counts = [int(c.item()) for c in counts]
     nmax = max(max(counts), 1)
-    padded = torch.zeros((nmax, 4), dtype=torch.float64, device=dev)
+    padded = torch.empty((nmax, 4), dtype=torch.float64, device=dev)
     padded[:t.shape[0]] = t
+    padded[t.shape[0]:] = 0
     if rank == dst:
-        bufs = [torch.zeros_like(padded) for _ in range(world)]
+        bufs = [torch.empty_like(padded) for _ in range(world)]
         dist.gather(padded, bufs, dst=dst, group=group)
+        if not to_host:
+            return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
         return np.concatenate([b[:c].cpu().numpy() for b, c in zip(bufs, counts)], axis=0)
     dist.gather(padded, None, dst=dst, group=group)
     return None
