@@ -101,24 +101,23 @@ __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __
 // Roles 1/2 run one element behind role 0 and receive (dn, lam c_{j-1}) of their element by warp shuffle, so
 // a step costs the warp ONE IEEE division sequence for all three quotients and the serial chain per
 // element is fmul -> fsub -> fdiv.  The zero initial state reproduces the oracle's special-cased first
-// element bit for bit (x + 0, x - 0 and 0 * 0 are exact).  A warp carries FGS_LPW lines and streams
-// straight from/to global memory (L1 turns the per-row 4-byte accesses of the horizontal pass into one
-// sector fetch per 8 steps; the vertical pass is coalesced): no shared memory, 72-116 one-warp CTAs per
-// pass, so the solver leaves every SM free for the matcher kernels of the other frames in flight.
-// D goes to a scratch plane for the back substitution (role 0 reloads it, shuffles it to roles 1/2).
+// element bit for bit (x + 0, x - 0 and 0 * 0 are exact).  A warp carries FGS_LPW lines.  This kernel is the
+// vertical pass: lines are image columns, a step reads and writes three runs of FGS_LPW adjacent floats
+// straight from/to global memory -- no shared memory, one-warp CTAs (116 at config 3), so the solver leaves
+// every SM free for the matcher kernels of the other frames in flight.  D goes to a scratch plane for the
+// back substitution (role 0 reloads it and shuffles it to roles 1/2).
 constexpr int FGS_LPW = 10;   // lines per warp: lanes [0,10) role 0, [10,20) role 1, [20,30) role 2
 constexpr int FGS_BLK = 8;    // elements per register block (the next block is prefetched during the current one)
 
-template <bool HORIZ>
-__global__ void __launch_bounds__(32) fgs_lines_kernel(float* num, float* den, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(32) fgs_cols_kernel(float* num, float* den, const float* __restrict__ wgt,
                                                        float* Dscr, int w, int h, float lam) {
-    const int nlines = HORIZ ? h : w, len = HORIZ ? w : h;
+    const int nlines = w, len = h;  // lines are image columns (the row pass is fgs_rows_kernel below)
     const int lane = threadIdx.x;
     const int role = lane / FGS_LPW, li = lane - role * FGS_LPW;
     const int line = min(blockIdx.x * FGS_LPW + li, nlines - 1);
     const bool active = role < 3 && blockIdx.x * FGS_LPW + li < nlines;
     const int src = li;                                   // role-0 lane of this lane's line
-    const size_t ls = HORIZ ? (size_t)w : 1, es = HORIZ ? 1 : (size_t)w;
+    const size_t ls = 1, es = (size_t)w;
     const float* in = role == 0 ? wgt : (role == 1 ? num : den);
     float* out = role == 0 ? Dscr : (role == 1 ? num : den);
     in += (size_t)line * ls; out += (size_t)line * ls;
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(32) fgs_rows_kernel(float* num, float* den, co
             }
         }
     };
-    // ---- forward elimination: steps j = 0 .. w, roles 1/2 one element behind role 0 (see fgs_lines_kernel)
+    // ---- forward elimination: steps j = 0 .. w, roles 1/2 one element behind role 0 (see fgs_cols_kernel)
     float p = 0.f, cm = 0.f, dn_pub = 1.f, lcm_pub = 0.f;
     const int nsteps_t = (w + 1 + FGS_T - 1) / FGS_T;
     load_tile(0, true);
@@ -365,7 +364,7 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     float* Dscr = aR;  // aR/bR are free as well: elimination factors of the current pass
     for (int it = 0; it < 3; it++) {
         L3D_LAUNCH(L, fgs_rows_kernel, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
-        L3D_LAUNCH(L, fgs_lines_kernel<false>, cdiv(w, FGS_LPW), 32, 0, num, den, cv, Dscr, w, h, lam);
+        L3D_LAUNCH(L, fgs_cols_kernel, cdiv(w, FGS_LPW), 32, 0, num, den, cv, Dscr, w, h, lam);
         lam *= 0.25f;
     }
     L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, num, den, conf, W, H, x0, w, outside, out, conf_out);

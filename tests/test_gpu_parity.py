@@ -444,3 +444,32 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
     wrect, wdepth, aux = ref_ops.depth_path(frames[8][0], frames[8][1], maps, D, bs, mode, Q, want_all=True)
     diff = np.abs(results[14][8]["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
     assert (diff <= 1).mean() >= 0.999
+
+
+def test_cost_kernel_block_synchronous_form():
+    """The block-synchronous cost kernel (L3D_COST_CLASSIC=1; the default for D = 64 / 128 is the warp-decoupled form)
+    still gives cv2's bits at the c1 and c3 geometries.  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np, cv2
+sys.path.insert(0, %r)
+from laser_3d_reconstruction_b200 import _native as N, synth
+ctx = N.Context(0)
+for (W, H, D, bs, mode) in ((320, 360, 64, 5, 0), (1280, 720, 128, 9, 1)):
+    l, r = synth.stereo_pair(W, H, D, seed=5)
+    lg, rg = cv2.cvtColor(l, cv2.COLOR_BGR2GRAY), cv2.cvtColor(r, cv2.COLOR_BGR2GRAY)
+    for minD, a, b in ((0, lg, rg), (-(D - 1), rg, lg)):
+        p = N.SgbmParams(minD, D, bs, 24 * bs * bs, 96 * bs * bs, 1, 63, 10, 100, 32, mode)
+        want = cv2.StereoSGBM_create(minDisparity=minD, numDisparities=D, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs,
+                                     disp12MaxDiff=1, preFilterCap=63, uniquenessRatio=10, speckleWindowSize=100,
+                                     speckleRange=32, mode=mode).compute(a, b)
+        got = ctx.sgbm_compute(p, a, b)
+        assert np.array_equal(got, want), (W, H, D, bs, mode, minD, int((got != want).sum()))
+print("classic cost kernel ok")
+""" % root
+    env = dict(os.environ, L3D_COST_CLASSIC="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "classic cost kernel ok" in res.stdout, res.stdout + res.stderr

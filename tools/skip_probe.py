@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from laser_3d_reconstruction_b200 import _native as N, pipeline, synth
 W, H, D, BS = 1280, 720, 128, 9
+if os.environ.get('L3D_PROBE_CFG') == 'c4':
+    W, H, D, BS = 1920, 1080, 256, 11
+if os.environ.get('L3D_PROBE_CFG') == 'c1':
+    W, H, D, BS = 320, 360, 64, 5
 lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 14
 nfr = int(sys.argv[2]) if len(sys.argv) > 2 else 56
 K, Q = synth.camera_model(W, H)
