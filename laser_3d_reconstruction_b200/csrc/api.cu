@@ -817,6 +817,8 @@ int l3d_pipeline_set_maps(l3d_pipeline* p, int eye, const float* mapx, const flo
 constexpr int VG_WAVE = 15;
 static int pipe_group_size(const l3d_pipeline* p) {
     const int jobs_per_frame = p->cfg.depth.use_wls ? 2 : 1;
+    static const int forced = getenv("L3D_GROUP") ? atoi(getenv("L3D_GROUP")) : 0;  // experiment: frames per lane set
+    if (forced > 0) return std::min((int)p->lanes.size(), forced);
     return std::min((int)p->lanes.size(), std::max(1, VG_WAVE / jobs_per_frame));
 }
 static bool pipe_grouped(const l3d_pipeline* p) {
