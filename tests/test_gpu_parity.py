@@ -222,6 +222,21 @@ def test_wls_and_depth(ctx, cfg):
     eq(ctx.disp_to_depth(want, None), ref_ops.depth_from_disparity(want, None), "depth default branch")
 
 
+@pytest.mark.parametrize("W,H,D", [(150, 37, 16), (97, 11, 32), (49, 3, 16), (200, 64, 64)])
+def test_wls_ragged_sizes_bit_identical(ctx, W, H, D):
+    """FGS solver edge cases: ROI widths that are not a multiple of the 32-column tile, fewer rows/columns than a warp's
+    ten lines, single-tile rows.  The GPU repeats the oracle's f32 operation order, so the output is bit-identical."""
+    rng = np.random.default_rng(W * 1000 + H)
+    guide = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 1.2)
+    dl = (rng.integers(0, D * 16, (H, W))).astype(np.int16)
+    dl[rng.random((H, W)) < 0.1] = -16
+    dr = (-rng.integers(0, D * 16, (H, W))).astype(np.int16)
+    want, wconf = cref.wls_filter(dl, dr, guide, 0, D, 3, 8000.0, 1.5, want_conf=True)
+    got, conf = ctx.wls_filter(N.WlsParams(8000.0, 1.5, 0, D, 3, 24), dl, dr, guide, want_conf=True)
+    assert np.array_equal(got, want), "wls ragged: %d pixels differ" % int((got != want).sum())
+    assert np.array_equal(conf, wconf)
+
+
 # ---- K4 extractors -------------------------------------------------------------------------
 CFG = dict(hsv_lower=(50, 100, 180), hsv_upper=(70, 255, 255), brightness_threshold=200, min_area=50)
 
