@@ -461,6 +461,36 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
     assert (diff <= 1).mean() >= 0.999
 
 
+@pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7)])
+def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
+    """Cluster-fused aggregation on volumes that do not fill the cluster's column strips: the last CTA / last warps own
+    fewer (or no) valid columns, neighbour-CTA halo hand-off (st.async + mbarrier) still has to deliver "no predecessor"
+    there.  Grouped (14 lanes) == lane-per-frame (2 lanes, direction-split kernels) bit for bit, and the raw matcher
+    output equals cv2."""
+    mode = 1
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, 40 + s) for s in range(8)]
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    results = {}
+    for lanes in (2, 14):
+        cfg = pipeline.make_pipeline_config(W, H, D, bs, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=8000)
+        fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+        try:
+            dl, dr = fp.upload(L), fp.upload(R)
+            fp.run_dev(dl, dr, len(frames))
+            results[lanes] = [fp.fetch(i) for i in range(len(frames))]
+        finally:
+            fp.close()
+    for i in range(len(frames)):
+        for k in ("left_rect", "depth", "disp16", "points_2d", "points_3d"):
+            eq(results[2][i][k], results[14][i][k], "ragged grouped vs per-lane %s frame %d" % (k, i))
+    wrect, wdepth, aux = ref_ops.depth_path(frames[7][0], frames[7][1], maps, D, bs, mode, Q, want_all=True)
+    diff = np.abs(results[14][7]["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999
+
+
 def test_cost_kernel_block_synchronous_form():
     """The block-synchronous cost kernel (L3D_COST_CLASSIC=1; the default for D = 64 / 128 is the warp-decoupled form)
     still gives cv2's bits at the c1 and c3 geometries.  The switch is read once per process, hence the subprocess."""
