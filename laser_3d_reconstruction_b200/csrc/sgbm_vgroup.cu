@@ -389,9 +389,10 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
         // lateness (the wait for the store's shared-memory read) is absorbed by the slack before the next cluster
         // barrier wait, and rotating the role keeps any one warp from falling behind row after row.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const uint32_t bar_id = 1u + (uint32_t)(it & 1);
+        // named barriers 1 / 2 alternate by row (immediate ids: a register id would make ptxas reserve all 16 barriers)
         if (warp == (it & (VG_WARPS - 1))) {
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(VG_THREADS) : "memory");
+            if (it & 1) asm volatile("bar.sync 2, %0;" ::"r"(VG_THREADS) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"r"(VG_THREADS) : "memory");
             if (lane == 0 && wc > 0) {
                 if (!final) {
                     const int row = dir > 0 ? it : H - 1 - it;
@@ -404,7 +405,8 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
             }
             __syncwarp();
         } else {
-            asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "r"(VG_THREADS) : "memory");
+            if (it & 1) asm volatile("bar.arrive 2, %0;" ::"r"(VG_THREADS) : "memory");
+            else asm volatile("bar.arrive 1, %0;" ::"r"(VG_THREADS) : "memory");
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every warp owned some rows' stores
