@@ -101,21 +101,24 @@ __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __
 // Roles 1/2 run one element behind role 0 and receive (dn, lam c_{j-1}) of their element by warp shuffle, so
 // a step costs the warp ONE IEEE division sequence for all three quotients and the serial chain per
 // element is fmul -> fsub -> fdiv.  The zero initial state reproduces the oracle's special-cased first
-// element bit for bit (x + 0, x - 0 and 0 * 0 are exact).  A warp carries FGS_LPW lines.  This kernel is the
-// vertical pass: lines are image columns, a step reads and writes three runs of FGS_LPW adjacent floats
+// element bit for bit (x + 0, x - 0 and 0 * 0 are exact).  A warp carries LPW lines.  This kernel is the
+// vertical pass: lines are image columns, a step reads and writes three runs of LPW adjacent floats
 // straight from/to global memory -- no shared memory, one-warp CTAs (116 at config 3), so the solver leaves
 // every SM free for the matcher kernels of the other frames in flight.  D goes to a scratch plane for the
 // back substitution (role 0 reloads it and shuffles it to roles 1/2).
 constexpr int FGS_LPW = 10;   // lines per warp: lanes [0,10) role 0, [10,20) role 1, [20,30) role 2
+constexpr int FGS_CPW = 8;    // columns per warp in the vertical pass
 constexpr int FGS_BLK = 8;    // elements per register block (the next block is prefetched during the current one)
 
+// LPW: columns per warp (8: each role's run of floats is exactly one aligned 32-byte sector per step)
+template <int LPW>
 __global__ void __launch_bounds__(32) fgs_cols_kernel(float* num, float* den, const float* __restrict__ wgt,
                                                        float* Dscr, int w, int h, float lam) {
     const int nlines = w, len = h;  // lines are image columns (the row pass is fgs_rows_kernel below)
     const int lane = threadIdx.x;
-    const int role = lane / FGS_LPW, li = lane - role * FGS_LPW;
-    const int line = min(blockIdx.x * FGS_LPW + li, nlines - 1);
-    const bool active = role < 3 && blockIdx.x * FGS_LPW + li < nlines;
+    const int role = lane / LPW, li = lane - role * LPW;
+    const int line = min(blockIdx.x * LPW + li, nlines - 1);
+    const bool active = role < 3 && blockIdx.x * LPW + li < nlines;
     const int src = li;                                   // role-0 lane of this lane's line
     const size_t ls = 1, es = (size_t)w;
     const float* in = role == 0 ? wgt : (role == 1 ? num : den);
@@ -364,7 +367,7 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     float* Dscr = aR;  // aR/bR are free as well: elimination factors of the current pass
     for (int it = 0; it < 3; it++) {
         L3D_LAUNCH(L, fgs_rows_kernel, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
-        L3D_LAUNCH(L, fgs_cols_kernel, cdiv(w, FGS_LPW), 32, 0, num, den, cv, Dscr, w, h, lam);
+        L3D_LAUNCH(L, fgs_cols_kernel<FGS_CPW>, cdiv(w, FGS_CPW), 32, 0, num, den, cv, Dscr, w, h, lam);
         lam *= 0.25f;
     }
     L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, num, den, conf, W, H, x0, w, outside, out, conf_out);
