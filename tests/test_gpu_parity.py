@@ -461,7 +461,7 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
     assert (diff <= 1).mean() >= 0.999
 
 
-@pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7)])
+@pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5)])
 def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
     """Cluster-fused aggregation on volumes that do not fill the cluster's column strips: the last CTA / last warps own
     fewer (or no) valid columns, neighbour-CTA halo hand-off (st.async + mbarrier) still has to deliver "no predecessor"
