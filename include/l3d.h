@@ -184,6 +184,11 @@ int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* de
 int l3d_pipeline_pack_points_dev(l3d_pipeline* p, int nframes, const int* frame_ids, double* table_dev,
                                  long long* total_rows);
 long long l3d_pipeline_launch_count(l3d_pipeline* p);
+/* Number of steps the pipeline replayed as a captured CUDA graph so far.  A step (run_dev / run_host) that is
+ * repeated with the same buffers and frame count and whose direct enqueue is launch-bound (host enqueue time
+ * > 40 % of its GPU time, e.g. 320x360 frames) is captured on its third occurrence and replayed afterwards;
+ * L3D_GRAPH=1 forces, L3D_NO_GRAPH=1 disables the replay. */
+long long l3d_pipeline_graph_replays(l3d_pipeline* p);
 /* CUDA-event time (ms) of the whole last run (first enqueue -> last lane done) */
 float l3d_pipeline_last_ms(l3d_pipeline* p);
 /* Per-kernel CUDA-event timing (bench.py's roofline leg).  set_timing(1) brackets every launch of

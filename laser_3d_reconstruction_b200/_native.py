@@ -64,7 +64,7 @@ EXPORTS = (
     "l3d_sgbm_vgroup_time l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
     "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
-    "l3d_pipeline_pack_points_dev l3d_pipeline_launch_count l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
+    "l3d_pipeline_pack_points_dev l3d_pipeline_launch_count l3d_pipeline_graph_replays l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
     "l3d_host_alloc l3d_host_free l3d_dev_alloc l3d_dev_free l3d_memcpy_h2d l3d_memcpy_d2h"
 ).split()
 
@@ -92,6 +92,8 @@ def load():
         lib.l3d_version.restype = C.c_char_p
         lib.l3d_launch_count.restype = C.c_longlong
         lib.l3d_pipeline_launch_count.restype = C.c_longlong
+        lib.l3d_pipeline_graph_replays.restype = C.c_longlong
+        lib.l3d_pipeline_graph_replays.argtypes = [C.c_void_p]
         lib.l3d_pipeline_last_ms.restype = C.c_float
         lib.l3d_host_alloc.restype = C.c_void_p
         lib.l3d_host_alloc.argtypes = [C.c_long]

@@ -130,6 +130,11 @@ class FramePipeline:
     def launches(self):
         return int(self.lib.l3d_pipeline_launch_count(self.h))
 
+    @property
+    def graph_replays(self):
+        """steps replayed as a captured CUDA graph so far (launch-bound repeated steps, see include/l3d.h)"""
+        return int(self.lib.l3d_pipeline_graph_replays(self.h))
+
     def set_timing(self, on):
         self.lib.l3d_pipeline_set_timing(self.h, int(on))
 

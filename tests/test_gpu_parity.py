@@ -447,8 +447,10 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
         fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
         try:
             dl, dr = fp.upload(L), fp.upload(R)
-            fp.run_dev(dl, dr, len(frames))
-            fp.run_dev(dl, dr, len(frames))  # steady state: scratch reuse across runs
+            for _ in range(5):  # steady state: scratch reuse across runs; a launch-bound step (this size is) is captured
+                fp.run_dev(dl, dr, len(frames))  # on its third occurrence and replayed as a CUDA graph afterwards
+            if lanes == 14:
+                assert fp.graph_replays >= 1, "the repeated 320x360 step should have been replayed as a CUDA graph"
             results[lanes] = [fp.fetch(i) for i in range(len(frames))]
         finally:
             fp.close()
