@@ -853,7 +853,7 @@ static bool pipe_grouped(const l3d_pipeline* p) {
     if (off) return false;
     const l3d_pipeline_config& c = p->cfg;
     const int jobs_per_frame = c.depth.use_wls ? 2 : 1;
-    if (pipe_group_size(p) * jobs_per_frame < 8 || c.depth.left.mode == 2) return false;
+    if (pipe_group_size(p) * jobs_per_frame < 8 || c.depth.left.mode >= 2) return false;  // 3WAY / HH4: direction-split
     const l3d_sgbm_params& q = c.depth.left;
     const int width1 = (c.W + std::min(q.minDisparity, 0)) - std::max(q.minDisparity + q.numDisparities, 0);
     return width1 > 0 && vgroup_supported(width1, c.H, q.numDisparities);

@@ -1,4 +1,4 @@
-// sgbm.cu -- cv2.StereoSGBM.compute on sm_100a (modes SGBM / HH / SGBM_3WAY), bit-exact.
+// sgbm.cu -- cv2.StereoSGBM.compute on sm_100a (modes SGBM / HH / SGBM_3WAY / HH4), bit-exact.
 //
 // Replaces stereo_matcher.compute / right_matcher.compute of the reference
 // (camera/single_usb_stereo_camera.py:252-274 parameters, :324-325 calls).
@@ -51,7 +51,7 @@ static int make_geom(const l3d_sgbm_params& p, int W, int H, Geom& g, std::strin
         set_err(err, "sgbm: blockSize must be odd in [1,21], got %d", p.blockSize);
         return L3D_ERR_UNSUPPORTED;
     }
-    if (p.mode < 0 || p.mode > 2) { set_err(err, "sgbm: mode %d unsupported (0,1,2)", p.mode); return L3D_ERR_UNSUPPORTED; }
+    if (p.mode < 0 || p.mode > 3) { set_err(err, "sgbm: mode %d unsupported (0 SGBM, 1 HH, 2 SGBM_3WAY, 3 HH4)", p.mode); return L3D_ERR_UNSUPPORTED; }
     g.bs = p.blockSize; g.SW2 = p.blockSize / 2;
     g.uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
     g.d12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
@@ -1241,6 +1241,14 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
     else COST_CASE((sgbm_cost_kernel<0, 0, 0, 0>))
 #undef COST_CASE
     L.t_end("sgbm_cost");
+    if (g.mode == 3 && g.SW2 > 0 && H > 1) {
+        // MODE_HH4: OpenCV's cost loop of this mode has no branch for window rows below the image, so the last
+        // blockSize/2 rows of C (from row 1 on) keep their initial value P2 for every disparity (found by
+        // differential testing against cv2 4.13, restated in oracle/csrc/orc_sgbm.c)
+        const int y0 = std::max(H - g.SW2, 1);
+        const size_t rowel = (size_t)g.width1 * g.D;
+        L3D_LAUNCH(L, fill_s16_kernel, cdiv(rowel * (H - y0), 256), 256, 0, r.C + rowel * y0, rowel * (H - y0), (int16_t)g.P2);
+    }
     r.d2 = L.get<unsigned>(set ? S_DISP22 : S_DISP2, (size_t)H * (W + 2));
     L3D_CHECK(L, cudaMemsetAsync(r.d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
     // --- both horizontal paths in one launch
@@ -1254,7 +1262,7 @@ int sgbm_front(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uin
 
 // can the previous-row paths of this run go through the cluster-fused kernel?
 bool sgbm_vgroup_ok(const SgbmRun& r) {
-    return r.g.width1 > 0 && r.g.mode != 2 && vgroup_supported(r.g.width1, r.g.HV, r.g.D);
+    return r.g.width1 > 0 && r.g.mode <= 1 && vgroup_supported(r.g.width1, r.g.HV, r.g.D);
 }
 
 // the previous-row paths with the direction-split scan kernels (any geometry and mode); the last path fuses
@@ -1266,8 +1274,9 @@ int sgbm_middle_split(Lane& L, SgbmRun& r, bool keep_S) {
     scan_args_of(r, sa);
     int kinds[6], nk = 0;
     kinds[nk++] = 2;  // down: all modes
-    if (g.mode != 2) { kinds[nk++] = 3; kinds[nk++] = 4; }
+    if (g.mode <= 1) { kinds[nk++] = 3; kinds[nk++] = 4; }
     if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
+    if (g.mode == 3) kinds[nk++] = 5;  // HH4: horizontal pair (front) + down + up
     const bool fuse_wta = g.mode != 2 && !keep_S;
     for (int i = 0; i < nk; i++) {
         const int k = kinds[i];

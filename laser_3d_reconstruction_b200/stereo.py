@@ -14,6 +14,7 @@ from . import _native as N
 STEREO_SGBM_MODE_SGBM = 0
 STEREO_SGBM_MODE_HH = 1
 STEREO_SGBM_MODE_SGBM_3WAY = 2
+STEREO_SGBM_MODE_HH4 = 3
 
 _FIELDS = ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap",
            "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")

@@ -1,5 +1,5 @@
 /*
- * orc_sgbm.c -- CPU restatement of cv2.StereoSGBM.compute (modes SGBM, HH, SGBM_3WAY) as the
+ * orc_sgbm.c -- CPU restatement of cv2.StereoSGBM.compute (modes SGBM, HH, SGBM_3WAY, HH4) as the
  * reference calls it (camera/single_usb_stereo_camera.py:252-274 parameters, :324-325 calls,
  * test_improved_laser.py:151, test_depth.py:68).
  *
@@ -173,7 +173,7 @@ static inline int subpixel(const int16_t* Sp, int d, int D) {
     return d * DISP_SCALE;
 }
 
-/* modes 0 (5 paths) and 1 (8 paths) */
+/* modes 0 (5 paths), 1 (8 paths) and 3 (HH4: the horizontal and the vertical path of each of the two passes) */
 static int sgbm_full(const uint8_t* img1, const uint8_t* img2, int W, int H,
                      const orc_sgbm_params* p, int16_t* disp, int16_t* C_out, int16_t* S_out) {
     int minD = p->minDisparity, D = p->numDisparities, maxD = minD + D;
@@ -183,7 +183,8 @@ static int sgbm_full(const uint8_t* img1, const uint8_t* img2, int W, int H,
     int minX1 = imax(maxD, 0), maxX1 = W + imin(minD, 0), width1 = maxX1 - minX1;
     int INVALID = minD - 1, INVALID_SCALED = INVALID * DISP_SCALE;
     int SW2 = p->blockSize / 2, SH2 = p->blockSize / 2;
-    int npasses = p->mode == 1 ? 2 : 1;
+    int npasses = (p->mode == 1 || p->mode == 3) ? 2 : 1;
+    int hh4 = p->mode == 3; /* MODE_HH4: only the horizontal (r = 0) and the vertical (r = 2) path of each pass */
     for (long i = 0; i < (long)W * H; i++) disp[i] = (int16_t)INVALID_SCALED;
     if (minX1 >= maxX1) return 0;
 
@@ -193,6 +194,13 @@ static int sgbm_full(const uint8_t* img1, const uint8_t* img2, int W, int H,
     int16_t* C = (int16_t*)malloc(sizeof(int16_t) * row * (size_t)H);
     int16_t* S = (int16_t*)calloc((size_t)row * H, sizeof(int16_t));
     cost_volume(&cc, img1, img2, 0, H, SW2, SH2, P2, C);
+    if (hh4) {
+        /* OpenCV's HH4 cost loop (CalcVerticalSums) has no branch for window rows below the image: C(y) of a row
+         * y >= 1 is only written while y + SH2 < H, so the last SH2 rows keep their initial value P2 for every
+         * disparity.  Found by differential testing against cv2 4.13 (mode = 3); reproduced here bit for bit. */
+        for (int y = imax(H - SH2, 1); y < H; y++)
+            for (long i = 0; i < row; i++) C[row * y + i] = (int16_t)P2;
+    }
 
     /* Lr ring: [2 rows][width1+2][4 paths][D], minLr [2][width1+2][4] */
     long lrrow = (long)(width1 + 2) * 4 * D;
@@ -221,13 +229,17 @@ static int sgbm_full(const uint8_t* img1, const uint8_t* img2, int W, int H,
                 int mp[4] = {MLR(id, x - dx, 0), MLR(1 - id, x - 1, 1), MLR(1 - id, x, 2),
                              MLR(1 - id, x + 1, 3)};
                 for (int r = 0; r < 4; r++) {
+                    if (hh4 && (r & 1)) continue;
                     int16_t* L = LR(id, x, r);
                     int mn = path_update(Lp[r], mp[r], Cp, D, P1, P2, L);
                     MLR(id, x, r) = (int16_t)mn;
                 }
                 for (int d = 0; d < D; d++) {
                     int s = Sp[d];
-                    for (int r = 0; r < 4; r++) s = sat16(s + LR(id, x, r)[d]);
+                    for (int r = 0; r < 4; r++) {
+                        if (hh4 && (r & 1)) continue;
+                        s = sat16(s + LR(id, x, r)[d]);
+                    }
                     Sp[d] = (int16_t)s;
                 }
             }
@@ -439,7 +451,7 @@ int orc_sgbm_compute(const uint8_t* left, const uint8_t* right, int W, int H,
     int rc;
     int16_t* raw = (int16_t*)malloc(sizeof(int16_t) * (size_t)W * H);
     if (p->mode == 2) rc = sgbm_3way(left, right, W, H, p, raw);
-    else if (p->mode == 0 || p->mode == 1) rc = sgbm_full(left, right, W, H, p, raw, C_out, S_out);
+    else if (p->mode == 0 || p->mode == 1 || p->mode == 3) rc = sgbm_full(left, right, W, H, p, raw, C_out, S_out);
     else { free(raw); return -1; }
     if (raw_out) memcpy(raw_out, raw, sizeof(int16_t) * (size_t)W * H);
     orc_median3_s16(raw, W, H, disp);

@@ -79,7 +79,7 @@ SMALL = [(96, 48, 16, 3), (130, 50, 32, 5), (200, 64, 64, 9), (300, 56, 128, 7),
          (120, 50, 48, 3)]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])  # 3 = MODE_HH4
 @pytest.mark.parametrize("shape", SMALL)
 def test_sgbm_small_all_roles(ctx, mode, shape):
     W, H, D, bs = shape
@@ -108,7 +108,7 @@ def test_sgbm_small_all_roles(ctx, mode, shape):
             eq(ctx.sgbm_compute(p, lg, rg), want, tag + " fused-WTA disp vs cv2")
 
 
-@pytest.mark.parametrize("mode", [2, 0, 1])
+@pytest.mark.parametrize("mode", [2, 0, 1, 3])
 def test_sgbm_c1_parameter_sets(ctx, mode):
     lg, rg = gray_pair(320, 360, 64, 7)
     base, mut, right = ref_ops.sgbm_param_sets(64, 5, mode)
@@ -125,7 +125,7 @@ def test_sgbm_real_pairs(ctx, golden_real):
         eq(ctx.sgbm_compute(N.SgbmParams(**base), lg, rg), golden_real["disp16_" + tag], "real pair " + tag)
 
 
-@pytest.mark.parametrize("mode", [1, 0, 2])
+@pytest.mark.parametrize("mode", [1, 0, 2, 3])
 def test_sgbm_c3_full_size(ctx, mode):
     """BASELINE config 3: 1280x720, 128 disparities, block 9."""
     lg, rg = gray_pair(1280, 720, 128, 11)
@@ -143,7 +143,7 @@ def test_sgbm_c4_full_size(ctx):
     eq(ctx.sgbm_compute(N.SgbmParams(**mut), lg, rg), cv2.StereoSGBM_create(**mut).compute(lg, rg), "c4")
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_sgbm_noise_saturation(ctx, mode):
     rng = np.random.default_rng(0)
     ln = rng.integers(0, 256, (96, 400)).astype(np.uint8)
@@ -172,6 +172,36 @@ def test_sgbm_properties_full_size(ctx):
     truth = np.take_along_axis(field, np.clip(xs, 0, 1279), axis=1)[:, 140:]
     err = np.abs(a[:, 140:] / 16.0 - truth)[valid]
     assert np.median(err) < 0.6  # the matcher recovers the rendered disparity field
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 5, 8])
+def test_sgbm_hh4_short_images(ctx, H):
+    """MODE_HH4's constant bottom rows of C (oracle/csrc/orc_sgbm.c) on images shorter than the window."""
+    lg, rg = gray_pair(160, H, 32, 11)
+    for bs in (3, 7, 11):
+        kw = dict(minDisparity=0, numDisparities=32, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs, disp12MaxDiff=1,
+                  preFilterCap=63, uniquenessRatio=10, speckleWindowSize=0, speckleRange=32, mode=3)
+        eq(ctx.sgbm_compute(N.SgbmParams(**kw), lg, rg), cv2.StereoSGBM_create(**kw).compute(lg, rg), "hh4 H=%d bs=%d" % (H, bs))
+
+
+def test_pipeline_mode_hh4(ctx):
+    """The frame pipeline with MODE_HH4 matchers (direction-split aggregation even with many lanes) against the oracle path."""
+    W, H, D, bs = 320, 120, 64, 5
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, 70 + s) for s in range(3)]
+    L = np.stack([f[0] for f in frames]); R = np.stack([f[1] for f in frames])
+    cfg = pipeline.make_pipeline_config(W, H, D, bs, 3, Q, K, extractor=N.STEGER_IMPROVED, lanes=14, max_points=8000)
+    fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+    try:
+        fp.run_dev(fp.upload(L), fp.upload(R), len(frames))
+        got = fp.fetch(2)
+    finally:
+        fp.close()
+    wrect, wdepth, aux = ref_ops.depth_path(frames[2][0], frames[2][1], maps, D, bs, 3, Q, want_all=True)
+    eq(got["left_rect"], wrect, "hh4 pipeline rectified image")
+    diff = np.abs(got["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999
 
 
 def test_sgbm_rejects_unsupported(ctx):

@@ -49,7 +49,7 @@ SGBM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])  # 3 = MODE_HH4
 @pytest.mark.parametrize("case", SGBM_CASES)
 def test_sgbm_vs_cv2(mode, case):
     W, H, D, bs, mk, pk, quant = case
@@ -64,7 +64,7 @@ def test_sgbm_vs_cv2(mode, case):
     assert np.array_equal(cref.sgbm_compute(lg, rg, **kw), want)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_sgbm_c1_and_saturation(mode):
     lg, rg = gray_pair(320, 360, 64, 7)
     base, mut, right = ref_ops.sgbm_param_sets(64, 5, mode)
@@ -77,6 +77,17 @@ def test_sgbm_c1_and_saturation(mode):
     kw = dict(minDisparity=0, numDisparities=256, blockSize=11, P1=2904, P2=11616, disp12MaxDiff=1000000,
               preFilterCap=63, uniquenessRatio=0, speckleWindowSize=0, speckleRange=32, mode=mode)
     assert np.array_equal(cref.sgbm_compute(ln, rn, **kw), cv2.StereoSGBM_create(**kw).compute(ln, rn))
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 5, 8])
+def test_sgbm_hh4_short_images(H):
+    """MODE_HH4 leaves the last blockSize/2 rows of the cost volume at P2 (no branch for window rows below the image
+    in OpenCV's HH4 cost loop): images shorter than the window exercise every clamp of that rule."""
+    lg, rg = gray_pair(160, H, 32, 11)
+    for bs in (3, 7, 11):
+        kw = dict(minDisparity=0, numDisparities=32, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs, disp12MaxDiff=1,
+                  preFilterCap=63, uniquenessRatio=10, speckleWindowSize=0, speckleRange=32, mode=3)
+        assert np.array_equal(cref.sgbm_compute(lg, rg, **kw), cv2.StereoSGBM_create(**kw).compute(lg, rg)), (H, bs)
 
 
 def test_sgbm_real_pair(golden_real):
