@@ -7,7 +7,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("orc_sgbm.c", "orc_image.c", "orc_wls.c")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("orc_sgbm.c", "orc_image.c", "orc_wls.c", "orc_bm.c")]
 OUT_DIR = os.path.join(HERE, "_ref")
 OUT = os.path.join(OUT_DIR, "liborc.so")
 

@@ -18,6 +18,12 @@ class SgbmParams(C.Structure):
         "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")]
 
 
+class BmParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "minDisparity", "numDisparities", "blockSize", "preFilterCap", "textureThreshold", "uniquenessRatio",
+        "speckleWindowSize", "speckleRange", "disp12MaxDiff")]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -80,6 +86,27 @@ def sgbm_compute(left, right, want_volumes=False, want_raw=False, **kw):
     if want_volumes:
         res += [Cv, Sv]
     return res[0] if len(res) == 1 else tuple(res)
+
+
+def bm_compute(left, right, numDisparities=64, blockSize=15, minDisparity=0, preFilterCap=31, textureThreshold=10,
+               uniquenessRatio=15, speckleWindowSize=0, speckleRange=0, disp12MaxDiff=-1):
+    """cv2.StereoBM_create(numDisparities, blockSize).compute(left, right) with the setters' parameters."""
+    left, right = _c(left, np.uint8), _c(right, np.uint8)
+    H, W = left.shape
+    p = BmParams(minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
+                 speckleWindowSize, speckleRange, disp12MaxDiff)
+    disp = np.empty((H, W), np.int16)
+    rc = lib().orc_bm_compute(_p(left), _p(right), W, H, C.byref(p), _p(disp))
+    if rc != 0:
+        raise ValueError("orc_bm_compute: unsupported parameters")
+    return disp
+
+
+def bm_prefilter(img, cap=31):
+    img = _c(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_bm_prefilter_xsobel(_p(img), img.shape[1], img.shape[0], int(cap), _p(out))
+    return out
 
 
 def median3_s16(a):

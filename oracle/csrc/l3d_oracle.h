@@ -30,7 +30,7 @@ void orc_remap_bilinear(const uint8_t* src, int sw, int sh, int cn, const float*
 
 typedef struct {
     int minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap,
-        uniquenessRatio, speckleWindowSize, speckleRange, mode; /* 0 SGBM, 1 HH, 2 3WAY */
+        uniquenessRatio, speckleWindowSize, speckleRange, mode; /* 0 SGBM, 1 HH, 2 3WAY, 3 HH4 */
 } orc_sgbm_params;
 
 /* cv2.StereoSGBM.compute(left, right): camera/single_usb_stereo_camera.py:252-274 (params),
@@ -68,6 +68,14 @@ void orc_close_open3(const uint8_t* src, int W, int H, uint8_t* dst);
 void orc_gaussian_blur_f32(const float* src, int W, int H, double sigma, float* dst);
 /* cv2.Sobel(f32, CV_32F, dx, dy, ksize=3), REFLECT_101: improved_steger.py:63-69 */
 void orc_sobel3_f32(const float* src, int W, int H, int dx, int dy, float* dst);
+
+/* cv2.StereoBM (readme.md:392-397 suggests it as a drop-in matcher); see orc_bm.c for the supported subset */
+typedef struct {
+    int minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio, speckleWindowSize,
+        speckleRange, disp12MaxDiff;
+} orc_bm_params;
+void orc_bm_prefilter_xsobel(const uint8_t* src, int W, int H, int ftzero, uint8_t* dst);
+int orc_bm_compute(const uint8_t* left, const uint8_t* right, int W, int H, const orc_bm_params* p, int16_t* disp);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,27 @@ def test_sgbm_real_pair(golden_real):
         assert np.array_equal(cref.sgbm_compute(lg, rg, **base), g["disp16_" + tag])
 
 
+BM_CASES = [(320, 121, 64, 15), (200, 60, 32, 9), (400, 90, 128, 21), (160, 40, 16, 5), (640, 48, 128, 15), (100, 9, 16, 7),
+            (64, 30, 48, 11)]
+
+
+@pytest.mark.parametrize("case", BM_CASES)
+def test_stereobm_vs_cv2(case):
+    """cv2.StereoBM (readme.md:392-397): the restatement against the cv2 binary, bit-exact, over the
+    parameters its setters expose (minDisparity <= 0, disp12MaxDiff off)."""
+    W, H, D, bs = case
+    lg, rg = gray_pair(W, H, D, 21)
+    if W == 160:  # heavy ties
+        lg, rg = (lg // 32 * 32).astype(np.uint8), (rg // 32 * 32).astype(np.uint8)
+    for minD in (0, -8, -(D - 1)):
+        for cap, tex, uq, sw, sr in ((31, 10, 15, 0, 0), (63, 0, 0, 100, 32), (15, 50, 5, 50, 2), (1, 10, 15, 0, 0)):
+            m = cv2.StereoBM_create(numDisparities=D, blockSize=bs)
+            m.setMinDisparity(minD); m.setPreFilterCap(cap); m.setTextureThreshold(tex); m.setUniquenessRatio(uq)
+            m.setSpeckleWindowSize(sw); m.setSpeckleRange(sr)
+            got = cref.bm_compute(lg, rg, D, bs, minD, cap, tex, uq, sw, sr)
+            assert np.array_equal(got, m.compute(lg, rg)), (case, minD, cap, tex, uq, sw, sr)
+
+
 def test_median_speckles():
     rng = np.random.default_rng(1)
     for t in range(4):
