@@ -46,6 +46,17 @@ int l3d_remap_gray(l3d_ctx* ctx, int eye, const uint8_t* src_bgr, int sw, int sh
 /* cv2.cvtColor(BGR2GRAY) alone (core/laser_extractor.py:60,174) */
 int l3d_bgr2gray(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray);
 
+/* -------- StereoBM ------------------------------------------------------------
+ * cv2.StereoBM_create(numDisparities, blockSize).compute(left, right) -> int16 disparity x16, the matcher
+ * readme.md:392-397 offers as a drop-in for StereoSGBM.  PREFILTER_XSOBEL; minDisparity <= 0 and disp12MaxDiff < 0
+ * only (L3D_ERR_UNSUPPORTED otherwise); bit-exact against cv2 4.13. */
+typedef struct {
+    int minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
+        speckleWindowSize, speckleRange, disp12MaxDiff;
+} l3d_bm_params;
+int l3d_bm_compute(l3d_ctx* ctx, const l3d_bm_params* p, const uint8_t* left, const uint8_t* right,
+                   int W, int H, int16_t* disp);
+
 /* -------- K2: StereoSGBM ------------------------------------------------------------------ */
 typedef struct {
     int minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap,

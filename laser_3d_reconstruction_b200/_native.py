@@ -25,6 +25,13 @@ class SgbmParams(C.Structure):
         "preFilterCap", "uniquenessRatio", "speckleWindowSize", "speckleRange", "mode")]
 
 
+class BmParams(C.Structure):
+    """cv2.StereoBM parameters (include/l3d.h: l3d_bm_params)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "minDisparity", "numDisparities", "blockSize", "preFilterCap", "textureThreshold", "uniquenessRatio",
+        "speckleWindowSize", "speckleRange", "disp12MaxDiff")]
+
+
 class WlsParams(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("sigma_color", C.c_double), ("min_disp", C.c_int),
                 ("num_disp", C.c_int), ("dd_radius", C.c_int), ("lrc_thresh", C.c_int)]
@@ -61,7 +68,7 @@ RECON_PLANE, RECON_DEPTH, RECON_DISPARITY, RECON_DISPARITY_MEDIAN = 0, 1, 2, 3
 EXPORTS = (
     "l3d_ctx_create l3d_ctx_destroy l3d_last_error l3d_sync l3d_device_count l3d_version l3d_launch_count "
     "l3d_set_rectify_maps l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_debug l3d_sgbm_volume_rows "
-    "l3d_sgbm_vgroup_time l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
+    "l3d_sgbm_vgroup_time l3d_bm_compute l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
     "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
     "l3d_pipeline_pack_points_dev l3d_pipeline_launch_count l3d_pipeline_graph_replays l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
@@ -181,6 +188,16 @@ class Context:
         out = np.empty(bgr.shape[:2], np.uint8)
         self.check(self.lib.l3d_bgr2gray(self.h, _ptr(bgr), bgr.shape[1], bgr.shape[0], _ptr(out)), "l3d_bgr2gray")
         return out
+
+    def bm_compute(self, params, left, right):
+        """cv2.StereoBM.compute(left, right) -> int16 disparity x16 (include/l3d.h: l3d_bm_compute)."""
+        left, right = _arr(left, np.uint8), _arr(right, np.uint8)
+        if left.ndim != 2 or left.shape != right.shape:
+            raise ValueError("StereoBM.compute expects two single-channel uint8 images of equal size")
+        H, W = left.shape
+        disp = np.empty((H, W), np.int16)
+        self.check(self.lib.l3d_bm_compute(self.h, C.byref(params), _ptr(left), _ptr(right), W, H, _ptr(disp)), "l3d_bm_compute")
+        return disp
 
     def sgbm_compute(self, params, left, right, want_raw=False, want_volumes=False):
         left, right = _arr(left, np.uint8), _arr(right, np.uint8)

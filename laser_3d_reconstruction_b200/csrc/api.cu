@@ -271,6 +271,25 @@ __global__ void fill_pattern_kernel(uint32_t* p, size_t n, uint32_t seed) {
     }
 }
 
+int l3d_bm_compute(l3d_ctx* ctx, const l3d_bm_params* p, const uint8_t* left, const uint8_t* right, int W, int H,
+                   int16_t* disp) {
+    API_BEGIN(ctx)
+    NEED(ctx, p && left && right && disp && W > 0 && H > 0, "StereoBM arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    uint8_t* l = L.get<uint8_t>(S_GRAY_L, n);
+    uint8_t* r = L.get<uint8_t>(S_GRAY_R, n);
+    int16_t* d = L.get<int16_t>(S_DISP_L, n);
+    RC(h2d(ctx, l, left, n));
+    RC(h2d(ctx, r, right, n));
+    RC(dev_bm(L, *p, l, r, W, H, d));
+    RC(d2h(ctx, disp, d, n * 2));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
 int l3d_sgbm_vgroup_time(l3d_ctx* ctx, int width1, int H, int D, int P1, int P2, int njobs, int dir, int reps,
                          float* ms_per_launch) {
     API_BEGIN(ctx)

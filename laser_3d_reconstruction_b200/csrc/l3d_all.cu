@@ -7,6 +7,7 @@
 #include "sgbm.cu"
 #include "post.cu"
 #include "wls.cu"
+#include "bm.cu"
 #include "laser.cu"
 #include "recon.cu"
 #include "api.cu"

@@ -64,6 +64,46 @@ def StereoSGBM_create(**kw):
     return StereoSGBM(**kw)
 
 
+_BM_FIELDS = ("minDisparity", "numDisparities", "blockSize", "preFilterCap", "textureThreshold", "uniquenessRatio",
+              "speckleWindowSize", "speckleRange", "disp12MaxDiff")
+
+
+class StereoBM:
+    """cv2.StereoBM_create(numDisparities, blockSize) look-alike (the matcher readme.md:392-397 suggests for speed):
+    same defaults (preFilterCap 31, textureThreshold 10, uniquenessRatio 15, no speckle filter, disp12MaxDiff -1),
+    the same getters / setters and ``compute``.  PREFILTER_XSOBEL only; minDisparity <= 0 and disp12MaxDiff < 0 only."""
+
+    def __init__(self, numDisparities=0, blockSize=21, device=0):
+        self._p = dict(minDisparity=0, numDisparities=int(numDisparities) if numDisparities else 64, blockSize=int(blockSize),
+                       preFilterCap=31, textureThreshold=10, uniquenessRatio=15, speckleWindowSize=0, speckleRange=0,
+                       disp12MaxDiff=-1)
+        self.device = device
+
+    def params(self):
+        return N.BmParams(**self._p)
+
+    def compute(self, left, right):
+        """left/right: single-channel uint8 HxW -> int16 HxW disparity x16, invalid = (minD-1)*16."""
+        left, right = np.asarray(left), np.asarray(right)
+        if left.dtype != np.uint8 or right.dtype != np.uint8:
+            raise TypeError("StereoBM.compute expects uint8 images")
+        return N.default_context(self.device).bm_compute(self.params(), left, right)
+
+
+def _add_bm_accessors():
+    for f in _BM_FIELDS:
+        cap = f[0].upper() + f[1:]
+        setattr(StereoBM, "get" + cap, (lambda f: lambda self: self._p[f])(f))
+        setattr(StereoBM, "set" + cap, (lambda f: lambda self, v: self._p.__setitem__(f, int(v)))(f))
+
+
+_add_bm_accessors()
+
+
+def StereoBM_create(numDisparities=0, blockSize=21, device=0):
+    return StereoBM(numDisparities, blockSize, device)
+
+
 def createRightMatcher(matcher_left):
     """cv2.ximgproc.createRightMatcher for a StereoSGBM (camera/single_usb_stereo_camera.py:277):
     minDisparity = -(minD + numD) + 1, uniqueness 0, disp12MaxDiff 1e6, speckle off."""

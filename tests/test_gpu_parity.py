@@ -204,6 +204,41 @@ def test_pipeline_mode_hh4(ctx):
     assert (diff <= 1).mean() >= 0.999
 
 
+BM_CASES = [(320, 121, 64, 15), (200, 60, 32, 9), (400, 90, 128, 21), (160, 40, 16, 5), (640, 48, 128, 15), (100, 9, 16, 7),
+            (64, 30, 48, 11), (330, 64, 256, 9), (320, 360, 64, 15), (1280, 720, 128, 15)]
+
+
+@pytest.mark.parametrize("case", BM_CASES)
+def test_stereobm_vs_cv2(ctx, case):
+    """cv2.StereoBM (readme.md:392-397) on the GPU, bit-exact against the cv2 binary."""
+    W, H, D, bs = case
+    lg, rg = gray_pair(W, H, D, 21)
+    if W == 160:  # heavy ties
+        lg, rg = (lg // 32 * 32).astype(np.uint8), (rg // 32 * 32).astype(np.uint8)
+    big = W * H > 200000
+    for minD in ((0,) if big else (0, -8, -(D - 1))):
+        for cap, tex, uq, sw, sr in (((31, 10, 15, 0, 0), (63, 0, 0, 100, 32)) if big else
+                                    ((31, 10, 15, 0, 0), (63, 0, 0, 100, 32), (15, 50, 5, 50, 2), (1, 10, 15, 0, 0))):
+            m = cv2.StereoBM_create(numDisparities=D, blockSize=bs)
+            m.setMinDisparity(minD); m.setPreFilterCap(cap); m.setTextureThreshold(tex); m.setUniquenessRatio(uq)
+            m.setSpeckleWindowSize(sw); m.setSpeckleRange(sr)
+            got = ctx.bm_compute(N.BmParams(minD, D, bs, cap, tex, uq, sw, sr, -1), lg, rg)
+            eq(got, m.compute(lg, rg), "StereoBM %s minD %d cap %d tex %d uq %d speckle %d/%d" % (case, minD, cap, tex, uq, sw, sr))
+
+
+def test_stereobm_class_and_limits(ctx):
+    from laser_3d_reconstruction_b200 import stereo
+    lg, rg = gray_pair(320, 120, 64, 5)
+    m = stereo.StereoBM_create(numDisparities=64, blockSize=15)
+    assert m.getPreFilterCap() == 31 and m.getTextureThreshold() == 10 and m.getUniquenessRatio() == 15
+    eq(m.compute(lg, rg), cv2.StereoBM_create(numDisparities=64, blockSize=15).compute(lg, rg), "StereoBM class defaults")
+    m.setMinDisparity(3)
+    with pytest.raises(N.L3DError):
+        m.compute(lg, rg)  # positive minDisparity: OpenCV itself writes past the row end there; unsupported
+    with pytest.raises(N.L3DError):
+        ctx.bm_compute(N.BmParams(0, 64, 15, 31, 10, 15, 0, 0, 1), lg, rg)  # disp12MaxDiff >= 0
+
+
 def test_sgbm_rejects_unsupported(ctx):
     lg, rg = gray_pair(96, 48, 16, 0)
     with pytest.raises(N.L3DError):
