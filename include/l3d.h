@@ -46,6 +46,14 @@ int l3d_remap_gray(l3d_ctx* ctx, int eye, const uint8_t* src_bgr, int sw, int sh
 /* cv2.cvtColor(BGR2GRAY) alone (core/laser_extractor.py:60,174) */
 int l3d_bgr2gray(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray);
 
+/* -------- init-time rectification maps ------------------------------------------
+ * cv2.initUndistortRectifyMap(K, dist, R, P, (W, H), CV_32FC1) -> mapx, mapy (f32 HxW), as called once per eye in
+ * camera/single_usb_stereo_camera.py:190-206.  K = 3x3 row-major; dist = ndist <= 14 coefficients
+ * (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 [tau_x tau_y = 0]); iR = inverse of P[:3,:3] * R (3x3 row-major, computed by the
+ * caller in f64).  Bit-exact against cv2 4.13. */
+int l3d_init_undistort_rectify_map(l3d_ctx* ctx, const double* K, const double* dist, int ndist, const double* iR,
+                                   int W, int H, float* mapx, float* mapy);
+
 /* -------- StereoBM ------------------------------------------------------------
  * cv2.StereoBM_create(numDisparities, blockSize).compute(left, right) -> int16 disparity x16, the matcher
  * readme.md:392-397 offers as a drop-in for StereoSGBM.  PREFILTER_XSOBEL; minDisparity <= 0 and disp12MaxDiff < 0

@@ -67,7 +67,7 @@ RECON_PLANE, RECON_DEPTH, RECON_DISPARITY, RECON_DISPARITY_MEDIAN = 0, 1, 2, 3
 
 EXPORTS = (
     "l3d_ctx_create l3d_ctx_destroy l3d_last_error l3d_sync l3d_device_count l3d_version l3d_launch_count "
-    "l3d_set_rectify_maps l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_debug l3d_sgbm_volume_rows "
+    "l3d_set_rectify_maps l3d_init_undistort_rectify_map l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_debug l3d_sgbm_volume_rows "
     "l3d_sgbm_vgroup_time l3d_bm_compute l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
     "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
@@ -164,6 +164,19 @@ class Context:
         return int(self.lib.l3d_launch_count(self.h))
 
     # ---- stage wrappers (host numpy in / out) ---------------------------------------------
+    def init_undistort_rectify_map(self, K, dist, R, P, size):
+        """cv2.initUndistortRectifyMap(K, dist, R, P, size, cv2.CV_32FC1) -> (mapx, mapy), computed on the GPU."""
+        W, H = int(size[0]), int(size[1])
+        K = np.ascontiguousarray(K, np.float64).reshape(3, 3)
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).ravel()) if dist is not None else np.zeros(0)
+        A = np.asarray(P, np.float64)[:3, :3] if P is not None else K
+        Rm = np.asarray(R, np.float64).reshape(3, 3) if R is not None else np.eye(3)
+        iR = np.ascontiguousarray(np.linalg.inv(A @ Rm))
+        mapx, mapy = np.empty((H, W), np.float32), np.empty((H, W), np.float32)
+        self.check(self.lib.l3d_init_undistort_rectify_map(self.h, _ptr(K), _ptr(d) if d.size else None, int(d.size), _ptr(iR),
+                                                           W, H, _ptr(mapx), _ptr(mapy)), "l3d_init_undistort_rectify_map")
+        return mapx, mapy
+
     def set_rectify_maps(self, eye, mapx, mapy):
         mapx, mapy = _arr(mapx, np.float32), _arr(mapy, np.float32)
         if mapx.shape != mapy.shape or mapx.ndim != 2:

@@ -26,7 +26,8 @@ class SingleUSBStereoCameraManager:
     def __init__(self, camera_id: int = 0, width: int = 640, height: int = 240, fps: int = 30,
                  split_mode: str = 'horizontal', calibration_file: str = 'stereo_calibration.json', *,
                  num_disparities: Optional[int] = None, block_size: Optional[int] = None,
-                 sgbm_mode: Optional[int] = None, use_wls: bool = True, device: int = 0, verbose: bool = True):
+                 sgbm_mode: Optional[int] = None, use_wls: bool = True, device: int = 0, verbose: bool = True,
+                 gpu_maps: bool = False):
         self.camera_id = camera_id
         self.width = width
         self.height = height
@@ -55,6 +56,7 @@ class SingleUSBStereoCameraManager:
         self._block_size = block_size
         self._sgbm_mode = sgbm_mode
         self._use_wls = bool(use_wls)
+        self._gpu_maps = bool(gpu_maps)  # rectification maps by l3d_init_undistort_rectify_map instead of cv2 (same bits)
         self.device = device
         self.verbose = verbose
         self._ctx = None
@@ -123,10 +125,17 @@ class SingleUSBStereoCameraManager:
             self.R1, self.R2, self.P1, self.P2, self.Q, _roi_l, _roi_r = cv2.stereoRectify(
                 self.camera_matrix_left, self.dist_coeffs_left, self.camera_matrix_right, self.dist_coeffs_right,
                 size, self.R, self.T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
-            self.map_left_x, self.map_left_y = cv2.initUndistortRectifyMap(
-                self.camera_matrix_left, self.dist_coeffs_left, self.R1, self.P1, size, cv2.CV_32FC1)
-            self.map_right_x, self.map_right_y = cv2.initUndistortRectifyMap(
-                self.camera_matrix_right, self.dist_coeffs_right, self.R2, self.P2, size, cv2.CV_32FC1)
+            if self._gpu_maps:
+                ctx = self._context()
+                self.map_left_x, self.map_left_y = ctx.init_undistort_rectify_map(
+                    self.camera_matrix_left, self.dist_coeffs_left, self.R1, self.P1, size)
+                self.map_right_x, self.map_right_y = ctx.init_undistort_rectify_map(
+                    self.camera_matrix_right, self.dist_coeffs_right, self.R2, self.P2, size)
+            else:
+                self.map_left_x, self.map_left_y = cv2.initUndistortRectifyMap(
+                    self.camera_matrix_left, self.dist_coeffs_left, self.R1, self.P1, size, cv2.CV_32FC1)
+                self.map_right_x, self.map_right_y = cv2.initUndistortRectifyMap(
+                    self.camera_matrix_right, self.dist_coeffs_right, self.R2, self.P2, size, cv2.CV_32FC1)
             self._say(f"✓ 从 {self.calibration_file} 加载标定参数, 基线距离: {np.linalg.norm(self.T):.3f}m")
             return True
         except Exception as e:  # the reference swallows and reports, :211-213

@@ -271,6 +271,23 @@ __global__ void fill_pattern_kernel(uint32_t* p, size_t n, uint32_t seed) {
     }
 }
 
+int l3d_init_undistort_rectify_map(l3d_ctx* ctx, const double* K, const double* dist, int ndist, const double* iR,
+                                   int W, int H, float* mapx, float* mapy) {
+    API_BEGIN(ctx)
+    NEED(ctx, K && iR && mapx && mapy && W > 0 && H > 0 && (dist || ndist == 0), "initUndistortRectifyMap arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    float* mx = L.get<float>(S_IO_A, n);
+    float* my = L.get<float>(S_IO_B, n);
+    RC(dev_init_undistort_map(L, K, dist, ndist, iR, W, H, mx, my));
+    RC(d2h(ctx, mapx, mx, n * 4));
+    RC(d2h(ctx, mapy, my, n * 4));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
 int l3d_bm_compute(l3d_ctx* ctx, const l3d_bm_params* p, const uint8_t* left, const uint8_t* right, int W, int H,
                    int16_t* disp) {
     API_BEGIN(ctx)

@@ -106,4 +106,54 @@ int dev_copy_gray(Lane& L, const uint8_t* src, int W, int H, long stride, uint8_
     return L3D_OK;
 }
 
+// ---- cv2.initUndistortRectifyMap(K, dist, R, P, size, CV_32FC1) (camera/single_usb_stereo_camera.py:190-206)
+// per destination pixel, f64, every operation rounded on its own in cv2's order (restated and pinned against cv2 in
+// oracle/ref_ops.py::init_undistort_rectify_map): [x y w] = iR [u v 1], x/w, y/w, rational radial + tangential +
+// thin-prism distortion, projection with K, stored as f32.  iR = (P[:3,:3] R)^-1 comes from the caller.
+struct UndistArgs { double ir[9]; double k[12]; double fx, fy, u0, v0; };
+
+__global__ void init_undistort_map_kernel(UndistArgs a, int W, int H, float* __restrict__ mapx, float* __restrict__ mapy) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= W) return;
+    const double di = (double)i, dj = (double)j;
+    const double _x = __dadd_rn(__dadd_rn(__dmul_rn(di, a.ir[1]), a.ir[2]), __dmul_rn(dj, a.ir[0]));
+    const double _y = __dadd_rn(__dadd_rn(__dmul_rn(di, a.ir[4]), a.ir[5]), __dmul_rn(dj, a.ir[3]));
+    const double _w = __dadd_rn(__dadd_rn(__dmul_rn(di, a.ir[7]), a.ir[8]), __dmul_rn(dj, a.ir[6]));
+    const double w = __ddiv_rn(1.0, _w);
+    const double x = __dmul_rn(_x, w), y = __dmul_rn(_y, w);
+    const double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y);
+    const double r2 = __dadd_rn(x2, y2), _2xy = __dmul_rn(__dmul_rn(2.0, x), y);
+    const double k1 = a.k[0], k2 = a.k[1], p1 = a.k[2], p2 = a.k[3], k3 = a.k[4], k4 = a.k[5], k5 = a.k[6], k6 = a.k[7];
+    const double s1 = a.k[8], s2 = a.k[9], s3 = a.k[10], s4 = a.k[11];
+    const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
+    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k6, r2), k5), r2), k4), r2));
+    const double kr = __ddiv_rn(num, den);
+    double xd = __dadd_rn(__dmul_rn(x, kr), __dmul_rn(p1, _2xy));
+    xd = __dadd_rn(xd, __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(2.0, x2))));
+    xd = __dadd_rn(xd, __dmul_rn(s1, r2));
+    xd = __dadd_rn(xd, __dmul_rn(__dmul_rn(s2, r2), r2));
+    double yd = __dadd_rn(__dmul_rn(y, kr), __dmul_rn(p1, __dadd_rn(r2, __dmul_rn(2.0, y2))));
+    yd = __dadd_rn(yd, __dmul_rn(p2, _2xy));
+    yd = __dadd_rn(yd, __dmul_rn(s3, r2));
+    yd = __dadd_rn(yd, __dmul_rn(__dmul_rn(s4, r2), r2));
+    const size_t o = (size_t)i * W + j;
+    mapx[o] = (float)__dadd_rn(__dmul_rn(a.fx, xd), a.u0);
+    mapy[o] = (float)__dadd_rn(__dmul_rn(a.fy, yd), a.v0);
+}
+
+int dev_init_undistort_map(Lane& L, const double* K, const double* dist, int ndist, const double* iR, int W, int H,
+                           float* mapx, float* mapy) {
+    L3D_ARG(L, ndist >= 0 && ndist <= 14, "initUndistortRectifyMap: at most 14 distortion coefficients");
+    UndistArgs a;
+    for (int i = 0; i < 9; i++) a.ir[i] = iR[i];
+    for (int i = 0; i < 12; i++) a.k[i] = i < ndist ? dist[i] : 0.0;
+    if (ndist > 12 && (dist[12] != 0.0 || (ndist > 13 && dist[13] != 0.0))) {
+        set_err(L.err, "initUndistortRectifyMap: tilted-sensor coefficients are not supported");
+        return L3D_ERR_UNSUPPORTED;
+    }
+    a.fx = K[0]; a.fy = K[4]; a.u0 = K[2]; a.v0 = K[5];
+    L3D_LAUNCH(L, init_undistort_map_kernel, dim3(cdiv(W, 128), H), 128, 0, a, W, H, mapx, mapy);
+    return L3D_OK;
+}
+
 }  // namespace l3d

@@ -204,6 +204,18 @@ def test_pipeline_mode_hh4(ctx):
     assert (diff <= 1).mean() >= 0.999
 
 
+def test_init_undistort_rectify_map_vs_cv2(ctx, rect_cases):
+    """cv2.initUndistortRectifyMap on the GPU, bit-exact f32 maps (real rig at two sizes, a synthetic rig
+    with 12 distortion coefficients at 1280x720), and the rectified image that follows from them."""
+    for K, d, R, P, size in rect_cases:
+        mx, my = cv2.initUndistortRectifyMap(K, d, R, P, size, cv2.CV_32FC1)
+        gx, gy = ctx.init_undistort_rectify_map(K, d, R, P, size)
+        eq(gx, mx, "mapx %s" % (size,))
+        eq(gy, my, "mapy %s" % (size,))
+    with pytest.raises(N.L3DError):
+        ctx.init_undistort_rectify_map(K, np.r_[d, 0.01, 0.0], R, P, size)  # tilted sensor model
+
+
 BM_CASES = [(320, 121, 64, 15), (200, 60, 32, 9), (400, 90, 128, 21), (160, 40, 16, 5), (640, 48, 128, 15), (100, 9, 16, 7),
             (64, 30, 48, 11), (330, 64, 256, 9), (320, 360, 64, 15), (1280, 720, 128, 15)]
 

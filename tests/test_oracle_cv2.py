@@ -121,6 +121,14 @@ def test_stereobm_vs_cv2(case):
             assert np.array_equal(got, m.compute(lg, rg)), (case, minD, cap, tex, uq, sw, sr)
 
 
+def test_init_undistort_rectify_map_vs_cv2(rect_cases):
+    """the f64 restatement of cv2.initUndistortRectifyMap gives cv2's f32 maps bit for bit."""
+    for K, d, R, P, size in rect_cases:
+        mx, my = cv2.initUndistortRectifyMap(K, d, R, P, size, cv2.CV_32FC1)
+        ax, ay = ref_ops.init_undistort_rectify_map(K, d, R, P, size)
+        assert np.array_equal(ax, mx) and np.array_equal(ay, my), (size, int((ax != mx).sum()), int((ay != my).sum()))
+
+
 def test_median_speckles():
     rng = np.random.default_rng(1)
     for t in range(4):
