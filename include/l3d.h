@@ -46,6 +46,20 @@ int l3d_remap_gray(l3d_ctx* ctx, int eye, const uint8_t* src_bgr, int sw, int sh
 /* cv2.cvtColor(BGR2GRAY) alone (core/laser_extractor.py:60,174) */
 int l3d_bgr2gray(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray);
 
+/* -------- point-cloud sink ------------------------------------------------------
+ * PointCloudProcessor.voxel_downsample / .statistical_outlier_removal of utils/point_cloud.py in the form that file
+ * runs without Open3D (:54-78, :108-131).  points = n x 3 f64 (host); out has room for n x 3; *n_out = rows written.
+ * voxel_downsample: one point per occupied voxel (floor(p / voxel_size)), the f64 mean of its points, voxels in order
+ * of first appearance; voxel indices must lie inside +-2^20.  f32_arithmetic != 0: the points are float32 values (passed
+ * as doubles) and division, floor, running sum and mean are float32 operations, as numpy does for the float32 cloud
+ * main.py:208 builds.  statistical_outlier_removal: the reference's predicate
+ * as written (mean of the nb_neighbors nearest distances < mean + std_ratio * std), exact brute-force neighbours
+ * (O(n^2): meant for down-sampled clouds); nb_neighbors <= 63. */
+int l3d_voxel_downsample(l3d_ctx* ctx, const double* points, int n, double voxel_size, int f32_arithmetic, double* out,
+                         int* n_out);
+int l3d_statistical_outlier_removal(l3d_ctx* ctx, const double* points, int n, int nb_neighbors, double std_ratio,
+                                    double* out, int* n_out);
+
 /* -------- init-time rectification maps ------------------------------------------
  * cv2.initUndistortRectifyMap(K, dist, R, P, (W, H), CV_32FC1) -> mapx, mapy (f32 HxW), as called once per eye in
  * camera/single_usb_stereo_camera.py:190-206.  K = 3x3 row-major; dist = ndist <= 14 coefficients

@@ -69,7 +69,7 @@ EXPORTS = (
     "l3d_ctx_create l3d_ctx_destroy l3d_last_error l3d_sync l3d_device_count l3d_version l3d_launch_count "
     "l3d_set_rectify_maps l3d_init_undistort_rectify_map l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_debug l3d_sgbm_volume_rows "
     "l3d_sgbm_vgroup_time l3d_bm_compute l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
-    "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_pipeline_create l3d_pipeline_destroy "
+    "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_voxel_downsample l3d_statistical_outlier_removal l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
     "l3d_pipeline_pack_points_dev l3d_pipeline_launch_count l3d_pipeline_graph_replays l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
     "l3d_host_alloc l3d_host_free l3d_dev_alloc l3d_dev_free l3d_memcpy_h2d l3d_memcpy_d2h"
@@ -201,6 +201,29 @@ class Context:
         out = np.empty(bgr.shape[:2], np.uint8)
         self.check(self.lib.l3d_bgr2gray(self.h, _ptr(bgr), bgr.shape[1], bgr.shape[0], _ptr(out)), "l3d_bgr2gray")
         return out
+
+    def voxel_downsample(self, points, voxel_size):
+        """PointCloudProcessor.voxel_downsample without Open3D (utils/point_cloud.py:54-78) on the GPU."""
+        f32 = np.asarray(points).dtype == np.float32  # numpy then works in float32 (main.py:208 hands over such a cloud)
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        out = np.empty_like(pts)
+        m = C.c_int(0)
+        self.check(self.lib.l3d_voxel_downsample(self.h, _ptr(pts), int(pts.shape[0]), C.c_double(float(voxel_size)), int(f32),
+                                                 _ptr(out), C.byref(m)), "l3d_voxel_downsample")
+        res = out[:m.value]
+        return res.astype(np.float32) if f32 else res.copy()
+
+    def statistical_outlier_removal(self, points, nb_neighbors, std_ratio):
+        """PointCloudProcessor.statistical_outlier_removal without Open3D (utils/point_cloud.py:108-131) on the GPU."""
+        f32 = np.asarray(points).dtype == np.float32  # cKDTree promotes to f64 exactly; the kept rows keep their dtype
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        out = np.empty_like(pts)
+        m = C.c_int(0)
+        self.check(self.lib.l3d_statistical_outlier_removal(self.h, _ptr(pts), int(pts.shape[0]), int(nb_neighbors),
+                                                            C.c_double(float(std_ratio)), _ptr(out), C.byref(m)),
+                   "l3d_statistical_outlier_removal")
+        res = out[:m.value]
+        return res.astype(np.float32) if f32 else res.copy()
 
     def bm_compute(self, params, left, right):
         """cv2.StereoBM.compute(left, right) -> int16 disparity x16 (include/l3d.h: l3d_bm_compute)."""

@@ -271,6 +271,34 @@ __global__ void fill_pattern_kernel(uint32_t* p, size_t n, uint32_t seed) {
     }
 }
 
+static int cloud_op(l3d_ctx* ctx, const double* points, int n, double* out, int* n_out, int op, double a, int k, int f32) {
+    API_BEGIN(ctx)
+    NEED(ctx, n >= 0 && n_out && (n == 0 || (points && out)), "point cloud arguments");
+    *n_out = 0;
+    if (n == 0) return L3D_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    double* dp = L.get<double>(S_RC_XY, (size_t)n * 3);
+    double* dout = L.get<double>(S_RC_XYZ, (size_t)n * 3);
+    RC(h2d(ctx, dp, points, (size_t)n * 24));
+    int m = 0;
+    if (op == 0) RC(dev_voxel_downsample(L, dp, n, a, f32, dout, &m));
+    else RC(dev_outlier_removal(L, dp, n, k, a, dout, &m));
+    if (m > 0) RC(d2h(ctx, out, dout, (size_t)m * 24));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    *n_out = m;
+    return L3D_OK;
+    API_END(ctx)
+}
+int l3d_voxel_downsample(l3d_ctx* ctx, const double* points, int n, double voxel_size, int f32_arithmetic, double* out,
+                         int* n_out) {
+    return cloud_op(ctx, points, n, out, n_out, 0, voxel_size, 0, f32_arithmetic);
+}
+int l3d_statistical_outlier_removal(l3d_ctx* ctx, const double* points, int n, int nb_neighbors, double std_ratio,
+                                    double* out, int* n_out) {
+    return cloud_op(ctx, points, n, out, n_out, 1, std_ratio, nb_neighbors, 0);
+}
+
 int l3d_init_undistort_rectify_map(l3d_ctx* ctx, const double* K, const double* dist, int ndist, const double* iR,
                                    int W, int H, float* mapx, float* mapy) {
     API_BEGIN(ctx)

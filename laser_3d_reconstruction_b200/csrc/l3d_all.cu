@@ -10,4 +10,5 @@
 #include "bm.cu"
 #include "laser.cu"
 #include "recon.cu"
+#include "pointcloud.cu"
 #include "api.cu"

@@ -5,8 +5,8 @@ the accumulation rule (rows with a NaN are dropped, main.py:181-184).  `process_
 batched, device-resident form of the same loop: many already captured stereo pairs go through
 `l3d_pipeline_*` (rectify -> SGBM x2 -> WLS -> depth -> extractor -> reconstruct_from_depth without a
 host round trip between the stages) and produce exactly what calling `process_frame` once per pair
-produces.  The point-cloud sink (`utils/point_cloud.py`, Open3D) stays out of scope: the
-system only accumulates the points.
+produces.  `save_point_cloud` (main.py:190-232) runs the point-cloud sink (voxel down-sampling, outlier removal,
+PLY) through `utils.PointCloudProcessor`, the GPU form of the reference's Open3D-free code.
 """
 import numpy as np
 
@@ -16,6 +16,7 @@ from .camera.single_usb_stereo_camera import SingleUSBStereoCameraManager
 from .config import Config
 from .core.laser_extractor import FastStegerExtractor, SimpleLaserExtractor
 from .core.reconstruction import Reconstructor
+from .utils.point_cloud import PointCloudProcessor
 
 
 class LaserReconstructionSystem:
@@ -26,7 +27,7 @@ class LaserReconstructionSystem:
         self.camera = None
         self.laser_extractor = None
         self.reconstructor = None
-        self.point_cloud_processor = None  # Open3D sink: out of scope, kept as an attribute for drop-in code
+        self.point_cloud_processor = None  # utils.PointCloudProcessor (GPU form of the Open3D-free reference code)
         self.point_cloud = []
         self.frame_count = 0
         self.start_time = None
@@ -84,6 +85,11 @@ class LaserReconstructionSystem:
                                                use_refraction_correction=cfg.USE_REFRACTION_CORRECTION)
         except Exception as e:
             print(f"❌ 重建器初始化错误: {e}")
+            return False
+        try:
+            self.point_cloud_processor = PointCloudProcessor(device=getattr(self.camera, "device", 0), verbose=False)
+        except Exception as e:
+            print(f"❌ 点云处理器初始化错误: {e}")
             return False
         self._say("✅ 系统初始化完成!")
         return True
@@ -162,6 +168,30 @@ class LaserReconstructionSystem:
             self.frame_count += 1
             out.append((got["left_rect"], got["depth"], pts2) if want_images else (None, None, pts2))
         return out
+
+    # ---- reference :190-232 ---------------------------------------------------------------------
+    def save_point_cloud(self, filename=None):
+        import time
+        from pathlib import Path
+        cfg = self.config
+        if len(self.point_cloud) < cfg.MIN_POINT_CLOUD_SIZE:
+            print(f"⚠️  点云太少 ({len(self.point_cloud)} < {cfg.MIN_POINT_CLOUD_SIZE})，跳过保存")
+            return False
+        output_dir = Path(cfg.OUTPUT_DIR)
+        output_dir.mkdir(exist_ok=True)
+        if filename is None:
+            filename = f"point_cloud_{time.strftime('%Y%m%d_%H%M%S')}.{cfg.SAVE_FORMAT}"
+        filepath = output_dir / filename
+        points = np.array(self.point_cloud, dtype=np.float32)
+        points = self.point_cloud_processor.voxel_downsample(points, voxel_size=cfg.VOXEL_SIZE)
+        points = self.point_cloud_processor.statistical_outlier_removal(points, nb_neighbors=cfg.OUTLIER_REMOVAL_NEIGHBORS,
+                                                                        std_ratio=cfg.OUTLIER_REMOVAL_STD_RATIO)
+        if cfg.SAVE_FORMAT == 'ply':
+            self.point_cloud_processor.save_ply(points, str(filepath))
+        else:
+            self.point_cloud_processor.save_pcd(points, str(filepath))
+        self._say(f"✓ 点云已保存: {filepath}")
+        return True
 
     def stop(self):
         if self._pipe is not None:

@@ -76,3 +76,19 @@ def test_depth_path_real_pair(golden_real):
         assert np.array_equal(lrect, g["lrect_" + tag])
         assert np.array_equal(aux["dl"], g["disp16_" + tag])
         assert np.array_equal(depth, g["depth_" + tag])
+
+
+def test_point_cloud_sink_restatement_matches_golden():
+    """oracle restatement of the reference's Open3D-free PointCloudProcessor code against vectors the real
+    class produced (tests/golden/make_golden_cloud.py)."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cloud.npz")))
+    cloud = g["cloud"]
+    assert np.array_equal(ref_ops.simple_voxel_downsample(cloud, 0.002), g["voxel_2mm"])
+    assert np.array_equal(ref_ops.simple_voxel_downsample(cloud, 0.005), g["voxel_5mm"])
+    assert np.array_equal(ref_ops.simple_outlier_removal(cloud, 20, 2.0), g["sor_20_2"])
+    assert ref_ops.simple_outlier_removal(cloud, 8, 0.0).shape == g["sor_8_0"].shape == (0,)
+    assert ref_ops.simple_outlier_removal(cloud, 20, 1e-20).shape == (0,)
+    v32 = ref_ops.simple_voxel_downsample(cloud.astype(np.float32), 0.002)  # main.py:208: float32 cloud, float32 arithmetic
+    assert v32.dtype == np.float32 and np.array_equal(v32, g["voxel_2mm_f32"])
+    assert np.array_equal(ref_ops.simple_outlier_removal(v32, 20, 2.0), g["sor_20_2_f32"])
