@@ -540,6 +540,37 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
     assert (diff <= 1).mean() >= 0.999
 
 
+def test_pipeline_graph_replay_host_buffers(ctx):
+    """A repeated launch-bound step through HOST buffers (H2D / D2H copies inside the captured graph): replays give the
+    same depth maps and point clouds as the direct launches of the first occurrences, also after the input CONTENT
+    changes in place (same pointers, new frames)."""
+    W, H, D, bs = 320, 360, 64, 5
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    cap = 8000
+    cfg = pipeline.make_pipeline_config(W, H, D, bs, 1, Q, K, extractor=N.STEGER_IMPROVED, lanes=14, max_points=cap)
+    fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+    try:
+        frames = [synth.stereo_pair(W, H, D, 90 + s) for s in range(14)]
+        pL = pipeline.pinned_empty((14, H, W, 3), np.uint8); pR = pipeline.pinned_empty((14, H, W, 3), np.uint8)
+        depth = pipeline.pinned_empty((14, H, W), np.float32); xyz = pipeline.pinned_empty((14, cap, 3), np.float64)
+        pL[:] = np.stack([f[0] for f in frames]); pR[:] = np.stack([f[1] for f in frames])
+        counts0 = fp.run_host(pL, pR, depth, xyz)
+        d0, x0 = depth.copy(), [xyz[i, :counts0[i]].copy() for i in range(14)]
+        for _ in range(4):
+            counts = fp.run_host(pL, pR, depth, xyz)
+        assert fp.graph_replays >= 1
+        assert list(counts) == list(counts0) and np.array_equal(depth, d0)
+        for i in range(14):
+            assert np.array_equal(xyz[i, :counts[i]], x0[i])
+        # new content in the same buffers: the replayed graph must pick it up
+        pL[:] = pL[::-1].copy(); pR[:] = pR[::-1].copy()
+        counts2 = fp.run_host(pL, pR, depth, xyz)
+        assert list(counts2) == list(counts0)[::-1] and np.array_equal(depth, d0[::-1])
+    finally:
+        fp.close()
+
+
 @pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5)])
 def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
     """Cluster-fused aggregation on volumes that do not fill the cluster's column strips: the last CTA / last warps own
