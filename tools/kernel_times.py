@@ -13,7 +13,8 @@ base = [synth.stereo_pair(W, H, D, s) for s in range(4)]
 nfr = 14
 L = np.stack([base[i % 4][0] for i in range(nfr)]); R = np.stack([base[i % 4][1] for i in range(nfr)])
 ctx = N.Context(0)
-cfg = pipeline.make_pipeline_config(W, H, D, BS, 1, Q, K, lanes=14, max_points=20000, extractor=N.STEGER_IMPROVED)
+MODE = int(os.environ.get('L3D_PROBE_MODE', '1'))
+cfg = pipeline.make_pipeline_config(W, H, D, BS, MODE, Q, K, lanes=14, max_points=20000, extractor=N.STEGER_IMPROVED)
 fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
 dL, dR = fp.upload(L), fp.upload(R)
 for _ in range(2): fp.run_dev(dL, dR, nfr)
@@ -21,7 +22,7 @@ fp.set_timing(True)
 for r in range(reps):
     fp.run_dev(dL, dR, nfr)
     out = []
-    for g in ["sgbm_cost", "sgbm_scan_k0", "sgbm_vgroup_down", "sgbm_vgroup_up", "wls"]:
+    for g in ["sgbm_cost", "sgbm_scan_k0", "sgbm_scan_k2", "sgbm_scan_k5", "sgbm_wta", "sgbm_vgroup_down", "sgbm_vgroup_up", "wls"]:
         t, k = fp.kernel_time(g)
         out.append("%s %.4f" % (g, t / (nfr if g == "wls" else 2 * nfr)))
     print("  ".join(out), flush=True)

@@ -18,7 +18,8 @@ maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
 base = [synth.stereo_pair(W, H, D, s) for s in range(4)]
 L = np.stack([base[i % 4][0] for i in range(nfr)]); R = np.stack([base[i % 4][1] for i in range(nfr)])
 ctx = N.Context(0)
-cfg = pipeline.make_pipeline_config(W, H, D, BS, 1, Q, K, lanes=lanes, max_points=20000, extractor=N.STEGER_IMPROVED)
+MODE = int(os.environ.get('L3D_PROBE_MODE', '1'))  # cv2.StereoSGBM mode: 0 SGBM, 1 HH, 2 3WAY (the reference's default), 3 HH4
+cfg = pipeline.make_pipeline_config(W, H, D, BS, MODE, Q, K, lanes=lanes, max_points=20000, extractor=N.STEGER_IMPROVED)
 fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
 dL, dR = fp.upload(L), fp.upload(R)
 for _ in range(3): fp.run_dev(dL, dR, nfr)
