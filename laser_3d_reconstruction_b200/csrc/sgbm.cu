@@ -953,16 +953,23 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_kernel(const WtaArgs 
 #pragma unroll
         for (int j = 0; j < DPL; j++) m = min(m, s[j]);
         minS = __reduce_min_sync(FULL_MASK, m);
+        // OpenCV's 8-lane SIMD arg-min: per residue class d mod 8 the LAST disparity that attains the minimum, then the
+        // smallest of those.  One ballot per register slot j gives the lanes holding the minimum at d = lane * DPL + j;
+        // the classes of a slot are lane patterns (d mod 8 = (lane * DPL + j) mod 8), so "last in class" is the highest
+        // set bit of the ballot under the class's lane mask.
         best = 0x7fffffff;
-        for (int c = 0; c < 8; c++) {
-            int v = -1;
 #pragma unroll
-            for (int j = 0; j < DPL; j++) {
-                int d = d0 + j;
-                if (lane < a.nact && (d & 7) == c && s[j] == minS) v = max(v, d);
+        for (int j = 0; j < DPL; j++) {
+            const unsigned b = __ballot_sync(FULL_MASK, lane < a.nact && s[j] == minS);
+            constexpr int LPC = 8 / DPL > 0 ? 8 / DPL : 1;   // lanes per period of d mod 8 (DPL 2: 4, DPL 4: 2, DPL 8: 1)
+#pragma unroll
+            for (int r = 0; r < LPC; r++) {
+                unsigned pat = 0;                            // lanes with lane % LPC == r
+#pragma unroll
+                for (int l = r; l < 32; l += LPC) pat |= 1u << l;
+                const unsigned m = b & pat;
+                if (m) best = min(best, (31 - __clz(m)) * DPL + j);
             }
-            v = __reduce_max_sync(FULL_MASK, v);
-            if (v >= 0) best = min(best, v);
         }
         if (a.uniq > 0) {
             int thresh = (100 * minS) / (100 - a.uniq);
