@@ -1067,6 +1067,93 @@ __global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_lean_kernel(const Wta
     }
 }
 
+// Lean WTA for mode SGBM_3WAY: the same 32-pixels-per-warp walk over the stripe volumes, with that mode's rules (the
+// 8-lane SIMD arg-min, the SIMD form of the uniqueness test, disp2 votes only inside [0, W), overlap rows of a stripe
+// not emitted) -- see sgbm_wta_kernel for the per-pixel restatement this kernel batches.
+template <int NP>
+__global__ void __launch_bounds__(WTA_WARPS * 32) sgbm_wta_lean3_kernel(const WtaArgs a) {
+    typedef typename VecOf<NP>::T vec;
+    constexpr int DPL = NP * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int width1 = a.width1;
+    const long npix = (long)a.HV * width1;
+    const long base = ((long)blockIdx.x * WTA_WARPS + warp) * 32;
+    if (base >= npix) return;
+    const int cnt = (int)min(32L, npix - base);
+    const int nact = a.nact;
+    const bool active = lane < nact;
+    // this lane's pixel (lane < cnt): volume row -> stripe -> image row; rows of a stripe's overlap are not emitted
+    const long mypix = base + min(lane, cnt - 1);
+    const int vr = (int)(mypix / width1), x = (int)(mypix - (long)vr * width1);
+    int seg = 0;
+    for (int q = 1; q < a.nseg; q++) if (vr >= a.seg_vr0[q]) seg = q;
+    const int y = a.seg_y0[seg] + (vr - a.seg_vr0[seg]);
+    const bool emit = lane < cnt && y >= a.seg_emit[seg];
+    const unsigned emit_mask = __ballot_sync(FULL_MASK, emit);
+    if (!emit_mask) return;
+    const vec* __restrict__ Sv = (const vec*)a.S + (size_t)base * nact + lane;
+    const int uniq = a.uniq;
+    unsigned mykey = 0;
+    bool myok = false;
+    for (int k = 0; k < cnt; k++) {
+        if (!((emit_mask >> k) & 1u)) continue;  // warp-uniform
+        uint32_t w[NP];
+        if (active) vec_unpack<NP>(__ldg(Sv + (size_t)k * nact), w);
+        else {
+#pragma unroll
+            for (int q = 0; q < NP; q++) w[q] = INF2;
+        }
+        int sv[DPL];
+#pragma unroll
+        for (int q = 0; q < NP; q++) { sv[2 * q] = (int)(w[q] & 0xffffu); sv[2 * q + 1] = (int)(w[q] >> 16); }
+        int m = 32767;
+#pragma unroll
+        for (int j = 0; j < DPL; j++) m = min(m, sv[j]);
+        const int minS = __reduce_min_sync(FULL_MASK, m);
+        int best = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < DPL; j++) {
+            const unsigned b = __ballot_sync(FULL_MASK, active && sv[j] == minS);
+            constexpr int LPC = 8 / DPL > 0 ? 8 / DPL : 1;
+#pragma unroll
+            for (int r = 0; r < LPC; r++) {
+                unsigned pat = 0;
+#pragma unroll
+                for (int l = r; l < 32; l += LPC) pat |= 1u << l;
+                const unsigned mm = b & pat;
+                if (mm) best = min(best, (31 - __clz(mm)) * DPL + j);
+            }
+        }
+        bool ok = true;
+        if (uniq > 0) {
+            const int thresh = (100 * minS) / (100 - uniq);
+            const int tr = (int)(short)(thresh + 1);
+            bool rej = false;
+#pragma unroll
+            for (int j = 0; j < DPL; j++) {
+                const int d = lane * DPL + j;
+                if (active && sv[j] < tr && (d < best - 1 || d > best + 1)) rej = true;
+            }
+            ok = !__any_sync(FULL_MASK, rej);
+        }
+        if (lane == k) { mykey = ((unsigned)minS << 8) | (unsigned)best; myok = ok; }
+    }
+    if (emit && myok) {
+        const int minS = (int)(mykey >> 8), d = (int)(mykey & 255u);
+        const int x2 = x + a.minX1 - d - a.minD;
+        if (x2 >= 0 && x2 < a.W && minS < 32767)
+            atomicMax(a.disp2key + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
+        int dd = d * 16;
+        if (0 < d && d < a.D - 1) {
+            const int16_t* Sp = a.S + (size_t)mypix * a.D;
+            const int sm = Sp[d - 1], sp = Sp[d + 1], sc = Sp[d];
+            const int denom2 = max(sm + sp - 2 * sc, 1);
+            dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
+        }
+        a.raw[(size_t)y * a.W + x + a.minX1] = (int16_t)(dd + a.minD * 16);
+    }
+}
+
 __global__ void sgbm_lrcheck_kernel(int16_t* __restrict__ raw, const unsigned* __restrict__ disp2key, int W, int H,
                                     int minX1, int maxX1, int minD, int d12) {
     int x = minX1 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -1329,10 +1416,18 @@ int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg) {
             if (g.NP == 1) L3D_WTA(1); else if (g.NP == 2) L3D_WTA(2); else L3D_WTA(4);
 #undef L3D_WTA
         } else {
-            const int wgrid = cdiv((long)g.HV * g.width1, WTA_WARPS);
-            if (g.NP == 1) L3D_LAUNCH(L, sgbm_wta_kernel<1>, wgrid, WTA_WARPS * 32, 0, wa);
-            else if (g.NP == 2) L3D_LAUNCH(L, sgbm_wta_kernel<2>, wgrid, WTA_WARPS * 32, 0, wa);
-            else L3D_LAUNCH(L, sgbm_wta_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
+            static const bool per_pixel = getenv("L3D_WTA_PER_PIXEL") != nullptr;  // the warp-per-pixel restatement
+            if (per_pixel) {
+                const int wgrid = cdiv((long)g.HV * g.width1, WTA_WARPS);
+                if (g.NP == 1) L3D_LAUNCH(L, sgbm_wta_kernel<1>, wgrid, WTA_WARPS * 32, 0, wa);
+                else if (g.NP == 2) L3D_LAUNCH(L, sgbm_wta_kernel<2>, wgrid, WTA_WARPS * 32, 0, wa);
+                else L3D_LAUNCH(L, sgbm_wta_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
+            } else {
+                const int wgrid = cdiv(cdiv((long)g.HV * g.width1, 32), WTA_WARPS);
+                if (g.NP == 1) L3D_LAUNCH(L, sgbm_wta_lean3_kernel<1>, wgrid, WTA_WARPS * 32, 0, wa);
+                else if (g.NP == 2) L3D_LAUNCH(L, sgbm_wta_lean3_kernel<2>, wgrid, WTA_WARPS * 32, 0, wa);
+                else L3D_LAUNCH(L, sgbm_wta_lean3_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
+            }
         }
         L.t_end("sgbm_wta");
         L3D_LAUNCH(L, sgbm_lrcheck_kernel, dim3(cdiv(g.width1, 128), H), 128, 0, r.raw, r.d2, W, H, g.minX1, g.maxX1, g.minD, g.d12);
