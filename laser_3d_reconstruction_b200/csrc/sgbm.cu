@@ -9,14 +9,18 @@
 // access is one contiguous 64..512 B segment.
 //
 // Kernels:
-//   sgbm_prefilter_kernel   x-Sobel clip + half-pixel min/max descriptors (8 B / pixel)
-//   sgbm_cost_kernel        Birchfield-Tomasi pixel cost -> blockSize^2 box sum -> C (+P2), fused;
-//                           pixel costs and the row ring of horizontal sums live in shared memory
-//   sgbm_scan_kernel        one SGM path direction per launch, one warp per scan line, path
-//                           state in registers, DPX u16x2 min/add, warp-wide min via CREDUX,
-//                           C/S streamed through a per-lane cp.async ring
-//   sgbm_wta_kernel         WTA + uniqueness + disp2 (atomicMax key) + sub-pixel
-//   sgbm_lrcheck_kernel     left-right consistency
+//   sgbm_prefilter_kernel     x-Sobel clip + half-pixel min/max, as pixel-pair operand entries (2 planes x 16 B / pixel)
+//   sgbm_cost_warp_kernel     Birchfield-Tomasi pixel cost -> blockSize^2 box sum -> C (+P2); disparity pairs split over
+//                             the warps, warp-private cost strips and row-sum rings, TMA operand ring, no block barrier
+//   sgbm_cost_kernel          the block-synchronous form (D = 256 and every other geometry)
+//   sgbm_scan_hpair_kernel    both horizontal paths of a row in one CTA
+//   sgbm_scan_kernel          one SGM path direction per launch, one warp per scan line, path state in registers,
+//                             DPX u16x2 min/add, warp-wide min via CREDUX, C/S streamed through a cp.async ring; the
+//                             last path can run the WTA (SCAN_FINAL)
+//   sgbm_vgroup_kernel        (sgbm_vgroup.cu) the three previous-row paths of a pass fused on a thread-block cluster
+//   sgbm_wta_lean_kernel      WTA + uniqueness + disp2 (atomicMax key) + sub-pixel, 32 pixels per warp (modes SGBM / HH / HH4)
+//   sgbm_wta_lean3_kernel     the same walk with SGBM_3WAY's rules; sgbm_wta_kernel is the warp-per-pixel restatement
+//   sgbm_lrcheck_kernel       left-right consistency
 // Value domain: 0 <= L,S <= 32767 and C >= P2, which holds whenever the block sum
 // does not wrap int16 (always for blockSize <= 9; for 11 unless every pixel of a block mismatches
 // by more than 92 % of the maximum cost).  Inside that domain OpenCV's saturating int16 SIMD and
