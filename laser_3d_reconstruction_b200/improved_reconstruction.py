@@ -35,7 +35,7 @@ class ImprovedLaserReconstructor:
         disp = np.asarray(disparity_map)
         if disp.ndim != 2:
             raise ValueError("disparity_map must be HxW")
-        xy = np.asarray([(float(x), float(y)) for x, y in laser_points], np.float64).reshape(-1, 2)
+        xy = np.asarray(laser_points, np.float64).reshape(-1, 2)
         out = N.default_context(self.device).reconstruct(self._params(kind, min_disparity, window), xy,
                                                          disp.astype(np.float32, copy=False))
         return out.astype(np.float32) if len(out) else np.array([])
@@ -61,7 +61,7 @@ class ImprovedLaserReconstructor:
         if len(laser_points) == 0:
             return out
         disp = np.asarray(disparity_map, np.float32)
-        xy = np.asarray([(float(x), float(y)) for x, y in laser_points], np.float64).reshape(-1, 2)
+        xy = np.asarray(laser_points, np.float64).reshape(-1, 2)
         px = np.rint(xy[:, 0]).astype(np.int64)
         py = np.rint(xy[:, 1]).astype(np.int64)
         ok = (px >= 0) & (px < w) & (py >= 0) & (py < h)
