@@ -108,7 +108,7 @@ __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __
 // back substitution (role 0 reloads it and shuffles it to roles 1/2).
 constexpr int FGS_LPW = 10;   // lines per warp: lanes [0,10) role 0, [10,20) role 1, [20,30) role 2
 constexpr int FGS_CPW = 8;    // columns per warp in the vertical pass
-constexpr int FGS_BLK = 8;    // elements per register block (the next block is prefetched during the current one)
+constexpr int FGS_BLK = 16;   // elements per register block (the next block is prefetched during the current one)
 
 // LPW: columns per warp (8: each role's run of floats is exactly one aligned 32-byte sector per step)
 template <int LPW>
