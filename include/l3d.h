@@ -70,8 +70,9 @@ int l3d_init_undistort_rectify_map(l3d_ctx* ctx, const double* K, const double* 
 
 /* -------- StereoBM ------------------------------------------------------------
  * cv2.StereoBM_create(numDisparities, blockSize).compute(left, right) -> int16 disparity x16, the matcher
- * readme.md:392-397 offers as a drop-in for StereoSGBM.  PREFILTER_XSOBEL; minDisparity <= 0 and disp12MaxDiff < 0
- * only (L3D_ERR_UNSUPPORTED otherwise); bit-exact against cv2 4.13. */
+ * readme.md:392-397 offers as a drop-in for StereoSGBM.  PREFILTER_XSOBEL; minDisparity <= 0 only
+ * (L3D_ERR_UNSUPPORTED otherwise: OpenCV itself writes past the row end for positive values); disp12MaxDiff >= 0 with
+ * preFilterCap <= 31 and blockSize <= 21 only; bit-exact against cv2 4.13. */
 typedef struct {
     int minDisparity, numDisparities, blockSize, preFilterCap, textureThreshold, uniquenessRatio,
         speckleWindowSize, speckleRange, disp12MaxDiff;

@@ -71,7 +71,7 @@ _BM_FIELDS = ("minDisparity", "numDisparities", "blockSize", "preFilterCap", "te
 class StereoBM:
     """cv2.StereoBM_create(numDisparities, blockSize) look-alike (the matcher readme.md:392-397 suggests for speed):
     same defaults (preFilterCap 31, textureThreshold 10, uniquenessRatio 15, no speckle filter, disp12MaxDiff -1),
-    the same getters / setters and ``compute``.  PREFILTER_XSOBEL only; minDisparity <= 0 and disp12MaxDiff < 0 only."""
+    the same getters / setters and ``compute``.  PREFILTER_XSOBEL only; minDisparity <= 0 only."""
 
     def __init__(self, numDisparities=0, blockSize=21, device=0):
         self._p = dict(minDisparity=0, numDisparities=int(numDisparities) if numDisparities else 64, blockSize=int(blockSize),

@@ -4,7 +4,9 @@
  * drop-in for StereoSGBM (readme.md:392-397).  TEST INFRASTRUCTURE ONLY (see l3d_oracle.h).
  * OpenCV's source is not in the image: the arithmetic is restated from the published algorithm and pinned by
  * differential tests against the cv2 4.13 binary (tests/test_oracle_cv2.py::test_stereobm_vs_cv2).  Supported:
- * minDisparity <= 0 (OpenCV itself writes past the row end for positive values), disp12MaxDiff < 0, PREFILTER_XSOBEL.
+ * minDisparity <= 0 (OpenCV itself writes past the row end for positive values), PREFILTER_XSOBEL; disp12MaxDiff >= 0
+ * runs cv2.validateDisparity between matching and masking (pinned for preFilterCap <= 31 and blockSize <= 21, OpenCV's
+ * 16-bit SIMD path; its scalar path combines the check with a differently laid out cost buffer and is not restated).
  */
 #include "l3d_oracle.h"
 #include <stdlib.h>
@@ -36,7 +38,8 @@ void orc_bm_prefilter_xsobel(const uint8_t* src, int W, int H, int ftzero, uint8
 }
 
 /* findStereoCorrespondenceBM, whole image (dy0 = dy1 = 0) */
-static void bm_correspond(const uint8_t* left, const uint8_t* right, int width, int height, const bm_params* st, int16_t* disp) {
+static void bm_correspond(const uint8_t* left, const uint8_t* right, int width, int height, const bm_params* st, int16_t* disp,
+                          int* cost) {
     int wsz = st->blockSize, wsz2 = wsz/2;
     int dy0 = 0, dy1 = 0;
     int ndisp = st->numDisparities, mindisp = st->minDisparity;
@@ -107,19 +110,55 @@ static void bm_correspond(const uint8_t* left, const uint8_t* right, int width, 
             int p = sad[mind+1], n = sad[mind-1];
             int d = p + n - 2*sad[mind] + abs(p - n);
             dptr[y*dstep] = (int16_t)(((ndisp - mind - 1 + mindisp)*256 + (d != 0 ? (p-n)*256/d : 0) + 15) >> 4);
+            if (cost) cost[(long)y*width + lofs + x] = sad[mind];
         }
     }
     free(sadb); free(hsad0); free(htextb); free(cbuf0);
 }
 
+/* cv2.validateDisparity as StereoBM applies it when disp12MaxDiff >= 0 (per row: the best-cost left pixel claims its right
+ * pixel, then a disparity survives if either of its two integer roundings agrees with the claim within the tolerance) */
+static void bm_validate(int16_t* disp, const int* cost, int cols, int rows, int minD, int ndisp, int disp12MaxDiff) {
+    int maxD = minD + ndisp;
+    int minX1 = imax(maxD, 0), maxX1 = cols + imin(minD, 0);
+    int INVALID_SCALED = (minD - 1) * 16;
+    int* disp2buf = (int*)malloc(sizeof(int) * cols * 2);
+    int* disp2cost = disp2buf + cols;
+    disp12MaxDiff *= 16;
+    for (int y = 0; y < rows; y++) {
+        int16_t* dptr = disp + (long)y * cols;
+        const int* cptr = cost + (long)y * cols;
+        for (int x = 0; x < cols; x++) { disp2buf[x] = INVALID_SCALED; disp2cost[x] = INT_MAX; }
+        for (int x = minX1; x < maxX1; x++) {
+            int d = dptr[x], c = cptr[x];
+            if (d == INVALID_SCALED) continue;
+            int x2 = x - ((d + 8) >> 4);
+            if (disp2cost[x2] > c) { disp2cost[x2] = c; disp2buf[x2] = d; }
+        }
+        for (int x = minX1; x < maxX1; x++) {
+            int d = dptr[x];
+            if (d == INVALID_SCALED) continue;
+            int d0 = d >> 4, d1 = (d + 15) >> 4;
+            int x0 = x - d0, x1 = x - d1;
+            if ((0 <= x0 && x0 < cols && disp2buf[x0] > INVALID_SCALED && abs(disp2buf[x0] - d) > disp12MaxDiff) &&
+                (0 <= x1 && x1 < cols && disp2buf[x1] > INVALID_SCALED && abs(disp2buf[x1] - d) > disp12MaxDiff))
+                dptr[x] = (int16_t)INVALID_SCALED;
+        }
+    }
+    free(disp2buf);
+}
+
 int orc_bm_compute(const uint8_t* l, const uint8_t* r, int W, int H, const orc_bm_params* st, int16_t* disp) {
     if (st->minDisparity > 0 || st->numDisparities < 16 || (st->numDisparities % 16) || st->blockSize < 5 || !(st->blockSize & 1) ||
-        st->blockSize > W || st->blockSize > H || st->disp12MaxDiff >= 0 || st->preFilterCap < 1 || st->preFilterCap > 63)
+        st->blockSize > W || st->blockSize > H || st->preFilterCap < 1 || st->preFilterCap > 63 ||
+        (st->disp12MaxDiff >= 0 && (st->preFilterCap > 31 || st->blockSize > 21)))
         return -1;
     uint8_t* lf = malloc((size_t)W*H); uint8_t* rf = malloc((size_t)W*H);
     orc_bm_prefilter_xsobel(l, W, H, st->preFilterCap, lf);
     orc_bm_prefilter_xsobel(r, W, H, st->preFilterCap, rf);
-    bm_correspond(lf, rf, W, H, st, disp);
+    int* cost = st->disp12MaxDiff >= 0 ? (int*)calloc((size_t)W * H, sizeof(int)) : NULL;
+    bm_correspond(lf, rf, W, H, st, disp, cost);
+    if (cost) { bm_validate(disp, cost, W, H, st->minDisparity, st->numDisparities, st->disp12MaxDiff); free(cost); }
     /* valid ROI */
     int SW2 = st->blockSize/2, minD = st->minDisparity, maxD = minD + st->numDisparities - 1;
     int xmin = imax(0, 0 + maxD) + SW2, xmax = W - SW2, ymin = SW2, ymax = H - SW2;

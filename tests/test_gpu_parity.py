@@ -228,14 +228,17 @@ def test_stereobm_vs_cv2(ctx, case):
     if W == 160:  # heavy ties
         lg, rg = (lg // 32 * 32).astype(np.uint8), (rg // 32 * 32).astype(np.uint8)
     big = W * H > 200000
+    d12_ok = bs <= 21
     for minD in ((0,) if big else (0, -8, -(D - 1))):
-        for cap, tex, uq, sw, sr in (((31, 10, 15, 0, 0), (63, 0, 0, 100, 32)) if big else
-                                    ((31, 10, 15, 0, 0), (63, 0, 0, 100, 32), (15, 50, 5, 50, 2), (1, 10, 15, 0, 0))):
+        for cap, tex, uq, sw, sr, d12 in (((31, 10, 15, 0, 0, -1), (63, 0, 0, 100, 32, -1), (31, 0, 0, 100, 32, 1)) if big else
+                                         ((31, 10, 15, 0, 0, -1), (63, 0, 0, 100, 32, -1), (31, 0, 0, 100, 32, 1), (15, 50, 5, 50, 2, 0), (1, 10, 15, 0, 0, 5))):
+            if d12 >= 0 and (cap > 31 or not d12_ok):
+                continue
             m = cv2.StereoBM_create(numDisparities=D, blockSize=bs)
             m.setMinDisparity(minD); m.setPreFilterCap(cap); m.setTextureThreshold(tex); m.setUniquenessRatio(uq)
-            m.setSpeckleWindowSize(sw); m.setSpeckleRange(sr)
-            got = ctx.bm_compute(N.BmParams(minD, D, bs, cap, tex, uq, sw, sr, -1), lg, rg)
-            eq(got, m.compute(lg, rg), "StereoBM %s minD %d cap %d tex %d uq %d speckle %d/%d" % (case, minD, cap, tex, uq, sw, sr))
+            m.setSpeckleWindowSize(sw); m.setSpeckleRange(sr); m.setDisp12MaxDiff(d12)
+            got = ctx.bm_compute(N.BmParams(minD, D, bs, cap, tex, uq, sw, sr, d12), lg, rg)
+            eq(got, m.compute(lg, rg), "StereoBM %s minD %d cap %d tex %d uq %d speckle %d/%d d12 %d" % (case, minD, cap, tex, uq, sw, sr, d12))
 
 
 def test_stereobm_class_and_limits(ctx):
@@ -247,8 +250,6 @@ def test_stereobm_class_and_limits(ctx):
     m.setMinDisparity(3)
     with pytest.raises(N.L3DError):
         m.compute(lg, rg)  # positive minDisparity: OpenCV itself writes past the row end there; unsupported
-    with pytest.raises(N.L3DError):
-        ctx.bm_compute(N.BmParams(0, 64, 15, 31, 10, 15, 0, 0, 1), lg, rg)  # disp12MaxDiff >= 0
 
 
 def test_sgbm_rejects_unsupported(ctx):

@@ -113,12 +113,12 @@ def test_stereobm_vs_cv2(case):
     if W == 160:  # heavy ties
         lg, rg = (lg // 32 * 32).astype(np.uint8), (rg // 32 * 32).astype(np.uint8)
     for minD in (0, -8, -(D - 1)):
-        for cap, tex, uq, sw, sr in ((31, 10, 15, 0, 0), (63, 0, 0, 100, 32), (15, 50, 5, 50, 2), (1, 10, 15, 0, 0)):
+        for cap, tex, uq, sw, sr, d12 in ((31, 10, 15, 0, 0, -1), (63, 0, 0, 100, 32, -1), (31, 0, 0, 100, 32, 1), (15, 50, 5, 50, 2, 0), (1, 10, 15, 0, 0, 5)):
             m = cv2.StereoBM_create(numDisparities=D, blockSize=bs)
             m.setMinDisparity(minD); m.setPreFilterCap(cap); m.setTextureThreshold(tex); m.setUniquenessRatio(uq)
-            m.setSpeckleWindowSize(sw); m.setSpeckleRange(sr)
-            got = cref.bm_compute(lg, rg, D, bs, minD, cap, tex, uq, sw, sr)
-            assert np.array_equal(got, m.compute(lg, rg)), (case, minD, cap, tex, uq, sw, sr)
+            m.setSpeckleWindowSize(sw); m.setSpeckleRange(sr); m.setDisp12MaxDiff(d12)
+            got = cref.bm_compute(lg, rg, D, bs, minD, cap, tex, uq, sw, sr, d12)
+            assert np.array_equal(got, m.compute(lg, rg)), (case, minD, cap, tex, uq, sw, sr, d12)
 
 
 def test_init_undistort_rectify_map_vs_cv2(rect_cases):
