@@ -563,6 +563,10 @@ struct ScanArgs {
     // SCAN_FINAL only: the winner-takes-all stage fused into the last path (modes SGBM / HH)
     int16_t* raw; unsigned* disp2key;
     int W, minD, minX1, uniq;
+    // SGBM_3WAY in SCAN_FINAL: that mode's WTA rules (see sgbm_wta_lean3_kernel) and its stripes (volume row -> image row,
+    // overlap rows not emitted)
+    int tway;
+    int seg_y0[MAXSEG], seg_emit[MAXSEG];
 };
 enum { SCAN_STORE = 0, SCAN_ACCUM = 1, SCAN_FINAL = 2 };  // S = L | S = sat(S + L) | sat(S + L) -> WTA, S not written
 
@@ -791,11 +795,21 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
     auto wta_flush = [&](int first_step, int count) {
         __syncwarp();
         const int minS = (int)(wkey >> 8), d = (int)(wkey & 255u);
-        if (lane < count && minS < 32767 && !wrej) {  // minS == 32767: nothing beat MAX_COST, pixel stays invalid
-            const int j = first_step + lane;
-            const int y = ln.vr + ln.dvr * j, x = ln.x + ln.dx * j;
+        const int j = first_step + lane;
+        int y = ln.vr + ln.dvr * j;
+        const int x = ln.x + ln.dx * j;
+        bool emit = lane < count && !wrej;
+        if (a.tway) {  // stripe volume row -> image row; the overlap rows of a stripe only feed the recurrence
+            int seg = 0;
+            for (int q = 1; q < a.nseg; q++) if (y >= a.seg_vr0[q]) seg = q;
+            y = a.seg_y0[seg] + (y - a.seg_vr0[seg]);
+            emit = emit && y >= a.seg_emit[seg];
+        } else {
+            emit = emit && minS < 32767;  // minS == 32767: nothing beat MAX_COST, pixel stays invalid
+        }
+        if (emit) {
             const int x2 = x + a.minX1 - d - a.minD;
-            if (x2 >= 0 && x2 < a.W + 2)
+            if (x2 >= 0 && x2 < (a.tway ? a.W : a.W + 2) && minS < 32767)
                 atomicMax(a.disp2key + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
             int dd = d * 16;
             if (0 < d && d < a.D - 1) {
@@ -832,16 +846,52 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
                 for (int q = 0; q < NP; q++) out[q] = INF2;
             }
             unsigned key = 0xffffffffu;
-#pragma unroll
-            for (int q = 0; q < NP; q++) {
-                key = min(key, ((out[q] << 8) & 0xffff00u) | (dkey + 2 * q));
-                key = min(key, ((out[q] >> 8) & 0xffff00u) | (dkey + 2 * q + 1));
-            }
-            key = __reduce_min_sync(FULL_MASK, key);
+            bool rej = false;
             const int slot = nsteps & 31;
             if (active) *(vec*)(stash + (size_t)slot * B + (size_t)lane * sizeof(vec)) = vec_pack<NP>(out);
-            bool rej = false;
-            if (a.uniq > 0) rej = wta_not_unique<NP>(out, key, a.uniq, dkey, active);
+            if (a.tway) {  // SGBM_3WAY: SIMD-lane arg-min and SIMD-form uniqueness test (sgbm_wta_lean3_kernel)
+                int sv[DPL];
+#pragma unroll
+                for (int q = 0; q < NP; q++) { sv[2 * q] = (int)(out[q] & 0xffffu); sv[2 * q + 1] = (int)(out[q] >> 16); }
+                int m = 32767;
+#pragma unroll
+                for (int jj = 0; jj < DPL; jj++) m = min(m, sv[jj]);
+                const int minS = __reduce_min_sync(FULL_MASK, m);
+                int best = 0x7fffffff;
+#pragma unroll
+                for (int jj = 0; jj < DPL; jj++) {
+                    const unsigned bb = __ballot_sync(FULL_MASK, active && sv[jj] == minS);
+                    constexpr int LPC = 8 / DPL > 0 ? 8 / DPL : 1;
+#pragma unroll
+                    for (int r = 0; r < LPC; r++) {
+                        unsigned pat = 0;
+#pragma unroll
+                        for (int l = r; l < 32; l += LPC) pat |= 1u << l;
+                        const unsigned mm = bb & pat;
+                        if (mm) best = min(best, (31 - __clz(mm)) * DPL + jj);
+                    }
+                }
+                if (a.uniq > 0) {
+                    const int thresh = (100 * minS) / (100 - a.uniq);
+                    const int tr = (int)(short)(thresh + 1);
+                    bool v = false;
+#pragma unroll
+                    for (int jj = 0; jj < DPL; jj++) {
+                        const int d = lane * DPL + jj;
+                        if (active && sv[jj] < tr && (d < best - 1 || d > best + 1)) v = true;
+                    }
+                    rej = __any_sync(FULL_MASK, v);
+                }
+                key = ((unsigned)minS << 8) | (unsigned)(best & 255);
+            } else {
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    key = min(key, ((out[q] << 8) & 0xffff00u) | (dkey + 2 * q));
+                    key = min(key, ((out[q] >> 8) & 0xffff00u) | (dkey + 2 * q + 1));
+                }
+                key = __reduce_min_sync(FULL_MASK, key);
+                if (a.uniq > 0) rej = wta_not_unique<NP>(out, key, a.uniq, dkey, active);
+            }
             if (lane == slot) { wkey = key; wrej = rej; }
             nsteps++;
         }
@@ -1252,6 +1302,8 @@ static void scan_args_of(const SgbmRun& r, ScanArgs& sa) {
     for (int s = 0; s < MAXSEG; s++) { sa.seg_vr0[s] = g.seg_vr0[s]; sa.seg_rows[s] = g.seg_rows[s]; }
     sa.raw = r.raw; sa.disp2key = r.d2; sa.W = r.W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
     sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0;
+    sa.tway = g.mode == 2;
+    for (int s = 0; s < MAXSEG; s++) { sa.seg_y0[s] = g.seg_y0[s]; sa.seg_emit[s] = g.seg_emit[s]; }
 }
 
 // set: 0 / 1 selects the scratch slots (the pipeline keeps the left and the right matcher's volumes alive
@@ -1375,7 +1427,10 @@ int sgbm_middle_split(Lane& L, SgbmRun& r, bool keep_S) {
     if (g.mode <= 1) { kinds[nk++] = 3; kinds[nk++] = 4; }
     if (g.mode == 1) { kinds[nk++] = 5; kinds[nk++] = 6; kinds[nk++] = 7; }
     if (g.mode == 3) kinds[nk++] = 5;  // HH4: horizontal pair (front) + down + up
-    const bool fuse_wta = g.mode != 2 && !keep_S;
+    // SGBM_3WAY: the stand-alone lean WTA is faster than the fused form (measured 834 vs 696 frames/s at 1280x720: the
+    // arg-min ballots sit on the scan's serial chain), so fusing is opt-in there
+    static const bool fuse3 = getenv("L3D_3WAY_FUSE_WTA") != nullptr;
+    const bool fuse_wta = !keep_S && (g.mode != 2 || fuse3);
     for (int i = 0; i < nk; i++) {
         const int k = kinds[i];
         sa.kind = k; sa.store = 0;
