@@ -602,9 +602,14 @@ def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
     assert (diff <= 1).mean() >= 0.999
 
 
-def test_cost_kernel_block_synchronous_form():
-    """The block-synchronous cost kernel (L3D_COST_CLASSIC=1; the default for D = 64 / 128 is the warp-decoupled form)
-    still gives cv2's bits at the c1 and c3 geometries.  The switch is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("switch,cases", [
+    ("L3D_COST_CLASSIC", ((320, 360, 64, 5, 0), (1280, 720, 128, 9, 1))),      # block-synchronous cost kernel
+    ("L3D_3WAY_FUSE_WTA", ((320, 360, 64, 5, 2), (1280, 200, 128, 9, 2))),     # SGBM_3WAY WTA fused into the last scan
+    ("L3D_WTA_PER_PIXEL", ((320, 360, 64, 5, 2), (640, 120, 128, 9, 2))),      # warp-per-pixel SGBM_3WAY WTA
+])
+def test_alternative_kernel_forms(switch, cases):
+    """Kernel forms that are not the default (selected by an environment switch that is read once per process, hence the
+    subprocess) still give cv2's bits."""
     import os
     import subprocess
     import sys
@@ -614,18 +619,20 @@ import sys, numpy as np, cv2
 sys.path.insert(0, %r)
 from laser_3d_reconstruction_b200 import _native as N, synth
 ctx = N.Context(0)
-for (W, H, D, bs, mode) in ((320, 360, 64, 5, 0), (1280, 720, 128, 9, 1)):
+for (W, H, D, bs, mode) in %r:
     l, r = synth.stereo_pair(W, H, D, seed=5)
     lg, rg = cv2.cvtColor(l, cv2.COLOR_BGR2GRAY), cv2.cvtColor(r, cv2.COLOR_BGR2GRAY)
     for minD, a, b in ((0, lg, rg), (-(D - 1), rg, lg)):
-        p = N.SgbmParams(minD, D, bs, 24 * bs * bs, 96 * bs * bs, 1, 63, 10, 100, 32, mode)
-        want = cv2.StereoSGBM_create(minDisparity=minD, numDisparities=D, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs,
-                                     disp12MaxDiff=1, preFilterCap=63, uniquenessRatio=10, speckleWindowSize=100,
-                                     speckleRange=32, mode=mode).compute(a, b)
-        got = ctx.sgbm_compute(p, a, b)
-        assert np.array_equal(got, want), (W, H, D, bs, mode, minD, int((got != want).sum()))
-print("classic cost kernel ok")
-""" % root
-    env = dict(os.environ, L3D_COST_CLASSIC="1")
+        for uq, d12, sw in ((10, 1, 100), (0, 1000000, 0)):
+            p = N.SgbmParams(minD, D, bs, 24 * bs * bs, 96 * bs * bs, d12, 63, uq, sw, 32, mode)
+            want = cv2.StereoSGBM_create(minDisparity=minD, numDisparities=D, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs,
+                                         disp12MaxDiff=d12, preFilterCap=63, uniquenessRatio=uq, speckleWindowSize=sw,
+                                         speckleRange=32, mode=mode).compute(a, b)
+            got = ctx.sgbm_compute(p, a, b)
+            assert np.array_equal(got, want), (W, H, D, bs, mode, minD, uq, int((got != want).sum()))
+print("alternative form ok")
+""" % (root, tuple(cases))
+    env = dict(os.environ)
+    env[switch] = "1"
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0 and "classic cost kernel ok" in res.stdout, res.stdout + res.stderr
+    assert res.returncode == 0 and "alternative form ok" in res.stdout, res.stdout + res.stderr
