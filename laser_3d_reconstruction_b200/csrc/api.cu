@@ -2,7 +2,7 @@
 #include <chrono>
 #include <stdexcept>
 
-#include "common.cuh"
+#include "sgbm.cuh"
 
 namespace l3d {
 
@@ -440,36 +440,6 @@ int l3d_disp_to_depth(l3d_ctx* ctx, const int16_t* disp16, int W, int H, const d
     API_END(ctx)
 }
 
-// get_frames() depth path on device buffers (camera/single_usb_stereo_camera.py:311-359)
-static int depth_path(Lane& L, const l3d_depth_config& cfg, const RectMap* maps, const uint8_t* lsrc,
-                      const uint8_t* rsrc, int W, int H, long stride, uint8_t* rectL, float* depth, int16_t* disp_f) {
-    size_t n = (size_t)W * H;
-    uint8_t* gl = L.get<uint8_t>(S_GRAY_L, n);
-    uint8_t* gr = L.get<uint8_t>(S_GRAY_R, n);
-    if (cfg.use_maps) {
-        L3D_ARG(L, maps[0].map && maps[1].map, "rectification maps not set");
-        L3D_ARG(L, maps[0].W == W && maps[0].H == H && maps[1].W == W && maps[1].H == H, "map size != image size");
-        RC(dev_remap_gray(L, maps[0], lsrc, W, H, stride, rectL, gl));
-        RC(dev_remap_gray(L, maps[1], rsrc, W, H, stride, nullptr, gr));
-    } else {
-        RC(dev_copy_gray(L, lsrc, W, H, stride, rectL, gl));
-        RC(dev_copy_gray(L, rsrc, W, H, stride, nullptr, gr));
-    }
-    int16_t* dl = L.get<int16_t>(S_DISP_L, n);
-    RC(dev_sgbm(L, cfg.left, gl, gr, W, H, dl, nullptr));
-    const int16_t* df = dl;
-    if (cfg.use_wls) {
-        int16_t* dr = L.get<int16_t>(S_DISP_R, n);
-        RC(dev_sgbm(L, cfg.right, gr, gl, W, H, dr, nullptr));
-        RC(dev_wls(L, cfg.wls, dl, dr, gl, W, H, disp_f, nullptr));
-        df = disp_f;
-    } else {
-        L3D_CHECK(L, cudaMemcpyAsync(disp_f, dl, n * 2, cudaMemcpyDeviceToDevice, L.stream));
-    }
-    RC(dev_depth(L, df, W, H, cfg.use_Q ? cfg.Q : nullptr, depth));
-    return L3D_OK;
-}
-
 // The same path split around the cluster-fused aggregation, for the grouped frame pipeline:
 // front = rectify + gray + BT operands + both matchers' cost volumes and horizontal paths;
 // back  = WTA / LR check / median / speckles of both matchers + WLS + depth.
@@ -493,13 +463,10 @@ static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps
     }
     uint4* dL = L.get<uint4>(S_DESC_L, 2 * n);  // two operand planes per view (sgbm_prefilter_kernel)
     uint4* dR = L.get<uint4>(S_DESC_R, 2 * n);
-    RC(sgbm_front(L, cfg.left, gl, gr, W, H, 0, dL, dR, true, dr.left));
     dr.has_right = cfg.use_wls != 0;
-    // the right matcher sees the views swapped: same BT operands, roles exchanged
-    if (dr.has_right) {
-        L3D_ARG(L, cfg.right.preFilterCap == cfg.left.preFilterCap, "left/right matcher preFilterCap differ");
-        RC(sgbm_front(L, cfg.right, gr, gl, W, H, 1, dR, dL, false, dr.right));
-    }
+    // the right matcher sees the views swapped: same BT operands, roles exchanged, one pixel-cost pass for both volumes
+    if (dr.has_right) RC(sgbm_front_pair(L, cfg.left, cfg.right, gl, gr, W, H, dL, dR, dr.left, dr.right));
+    else RC(sgbm_front(L, cfg.left, gl, gr, W, H, 0, dL, dR, true, dr.left));
     return L3D_OK;
 }
 static int depth_back(Lane& L, const l3d_depth_config& cfg, DepthRuns& dr, int W, int H, float* depth, int16_t* disp_f) {
@@ -518,6 +485,17 @@ static int depth_back(Lane& L, const l3d_depth_config& cfg, DepthRuns& dr, int W
     }
     RC(dev_depth(L, df, W, H, cfg.use_Q ? cfg.Q : nullptr, depth));
     return L3D_OK;
+}
+
+// get_frames() depth path on device buffers (camera/single_usb_stereo_camera.py:311-359), one frame start to finish
+// on its lane: the previous-row paths run direction-split (a lone volume would occupy 8 SMs in the cluster kernel)
+static int depth_path(Lane& L, const l3d_depth_config& cfg, const RectMap* maps, const uint8_t* lsrc,
+                      const uint8_t* rsrc, int W, int H, long stride, uint8_t* rectL, float* depth, int16_t* disp_f) {
+    DepthRuns dr;
+    RC(depth_front(L, cfg, maps, lsrc, rsrc, W, H, stride, rectL, dr));
+    RC(sgbm_middle_split(L, dr.left, false));
+    if (dr.has_right) RC(sgbm_middle_split(L, dr.right, false));
+    return depth_back(L, cfg, dr, W, H, depth, disp_f);
 }
 
 int l3d_compute_depth(l3d_ctx* ctx, const l3d_depth_config* cfg, const uint8_t* left_bgr, const uint8_t* right_bgr,

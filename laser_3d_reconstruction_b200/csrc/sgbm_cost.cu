@@ -1,0 +1,549 @@
+// sgbm_cost.cu -- BT operand planes and cost volumes of cv2.StereoSGBM, bit-exact.
+//
+// Replaces the pixel-cost / block-sum stage of stereo_matcher.compute / right_matcher.compute of the reference
+// (camera/single_usb_stereo_camera.py:252-274 parameters, :324-325 calls).
+//
+// Kernels:
+//   sgbm_prefilter_kernel     x-Sobel clip + half-pixel min/max, as pixel-pair operand entries (2 planes x 16 B / pixel)
+//   sgbm_cost_warp_kernel     Birchfield-Tomasi pixel cost -> blockSize^2 box sum -> C (+P2); disparity pairs split over
+//                             the warps, warp-private cost strips and row-sum rings, TMA operand ring, no block barrier
+//   sgbm_cost_kernel          the block-synchronous form (D = 256 and every other geometry)
+#include "sgbm.cuh"
+
+namespace l3d {
+
+constexpr int MAXBAND = 64;
+// ------------------------------------------------------------------------------------------
+// prefilter: per pixel and channel (0 = clipped x-Sobel, 1 = intensity) the Birchfield-Tomasi
+// operands as signed 16-bit values, ready for packed s16x2 DPX arithmetic:
+//   desc.x = v | (-v) << 16,  desc.y = lo | (-hi) << 16   (channel 0)      desc.z, desc.w (channel 1)
+// where lo / hi = min / max of v and its two half-pixel interpolants.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pre_pixel(const uint8_t* __restrict__ img, int W, int H, int y, int x,
+                                          int ftzero, int& c0, int& c1) {
+    if (x <= 0 || x >= W - 1) { c0 = ftzero; c1 = ftzero; return; }
+    const uint8_t* r = img + (size_t)y * W;
+    const uint8_t* rn = img + (size_t)(y > 0 ? y - 1 : y) * W;
+    const uint8_t* rs = img + (size_t)(y < H - 1 ? y + 1 : y) * W;
+    int g = ((int)r[x + 1] - (int)r[x - 1]) * 2 + (int)rn[x + 1] - (int)rn[x - 1] + (int)rs[x + 1] - (int)rs[x - 1];
+    c0 = min(max(g, -ftzero), ftzero) + ftzero;
+    c1 = r[x];
+}
+
+__device__ __forceinline__ uint32_t pack_s16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+// Output: two planes of W*H uint4 (plane c = channel c).  Entry x of a row holds the operands of the pixel PAIR
+// (x+1, x) -- low halves pixel x+1, high halves pixel x -- exactly the layout the cost kernel's packed
+// arithmetic wants for the disparity pair (d, d+1) of a left pixel (x - d = x_pair + 1):
+//   .x = v | v' << 16,  .y = -v | -v' << 16,  .z = lo | lo' << 16,  .w = -hi | -hi' << 16     (' = pixel x)
+// so a CTA's per-row operand table is a contiguous run of entries that one bulk async copy (TMA) moves
+// into shared memory with no register staging; the left pixel's own operands are the high halves.
+constexpr int PRE_THREADS = 128;
+__global__ void __launch_bounds__(PRE_THREADS) sgbm_prefilter_kernel(const uint8_t* __restrict__ img, int W, int H,
+                                                                     int ftzero, uint4* __restrict__ desc) {
+    __shared__ int sv[6][PRE_THREADS + 1];
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * PRE_THREADS, y = blockIdx.y;
+    auto vals = [&](int x, int slot) {
+        int a0, a1, b0, b1, c0, c1;
+        pre_pixel(img, W, H, y, x, ftzero, b0, b1);
+        int lo0 = b0, hi0 = b0, lo1 = b1, hi1 = b1;
+        if (x > 0) {
+            pre_pixel(img, W, H, y, x - 1, ftzero, a0, a1);
+            int t0 = (b0 + a0) >> 1, t1 = (b1 + a1) >> 1;
+            lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
+        }
+        if (x < W - 1) {
+            pre_pixel(img, W, H, y, x + 1, ftzero, c0, c1);
+            int t0 = (b0 + c0) >> 1, t1 = (b1 + c1) >> 1;
+            lo0 = min(lo0, t0); hi0 = max(hi0, t0); lo1 = min(lo1, t1); hi1 = max(hi1, t1);
+        }
+        sv[0][slot] = b0; sv[1][slot] = lo0; sv[2][slot] = hi0; sv[3][slot] = b1; sv[4][slot] = lo1; sv[5][slot] = hi1;
+    };
+    vals(min(x0 + t, W - 1), t);
+    if (t == PRE_THREADS - 1) vals(min(x0 + PRE_THREADS, W - 1), PRE_THREADS);  // pixel right of the block (clamped: pad)
+    __syncthreads();
+    const int x = x0 + t;
+    if (x >= W) return;
+    const size_t i = (size_t)y * W + x, plane = (size_t)W * H;
+    desc[i] = make_uint4(pack_s16(sv[0][t + 1], sv[0][t]), pack_s16(-sv[0][t + 1], -sv[0][t]),
+                         pack_s16(sv[1][t + 1], sv[1][t]), pack_s16(-sv[2][t + 1], -sv[2][t]));
+    desc[plane + i] = make_uint4(pack_s16(sv[3][t + 1], sv[3][t]), pack_s16(-sv[3][t + 1], -sv[3][t]),
+                                 pack_s16(sv[4][t + 1], sv[4][t]), pack_s16(-sv[5][t + 1], -sv[5][t]));
+}
+
+// ------------------------------------------------------------------------------------------
+// cost volume: C[y][x][d] = P2 + sum over the blockSize^2 window of the BT pixel cost
+// ------------------------------------------------------------------------------------------
+// A CTA owns TX output columns (TXH = TX + 2*SW2 computed columns) of a band of rows and walks the
+// band top to bottom.  Per image row:
+//   tables  thread 0 issues two bulk async copies (cp.async.bulk, mbarrier completion) that bring the row's
+//           right-image operand entries (prefilter layout above) into shared memory TWO rows ahead
+//   phase A thread <-> (column, every (256/TXH)-th disparity pair): BT cost of both channels in
+//           10 VIADD/VIADDMNMX/VIMNMX.S16x2 ops per two disparities -> pd[dp][col] (row stride TXH+1);
+//           the thread's left operands sit in registers (loaded one row ahead)
+//   phase B thread <-> (disparity pair, group of columns): running horizontal box sum along its
+//           columns, vertical running sum against a ring of the last blockSize row sums, C store
+//           (a warp writes 128 contiguous bytes per column)
+// pd is double-buffered, so ONE block barrier per row separates {phase A of row k+1, phase B of row k}
+// from the next pair.  All sums are wrap-around u16 like OpenCV's int16 arithmetic.
+struct CostArgs {
+    const uint4* Ldesc; const uint4* Rdesc; int16_t* C;  // two planes each (channel 0, channel 1)
+    int W, H, minD, D, minX1, width1, SW2, bs, P2, TX, TXH;
+    int nxg, cpg;  // phase B: column groups per CTA, columns per group
+    int nbands;
+    int band_vr0[MAXBAND], band_y0[MAXBAND], band_rows[MAXBAND], band_clo[MAXBAND], band_chi[MAXBAND];
+};
+
+constexpr int COST_THREADS = 512;
+constexpr int COST_MAXCPG = 8;
+
+__device__ __forceinline__ uint32_t bt_pair(uint32_t U, uint32_t nU, uint32_t U0, uint32_t nU1, const uint4& r) {
+    // r = (V, -V, V0, -V1) pairs; max(0, u - v1, v0 - u) and max(0, v - u1, u0 - v), then the smaller.
+    // One VIADD.16x2 + one VIADDMNMX.S16x2.RELU per term: no zero operand to materialise.
+    const uint32_t t = __viaddmax_s16x2_relu(r.z, nU, __vadd2(U, r.w));
+    const uint32_t q = __viaddmax_s16x2_relu(r.y, U0, __vadd2(r.x, nU1));
+    return __vmins2(t, q);
+}
+
+__device__ __forceinline__ void cost_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cost_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cost_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "COST_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra COST_DONE_%=;\n\t"
+        "bra COST_WAIT_%=;\n\t"
+        "COST_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cost_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// NIT: phase A items (disparity pairs) per thread and row when known at compile time (D/2 / (512/TXH)), 0 = generic
+// BS:  blockSize when known at compile time (phase B then keeps its window in registers), 0 = generic
+// DD:  numDisparities, TXHT: tile width incl. halo when known at compile time (all strides become immediates), 0 = generic
+template <int NIT, int BS, int DD, int TXHT>
+__global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int bs = BS ? BS : a.bs, SW2 = BS ? BS / 2 : a.SW2, D = DD ? DD : a.D, D2 = D >> 1;
+    const int TXH = TXHT ? TXHT : a.TXH, TX = TXH - 2 * SW2;
+    const int width1 = a.width1, W = a.W;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, x0 = blockIdx.x * TX;
+    const int y0 = a.band_y0[b], rows = a.band_rows[b], clo = a.band_clo[b], chi = a.band_chi[b], vr0 = a.band_vr0[b];
+    const int xa = min(max(x0 - SW2, 0), width1 - 1);
+    const int xb = min(max(x0 + TXH - 1 - SW2, 0), width1 - 1);
+    const int xr_base = xa + a.minX1 - (a.minD + D - 1);  // lowest right pixel any pair reads
+    const int nE = (xb - xa) + D - 1;                      // right operand entries (pair = pixels e+1, e)
+    const int PS = TXH + 1;                                // pd row stride (bank-conflict-free both ways)
+    const size_t plane = (size_t)W * a.H;
+    // smem carve-up: operand tables [2 stages][R0 | R1][nEmax], pixel costs [2][D2][PS], ring [bs][TX][D2], 2 mbarriers
+    const int nEmax = TXH + D;
+    const int tab_u4 = 2 * nEmax;                          // uint4 per operand table stage
+    uint4* tabs = (uint4*)smem_raw;
+    uint32_t* pdb = (uint32_t*)(tabs + 2 * tab_u4);
+    uint32_t* ring = pdb + 2 * D2 * PS;
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(ring + (size_t)bs * TX * D2);
+    // phase A role
+    const int ca = tid % TXH, dpa0 = tid / TXH, dpa_step = COST_THREADS / TXH;
+    const int xca = min(max(x0 - SW2 + ca, 0), width1 - 1);
+    // phase B role
+    const int dpb = tid % D2, xg = tid / D2;
+    const int cb0 = xg * a.cpg;                            // first output column (tile coordinates)
+    const int ncb = xg < a.nxg ? max(0, min(min(a.cpg, TX - cb0), width1 - (x0 + cb0))) : 0;
+    const uint32_t p2x2 = (uint32_t)a.P2 * 0x10001u;
+    uint32_t crun[COST_MAXCPG];
+#pragma unroll
+    for (int j = 0; j < COST_MAXCPG; j++) crun[j] = p2x2;
+    const int nk = rows + bs - 1;
+    const int nitA = NIT ? NIT : (dpa0 < D2 ? (D2 - dpa0 + dpa_step - 1) / dpa_step : 0);  // phase A items of this thread
+
+    auto row_of = [&](int k) { return min(max(y0 - SW2 + k, clo), chi); };
+    auto issue_tables = [&](int k) {  // thread 0: both channels' operand entries of band row k -> stage k & 1
+        const uint32_t bar = bars + 8 * (k & 1);
+        const uint32_t bytes = (uint32_t)nE * 16u;
+        const uint4* src = a.Rdesc + (size_t)row_of(k) * W + xr_base;
+        uint4* dst = tabs + (k & 1) * tab_u4;
+        cost_mbar_expect_tx(bar, 2 * bytes);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), src, bytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + nEmax), src + plane, bytes, bar);
+    };
+    if (tid == 0) {
+        cost_mbar_init(bars, 1);
+        cost_mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue_tables(0);
+        if (nk > 1) issue_tables(1);
+    }
+    // left operands of this thread's column: entry of pixel xca + minX1, loaded one row ahead
+    const uint4* Lcol = a.Ldesc + xca + a.minX1;
+    uint4 l0 = Lcol[(size_t)row_of(0) * W], l1 = Lcol[plane + (size_t)row_of(0) * W];
+    __syncthreads();  // mbarrier init visible to every waiter
+
+    auto phase_a = [&](int k) {  // pixel costs of band row k into pd[k & 1]
+        // broadcast the left pixel's operands (high halves of its entry) to both halves
+        const uint32_t u0 = __byte_perm(l0.x, l0.x, 0x3232), nu0 = __byte_perm(l0.y, l0.y, 0x3232);
+        const uint32_t ul0 = __byte_perm(l0.z, l0.z, 0x3232), nuh0 = __byte_perm(l0.w, l0.w, 0x3232);
+        const uint32_t u1 = __byte_perm(l1.x, l1.x, 0x3232), nu1 = __byte_perm(l1.y, l1.y, 0x3232);
+        const uint32_t ul1 = __byte_perm(l1.z, l1.z, 0x3232), nuh1 = __byte_perm(l1.w, l1.w, 0x3232);
+        if (k + 1 < nk) {  // next row's left operands: in flight during this row's arithmetic
+            const size_t ro = (size_t)row_of(k + 1) * W;
+            l0 = Lcol[ro]; l1 = Lcol[plane + ro];
+        }
+        cost_mbar_wait(bars + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
+        // this thread's disparity pairs dpa0, dpa0 + dpa_step, ...: table entry and pd slot move by constant strides
+        const uint4* r0p = tabs + (k & 1) * tab_u4 + (xca - xa + D - 2 - 2 * dpa0);
+        const uint4* r1p = r0p + nEmax;
+        uint32_t* pdp = pdb + (k & 1) * D2 * PS + dpa0 * PS + ca;
+        const int rstep = 2 * dpa_step, pstep = dpa_step * PS;
+        if (NIT) {
+            // batches of 4 items: all table loads first (the compiler cannot hoist them over the pd stores itself,
+            // both are shared-memory accesses), then the arithmetic, then the stores
+            constexpr int NB = 4;
+#pragma unroll
+            for (int i0 = 0; i0 < (NIT ? NIT : 1); i0 += NB) {
+                uint4 e0[NB], e1[NB];
+#pragma unroll
+                for (int i = 0; i < NB; i++) { e0[i] = r0p[-(i0 + i) * rstep]; e1[i] = r1p[-(i0 + i) * rstep]; }
+                uint32_t c[NB];
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
+                    const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
+                    c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                }
+#pragma unroll
+                for (int i = 0; i < NB; i++) pdp[(i0 + i) * pstep] = c[i];
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < nitA; i++) {
+                const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, *r0p);
+                const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, *r1p);
+                *pdp = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                r0p -= rstep; r1p -= rstep; pdp += pstep;
+            }
+        }
+    };
+    // Box sums.  Every packed half stays below 2^16 for the supported parameter range (checked on the
+    // host), so plain 32-bit adds on the u16x2 pairs are exact: no carry crosses the halves.
+    const uint32_t* ppb = pdb + dpb * PS + cb0;                 // + (k & 1) * D2 * PS per row
+    uint32_t* rpb = ring + (size_t)cb0 * D2 + dpb;              // + slot * TX * D2 per row
+    uint32_t* Cdst = (uint32_t*)(a.C + ((ptrdiff_t)(vr0 - (bs - 1)) * width1 + x0 + cb0) * D) + dpb;  // row k: + k * width1 * D2
+    const size_t crow = (size_t)width1 * D2;
+    int slot = 0;                                               // ring slot of row k (k % bs without the division)
+    auto phase_b = [&](int k) {
+        if (BS && ncb > 0) {
+            // all shared-memory loads first (window taps, ring entries that drop out), then the sums, then the stores:
+            // the compiler cannot move a load over the ring stores by itself
+            const uint32_t* pp = ppb + (k & 1) * D2 * PS;       // pp[j + i]: output column cb0 + j, tap i
+            uint32_t* rp = rpb + (size_t)slot * TX * D2;
+            const bool sub = k >= bs, emit = k >= bs - 1;
+            constexpr int NV = COST_MAXCPG + (BS ? BS : 1) - 1;
+            uint32_t pv[NV], old[COST_MAXCPG], hs[COST_MAXCPG];
+#pragma unroll
+            for (int i = 0; i < NV; i++) pv[i] = pp[i];         // taps beyond this group's columns are never used
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) old[j] = (sub && j < ncb) ? rp[j * D2] : 0u;
+            uint32_t h = 0;
+#pragma unroll
+            for (int i = 0; i < (BS ? BS : 1); i++) h += pv[i];
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j > 0) h = h + pv[j + (BS ? BS : 1) - 1] - pv[j - 1];
+                hs[j] = h;
+                crun[j] = crun[j] + h - old[j];
+            }
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j < ncb) {
+                    rp[j * D2] = hs[j];
+                    if (emit) Cdst[j * D2] = crun[j];
+                }
+            }
+        } else if (ncb > 0) {
+            const uint32_t* pp = ppb + (k & 1) * D2 * PS;       // pp[j + i]: output column cb0 + j, tap i
+            uint32_t h = 0;
+#pragma unroll 3
+            for (int i = 0; i < bs; i++) h += pp[i];
+            uint32_t* rp = rpb + (size_t)slot * TX * D2;
+            const bool sub = k >= bs, emit = k >= bs - 1;
+#pragma unroll
+            for (int j = 0; j < COST_MAXCPG; j++) {
+                if (j < ncb) {
+                    if (j > 0) h = h + pp[j + bs - 1] - pp[j - 1];
+                    uint32_t c = crun[j] + h;
+                    if (sub) c -= rp[j * D2];
+                    rp[j * D2] = h;
+                    crun[j] = c;
+                    if (emit) Cdst[j * D2] = c;
+                }
+            }
+        }
+        Cdst += crow;
+        slot = slot + 1 == bs ? 0 : slot + 1;
+    };
+    phase_a(0);
+    for (int k = 0; k < nk; k++) {
+        __syncthreads();  // pd[k & 1] complete; stage k & 1 of the tables and pd[(k + 1) & 1] are free again
+        if (tid == 0 && k + 2 < nk) issue_tables(k + 2);
+        if (k + 1 < nk) phase_a(k + 1);
+        phase_b(k);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// cost volume, warp-decoupled form (numDisparities 64 / 128, 64-column tiles)
+// ------------------------------------------------------------------------------------------
+// Same tile / band decomposition and the same arithmetic as sgbm_cost_kernel, but the disparity pairs are split
+// over the 16 warps (DPW = D/32 pairs each) and BOTH phases of a pair stay in one warp: the warp computes the pixel
+// costs of its pairs for all 64 tile columns (lane <-> columns lane and lane + 32), writes them to a private strip
+// of shared memory, and sums them itself (lane <-> pair x group of columns) against a private ring of row sums.
+// There is no block-wide barrier in the row loop: warps only meet at the mbarriers of the operand-table ring
+// (full: TMA bulk copies landed; empty: all 16 warps are done reading a stage) and drift apart by up to
+// CW_NS - 1 rows, so one warp's shared-memory latency is covered by another warp's arithmetic.  The left operands
+// come in with the same bulk copies (contiguous run of the tile's columns; replicate-clamped tile edges index the
+// run with a clamped column).  A warp stores DPW * 4 contiguous bytes per pixel; the 16 warps' pieces of a pixel's
+// vector meet in L2 before they reach HBM.
+constexpr int CW_NS = 4;        // operand-table stages
+constexpr int CW_TXH = 64;      // tile width incl. halo
+constexpr int CW_PDS = 88;      // pixel-cost strip stride per pair (== 24 mod 32: phase B's 32 lanes hit 32 banks)
+
+static size_t cost_warp_smem(int D, int bs) {
+    const int D2 = D / 2, TX = CW_TXH - (bs - 1);
+    return (size_t)CW_NS * (2 * (CW_TXH + D) + 2 * CW_TXH) * 16 + (size_t)D2 * CW_PDS * 4 + (size_t)bs * D2 * TX * 4 + 64;
+}
+
+template <int BS, int DD>
+__global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const CostArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int D = DD, D2 = DD / 2, SW2 = BS / 2, TXH = CW_TXH, TX = TXH - 2 * SW2;
+    constexpr int NW = COST_THREADS / 32, DPW = D2 / NW, NG = 32 / DPW, CPG = (TX + NG - 1) / NG;
+    constexpr int NEMAX = TXH + D;                      // right-operand entries per channel and stage
+    constexpr int STAGE_U4 = 2 * NEMAX + 2 * TXH;       // [R0 | R1 | L0 | L1]
+    static_assert(DPW >= 1 && 32 % DPW == 0 && CPG <= COST_MAXCPG, "tile geometry");
+    const int width1 = a.width1, W = a.W;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int b = blockIdx.y, x0 = blockIdx.x * TX;
+    const int y0 = a.band_y0[b], rows = a.band_rows[b], clo = a.band_clo[b], chi = a.band_chi[b], vr0 = a.band_vr0[b];
+    const int xa = min(max(x0 - SW2, 0), width1 - 1);
+    const int xb = min(max(x0 + TXH - 1 - SW2, 0), width1 - 1);
+    const int xr_base = xa + a.minX1 - (a.minD + D - 1);
+    const int nE = (xb - xa) + D - 1;
+    const size_t plane = (size_t)W * a.H;
+    // contiguous run of left columns this tile reads: tile columns [lc0, lc1) hold image columns x0 - SW2 + c unclamped
+    const int lc0 = max(0, SW2 - x0), lc1 = min(TXH, width1 - (x0 - SW2));
+    uint4* tabs = (uint4*)smem_raw;                                          // [CW_NS][STAGE_U4]
+    uint32_t* pdw = (uint32_t*)(tabs + CW_NS * STAGE_U4) + warp * DPW * CW_PDS;  // this warp's pixel-cost strip [DPW][CW_PDS]
+    uint32_t* ringw = (uint32_t*)(tabs + CW_NS * STAGE_U4) + D2 * CW_PDS + (size_t)warp * BS * DPW * TX;  // [BS][DPW][TX]
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared((uint32_t*)(tabs + CW_NS * STAGE_U4) + D2 * CW_PDS + (size_t)BS * D2 * TX);
+    // bars + 8 s: full[s], bars + 8 (CW_NS + s): empty[s]
+    const int nk = rows + BS - 1;
+    auto row_of = [&](int k) { return min(max(y0 - SW2 + k, clo), chi); };
+    auto issue_tables = [&](int k) {  // one thread: operand entries of band row k -> stage k % CW_NS
+        const int s = k % CW_NS;
+        const uint32_t bar = bars + 8 * s;
+        const uint32_t rbytes = (uint32_t)nE * 16u, lbytes = (uint32_t)(lc1 - lc0) * 16u;
+        const size_t ro = (size_t)row_of(k) * W;
+        const uint4* rsrc = a.Rdesc + ro + xr_base;
+        const uint4* lsrc = a.Ldesc + ro + (x0 - SW2 + lc0) + a.minX1;
+        uint4* dst = tabs + s * STAGE_U4;
+        cost_mbar_expect_tx(bar, 2 * rbytes + 2 * lbytes);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), rsrc, rbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + NEMAX), rsrc + plane, rbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + 2 * NEMAX + lc0), lsrc, lbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + 2 * NEMAX + TXH + lc0), lsrc + plane, lbytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CW_NS; s++) { cost_mbar_init(bars + 8 * s, 1); cost_mbar_init(bars + 8 * (CW_NS + s), NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < CW_NS - 1 && k < nk; k++) issue_tables(k);
+    }
+    __syncthreads();  // barrier init visible; the only block-wide barrier of the kernel
+
+    // phase A role: tile columns lane and lane + 32, pairs dp0 .. dp0 + DPW - 1
+    const int dp0 = warp * DPW;
+    int eoff[2], lcol[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+        const int c = lane + 32 * hh;
+        const int xc = min(max(x0 - SW2 + c, 0), width1 - 1);
+        eoff[hh] = xc - xa + D - 2 - 2 * dp0;               // entry of pair dp0; pair dp0 + i is 2 i entries lower
+        lcol[hh] = min(max(c, lc0), lc1 - 1);               // replicate clamp inside the staged run
+    }
+    // phase B role
+    const int dpi = lane % DPW, g = lane / DPW;
+    const int cb0 = g * CPG;
+    const int ncb = max(0, min(min(CPG, TX - cb0), width1 - (x0 + cb0)));
+    const uint32_t p2x2 = (uint32_t)a.P2 * 0x10001u;
+    uint32_t crun[CPG];
+#pragma unroll
+    for (int j = 0; j < CPG; j++) crun[j] = p2x2;
+    uint32_t* Cdst = (uint32_t*)(a.C + ((ptrdiff_t)(vr0 - (BS - 1)) * width1 + x0 + cb0) * D) + dp0 + dpi;
+    const size_t crow = (size_t)width1 * D2;
+    const uint32_t* ppb = pdw + dpi * CW_PDS + cb0;
+    uint32_t* rpb = ringw + dpi * TX + cb0;
+    int slot = 0;
+
+    for (int k = 0; k < nk; k++) {
+        const int s = k % CW_NS;
+        // refill duty: rows' tables are issued CW_NS - 1 rows ahead by the warp whose turn it is
+        if (warp == (k & (NW - 1)) && k + CW_NS - 1 < nk) {
+            if (lane == 0) {
+                const int kk = k + CW_NS - 1, sk = kk % CW_NS;  // stage last read for row k - 1
+                if (k >= 1) cost_mbar_wait(bars + 8 * (CW_NS + sk), (uint32_t)(((k - 1) / CW_NS) & 1));
+                issue_tables(kk);
+            }
+            __syncwarp();
+        }
+        cost_mbar_wait(bars + 8 * s, (uint32_t)((k / CW_NS) & 1));
+        const uint4* T0 = tabs + s * STAGE_U4;
+        // ---- phase A
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const uint4 l0 = T0[2 * NEMAX + lcol[hh]], l1 = T0[2 * NEMAX + TXH + lcol[hh]];
+            const uint32_t u0 = __byte_perm(l0.x, l0.x, 0x3232), nu0 = __byte_perm(l0.y, l0.y, 0x3232);
+            const uint32_t ul0 = __byte_perm(l0.z, l0.z, 0x3232), nuh0 = __byte_perm(l0.w, l0.w, 0x3232);
+            const uint32_t u1 = __byte_perm(l1.x, l1.x, 0x3232), nu1 = __byte_perm(l1.y, l1.y, 0x3232);
+            const uint32_t ul1 = __byte_perm(l1.z, l1.z, 0x3232), nuh1 = __byte_perm(l1.w, l1.w, 0x3232);
+            uint4 e0[DPW], e1[DPW];
+#pragma unroll
+            for (int i = 0; i < DPW; i++) { e0[i] = T0[eoff[hh] - 2 * i]; e1[i] = T0[NEMAX + eoff[hh] - 2 * i]; }
+            uint32_t c[DPW];
+#pragma unroll
+            for (int i = 0; i < DPW; i++) {
+                const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
+                const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
+                c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+            }
+#pragma unroll
+            for (int i = 0; i < DPW; i++) pdw[i * CW_PDS + lane + 32 * hh] = c[i];
+        }
+        __syncwarp();  // strip complete; every lane's table reads have returned
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (CW_NS + s)) : "memory");
+        // ---- phase B
+        if (ncb > 0) {
+            uint32_t* rp = rpb + (size_t)slot * DPW * TX;
+            const bool sub = k >= BS, emit = k >= BS - 1;
+            constexpr int NV = CPG + BS - 1;
+            uint32_t pv[NV], old[CPG], hs[CPG];
+#pragma unroll
+            for (int i = 0; i < NV; i++) pv[i] = ppb[i];
+#pragma unroll
+            for (int j = 0; j < CPG; j++) old[j] = (sub && j < ncb) ? rp[j] : 0u;
+            uint32_t h = 0;
+#pragma unroll
+            for (int i = 0; i < BS; i++) h += pv[i];
+#pragma unroll
+            for (int j = 0; j < CPG; j++) {
+                if (j > 0) h = h + pv[j + BS - 1] - pv[j - 1];
+                hs[j] = h;
+                crun[j] = crun[j] + h - old[j];
+            }
+#pragma unroll
+            for (int j = 0; j < CPG; j++) {
+                if (j < ncb) {
+                    rp[j] = hs[j];
+                    if (emit) Cdst[(size_t)j * D2] = crun[j];
+                }
+            }
+        }
+        __syncwarp();  // the strip is rewritten by the next row's phase A
+        Cdst += crow;
+        slot = slot + 1 == BS ? 0 : slot + 1;
+    }
+}
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+int sgbm_prefilter(Lane& L, const uint8_t* img, int W, int H, int ftzero, uint4* desc) {
+    dim3 pg(cdiv(W, PRE_THREADS), H);
+    L3D_LAUNCH(L, sgbm_prefilter_kernel, pg, PRE_THREADS, 0, img, W, H, ftzero, desc);
+    return L3D_OK;
+}
+
+// bands: split each segment (SGBM_3WAY stripe, else the image) so that the grid is close to `want` CTAs per x tile
+static void cost_bands(const Geom& g, int H, int want, CostArgs& ca) {
+    int per_seg = std::max(1, std::min(want / g.nseg, MAXBAND / g.nseg));
+    ca.nbands = 0;
+    for (int s = 0; s < g.nseg; s++) {
+        int rows = g.seg_rows[s];
+        int nb = std::max(1, std::min(per_seg, rows / (2 * g.bs) > 0 ? rows / (2 * g.bs) : 1));
+        int br = cdiv(rows, nb);
+        for (int r0 = 0; r0 < rows; r0 += br) {
+            int i = ca.nbands++;
+            ca.band_vr0[i] = g.seg_vr0[s] + r0;
+            ca.band_y0[i] = g.seg_y0[s] + r0;
+            ca.band_rows[i] = std::min(br, rows - r0);
+            ca.band_clo[i] = g.seg_y0[s];  // the vertical box sum restarts at the segment top
+            ca.band_chi[i] = H - 1;
+        }
+    }
+}
+
+int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, int16_t* C) {
+    const int W = g.W, H = g.H;
+    CostArgs ca;
+    ca.Ldesc = dL; ca.Rdesc = dR; ca.C = C;
+    ca.W = W; ca.H = H; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
+    ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
+    const int D2 = g.D / 2;
+    auto cost_smem = [&](int txh) {
+        int tx = txh - 2 * g.SW2;
+        return (size_t)2 * 2 * (txh + g.D) * 16 + (size_t)2 * D2 * (txh + 1) * 4 + (size_t)g.bs * tx * D2 * 4 + 16;
+    };
+    ca.nxg = std::max(1, COST_THREADS / D2);
+    int TXH = 64;
+    while (TXH > 2 * g.SW2 + 1 &&
+           (cost_smem(TXH) > 200 * 1024 || cdiv(TXH - 2 * g.SW2, ca.nxg) > COST_MAXCPG)) TXH /= 2;
+    L3D_ARG(L, TXH > 2 * g.SW2 && COST_THREADS % TXH == 0 && cost_smem(TXH) <= 200 * 1024 &&
+                   cdiv(TXH - 2 * g.SW2, ca.nxg) <= COST_MAXCPG,
+            "sgbm: blockSize / numDisparities combination exceeds the cost kernel's shared-memory tile");
+    ca.TXH = TXH; ca.TX = TXH - 2 * g.SW2;
+    ca.cpg = cdiv(ca.TX, ca.nxg);
+    size_t smem = cost_smem(TXH);
+    static const bool no_warp_cost = getenv("L3D_COST_CLASSIC") != nullptr;
+    const bool warp_form = !no_warp_cost && ((g.D == 128 && g.bs == 9) || (g.D == 64 && g.bs == 5));
+    if (warp_form) {
+        // warp-decoupled form: 64-column tiles
+        ca.TXH = CW_TXH; ca.TX = CW_TXH - 2 * g.SW2;
+        smem = cost_warp_smem(g.D, g.bs);
+    }
+    // the grid is close to one wave of CTAs (one CTA per SM: the row-sum ring takes most of the shared memory)
+    const int xtiles = cdiv(g.width1, ca.TX);
+    static const int waves = getenv("L3D_COST_WAVES") ? atoi(getenv("L3D_COST_WAVES")) : 1;
+    cost_bands(g, H, std::max(1, (waves * NUM_SMS) / xtiles), ca);
+    const int dpa_step = COST_THREADS / TXH;
+    const int nit = (D2 % dpa_step == 0) ? D2 / dpa_step : 0;
+#define COST_CASE(KERN)                                                                                          \
+    {                                                                                                            \
+        L3D_CHECK(L, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));       \
+        L3D_LAUNCH(L, KERN, dim3(xtiles, ca.nbands), COST_THREADS, smem, ca);                                    \
+    }
+    // specialised for the configurations of BASELINE.json (c3: D 128 / block 9, c1-c2: D 64 / block 5, c4: D 256 / block 11)
+    if (warp_form && g.D == 128) COST_CASE((sgbm_cost_warp_kernel<9, 128>))
+    else if (warp_form) COST_CASE((sgbm_cost_warp_kernel<5, 64>))
+    else if (nit == 8 && g.bs == 9 && g.D == 128 && TXH == 64) COST_CASE((sgbm_cost_kernel<8, 9, 128, 64>))
+    else if (nit == 4 && g.bs == 5 && g.D == 64 && TXH == 64) COST_CASE((sgbm_cost_kernel<4, 5, 64, 64>))
+    else if (nit == 8 && g.bs == 11 && g.D == 256 && TXH == 32) COST_CASE((sgbm_cost_kernel<8, 11, 256, 32>))
+    else COST_CASE((sgbm_cost_kernel<0, 0, 0, 0>))
+#undef COST_CASE
+    return L3D_OK;
+}
+
+bool sgbm_cost_dual_ok(const Geom& gl, const Geom& gr) { (void)gl; (void)gr; return false; }
+int sgbm_cost_dual(Lane& L, const Geom& gl, const Geom& gr, const uint4* dLv, const uint4* dRv, int16_t* Cl, int16_t* Cr) {
+    (void)gl; (void)gr; (void)dLv; (void)dRv; (void)Cl; (void)Cr;
+    set_err(L.err, "sgbm_cost_dual: not built");
+    return L3D_ERR_UNSUPPORTED;
+}
+
+}  // namespace l3d
