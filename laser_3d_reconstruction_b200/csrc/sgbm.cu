@@ -28,6 +28,7 @@
 #include <cuda_pipeline.h>
 
 #include "sgbm.cuh"
+#include "sgm_step.cuh"
 
 namespace l3d {
 
@@ -97,6 +98,7 @@ int sgbm_volume_rows(const l3d_sgbm_params& p, int W, int H) {
 struct ScanArgs {
     const int16_t* C; int16_t* S;
     int width1, D, nact, P1, P2;
+    uint32_t zero;  // 0, as a value the compiler cannot see (sgm_step.cuh)
     int kind;   // 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up, 6 up-left, 7 up-right
     int store;  // 1: S = L ; 0: S = min(S + L, 32767)
     int HV, nseg;
@@ -127,47 +129,6 @@ template <> __device__ __forceinline__ uint2 vec_pack<2>(const uint32_t (&o)[2])
 template <> __device__ __forceinline__ uint4 vec_pack<4>(const uint32_t (&o)[4]) { return make_uint4(o[0], o[1], o[2], o[3]); }
 
 constexpr int SCAN_WARPS = 4;
-
-// One SGM step for the disparities held by this lane.  State: L (u16x2 words) and minL2 = the
-// warp-wide minimum of L replicated in both halves.  With delta = minL + P2,
-//     L'[d] = C[d] + min(L[d] - delta, L[d-1] + P1 - delta, L[d+1] + P1 - delta, 0)
-// which is OpenCV's  C + min(L[d], L[d+-1] + P1, delta) - delta  with the subtraction folded into
-// the operands: three VIADDMNMX.S16x2 and one VIADD.16x2 per word.  -delta and P1 - delta are taken
-// modulo 2^16; every true intermediate lies in [-P2, 32767], so the wrapped s16 arithmetic is exact.
-// k2 = (0x10000 - P2) * 0x10001, p1x2 = P1 * 0x10001; neither k2 - minL2 nor (k2 - minL2) + p1x2 can
-// carry between the halves (minL <= 32767, P1 < P2 <= 16000).
-// Inactive lanes (lane >= nact, only when !FULL) keep L = INF2 so that neither the neighbour
-// exchange nor the min-reduction sees them.
-template <int NP, bool FULL>
-__device__ __forceinline__ uint32_t sgm_step(uint32_t (&L)[NP], uint32_t minL2, const uint32_t (&Cv)[NP],
-                                             uint32_t p1x2, uint32_t k2, int lane, bool active) {
-    const uint32_t up = __shfl_up_sync(FULL_MASK, L[NP - 1], 1);
-    const uint32_t dn = __shfl_down_sync(FULL_MASK, L[0], 1);
-    // lane 0 has no d-1 and lane 31 no d+1 neighbour: their byte-permute selectors (loop-invariant per-lane
-    // constants) put the word's own value into the missing slot -- L[d] + P1 - delta >= L[d] - delta never wins
-    const uint32_t selA = lane == 0 ? 0x5454u : 0x5432u, selB = lane == 31 ? 0x3232u : 0x5432u;
-    const uint32_t nd2 = k2 - minL2;   // -(minL + P2) mod 2^16, both halves
-    const uint32_t pm2 = nd2 + p1x2;   // P1 - (minL + P2) mod 2^16
-    uint32_t mn = INF2;
-    uint32_t Ln[NP];
-#pragma unroll
-    for (int k = 0; k < NP; k++) {
-        uint32_t prev = k ? L[k - 1] : up;
-        uint32_t next = (k < NP - 1) ? L[k + 1] : dn;
-        uint32_t dm1 = k ? __byte_perm(prev, L[k], 0x5432) : __byte_perm(prev, L[k], selA);
-        uint32_t dp1 = (k < NP - 1) ? __byte_perm(L[k], next, 0x5432) : __byte_perm(L[k], next, selB);
-        uint32_t t = __viaddmin_s16x2(L[k], nd2, 0u);
-        t = __viaddmin_s16x2(dm1, pm2, t);
-        t = __viaddmin_s16x2(dp1, pm2, t);
-        Ln[k] = __vadd2(Cv[k], t);
-        if (!FULL && !active) Ln[k] = INF2;
-        mn = __vminu2(mn, Ln[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < NP; k++) L[k] = Ln[k];
-    mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));  // both halves = min of the two
-    return __reduce_min_sync(FULL_MASK, mn);          // packed halves are equal, so the u32 min is the packed min
-}
 
 // Scan lines of one path direction.  kinds: 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up,
 // 6 up-left, 7 up-right (direction of travel; the predecessor is one step behind).  Horizontal
@@ -323,6 +284,7 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
 
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const uint32_t k2 = (0x10000u - (uint32_t)a.P2) * 0x10001u;
+    const SgmLane sl = sgm_lane_init(lane, a.zero);
     const int vstride = (int)pstride * nact;                    // vec-index step
     unsigned so = (unsigned)pix0 * (unsigned)nact + (unsigned)lane;
 
@@ -374,7 +336,7 @@ __device__ __forceinline__ void scan_run(const ScanArgs& a, const ScanLine& ln, 
 #pragma unroll
             for (int q = 0; q < NP; q++) { Cw[q] = 0; Sw[q] = 0; }
         }
-        minL = sgm_step<NP, FULL>(L, minL, Cw, p1x2, k2, lane, active);
+        minL = sgm_step<NP, false, FULL>(L, L, minL, Cw, p1x2, k2, sl, active);
         uint32_t out[NP];
 #pragma unroll
         for (int q = 0; q < NP; q++) out[q] = STORE ? L[q] : __viaddmin_u16x2(Sw[q], L[q], INF2);
@@ -833,7 +795,7 @@ static void scan_args_of(const SgbmRun& r, ScanArgs& sa) {
     sa.HV = g.HV; sa.nseg = g.nseg;
     for (int s = 0; s < MAXSEG; s++) { sa.seg_vr0[s] = g.seg_vr0[s]; sa.seg_rows[s] = g.seg_rows[s]; }
     sa.raw = r.raw; sa.disp2key = r.d2; sa.W = r.W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
-    sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0;
+    sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0; sa.zero = 0;
     sa.tway = g.mode == 2;
     for (int s = 0; s < MAXSEG; s++) { sa.seg_y0[s] = g.seg_y0[s]; sa.seg_emit[s] = g.seg_emit[s]; }
 }

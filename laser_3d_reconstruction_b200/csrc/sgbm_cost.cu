@@ -91,6 +91,7 @@ struct CostArgs {
     const uint4* Ldesc; const uint4* Rdesc; int16_t* C;  // two planes each (channel 0, channel 1)
     int W, H, minD, D, minX1, width1, SW2, bs, P2, TX, TXH;
     int nxg, cpg;  // phase B: column groups per CTA, columns per group
+    int dbg;       // L3D_COST_DBG experiment bits: 1 no C stores, 2 no phase B, 4 no phase A (results are garbage)
     int nbands;
     int band_vr0[MAXBAND], band_y0[MAXBAND], band_rows[MAXBAND], band_clo[MAXBAND], band_chi[MAXBAND];
 };
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
         cost_mbar_wait(bars + 8 * s, (uint32_t)((k / CW_NS) & 1));
         const uint4* T0 = tabs + s * STAGE_U4;
         // ---- phase A
+        if (!(a.dbg & 4))
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
             const uint4 l0 = T0[2 * NEMAX + lcol[hh]], l1 = T0[2 * NEMAX + TXH + lcol[hh]];
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
         __syncwarp();  // strip complete; every lane's table reads have returned
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars + 8 * (CW_NS + s)) : "memory");
         // ---- phase B
-        if (ncb > 0) {
+        if (ncb > 0 && !(a.dbg & 2)) {
             uint32_t* rp = rpb + (size_t)slot * DPW * TX;
             const bool sub = k >= BS, emit = k >= BS - 1;
             constexpr int NV = CPG + BS - 1;
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
             for (int j = 0; j < CPG; j++) {
                 if (j < ncb) {
                     rp[j] = hs[j];
-                    if (emit) Cdst[(size_t)j * D2] = crun[j];
+                    if (emit && !((a.dbg & 1) && crun[j] != 0x12345u)) Cdst[(size_t)j * D2] = crun[j];
                 }
             }
         }
@@ -495,6 +497,8 @@ int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, i
     ca.Ldesc = dL; ca.Rdesc = dR; ca.C = C;
     ca.W = W; ca.H = H; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
     ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
+    static const int cost_dbg = getenv("L3D_COST_DBG") ? atoi(getenv("L3D_COST_DBG")) : 0;
+    ca.dbg = cost_dbg;
     const int D2 = g.D / 2;
     auto cost_smem = [&](int txh) {
         int tx = txh - 2 * g.SW2;

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "sgm_step.cuh"
 
 namespace l3d {
 namespace cg = cooperative_groups;
@@ -32,6 +33,8 @@ constexpr int VG_MAXJOBS = 64;
 // 16 warps x 120 registers leave 4096 registers of the SM free: the one-warp CTAs of the back-half kernels (FGS
 // solver, ...) can then share an SM with an aggregation CTA instead of blocking a whole cluster from launching
 #define VG_MAXREG 120
+// interior neighbour words of the SGM step on the FMA pipe (sgm_step.cuh); only D = 256 has any that would pay
+constexpr bool VG_FMAFUNNEL = false;
 
 struct VGroupArgs {
     const int16_t* C[VG_MAXJOBS];
@@ -42,6 +45,7 @@ struct VGroupArgs {
     // are still in shared memory and S is NOT written back (per job: raw disparity image, disp2 vote buffer,
     // minDisparity, minX1, uniquenessRatio; W = image width)
     int final, W;
+    uint32_t zero;                       // 0, as a value the compiler cannot see (sgm_step.cuh)
     int16_t* raw[VG_MAXJOBS];
     unsigned* d2[VG_MAXJOBS];
     int minD[VG_MAXJOBS], minX1[VG_MAXJOBS], uniq[VG_MAXJOBS];
@@ -98,40 +102,6 @@ template <> __device__ __forceinline__ void vg_st_async_vec<2>(uint32_t raddr, c
 template <> __device__ __forceinline__ void vg_st_async_vec<4>(uint32_t raddr, const uint32_t (&v)[4], uint32_t rbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(raddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(rbar) : "memory");
-}
-
-// the SGM step of sgbm.cu (sgm_step<NP, true>): O[d] = C[d] + min(I[d]-delta, I[d+-1]+P1-delta, 0), delta = minI + P2.
-// In and out may be the same registers (every output word is computed before any is stored).
-// Lane 0 has no d-1 neighbour and lane 31 no d+1 neighbour.  Instead of substituting "infinity" after the shuffles
-// (two SELs per step) the byte-permute selectors of those two lanes (selA / selB, per-lane constants) feed the
-// word's own value into the missing slot: L[d] + P1 - delta >= L[d] - delta, so that term never wins.
-template <int NP>
-__device__ __forceinline__ uint32_t vg_step(uint32_t (&O)[NP], const uint32_t (&I)[NP], uint32_t minI2,
-                                            const uint32_t (&Cv)[NP], uint32_t p1x2, uint32_t k2, uint32_t selA,
-                                            uint32_t selB) {
-    constexpr uint32_t INF = 0x7fff7fffu;
-    const uint32_t up = __shfl_up_sync(0xffffffffu, I[NP - 1], 1);
-    const uint32_t dn = __shfl_down_sync(0xffffffffu, I[0], 1);
-    const uint32_t nd2 = k2 - minI2;
-    const uint32_t pm2 = nd2 + p1x2;
-    uint32_t mn = INF;
-    uint32_t Ln[NP];
-#pragma unroll
-    for (int k = 0; k < NP; k++) {
-        const uint32_t prev = k ? I[k - 1] : up;
-        const uint32_t next = (k < NP - 1) ? I[k + 1] : dn;
-        const uint32_t dm1 = k ? __byte_perm(prev, I[k], 0x5432) : __byte_perm(prev, I[k], selA);
-        const uint32_t dp1 = (k < NP - 1) ? __byte_perm(I[k], next, 0x5432) : __byte_perm(I[k], next, selB);
-        uint32_t t = __viaddmin_s16x2(I[k], nd2, 0u);
-        t = __viaddmin_s16x2(dm1, pm2, t);
-        t = __viaddmin_s16x2(dp1, pm2, t);
-        Ln[k] = __vadd2(Cv[k], t);
-        mn = __vminu2(mn, Ln[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < NP; k++) O[k] = Ln[k];
-    mn = __vminu2(mn, __byte_perm(mn, mn, 0x1032));
-    return __reduce_min_sync(0xffffffffu, mn);
 }
 
 template <int NP> struct VgVec;
@@ -235,7 +205,7 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
     }
     const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
     const uint32_t k2 = (0x10000u - (uint32_t)a.P2) * 0x10001u;
-    const uint32_t selA = lane == 0 ? 0x5454u : 0x5432u, selB = lane == 31 ? 0x3232u : 0x5432u;
+    const SgmLane sl = sgm_lane_init(lane, a.zero);
     const int c0 = warp * cpw;  // first column of this warp inside the strip
     // where this warp's exports go: A state leaves to the right (warp + 1 or the next CTA's warp 0),
     // B state leaves to the left (warp - 1 or the previous CTA's last warp)
@@ -283,18 +253,18 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
 #pragma unroll
         for (int j = CPW - 1; j >= 1; j--) {
             vg_unpack<NP>(cs[j * 32], Cw);
-            mA[j] = vg_step<NP>(LA[j], LA[j - 1], mA[j - 1], Cw, p1x2, k2, selA, selB);
+            mA[j] = sgm_step<NP, VG_FMAFUNNEL>(LA[j], LA[j - 1], mA[j - 1], Cw, p1x2, k2, sl);
         }
         vg_unpack<NP>(cs[0], Cw);
-        mA[0] = vg_step<NP>(LA[0], inA, inAm, Cw, p1x2, k2, selA, selB);
+        mA[0] = sgm_step<NP, VG_FMAFUNNEL>(LA[0], inA, inAm, Cw, p1x2, k2, sl);
         // ---- diagonal B (fed from the right): in place, left to right
 #pragma unroll
         for (int j = 0; j < CPW - 1; j++) {
             vg_unpack<NP>(cs[j * 32], Cw);
-            mB[j] = vg_step<NP>(LB[j], LB[j + 1], mB[j + 1], Cw, p1x2, k2, selA, selB);
+            mB[j] = sgm_step<NP, VG_FMAFUNNEL>(LB[j], LB[j + 1], mB[j + 1], Cw, p1x2, k2, sl);
         }
         vg_unpack<NP>(cs[(CPW - 1) * 32], Cw);
-        mB[CPW - 1] = vg_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, selA, selB);
+        mB[CPW - 1] = sgm_step<NP, VG_FMAFUNNEL>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, sl);
         if (x0 + c0 + CPW > width1) {
             // columns outside the image: their state must read as "no predecessor" (0) for the last valid column
 #pragma unroll
@@ -336,7 +306,7 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
 #pragma unroll
         for (int j = 0; j < CPW; j++) {
             vg_unpack<NP>(cs[j * 32], Cw);
-            mV[j] = vg_step<NP>(LV[j], LV[j], mV[j], Cw, p1x2, k2, selA, selB);
+            mV[j] = sgm_step<NP, VG_FMAFUNNEL>(LV[j], LV[j], mV[j], Cw, p1x2, k2, sl);
             uint32_t Sw[NP];
             vg_unpack<NP>(ss[j * 32], Sw);
 #pragma unroll
@@ -447,6 +417,7 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
             }
         }
         a.final = wta ? 1 : 0; a.W = wta ? wta[0].W : 0;
+        a.zero = 0;
         a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir;
         a.cluster = vgroup_cluster_size(width1, D);
         a.cpw = cdiv(width1, a.cluster * VG_WARPS);
