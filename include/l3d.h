@@ -95,6 +95,14 @@ int l3d_sgbm_compute(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left
 int l3d_sgbm_debug(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left,
                    const uint8_t* right, int W, int H, int16_t* disp, int16_t* raw,
                    int16_t* C_out, int16_t* S_out);
+/* The matcher pair of the reference's get_frames(): stereo_matcher.compute(left, right) and
+ * right_matcher.compute(right, left) (camera/single_usb_stereo_camera.py:324-325) in one call.  BT operands are
+ * built once per view and -- for the geometries the shared pass covers (right->minDisparity = -(D-1), equal
+ * blockSize / P2, D 64 with block 5 or D 128 with block 9) -- both cost volumes come from ONE pixel-cost pass.
+ * Cl_out / Cr_out (may be NULL): the two HV*width1*D int16 cost volumes, for parity tests. */
+int l3d_sgbm_compute_pair(l3d_ctx* ctx, const l3d_sgbm_params* left_params, const l3d_sgbm_params* right_params,
+                          const uint8_t* left, const uint8_t* right, int W, int H, int16_t* disp_left,
+                          int16_t* disp_right, int16_t* Cl_out, int16_t* Cr_out);
 /* rows of the C/S volumes l3d_sgbm_debug writes (H, or the sum of 3WAY stripe heights) */
 int l3d_sgbm_volume_rows(const l3d_sgbm_params* p, int W, int H);
 /* Measurement hook for the cluster-fused aggregation kernel (sgbm_vgroup.cu): runs pass `dir` over njobs

@@ -67,7 +67,7 @@ RECON_PLANE, RECON_DEPTH, RECON_DISPARITY, RECON_DISPARITY_MEDIAN = 0, 1, 2, 3
 
 EXPORTS = (
     "l3d_ctx_create l3d_ctx_destroy l3d_last_error l3d_sync l3d_device_count l3d_version l3d_launch_count "
-    "l3d_set_rectify_maps l3d_init_undistort_rectify_map l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_debug l3d_sgbm_volume_rows "
+    "l3d_set_rectify_maps l3d_init_undistort_rectify_map l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_compute_pair l3d_sgbm_debug l3d_sgbm_volume_rows "
     "l3d_sgbm_vgroup_time l3d_bm_compute l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
     "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_voxel_downsample l3d_statistical_outlier_removal l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch "
@@ -259,6 +259,28 @@ class Context:
         if want_volumes:
             out += [Cv, Sv]
         return out[0] if len(out) == 1 else tuple(out)
+
+    def sgbm_compute_pair(self, params_left, params_right, left, right, want_volumes=False):
+        """stereo_matcher.compute(left, right) and right_matcher.compute(right, left) in one call (shared BT operands
+        and, where covered, one pixel-cost pass for both cost volumes).  -> (disp_left, disp_right[, C_left, C_right])"""
+        left, right = _arr(left, np.uint8), _arr(right, np.uint8)
+        if left.ndim != 2 or left.shape != right.shape:
+            raise ValueError("StereoSGBM.compute expects two single-channel uint8 images of equal size")
+        H, W = left.shape
+        dl, dr = np.empty((H, W), np.int16), np.empty((H, W), np.int16)
+        vols = [None, None]
+        if want_volumes:
+            for i, p in enumerate((params_left, params_right)):
+                hv = self.lib.l3d_sgbm_volume_rows(C.byref(p), W, H)
+                if hv <= 0:
+                    raise L3DError("unsupported StereoSGBM parameters")
+                minD, D = p.minDisparity, p.numDisparities
+                width1 = (W + min(minD, 0)) - max(minD + D, 0)
+                vols[i] = np.zeros((hv, max(width1, 0), D), np.int16)
+        self.check(self.lib.l3d_sgbm_compute_pair(self.h, C.byref(params_left), C.byref(params_right), _ptr(left), _ptr(right),
+                                                  W, H, _ptr(dl), _ptr(dr), _ptr(vols[0]), _ptr(vols[1])),
+                   "l3d_sgbm_compute_pair")
+        return (dl, dr, vols[0], vols[1]) if want_volumes else (dl, dr)
 
     def median3_s16(self, a):
         a = _arr(a, np.int16)

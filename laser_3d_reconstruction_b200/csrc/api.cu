@@ -257,6 +257,37 @@ int l3d_sgbm_debug(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left, 
     API_END(ctx)
 }
 
+int l3d_sgbm_compute_pair(l3d_ctx* ctx, const l3d_sgbm_params* pl, const l3d_sgbm_params* pr, const uint8_t* left,
+                          const uint8_t* right, int W, int H, int16_t* disp_left, int16_t* disp_right, int16_t* Cl_out,
+                          int16_t* Cr_out) {
+    API_BEGIN(ctx)
+    NEED(ctx, pl && pr && left && right && disp_left && disp_right && W > 0 && H > 0, "sgbm pair arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    size_t n = (size_t)W * H;
+    uint8_t* l = L.get<uint8_t>(S_GRAY_L, n);
+    uint8_t* r = L.get<uint8_t>(S_GRAY_R, n);
+    int16_t* dl = L.get<int16_t>(S_DISP_L, n);
+    int16_t* dr = L.get<int16_t>(S_DISP_R, n);
+    uint4* dL = L.get<uint4>(S_DESC_L, 2 * n);
+    uint4* dR = L.get<uint4>(S_DESC_R, 2 * n);
+    RC(h2d(ctx, l, left, n));
+    RC(h2d(ctx, r, right, n));
+    SgbmRun rl, rr;
+    RC(sgbm_front_pair(L, *pl, *pr, l, r, W, H, dL, dR, rl, rr));
+    if (Cl_out && rl.C) RC(d2h(ctx, Cl_out, rl.C, (size_t)rl.g.HV * rl.g.width1 * rl.g.D * 2));
+    if (Cr_out && rr.C) RC(d2h(ctx, Cr_out, rr.C, (size_t)rr.g.HV * rr.g.width1 * rr.g.D * 2));
+    RC(sgbm_middle_split(L, rl, false));
+    RC(sgbm_middle_split(L, rr, false));
+    RC(sgbm_back(L, rl, dl, nullptr));
+    RC(sgbm_back(L, rr, dr, nullptr));
+    RC(d2h(ctx, disp_left, dl, n * 2));
+    RC(d2h(ctx, disp_right, dr, n * 2));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
 int l3d_sgbm_compute(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left, const uint8_t* right,
                      int W, int H, int16_t* disp) {
     return l3d_sgbm_debug(ctx, p, left, right, W, H, disp, nullptr, nullptr, nullptr);

@@ -873,17 +873,26 @@ int sgbm_front_pair(Lane& L, const l3d_sgbm_params& pl, const l3d_sgbm_params& p
     if ((rc = sgbm_prefilter(L, left, W, H, rl.g.ftzero, dL)) != L3D_OK) return rc;
     if ((rc = sgbm_prefilter(L, right, W, H, rl.g.ftzero, dR)) != L3D_OK) return rc;
     static const bool no_dual = getenv("L3D_COST_NO_DUAL") != nullptr;
-    L.t_begin("sgbm_cost");
     if (!no_dual && rl.g.width1 > 0 && rr.g.width1 > 0 && sgbm_cost_dual_ok(rl.g, rr.g)) {
+        L.t_begin("sgbm_cost");
         rc = sgbm_cost_dual(L, rl.g, rr.g, dL, dR, rl.C, rr.C);
-    } else {
-        if (rl.g.width1 > 0) rc = sgbm_cost_single(L, rl.g, dL, dR, rl.C);
-        if (rc == L3D_OK && rr.g.width1 > 0) rc = sgbm_cost_single(L, rr.g, dR, dL, rr.C);
+        L.t_end("sgbm_cost");
+        if (rc != L3D_OK) return rc;
+        if ((rc = sgbm_front_end(L, rl)) != L3D_OK) return rc;
+        return sgbm_front_end(L, rr);
     }
-    L.t_end("sgbm_cost");
-    if (rc != L3D_OK) return rc;
-    if ((rc = sgbm_front_end(L, rl)) != L3D_OK) return rc;
-    return sgbm_front_end(L, rr);
+    // two single passes; each volume's horizontal paths follow its cost pass (the tail of C is still in L2)
+    SgbmRun* runs[2] = {&rl, &rr};
+    for (int i = 0; i < 2; i++) {
+        SgbmRun& r = *runs[i];
+        if (r.g.width1 <= 0) continue;
+        L.t_begin("sgbm_cost");
+        rc = i == 0 ? sgbm_cost_single(L, r.g, dL, dR, r.C) : sgbm_cost_single(L, r.g, dR, dL, r.C);
+        L.t_end("sgbm_cost");
+        if (rc != L3D_OK) return rc;
+        if ((rc = sgbm_front_end(L, r)) != L3D_OK) return rc;
+    }
+    return L3D_OK;
 }
 
 // can the previous-row paths of this run go through the cluster-fused kernel?

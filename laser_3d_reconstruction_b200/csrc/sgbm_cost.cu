@@ -464,6 +464,273 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
     }
 }
 // ------------------------------------------------------------------------------------------
+// cost volumes of BOTH matchers of a frame from one pixel-cost pass (numDisparities 64 / 128)
+// ------------------------------------------------------------------------------------------
+// The right matcher (minDisparity = -(D-1), views swapped: camera/single_usb_stereo_camera.py:277,325) evaluates the
+// same Birchfield-Tomasi pixel costs as the left one -- the BT cost is symmetric in its two pixels -- and the box sum
+// runs along x and y at a fixed disparity, so away from the replicate-clamped borders of the two width1 windows
+//     C_right[y][x'][D-1-k] = C_left[y][x' + k - (D-1)][k]        (x, x' in width1 coordinates, k = 0 .. D-1)
+// holds exactly, for x' in [SW2 + D-1, width1 - SW2) (derivation in DESIGN.md).  So:
+//   role-0 CTAs  compute a tile of the LEFT matcher's volume as sgbm_cost_warp_kernel does (same arithmetic, same
+//                warp-private strips and rings), stage every finished row [column][disparity] in shared memory, and
+//                all 16 warps then write the row out twice: as it is (coalesced 16-byte chunks, whole 256-byte
+//                vectors) into C_left, and sheared into C_right for the columns RA <= x' < RB.  One right-volume word
+//                (disparity indices 2w, 2w+1 of column x') is the high half of the staged word (column A = x' - 2w,
+//                pair D/2-1-w) and the low half of the same pair one column to the left: two LDS + one PRMT.  The
+//                words are walked along wrapped lines A = (s - 2w) mod TX so that consecutive lanes hold consecutive w
+//                of the same x' (runs of ~TX/2 words = contiguous global bytes) and hit 32 different banks.  Tiles
+//                step by TX - 1 columns: column A - 1 of a tile's first column belongs to the previous tile.
+//   role-1 CTAs  compute, natively with the roles of the views exchanged, the right-volume columns the identity does
+//                not cover (x' < RA: the first D-1+SW2 columns; x' >= RB: the last tile) -- about a sixth of a pass.
+// Rows are handed from the phase-B lanes to the write-out by two shared-memory stages with full / empty mbarriers
+// (split arrive / wait: a warp runs at most one row ahead of the slowest).
+constexpr int CD_NS = 4;        // operand-table stages
+constexpr int CD_PDS = 88;      // pixel-cost strip stride per pair
+constexpr int CD_MAXT1 = 8;
+
+struct DualArgs {
+    const uint4* desc[2];       // BT operand planes of the left view [0] and the right view [1]
+    int16_t* C[2];              // role r computes C[r]
+    int W, H, width1, P2;
+    int viewL[2], minD[2], minX1[2];  // role r: which view is its left image, its minDisparity, its minX1
+    int ntiles[2], nbands[2];
+    int stride0;                // role-0 tile origins: t * stride0; role-1 origins: x1[t]
+    int x1[CD_MAXT1];
+    int emit, RA, RB;           // role-0 tiles also write columns RA <= x' < RB of C[1]
+    int dbg;
+};
+
+template <int BS, int DD>
+struct CdCfg {
+    static constexpr int D = DD, D2 = DD / 2, SW2 = BS / 2, TXH = 64, TX = TXH - 2 * SW2;
+    static constexpr int NW = COST_THREADS / 32, DPW = D2 / NW, NG = 32 / DPW, CPG = (TX + NG - 1) / NG;
+    static constexpr int NEMAX = TXH + D;                 // right-operand entries per channel and stage
+    static constexpr int STAGE_U4 = 2 * NEMAX + 2 * TXH;  // [R0 | R1 | L0 | L1]
+    // staged row: column stride in words.  D = 128: 68 (== 4 mod 32: the phase-B lanes (pair, 7-column group) hit 32
+    // banks, the sheared walk moves by -(2 * 68 + 1) == -9 words per lane and wraps by 56 * 68 == 0 mod 32)
+    static constexpr int CS = D2 % 32 == 0 && D2 >= 64 ? D2 + 4 : D2 + 1;
+    static constexpr int NH = D2 / 32;                    // 32-word halves of a right-volume vector
+    static constexpr size_t smem_bytes() {
+        return (size_t)CD_NS * STAGE_U4 * 16 + (size_t)D2 * CD_PDS * 4 + (size_t)BS * D2 * TX * 4 + (size_t)2 * TX * CS * 4 +
+               (size_t)(2 * CD_NS + 4) * 8;
+    }
+    static_assert(DPW >= 1 && 32 % DPW == 0 && CPG <= COST_MAXCPG && D2 % 32 == 0, "tile geometry");
+};
+
+__device__ __forceinline__ void cost_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BS, int DD>
+__global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const DualArgs a) {
+    typedef CdCfg<BS, DD> K;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int D = K::D, D2 = K::D2, SW2 = K::SW2, TXH = K::TXH, TX = K::TX;
+    constexpr int NW = K::NW, DPW = K::DPW, CPG = K::CPG, NEMAX = K::NEMAX, STAGE_U4 = K::STAGE_U4, CS = K::CS, NH = K::NH;
+    const int width1 = a.width1, W = a.W;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    // ---- CTA -> (role, tile, band)
+    int cta = blockIdx.x;
+    const int n0 = a.ntiles[0] * a.nbands[0];
+    const int role = cta >= n0 ? 1 : 0;
+    if (role) cta -= n0;
+    const int nb = a.nbands[role];
+    const int tile = cta / nb, b = cta - tile * nb;
+    const int x0 = role ? a.x1[tile] : tile * a.stride0;
+    const int br = (a.H + nb - 1) / nb;
+    const int y0 = b * br, rows = min(br, a.H - y0);
+    if (rows <= 0) return;
+    const int chi = a.H - 1;
+    const uint4* __restrict__ Ldesc = a.desc[a.viewL[role]];
+    const uint4* __restrict__ Rdesc = a.desc[1 - a.viewL[role]];
+    const int minD = a.minD[role], minX1 = a.minX1[role];
+    const bool emitR = role == 0 && a.emit != 0;
+    // columns of the own volume this tile writes (role 0 tiles overlap by one column when they feed the shear)
+    const int next0 = role ? x0 + TX : x0 + a.stride0;
+    const int ncopy = next0 < width1 ? min(TX, next0 - x0) : width1 - x0;
+
+    const int xa = min(max(x0 - SW2, 0), width1 - 1);
+    const int xb = min(max(x0 + TXH - 1 - SW2, 0), width1 - 1);
+    const int xr_base = xa + minX1 - (minD + D - 1);
+    const int nE = (xb - xa) + D - 1;
+    const size_t plane = (size_t)W * a.H;
+    const int lc0 = max(0, SW2 - x0), lc1 = min(TXH, width1 - (x0 - SW2));
+    uint4* tabs = (uint4*)smem_raw;                                              // [CD_NS][STAGE_U4]
+    uint32_t* u32base = (uint32_t*)(tabs + CD_NS * STAGE_U4);
+    uint32_t* pdw = u32base + warp * DPW * CD_PDS;                               // this warp's pixel-cost strip [DPW][CD_PDS]
+    uint32_t* ringw = u32base + D2 * CD_PDS + (size_t)warp * BS * DPW * TX;      // this warp's row sums [BS][DPW][TX]
+    uint32_t* Ls = u32base + D2 * CD_PDS + (size_t)BS * D2 * TX;                 // staged rows [2][TX][CS]
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(Ls + 2 * TX * CS);
+    // bars + 8 s: full[s]; + 8 (CD_NS + s): empty[s]; + 8 (2 CD_NS + s): row staged[s]; + 8 (2 CD_NS + 2 + s): row written out[s]
+    const uint32_t bar_lsf = bars + 8 * (2 * CD_NS), bar_lse = bars + 8 * (2 * CD_NS + 2);
+    const int nk = rows + BS - 1;
+    auto row_of = [&](int k) { return min(max(y0 - SW2 + k, 0), chi); };
+    auto issue_tables = [&](int k) {
+        const int s = k % CD_NS;
+        const uint32_t bar = bars + 8 * s;
+        const uint32_t rbytes = (uint32_t)nE * 16u, lbytes = (uint32_t)(lc1 - lc0) * 16u;
+        const size_t ro = (size_t)row_of(k) * W;
+        const uint4* rsrc = Rdesc + ro + xr_base;
+        const uint4* lsrc = Ldesc + ro + (x0 - SW2 + lc0) + minX1;
+        uint4* dst = tabs + s * STAGE_U4;
+        cost_mbar_expect_tx(bar, 2 * rbytes + 2 * lbytes);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst), rsrc, rbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + NEMAX), rsrc + plane, rbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + 2 * NEMAX + lc0), lsrc, lbytes, bar);
+        cost_bulk_g2s((uint32_t)__cvta_generic_to_shared(dst + 2 * NEMAX + TXH + lc0), lsrc + plane, lbytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CD_NS; s++) { cost_mbar_init(bars + 8 * s, 1); cost_mbar_init(bars + 8 * (CD_NS + s), NW); }
+        for (int s = 0; s < 2; s++) { cost_mbar_init(bar_lsf + 8 * s, NW); cost_mbar_init(bar_lse + 8 * s, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < CD_NS - 1 && k < nk; k++) issue_tables(k);
+    }
+    __syncthreads();  // barrier init visible; the only block-wide barrier of the kernel
+
+    // phase A role: tile columns lane and lane + 32, pairs dp0 .. dp0 + DPW - 1
+    const int dp0 = warp * DPW;
+    int eoff[2], lcol[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+        const int c = lane + 32 * hh;
+        const int xc = min(max(x0 - SW2 + c, 0), width1 - 1);
+        eoff[hh] = xc - xa + D - 2 - 2 * dp0;
+        lcol[hh] = min(max(c, lc0), lc1 - 1);
+    }
+    // phase B role
+    const int dpi = lane % DPW, g = lane / DPW;
+    const int cb0 = g * CPG;
+    const int ncb = max(0, min(min(CPG, TX - cb0), width1 - (x0 + cb0)));
+    const uint32_t p2x2 = (uint32_t)a.P2 * 0x10001u;
+    uint32_t crun[CPG];
+#pragma unroll
+    for (int j = 0; j < CPG; j++) crun[j] = p2x2;
+    const uint32_t* ppb = pdw + dpi * CD_PDS + cb0;
+    uint32_t* rpb = ringw + dpi * TX + cb0;
+    uint32_t* lsb = Ls + cb0 * CS + dp0 + dpi;                 // + stage * TX * CS, + j * CS
+    int slot = 0;
+    // write-out role: sheared walk constants, cw[h] = (-2 w) mod TX for w = 32 h + lane
+    const int cw0 = (TX * 8 - 2 * lane) % TX, cw1 = (TX * 8 - 2 * (32 + lane)) % TX;
+    static_assert(NH <= 2, "sheared walk: at most two 32-word halves per vector");
+    uint32_t* Cown32 = (uint32_t*)a.C[role];
+    uint32_t* Cother32 = (uint32_t*)a.C[1];
+
+    auto write_out = [&](int er) {  // emitted row er of the band (image row y0 + er), staged in Ls[er & 1]
+        const uint32_t* ls = Ls + (er & 1) * TX * CS;
+        const size_t rowbase = (size_t)(y0 + er) * width1;
+        if (!(a.dbg & 1)) {
+            if (CS % 4 == 0) {
+                constexpr int CPC = D2 / 4;                    // 16-byte chunks per column
+                for (int q = threadIdx.x; q < ncopy * CPC; q += COST_THREADS) {
+                    const int col = q / CPC, part = q - col * CPC;
+                    const uint4 v = *(const uint4*)(ls + col * CS + part * 4);
+                    *(uint4*)(Cown32 + (rowbase + x0 + col) * D2 + part * 4) = v;
+                }
+            } else {
+                for (int q = threadIdx.x; q < ncopy * D2; q += COST_THREADS) {
+                    const int col = q / D2, part = q - col * D2;
+                    Cown32[(rowbase + x0 + col) * D2 + part] = ls[col * CS + part];
+                }
+            }
+        }
+        if (emitR && !(a.dbg & 8)) {
+            for (int unit = warp; unit < TX * NH; unit += NW) {
+                const int s = unit / NH, h = unit - s * NH;
+                const int w = 32 * h + lane;
+                int u = s + ((NH == 1 || h == 0) ? cw0 : cw1);
+                if (u >= TX) u -= TX;
+                const int xq = x0 + u + 1 + 2 * w;             // right-volume column of this word
+                if (u < TX - 1 && xq >= a.RA && xq < a.RB) {
+                    const uint32_t Aw = ls[(u + 1) * CS + (D2 - 1 - w)], Bw = ls[u * CS + (D2 - 1 - w)];
+                    Cother32[(rowbase + xq) * D2 + w] = __byte_perm(Aw, Bw, 0x5432);
+                }
+            }
+        }
+    };
+
+    for (int k = 0; k <= nk; k++) {  // iteration nk only writes out the last row
+        const int e = k - (BS - 1);  // row this iteration emits
+        if (k < nk) {
+            const int s = k % CD_NS;
+            if (warp == (k & (NW - 1)) && k + CD_NS - 1 < nk) {
+                if (lane == 0) {
+                    const int kk = k + CD_NS - 1, sk = kk % CD_NS;
+                    if (k >= 1) cost_mbar_wait(bars + 8 * (CD_NS + sk), (uint32_t)(((k - 1) / CD_NS) & 1));
+                    issue_tables(kk);
+                }
+                __syncwarp();
+            }
+            cost_mbar_wait(bars + 8 * s, (uint32_t)((k / CD_NS) & 1));
+            const uint4* T0 = tabs + s * STAGE_U4;
+            // ---- phase A
+            if (!(a.dbg & 4))
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const uint4 l0 = T0[2 * NEMAX + lcol[hh]], l1 = T0[2 * NEMAX + TXH + lcol[hh]];
+                const uint32_t u0 = __byte_perm(l0.x, l0.x, 0x3232), nu0 = __byte_perm(l0.y, l0.y, 0x3232);
+                const uint32_t ul0 = __byte_perm(l0.z, l0.z, 0x3232), nuh0 = __byte_perm(l0.w, l0.w, 0x3232);
+                const uint32_t u1 = __byte_perm(l1.x, l1.x, 0x3232), nu1 = __byte_perm(l1.y, l1.y, 0x3232);
+                const uint32_t ul1 = __byte_perm(l1.z, l1.z, 0x3232), nuh1 = __byte_perm(l1.w, l1.w, 0x3232);
+                uint4 e0[DPW], e1[DPW];
+#pragma unroll
+                for (int i = 0; i < DPW; i++) { e0[i] = T0[eoff[hh] - 2 * i]; e1[i] = T0[NEMAX + eoff[hh] - 2 * i]; }
+                uint32_t c[DPW];
+#pragma unroll
+                for (int i = 0; i < DPW; i++) {
+                    const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
+                    const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
+                    c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                }
+#pragma unroll
+                for (int i = 0; i < DPW; i++) pdw[i * CD_PDS + lane + 32 * hh] = c[i];
+            }
+            __syncwarp();
+            if (lane == 0) cost_mbar_arrive(bars + 8 * (CD_NS + s));
+            // ---- phase B
+            const bool emit = e >= 0;
+            if (e >= 2) cost_mbar_wait(bar_lse + 8 * (e & 1), (uint32_t)(((e >> 1) - 1) & 1));  // row e - 2 written out
+            if (ncb > 0 && !(a.dbg & 2)) {
+                uint32_t* rp = rpb + (size_t)slot * DPW * TX;
+                uint32_t* lp = lsb + (e & 1) * TX * CS;
+                const bool sub = k >= BS;
+                constexpr int NV = CPG + BS - 1;
+                uint32_t pv[NV], old[CPG], hs[CPG];
+#pragma unroll
+                for (int i = 0; i < NV; i++) pv[i] = ppb[i];
+#pragma unroll
+                for (int j = 0; j < CPG; j++) old[j] = (sub && j < ncb) ? rp[j] : 0u;
+                uint32_t h = 0;
+#pragma unroll
+                for (int i = 0; i < BS; i++) h += pv[i];
+#pragma unroll
+                for (int j = 0; j < CPG; j++) {
+                    if (j > 0) h = h + pv[j + BS - 1] - pv[j - 1];
+                    hs[j] = h;
+                    crun[j] = crun[j] + h - old[j];
+                }
+#pragma unroll
+                for (int j = 0; j < CPG; j++) {
+                    if (j < ncb) {
+                        rp[j] = hs[j];
+                        if (emit) lp[j * CS] = crun[j];
+                    }
+                }
+            }
+            __syncwarp();  // the strip is rewritten by the next row's phase A; this warp's part of the staged row is complete
+            slot = slot + 1 == BS ? 0 : slot + 1;
+            if (emit && lane == 0) cost_mbar_arrive(bar_lsf + 8 * (e & 1));
+        }
+        if (e >= 1) {  // write out the previous row while the other warps finish this one
+            cost_mbar_wait(bar_lsf + 8 * ((e - 1) & 1), (uint32_t)(((e - 1) >> 1) & 1));
+            write_out(e - 1);
+            __syncwarp();
+            if (lane == 0) cost_mbar_arrive(bar_lse + 8 * ((e - 1) & 1));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 int sgbm_prefilter(Lane& L, const uint8_t* img, int W, int H, int ftzero, uint4* desc) {
@@ -491,6 +758,8 @@ static void cost_bands(const Geom& g, int H, int want, CostArgs& ca) {
     }
 }
 
+static int cost_single_staged(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, int16_t* C);
+
 int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, int16_t* C) {
     const int W = g.W, H = g.H;
     CostArgs ca;
@@ -515,7 +784,9 @@ int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, i
     ca.cpg = cdiv(ca.TX, ca.nxg);
     size_t smem = cost_smem(TXH);
     static const bool no_warp_cost = getenv("L3D_COST_CLASSIC") != nullptr;
+    static const bool no_staged = getenv("L3D_COST_NO_STAGED") != nullptr;
     const bool warp_form = !no_warp_cost && ((g.D == 128 && g.bs == 9) || (g.D == 64 && g.bs == 5));
+    if (warp_form && !no_staged && g.nseg == 1) return cost_single_staged(L, g, dL, dR, C);
     if (warp_form) {
         // warp-decoupled form: 64-column tiles
         ca.TXH = CW_TXH; ca.TX = CW_TXH - 2 * g.SW2;
@@ -543,11 +814,84 @@ int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, i
     return L3D_OK;
 }
 
-bool sgbm_cost_dual_ok(const Geom& gl, const Geom& gr) { (void)gl; (void)gr; return false; }
-int sgbm_cost_dual(Lane& L, const Geom& gl, const Geom& gr, const uint4* dLv, const uint4* dRv, int16_t* Cl, int16_t* Cr) {
-    (void)gl; (void)gr; (void)dLv; (void)dRv; (void)Cl; (void)Cr;
-    set_err(L.err, "sgbm_cost_dual: not built");
+// the (blockSize, numDisparities) pairs the dual kernel is instantiated for
+static bool cost_dual_cfg(int bs, int D) { return (bs == 9 && D == 128) || (bs == 5 && D == 64); }
+
+template <int BS, int DD>
+static int launch_cost_dual(Lane& L, const DualArgs& da) {
+    typedef CdCfg<BS, DD> K;
+    const int ncta = da.ntiles[0] * da.nbands[0] + da.ntiles[1] * da.nbands[1];
+    L3D_CHECK(L, cudaFuncSetAttribute((sgbm_cost_dual_kernel<BS, DD>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)K::smem_bytes()));
+    L3D_LAUNCH(L, (sgbm_cost_dual_kernel<BS, DD>), ncta, COST_THREADS, K::smem_bytes(), da);
+    return L3D_OK;
+}
+static int launch_cost_dual_any(Lane& L, int bs, int D, const DualArgs& da) {
+    if (bs == 9 && D == 128) return launch_cost_dual<9, 128>(L, da);
+    if (bs == 5 && D == 64) return launch_cost_dual<5, 64>(L, da);
+    set_err(L.err, "sgbm_cost_dual: no instantiation for blockSize %d / numDisparities %d", bs, D);
     return L3D_ERR_UNSUPPORTED;
+}
+
+// one volume through the staged-row kernel (role 0 only, nothing emitted into a second volume)
+static int cost_single_staged(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, int16_t* C) {
+    DualArgs da = {};
+    da.desc[0] = dL; da.desc[1] = dR; da.C[0] = C; da.C[1] = nullptr;
+    da.W = g.W; da.H = g.H; da.width1 = g.width1; da.P2 = g.P2;
+    da.viewL[0] = 0; da.minD[0] = g.minD; da.minX1[0] = g.minX1;
+    const int TX = 64 - 2 * g.SW2;
+    da.stride0 = TX; da.ntiles[0] = cdiv(g.width1, TX); da.ntiles[1] = 0; da.nbands[1] = 1;
+    da.nbands[0] = std::max(1, std::min(NUM_SMS / da.ntiles[0], g.H / (2 * g.bs) > 0 ? g.H / (2 * g.bs) : 1));
+    da.emit = 0; da.RA = da.RB = 0;
+    static const int cost_dbg = getenv("L3D_COST_DBG") ? atoi(getenv("L3D_COST_DBG")) : 0;
+    da.dbg = cost_dbg;
+    return launch_cost_dual_any(L, g.bs, g.D, da);
+}
+
+bool sgbm_cost_dual_ok(const Geom& gl, const Geom& gr) {
+    return cost_dual_cfg(gl.bs, gl.D) && gr.bs == gl.bs && gr.D == gl.D && gl.minD == 0 && gr.minD == -(gl.D - 1) &&
+           gl.P2 == gr.P2 && gl.ftzero == gr.ftzero && gl.nseg == 1 && gr.nseg == 1 && gl.W == gr.W && gl.H == gr.H &&
+           gl.width1 == gr.width1 && gl.width1 > 0;
+}
+
+int sgbm_cost_dual(Lane& L, const Geom& gl, const Geom& gr, const uint4* dLv, const uint4* dRv, int16_t* Cl, int16_t* Cr) {
+    L3D_ARG(L, sgbm_cost_dual_ok(gl, gr), "sgbm_cost_dual geometry");
+    const int D = gl.D, SW2 = gl.SW2, W1 = gl.width1, H = gl.H;
+    const int TX = 64 - 2 * SW2;
+    DualArgs da = {};
+    da.desc[0] = dLv; da.desc[1] = dRv; da.C[0] = Cl; da.C[1] = Cr;
+    da.W = gl.W; da.H = H; da.width1 = W1; da.P2 = gl.P2;
+    da.viewL[0] = 0; da.minD[0] = gl.minD; da.minX1[0] = gl.minX1;
+    da.viewL[1] = 1; da.minD[1] = gr.minD; da.minX1[1] = gr.minX1;
+    // role 0: the left volume in tiles that step by TX - 1 columns
+    da.stride0 = TX - 1;
+    da.ntiles[0] = W1 <= TX ? 1 : cdiv(W1 - TX, da.stride0) + 1;
+    // role 1: right-volume columns outside the identity's domain, natively
+    const int nbl = cdiv(D - 1 + SW2, TX);
+    da.RA = std::min(nbl * TX, W1);
+    da.RB = std::max(da.RA, W1 - TX);
+    da.emit = da.RB > da.RA;
+    int nt1 = 0;
+    for (int x = 0; x < da.RA; x += TX) da.x1[nt1++] = x;
+    if (da.RB < W1) da.x1[nt1++] = da.RB;
+    L3D_ARG(L, nt1 <= CD_MAXT1, "sgbm_cost_dual: border tiles");
+    da.ntiles[1] = nt1;
+    // bands: one wave of CTAs; a role-0 row costs about 1.35 role-1 rows (it also writes the sheared copy)
+    const int maxb = std::max(1, H / (2 * gl.bs));
+    int best0 = 1, best1 = 1;
+    double bestt = 1e30;
+    for (int b0 = 1; b0 <= maxb; b0++) {
+        for (int b1 = 1; b1 <= maxb; b1++) {
+            if (da.ntiles[0] * b0 + nt1 * b1 > NUM_SMS && !(b0 == 1 && b1 == 1)) continue;
+            const double t0 = 1.35 * (cdiv(H, b0) + gl.bs - 1), t1 = nt1 ? 1.0 * (cdiv(H, b1) + gl.bs - 1) : 0.0;
+            const double t = std::max(t0, t1) + 1e-3 * (b0 + b1);
+            if (t < bestt) { bestt = t; best0 = b0; best1 = b1; }
+        }
+    }
+    da.nbands[0] = best0; da.nbands[1] = best1;
+    static const int cost_dbg = getenv("L3D_COST_DBG") ? atoi(getenv("L3D_COST_DBG")) : 0;
+    da.dbg = cost_dbg;
+    return launch_cost_dual_any(L, gl.bs, D, da);
 }
 
 }  // namespace l3d

@@ -108,6 +108,37 @@ def test_sgbm_small_all_roles(ctx, mode, shape):
             eq(ctx.sgbm_compute(p, lg, rg), want, tag + " fused-WTA disp vs cv2")
 
 
+# the matcher pair of get_frames() in one call: one pixel-cost pass feeds both cost volumes (sgbm_cost_dual_kernel);
+# widths chosen so that the sheared range [RA, RB) is empty, a few columns, and most of the volume
+PAIR_SHAPES = [(200, 40, 64, 5), (330, 50, 64, 5), (320, 360, 64, 5), (300, 30, 128, 9), (420, 44, 128, 9),
+               (533, 37, 128, 9), (1280, 720, 128, 9), (260, 40, 32, 5), (400, 40, 128, 7)]
+
+
+@pytest.mark.parametrize("mode", [1, 0, 3, 2])
+@pytest.mark.parametrize("shape", PAIR_SHAPES)
+def test_sgbm_pair_shared_cost_pass(ctx, mode, shape):
+    W, H, D, bs = shape
+    if W >= 1280 and mode in (2, 3):
+        pytest.skip("full size only in the modes the shared pass serves by default")
+    lg, rg = gray_pair(W, H, D, 5, quant=8 if (W == 330 or W == 420) else 0)
+    _, mut, right = ref_ops.sgbm_param_sets(D, bs, mode)
+    pl, pr = N.SgbmParams(**mut), N.SgbmParams(**right)
+    if mode == 2:
+        dl, dr = ctx.sgbm_compute_pair(pl, pr, lg, rg)
+    else:
+        dl, dr, Cl, Cr = ctx.sgbm_compute_pair(pl, pr, lg, rg, want_volumes=True)
+        if H <= 64:  # the C restatement of the oracle, cv2 never exposes the volumes
+            _, oCl, _ = cref.sgbm_compute(lg, rg, want_volumes=True, **mut)
+            _, oCr, _ = cref.sgbm_compute(rg, lg, want_volumes=True, **right)
+        else:        # the single-matcher path (itself checked against the oracle above)
+            _, oCl, _ = ctx.sgbm_compute(pl, lg, rg, want_volumes=True)
+            _, oCr, _ = ctx.sgbm_compute(pr, rg, lg, want_volumes=True)
+        eq(Cl, oCl, "%s m%d left cost volume" % (shape, mode))
+        eq(Cr, oCr, "%s m%d right cost volume" % (shape, mode))
+    eq(dl, cv2.StereoSGBM_create(**mut).compute(lg, rg), "%s m%d left disparity vs cv2" % (shape, mode))
+    eq(dr, cv2.StereoSGBM_create(**right).compute(rg, lg), "%s m%d right disparity vs cv2" % (shape, mode))
+
+
 @pytest.mark.parametrize("mode", [2, 0, 1, 3])
 def test_sgbm_c1_parameter_sets(ctx, mode):
     lg, rg = gray_pair(320, 360, 64, 7)
