@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- the hot path of BASELINE.json on B200: frames/s and Gde/s of
-rectify -> SGBM (MODE_HH, left + right matcher) -> WLS -> depth -> Steger centre line -> 3D
-at 1280x720, 128 disparities, block 9 (BASELINE config 3), frames sharded frame-wise over the GPUs.
+rectify -> SGBM (left + right matcher) -> WLS -> depth -> laser centre line -> 3D,
+frames sharded frame-wise over the GPUs.  Default workload: BASELINE config 3 (1280x720, 128 disparities, block 9,
+MODE_HH + WLS + ImprovedSteger), the configuration the metric is quoted on; `--config c1|c2|c4|c5` select the others.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over a batch of `--frames` synthetic frames per GPU (weak
-scaling).  Prints ONE JSON line on rank 0:
+One "step" = one pass of the hot path over a batch of `--frames` synthetic frames per GPU (weak scaling; c5: the
+4096-frame job split r::world, strong scaling).  Prints ONE JSON line on rank 0:
   value / ms_per_step : inputs resident in HBM, CUDA-event timed (l3d_pipeline_run_dev), max over ranks
   e2e                 : the same batch through the host-buffer C-ABI call (l3d_pipeline_run_host):
                         pinned H2D of every frame + D2H of depth maps and point clouds inside the timed region
   roofline            : one SGBM matcher run (cost volume + aggregation + WTA kernels) timed alone with CUDA
                         events on its stream, algorithmic bytes / duration vs the measured HBM peak
+  latency_ms          : one frame at a time through the reference-facing calls (compute_depth, extract_centerline,
+                        reconstruct_*): host arrays in, host arrays out
   cpu_baseline        : the reference's CPU path (cv2.StereoSGBM etc. through oracle/ref_ops.py) on a bounded
-                        sample of the same frames, frame-parallel over the host cores (rank 0, N=1 only)
+                        sample of the same frames, frame-parallel over the host cores (rank 0, N=1 only), and the
+                        north_star acceptance list checked on one frame of the run (parity_check)
 `--impl reference` times only that CPU path (all host threads, bounded sample per step).
 """
 import argparse
@@ -33,16 +37,66 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-W, H, D, BS, MODE = 1280, 720, 128, 9, 1  # BASELINE config 3 (MODE_HH = 1)
 MAX_POINTS = 20000
-WORKLOAD = "c3: 1280x720 per eye, 128 disparities, block 9, SGBM MODE_HH (left+right matcher) + WLS(8000,1.5) " \
-           "+ ImprovedSteger sigma 3 + reconstruct_from_depth"
+# BASELINE.json `configs` (SURVEY 8d "Configs -> concrete runs").  mode: cv2.STEREO_SGBM_MODE_* (1 = HH, 2 = SGBM_3WAY,
+# the reference's own default); extractor / recon: what the reference's callers run at that configuration.
+CONFIGS = {
+    "c1": dict(W=320, H=360, D=64, BS=5, MODE=2, wls=False, extractor="simple", recon="depth", frames=448, lanes=28,
+               cpu_frames_per_core=16,
+               workload="c1: 320x360 per eye, 64 disparities, block 5, SGBM_3WAY (config.py defaults, as constructed) + "
+                        "Simple HSV extractor + reconstruct_from_depth"),
+    "c2": dict(W=320, H=360, D=64, BS=5, MODE=2, wls=True, extractor="fast", recon="plane_refraction", frames=448, lanes=28,
+               cpu_frames_per_core=8,
+               workload="c2: 320x360 per eye, 64 disparities, block 5, SGBM_3WAY (left+right matcher) + WLS(8000,1.5) + "
+                        "FastSteger sigma 3 + reconstruct_laser_line with refraction correction (underwater config)"),
+    "c3": dict(W=1280, H=720, D=128, BS=9, MODE=1, wls=True, extractor="improved", recon="depth", frames=112, lanes=28,
+               cpu_frames_per_core=8,
+               workload="c3: 1280x720 per eye, 128 disparities, block 9, SGBM MODE_HH (left+right matcher) + WLS(8000,1.5) "
+                        "+ ImprovedSteger sigma 3 + reconstruct_from_depth"),
+    "c4": dict(W=1920, H=1080, D=256, BS=11, MODE=1, wls=True, extractor="improved", recon="depth", frames=256, lanes=14,
+               cpu_frames_per_core=1,
+               workload="c4: 1920x1080 per eye, 256 disparities, block 11, SGBM MODE_HH (left+right matcher) + WLS(8000,1.5) "
+                        "+ ImprovedSteger sigma 3 + reconstruct_from_depth, 256 frames per GPU and step streamed through "
+                        "14 lanes of scratch volumes"),
+    "c5": dict(W=1280, H=720, D=128, BS=9, MODE=1, wls=True, extractor="improved", recon="depth", frames=112, lanes=28,
+               cpu_frames_per_core=8, job_frames=4096,
+               workload="c5: 4096 frames of c3 (1280x720, 128 disparities, block 9, MODE_HH + WLS + ImprovedSteger) sharded "
+                        "r::world over the GPUs, point clouds gathered to rank 0 by NCCL"),
+}
+W = H = D = BS = MODE = 0
+CFG = None
+WORKLOAD = ""
+
+
+def select_config(name):
+    global W, H, D, BS, MODE, CFG, WORKLOAD
+    CFG = dict(CONFIGS[name], name=name)
+    W, H, D, BS, MODE = CFG["W"], CFG["H"], CFG["D"], CFG["BS"], CFG["MODE"]
+    WORKLOAD = CFG["workload"]
 
 
 def sgbm_algorithmic_bytes():
-    """B_sgbm = (2 + 4*npasses)*N + 4*W*H bytes per matcher run; N = width1*H*D, npasses = 2 (HH)."""
+    """B_sgbm = (2 + 4*npasses)*N + 4*W*H bytes per matcher run; N = width1*H*D, npasses = 2 (HH), 1 (3WAY)."""
     n = (W - D) * H * D
-    return (2 + 4 * 2) * n + 4 * W * H
+    npasses = 2 if MODE == 1 else 1
+    return (2 + 4 * npasses) * n + 4 * W * H
+
+
+def pipeline_config(lanes):
+    from laser_3d_reconstruction_b200 import _native as N
+    from laser_3d_reconstruction_b200 import pipeline, synth
+    K, Q = synth.camera_model(W, H)
+    ex = {"simple": N.EXTRACT_SIMPLE, "fast": N.STEGER_FAST, "improved": N.STEGER_IMPROVED}[CFG["extractor"]]
+    kw = {}
+    if CFG["extractor"] == "simple":  # config.py:45-47 bounds
+        kw = dict(bright_thr=200, hsv_lo=(50, 100, 180), hsv_hi=(70, 255, 255), min_area=50.0)
+    cfg = pipeline.make_pipeline_config(W, H, D, BS, MODE, Q, K, extractor=ex, lanes=lanes, max_points=MAX_POINTS,
+                                        use_wls=CFG["wls"], **kw)
+    if CFG["recon"] == "plane_refraction":
+        cfg.recon.kind = N.RECON_PLANE
+        cfg.recon.plane[:] = [float(v) for v in synth.LASER_PLANE]
+        cfg.recon.use_refraction = 1
+    return cfg
 
 
 def make_frames(n_distinct, nframes, seed0):
@@ -69,9 +123,15 @@ def _cpu_frame(pair):
     from laser_3d_reconstruction_b200 import synth
     from oracle import ref_ops
     left, right = pair
-    rect, depth = ref_ops.depth_path(left, right, _CPU["maps"], D, BS, MODE, _CPU["Q"], use_wls=True)
-    pts = ref_ops.improved_steger_extract(rect, loop=True)  # per-pixel np.linalg.eig, as the reference does
-    xyz = ref_ops.ReconstructorRef(_CPU["K"], synth.LASER_PLANE, False).reconstruct_from_depth(pts, depth)
+    rect, depth = ref_ops.depth_path(left, right, _CPU["maps"], D, BS, MODE, _CPU["Q"], use_wls=CFG["wls"])
+    if CFG["extractor"] == "simple":
+        pts = ref_ops.simple_extract(rect, (50, 100, 180), (70, 255, 255), 200, 50)
+    elif CFG["extractor"] == "fast":
+        pts = ref_ops.fast_steger_extract(rect, loop=True)
+    else:
+        pts = ref_ops.improved_steger_extract(rect, loop=True)  # per-pixel np.linalg.eig, as the reference does
+    rec = ref_ops.ReconstructorRef(_CPU["K"], synth.LASER_PLANE, CFG["recon"] == "plane_refraction")
+    xyz = rec.reconstruct_laser_line(pts) if CFG["recon"] == "plane_refraction" else rec.reconstruct_from_depth(pts, depth)
     return int(len(xyz))
 
 
@@ -86,7 +146,7 @@ class CpuPath:
         self.cores = max(1, min(ncpu, max_workers))  # each worker holds ~0.5 GB of OpenCV cost volumes
         K, Q = synth.camera_model(W, H)
         maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(maps, K, Q))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(maps, K, Q))  # CFG is inherited
 
     def run(self, pairs):
         t0 = time.perf_counter()
@@ -98,8 +158,20 @@ class CpuPath:
         self.pool.join()
 
 
+def bench_config(nfr, n_distinct, lanes, world):
+    """the `config` object both arms print (same keys, so the driver's same_config check compares like with like)"""
+    return {"workload": WORKLOAD, "name": CFG["name"], "frames_per_step_per_gpu": nfr, "distinct_frames": n_distinct,
+            "lanes": lanes,
+            "sharding": "frame-wise r::world, no collective on the hot path; NCCL gather of point clouds to rank 0"
+                        " per step when N>1",
+            "l2": "inputs plus %.0f MB of C/S cost volumes per matcher run exceed the 126 MB L2"
+                  % (4.0 * (W - D) * H * D / 1e6),
+            "gde_definition": "W*H*D per frame, counted once although two matchers run (SURVEY 8d)"}
+
+
 def run_reference(args, rank):
-    """`--impl reference`: the reference's own CPU implementation of the path, all host threads."""
+    """`--impl reference`: the reference's own CPU implementation of the path, all host threads of ONE host (rank 0;
+    at N > 1 the other ranks exit -- the per-N ratio against it is therefore scaling, not a per-GPU speed-up)."""
     if rank != 0:
         return
     from laser_3d_reconstruction_b200 import synth
@@ -116,15 +188,19 @@ def run_reference(args, rank):
     cpu.close()
     fps = nfr * args.steps / t
     sample = "%d frames/step (one per worker), %d steps" % (nfr, args.steps)
+    cfg = bench_config(args.frames or CFG["frames"], min(args.distinct, args.frames or CFG["frames"]),
+                       args.lanes or CFG["lanes"], 1)
+    cfg["reference_frames_per_step"] = nfr
     out = {
         "impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "gde_per_s": fps * W * H * D / 1e9,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": nfr, "sharding": "frame-parallel over host cores"},
+        "config": cfg,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port", "sample": sample,
                          "note": "cv2 %s StereoSGBM/remap/cvtColor (the binary the reference calls) driven by "
                                  "oracle/ref_ops.py; WLS = oracle C restatement (cv2.ximgproc absent); Steger = "
-                                 "per-pixel np.linalg.eig loop as in the reference" % __import__("cv2").__version__},
+                                 "per-pixel np.linalg.eig loop as in the reference; one host's cores whatever N is"
+                                 % __import__("cv2").__version__},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -179,6 +255,89 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def parity_check(ctx, fp, frame, pair, maps, K, Q):
+    """north_star's acceptance list on one frame of the run: GPU results (frame slot `frame` of the pipeline's last run
+    and the single-call matcher pair) against cv2 / the reference restatement.  Executes oracle/ (checker only)."""
+    import cv2
+    from laser_3d_reconstruction_b200 import _native as N
+    from laser_3d_reconstruction_b200 import synth
+    from oracle import ref_ops
+    left, right = pair
+    got = fp.fetch(frame)
+    wrect, wdepth, aux = ref_ops.depth_path(left, right, maps, D, BS, MODE, Q, use_wls=CFG["wls"], want_all=True)
+    res = {"frame": int(frame), "rectified_equal_cv2_remap": bool(np.array_equal(got["left_rect"], wrect))}
+    base, mut, rgt = ref_ops.sgbm_param_sets(D, BS, MODE)
+    if CFG["wls"]:
+        dl, dr = ctx.sgbm_compute_pair(N.SgbmParams(**mut), N.SgbmParams(**rgt), aux["lg"], aux["rg"])
+        res["disparity_left_equal_cv2"] = bool(np.array_equal(dl, aux["dl"]))
+        res["disparity_right_equal_cv2"] = bool(np.array_equal(dr, aux["dr"]))
+        diff = np.abs(got["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
+        res["wls_within_1lsb_frac"] = float((diff <= 1).mean())
+        res["wls_note"] = "against the oracle's restatement of cv2.ximgproc (parity unpinned: ximgproc is not installed)"
+    else:
+        res["disparity_left_equal_cv2"] = bool(np.array_equal(got["disp16"], aux["dl"]))
+    if CFG["extractor"] == "simple":
+        wp = np.array(ref_ops.simple_extract(wrect, (50, 100, 180), (70, 255, 255), 200, 50), np.float64).reshape(-1, 2)
+        res["simple_points_equal"] = bool(wp.shape == got["points_2d"].shape and np.array_equal(wp, got["points_2d"]))
+    else:
+        fn = ref_ops.fast_steger_extract if CFG["extractor"] == "fast" else ref_ops.improved_steger_extract
+        wp = np.array(fn(wrect), np.float64).reshape(-1, 2)
+        gp = got["points_2d"].astype(np.float64)
+        if len(wp) and len(gp):
+            from scipy.spatial import cKDTree
+            d1, d2 = cKDTree(wp).query(gp)[0], cKDTree(gp).query(wp)[0]
+            res["steger_agreement_frac_0.01px"] = float(min((d1 <= 0.01).mean(), (d2 <= 0.01).mean()))
+        else:
+            res["steger_agreement_frac_0.01px"] = float(len(wp) == len(gp))
+    rec = ref_ops.ReconstructorRef(K, synth.LASER_PLANE, CFG["recon"] == "plane_refraction")
+    pts = [tuple(q) for q in got["points_2d"].astype(np.float64)]
+    w3 = (rec.reconstruct_laser_line(pts) if CFG["recon"] == "plane_refraction"
+          else rec.reconstruct_from_depth(pts, got["depth"])).reshape(-1, 3)
+    g3 = got["points_3d"]
+    res["points_3d"] = int(len(g3))
+    res["points_3d_max_rel_err"] = (float(np.max(np.abs(g3 - w3) / np.maximum(np.abs(w3), 1e-12)))
+                                    if g3.shape == w3.shape and len(g3) else (0.0 if g3.shape == w3.shape else None))
+    res["ok"] = bool(res["rectified_equal_cv2_remap"] and res.get("disparity_left_equal_cv2", True)
+                     and res.get("disparity_right_equal_cv2", True) and res.get("wls_within_1lsb_frac", 1.0) >= 0.999
+                     and res.get("simple_points_equal", True) and res.get("steger_agreement_frac_0.01px", 1.0) >= 0.999
+                     and res["points_3d_max_rel_err"] is not None and res["points_3d_max_rel_err"] <= 1e-5)
+    return res
+
+
+def single_frame_latency(ctx, pair, maps, K, Q, reps=10):
+    """One frame at a time through the reference-facing calls (host arrays in and out): compute_depth =
+    SingleUSBStereoCameraManager.get_frames without the capture, then extract_centerline, then reconstruct_*."""
+    import laser_3d_reconstruction_b200 as l3d
+    from laser_3d_reconstruction_b200 import pipeline, synth
+    ctx.set_rectify_maps(0, maps[0], maps[1])
+    ctx.set_rectify_maps(1, maps[2], maps[3])
+    dcfg = pipeline.depth_config(D, BS, MODE, Q, use_wls=CFG["wls"])
+    if CFG["extractor"] == "simple":
+        ex = l3d.SimpleLaserExtractor(hsv_lower=[50, 100, 180], hsv_upper=[70, 255, 255], brightness_threshold=200, min_area=50)
+    elif CFG["extractor"] == "fast":
+        ex = l3d.FastStegerExtractor(sigma=3.0)
+    else:
+        ex = l3d.ImprovedStegerExtractor(sigma=3.0)
+    rec = l3d.Reconstructor(K, synth.LASER_PLANE, CFG["recon"] == "plane_refraction")
+    t = {"compute_depth": [], "extract_centerline": [], "reconstruct": []}
+    for i in range(reps + 2):
+        t0 = time.perf_counter()
+        rect, depth = ctx.compute_depth(dcfg, pair[0], pair[1])
+        t1 = time.perf_counter()
+        pts = ex.extract_centerline(rect)
+        t2 = time.perf_counter()
+        if CFG["recon"] == "plane_refraction":
+            rec.reconstruct_laser_line(pts)
+        else:
+            rec.reconstruct_from_depth(pts, depth)
+        t3 = time.perf_counter()
+        if i >= 2:
+            t["compute_depth"].append(t1 - t0); t["extract_centerline"].append(t2 - t1); t["reconstruct"].append(t3 - t2)
+    out = {k: 1e3 * float(np.median(v)) for k, v in t.items()}
+    out["frame"] = sum(out.values())
+    return out
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -197,16 +356,22 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    nfr = args.frames
+    nfr = args.frames or CFG["frames"]      # frames per pipeline run (chunk) and GPU
+    lanes = args.lanes or CFG["lanes"]
+    strong = "job_frames" in CFG             # c5: a fixed job of 4096 frames, rank r takes frames r::world
+    job = CFG.get("job_frames", nfr * world)
     K, Q = synth.camera_model(W, H)
     maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
-    # frames are sharded r::world from one global list of nfr*world frames (weak scaling)
-    mine = sharding.shard_frames(nfr * world, rank, world)
+    if strong:
+        mine_all = sharding.shard_frames(job, rank, world)
+        chunks = [mine_all[i:i + nfr] for i in range(0, len(mine_all), nfr)]
+    else:
+        mine_all = sharding.shard_frames(nfr * world, rank, world)
+        chunks = [mine_all]
     n_distinct = min(args.distinct, nfr)
     L, R = make_frames(n_distinct, nfr, seed0=1000 * rank)
     ctx = N.Context(local_rank)
-    cfg = pipeline.make_pipeline_config(W, H, D, BS, MODE, Q, K, extractor=N.STEGER_IMPROVED, lanes=args.lanes,
-                                        max_points=MAX_POINTS)
+    cfg = pipeline_config(lanes)
     fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
     dL, dR = fp.upload(L), fp.upload(R)
     pL = pipeline.pinned_empty(L.shape, np.uint8)
@@ -216,25 +381,33 @@ def run_gpu(args, rank, world, local_rank):
     depth_h = pipeline.pinned_empty((nfr, H, W), np.float32)
     xyz_h = pipeline.pinned_empty((nfr, MAX_POINTS, 3), np.float64)
 
-    def gather(counts):
+    def gather(ids, counts):
         """NCCL gather of the per-frame point clouds to rank 0 (the only exchange, off the hot path)."""
         if world == 1:
             return None
         table = torch.empty((max(int(np.sum(counts)), 1), 4), dtype=torch.float64, device=dev)
-        rows = fp.pack_points_dev(mine, table.data_ptr())  # device-side pack; nothing goes through the host
+        rows = fp.pack_points_dev(ids, table.data_ptr())  # device-side pack; nothing goes through the host
         return sharding.gather_point_clouds(table[:rows], device=dev, to_host=False)  # stays on rank 0's GPU
 
     def step_dev():
-        counts = fp.run_dev(dL, dR, nfr)
-        gather(counts)
-        return counts, fp.last_ms
+        ms, counts = 0.0, None
+        for ids in chunks:  # one chunk unless the job is larger than the resident batch (c5)
+            counts = fp.run_dev(dL, dR, len(ids))
+            ms += fp.last_ms
+            gather(ids, counts)
+        return counts, ms
 
     def step_host():
-        counts = fp.run_host(pL, pR, depth_h, xyz_h)
-        return counts, fp.last_ms
+        ms, counts = 0.0, None
+        for ids in chunks:
+            n = len(ids)
+            counts = fp.run_host(pL[:n], pR[:n], depth_h[:n], xyz_h[:n])
+            ms += fp.last_ms
+        return counts, ms
 
     # ---- device-resident arm -----------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         counts, _ = step_dev()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -275,23 +448,25 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(ee, op=dist.ReduceOp.MAX)
     e2e_elapsed = float(ee[0])
     assert list(counts_h) == list(counts), "host-buffer and device-resident runs disagree"
-    h2d = int(L.nbytes + R.nbytes)
-    d2h = int(depth_h.nbytes + xyz_h.nbytes + 8 * nfr)
+    frames_step_rank = sum(len(c) for c in chunks)
+    per_frame_in = 2 * W * H * 3
+    per_frame_out = W * H * 4 + MAX_POINTS * 24 + 8
+    h2d = int(frames_step_rank * per_frame_in)
+    d2h = int(frames_step_rank * per_frame_out)
 
-    total_frames = nfr * world * args.steps
+    total_frames = (job if strong else nfr * world) * args.steps
     fps = total_frames / (elapsed_ms / 1e3)
     e2e_fps = total_frames / (e2e_elapsed / 1e3)
+    config = bench_config(nfr, n_distinct, lanes, world)
+    if strong:
+        config["job_frames"] = job
+        config["chunks_per_step_per_gpu"] = len(chunks)
     out = {
         "metric": "frames_per_s", "value": fps, "unit": "frames/s", "gde_per_s": fps * W * H * D / 1e9,
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
-        "wall_ms_per_step": wall_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": nfr, "distinct_frames": n_distinct, "lanes": args.lanes,
-                   "sharding": "frame-wise r::world, no collective on the hot path; NCCL gather of point clouds to rank 0"
-                               " per step when N>1",
-                   "l2": "inputs %.0f MB/step plus 425 MB of C/S cost volumes per matcher run exceed the 126 MB L2"
-                         % ((L.nbytes + R.nbytes) / 1e6),
-                   "gde_definition": "W*H*D per frame, counted once although two matchers run (SURVEY 8d)"},
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": elapsed_ms / args.steps,
+        "wall_ms_per_step": wall_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": config,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_elapsed / args.steps},
         "gpu_launches": int(launches),
@@ -302,9 +477,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- roofline leg: the SGBM kernels timed alone (lanes chained, nothing overlaps them) ----------
     if rank == 0:
-        cfg1 = pipeline.make_pipeline_config(W, H, D, BS, MODE, Q, K, extractor=N.STEGER_IMPROVED, lanes=args.lanes,
-                                             max_points=MAX_POINTS)
-        fp1 = pipeline.FramePipeline(cfg1, maps=maps, ctx=ctx)
+        fp1 = pipeline.FramePipeline(pipeline_config(lanes), maps=maps, ctx=ctx)
         nr = min(nfr, 14)
         for _ in range(2):
             fp1.run_dev(dL, dR, nr)
@@ -318,7 +491,7 @@ def run_gpu(args, rank, world, local_rank):
             if k:
                 groups[g] = {"ms_total": t, "timed_regions": k}
         fp1.set_timing(False)
-        runs = 2 * nr  # left + right matcher per frame
+        runs = (2 if CFG["wls"] else 1) * nr  # left (+ right) matcher per frame
         sgbm_ms = sum(v["ms_total"] for g, v in groups.items() if g.startswith("sgbm_")) / runs
         peaks = {}
         try:
@@ -327,36 +500,42 @@ def run_gpu(args, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = sgbm_algorithmic_bytes() / (sgbm_ms * 1e-3) / 1e9
-        traffic = None  # DRAM bytes of the same kernels from the committed ncu --set full capture
+        traffic = None  # DRAM bytes of the same kernels from the committed ncu --set full capture (static, per config)
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sgbm_run_dram_bytes"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "sgbm_run_dram_bytes" if CFG["name"] in ("c3", "c5") else "sgbm_run_dram_bytes_" + CFG["name"])
         except (OSError, ValueError, KeyError):
             pass
         out["roofline"] = {
-            "bound": "hbm", "kernel": "sgbm matcher run = cost volume + horizontal paths + cluster-fused previous-row "
-                                      "paths (both passes) + WTA",
+            "bound": "hbm", "kernel": "sgbm matcher run = cost volume (one pixel-cost pass feeds both matchers' volumes) + "
+                                      "horizontal paths + previous-row paths (all passes) + WTA",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "algorithmic_bytes_per_run": sgbm_algorithmic_bytes(), "ms_per_run": sgbm_ms, "traffic": traffic,
+            "traffic_source": "static: profiles/traffic.json (ncu --set full capture of this build's kernels), not "
+                              "re-measured in this run",
             "how": "CUDA events on the launching streams around every kernel group; lanes chained so each timed kernel "
-                   "runs alone; %d frames = %d matcher runs; the cluster-fused aggregation launches carry all runs of a "
-                   "lane set at once and their time is divided by the runs they process" % (nr, runs),
+                   "runs alone; %d frames = %d matcher runs; launches that serve several runs (the shared pixel-cost pass, "
+                   "the cluster-fused aggregation of a lane set) are divided by the runs they process" % (nr, runs),
             "groups_ms_per_run": {g: v["ms_total"] / runs for g, v in groups.items() if g.startswith("sgbm_")},
             "wls_ms_per_frame": groups.get("wls", {"ms_total": 0.0})["ms_total"] / nr,
         }
         fp1.close()
+        # the same pipeline object again after the timing run, for the parity check below
+        fp.run_dev(dL, dR, min(nfr, len(chunks[-1])))
+        out["latency_ms"] = single_frame_latency(ctx, (L[0], R[0]), maps, K, Q)
 
     # ---- CPU baseline leg (rank 0, N = 1 only): bounded sample ----------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = CpuPath()
-        ns = 8 * cpu.cores  # ~10-30 s of CPU work
+        ns = CFG["cpu_frames_per_core"] * cpu.cores  # ~10-30 s of CPU work
         pairs = [(L[i % nfr], R[i % nfr]) for i in range(ns)]
         dt, ccounts = cpu.run(pairs)
         cpu.close()
         out["cpu_baseline"] = {"value": ns / dt, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
                                "sample": "%d frames of the same workload, frame-parallel over %d worker processes, %.1f s"
                                          % (ns, cpu.cores, dt),
-                               "points_match_gpu": bool(abs(ccounts[0] - int(counts[0])) <= max(2, 0.001 * ccounts[0]))}
+                               "parity_check": parity_check(ctx, fp, 0, (L[0], R[0]), maps, K, Q)}
     if rank == 0:
         print(json.dumps(out), flush=True)
     fp.close()
@@ -372,11 +551,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=112, help="frames per step per GPU (a multiple of the 7-frame lane set)")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the one the metric is quoted on)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (default per config; a multiple of the 7-frame lane set)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames rendered per rank")
-    ap.add_argument("--lanes", type=int, default=28, help="frames in flight per GPU (streams): four lane sets of 7 frames")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (streams; default per config: 28 = four lane sets of 7 frames)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    select_config(args.config)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

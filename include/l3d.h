@@ -22,7 +22,7 @@ extern "C" {
 typedef struct l3d_ctx l3d_ctx;
 
 enum { L3D_OK = 0, L3D_ERR_ARG = -1, L3D_ERR_CUDA = -2, L3D_ERR_UNSUPPORTED = -3, L3D_ERR_STATE = -4 };
-enum { L3D_MODE_SGBM = 0, L3D_MODE_HH = 1, L3D_MODE_SGBM_3WAY = 2 }; /* cv2.STEREO_SGBM_MODE_* */
+enum { L3D_MODE_SGBM = 0, L3D_MODE_HH = 1, L3D_MODE_SGBM_3WAY = 2, L3D_MODE_HH4 = 3 }; /* cv2.STEREO_SGBM_MODE_* */
 
 /* -------- context ------------------------------------------------------------------------ */
 int l3d_ctx_create(int device, l3d_ctx** out);
@@ -219,6 +219,14 @@ int l3d_pipeline_run_host(l3d_pipeline* p, const uint8_t* left, const uint8_t* r
 /* fetch results of the last run for frame slot i (device -> host); any pointer may be NULL */
 int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* depth, int16_t* disp,
                        float* xy, double* xyz, int* n_xy, int* n_xyz);
+/* Laser points of frame slot i of the last run, with explicit capacities: up to xy_cap 2D centres (f64; the Simple
+ * extractor's exact f64 centroids, the Steger variants' f32 centres widened) and up to xyz_cap 3D points.
+ * *n_xy / *n_xyz are the counts the frame produced -- n_xy may exceed the pipeline's max_points, in which case the
+ * frame's lists were truncated and the caller should re-create the pipeline with max_points >= n_xy. */
+int l3d_pipeline_fetch_points(l3d_pipeline* p, int frame, double* xy, int xy_cap, double* xyz, int xyz_cap,
+                              int* n_xy, int* n_xyz);
+/* largest 2D point count any frame of the last run produced (compare with max_points); -1 on a null handle */
+int l3d_pipeline_points_needed(l3d_pipeline* p);
 /* Pack the 3D points of the first nframes frame slots of the last run into ONE device table of rows
  * (frame_id, x, y, z) (f64), frames in slot order: the payload of the NCCL gather to rank 0.
  * frame_ids[nframes] = global frame numbers; table_dev holds >= sum(counts) * 4 doubles (device

@@ -89,6 +89,21 @@ using namespace l3d;
         }                                                                                  \
     } while (0)
 #define RC(call) do { int rc__ = (call); if (rc__ != L3D_OK) return rc__; } while (0)
+
+// Device-side domain checks of the work that just finished on `flags` (stream already synchronised).  Bit 0: a cost
+// volume value reached 32768 -- OpenCV's int16 volume wraps there and this library's unsigned 16-bit arithmetic does
+// not, so the result would differ from cv2 silently; reported instead (only blockSize >= 11 with P2 near its maximum
+// can get there, and only on blocks whose every pixel mismatches by more than 92 % of the maximum cost).
+static int check_flags(l3d_ctx* ctx, unsigned* flags) {
+    if (!flags) return L3D_OK;
+    unsigned h = 0;
+    if (cudaMemcpy(&h, flags, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return L3D_OK; }
+    if (!h) return L3D_OK;
+    cudaMemset(flags, 0, sizeof(unsigned));
+    set_err(&ctx->err, "StereoSGBM: the cost volume left the int16 value domain (block sum + P2 >= 32768); cv2 wraps there, "
+                       "this input is not supported");
+    return L3D_ERR_UNSUPPORTED;
+}
 #define NEED(ctxp, cond, msg) do { if (!(cond)) { set_err(&(ctxp)->err, "invalid argument: %s", msg); return L3D_ERR_ARG; } } while (0)
 
 extern "C" {
@@ -127,6 +142,9 @@ int l3d_ctx_create(int device, l3d_ctx** out) {
     c->lane.err = &c->err;
     e = cudaStreamCreateWithFlags(&c->lane.stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_err(&g_create_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return L3D_ERR_CUDA; }
+    e = cudaMalloc(&c->lane.flags, 16);
+    if (e == cudaSuccess) e = cudaMemset(c->lane.flags, 0, 16);
+    if (e != cudaSuccess) { set_err(&g_create_err, "cudaMalloc: %s", cudaGetErrorString(e)); delete c; return L3D_ERR_CUDA; }
     *out = c;
     return L3D_OK;
 }
@@ -135,6 +153,7 @@ void l3d_ctx_destroy(l3d_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->lane.release();
+    if (ctx->lane.flags) cudaFree(ctx->lane.flags);
     for (auto& m : ctx->maps) if (m.map) cudaFree(m.map);
     delete ctx;
 }
@@ -253,7 +272,7 @@ int l3d_sgbm_debug(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left, 
     if (C_out && dbg.C) RC(d2h(ctx, C_out, dbg.C, nvol * 2));
     if (S_out && dbg.S) RC(d2h(ctx, S_out, dbg.S, nvol * 2));
     CK(ctx, cudaStreamSynchronize(L.stream));
-    return L3D_OK;
+    return check_flags(ctx, L.flags);
     API_END(ctx)
 }
 
@@ -284,7 +303,7 @@ int l3d_sgbm_compute_pair(l3d_ctx* ctx, const l3d_sgbm_params* pl, const l3d_sgb
     RC(d2h(ctx, disp_left, dl, n * 2));
     RC(d2h(ctx, disp_right, dr, n * 2));
     CK(ctx, cudaStreamSynchronize(L.stream));
-    return L3D_OK;
+    return check_flags(ctx, L.flags);
     API_END(ctx)
 }
 
@@ -548,7 +567,7 @@ int l3d_compute_depth(l3d_ctx* ctx, const l3d_depth_config* cfg, const uint8_t* 
     RC(d2h(ctx, depth, dp, n * 4));
     if (disp_out) RC(d2h(ctx, disp_out, df, n * 2));
     CK(ctx, cudaStreamSynchronize(L.stream));
-    return L3D_OK;
+    return check_flags(ctx, L.flags);
     API_END(ctx)
 }
 
@@ -668,6 +687,7 @@ struct l3d_pipeline {
     std::vector<FrameOut> outs;   // per frame slot
     void* arena = nullptr; size_t arena_cap = 0;
     int* counts_host = nullptr;   // pinned, 2*nframes
+    unsigned* flags = nullptr;    // device word shared by all lanes (domain checks, see check_flags)
     int counts_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> lane_done;
@@ -856,8 +876,11 @@ int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeli
     int prio[3] = {prio_hi, prio_lo, std::max(prio_hi, prio_lo - 2)};  // aggregation, front, back
     if (const char* e = getenv("L3D_PRIO")) sscanf(e, "%d,%d,%d", &prio[0], &prio[1], &prio[2]);
     for (int& q : prio) q = std::min(prio_lo, std::max(prio_hi, q));
+    CK(ctx, cudaMalloc(&p->flags, 16));
+    CK(ctx, cudaMemset(p->flags, 0, 16));
     for (auto& L : p->lanes) {
         L.err = &ctx->err;
+        L.flags = p->flags;
         CK(ctx, cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio[1]));
         CK(ctx, cudaStreamCreateWithPriority(&L.back_stream, cudaStreamNonBlocking, prio[2]));
         CK(ctx, cudaEventCreateWithFlags(&L.back_done, cudaEventDisableTiming));
@@ -873,6 +896,7 @@ int l3d_pipeline_create(l3d_ctx* ctx, const l3d_pipeline_config* cfg, l3d_pipeli
     p->runs.resize(cfg->lanes);
     for (int i = 0; i < l3d_pipeline::MAXSETS; i++) {
         p->mid[i].err = &ctx->err;
+        p->mid[i].flags = p->flags;
         CK(ctx, cudaStreamCreateWithPriority(&p->mid[i].stream, cudaStreamNonBlocking, prio[0]));
         CK(ctx, cudaEventCreateWithFlags(&p->ev_mid[i], cudaEventDisableTiming));
     }
@@ -889,6 +913,7 @@ void l3d_pipeline_destroy(l3d_pipeline* p) {
     for (auto e : p->lane_front) cudaEventDestroy(e);
     for (auto& m : p->maps) if (m.map) cudaFree(m.map);
     if (p->arena) cudaFree(p->arena);
+    if (p->flags) cudaFree(p->flags);
     if (p->counts_host) cudaFreeHost(p->counts_host);
     pipe_drop_graphs(p);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -1144,7 +1169,7 @@ static int pipe_run(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, 
     p->dbg_marks.clear();
     p->last_frames = nframes;
     if (counts) for (int f = 0; f < nframes; f++) counts[f] = p->counts_host[2 * f + 1];
-    return L3D_OK;
+    return check_flags(ctx, p->flags);
 }
 
 int l3d_pipeline_run_dev(l3d_pipeline* p, const uint8_t* left_dev, const uint8_t* right_dev, int nframes, int* counts) {
@@ -1192,6 +1217,40 @@ int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* de
     if (xyz && nxyz > 0) CK(ctx, cudaMemcpy(xyz, o.xyz, sizeof(double) * 3 * nxyz, cudaMemcpyDeviceToHost));
     return L3D_OK;
     API_END(ctx)
+}
+
+int l3d_pipeline_fetch_points(l3d_pipeline* p, int frame, double* xy, int xy_cap, double* xyz, int xyz_cap, int* n_xy,
+                              int* n_xyz) {
+    if (!p) return L3D_ERR_ARG;
+    l3d_ctx* ctx = p->ctx;
+    API_BEGIN(ctx)
+    NEED(ctx, frame >= 0 && frame < p->last_frames && xy_cap >= 0 && xyz_cap >= 0, "fetch_points arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const FrameOut& o = p->outs[frame];
+    const int nxy = p->counts_host[2 * frame], nxyz = p->counts_host[2 * frame + 1];
+    if (n_xy) *n_xy = nxy;
+    if (n_xyz) *n_xyz = nxyz;
+    const int m = std::min(std::min(nxy, p->cfg.max_points), xy_cap);
+    if (xy && m > 0) {
+        if (p->cfg.extractor == 4) {
+            CK(ctx, cudaMemcpy(xy, o.xy64, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<float> t((size_t)2 * m);
+            CK(ctx, cudaMemcpy(t.data(), o.xy, sizeof(float) * 2 * m, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 2 * m; i++) xy[i] = (double)t[i];
+        }
+    }
+    const int m3 = std::min(std::min(nxyz, p->cfg.max_points), xyz_cap);
+    if (xyz && m3 > 0) CK(ctx, cudaMemcpy(xyz, o.xyz, sizeof(double) * 3 * m3, cudaMemcpyDeviceToHost));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_pipeline_points_needed(l3d_pipeline* p) {
+    if (!p) return -1;
+    int m = 0;
+    for (int f = 0; f < p->last_frames; f++) m = std::max(m, p->counts_host[2 * f]);
+    return m;
 }
 
 long long l3d_pipeline_launch_count(l3d_pipeline* p) {

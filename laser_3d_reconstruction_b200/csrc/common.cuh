@@ -46,6 +46,7 @@ struct Lane {
     DevBuf bufs[S_NUM];
     long long launches = 0;
     std::string* err = nullptr;
+    unsigned* flags = nullptr;    // device word the owner (context / pipeline) provides: bit 0 = a cost volume left the int16 domain
     double wls_lut_sigma = -1.0;  // sigma_color the S_WLS_K table was built for
     // optional kernel-group timing (bench roofline leg)
     bool timing = false;
@@ -167,6 +168,7 @@ int dev_recon(Lane& L, const l3d_recon_params& p, const double* xy, const float*
 
 struct l3d_ctx {
     int device = 0;
+    unsigned* flags_host = nullptr;  // pinned mirror of lane.flags
     std::string err;
     l3d::Lane lane;
     l3d::RectMap maps[2];

@@ -91,6 +91,7 @@ struct CostArgs {
     const uint4* Ldesc; const uint4* Rdesc; int16_t* C;  // two planes each (channel 0, channel 1)
     int W, H, minD, D, minX1, width1, SW2, bs, P2, TX, TXH;
     int nxg, cpg;  // phase B: column groups per CTA, columns per group
+    unsigned* flags;  // bit 0 is set when a cost value reaches 32768 (OpenCV's int16 would wrap there; see make_geom)
     int dbg;       // L3D_COST_DBG experiment bits: 1 no C stores, 2 no phase B, 4 no phase A (results are garbage)
     int nbands;
     int band_vr0[MAXBAND], band_y0[MAXBAND], band_rows[MAXBAND], band_clo[MAXBAND], band_chi[MAXBAND];
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
     uint32_t crun[COST_MAXCPG];
 #pragma unroll
     for (int j = 0; j < COST_MAXCPG; j++) crun[j] = p2x2;
+    uint32_t ovf = 0;
     const int nk = rows + bs - 1;
     const int nitA = NIT ? NIT : (dpa0 < D2 ? (D2 - dpa0 + dpa_step - 1) / dpa_step : 0);  // phase A items of this thread
 
@@ -266,6 +268,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
             for (int j = 0; j < COST_MAXCPG; j++) {
                 if (j < ncb) {
                     rp[j * D2] = hs[j];
+                    ovf |= crun[j];
                     if (emit) Cdst[j * D2] = crun[j];
                 }
             }
@@ -284,6 +287,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
                     if (sub) c -= rp[j * D2];
                     rp[j * D2] = h;
                     crun[j] = c;
+                    ovf |= c;
                     if (emit) Cdst[j * D2] = c;
                 }
             }
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_kernel(const CostAr
         if (k + 1 < nk) phase_a(k + 1);
         phase_b(k);
     }
+    if ((ovf & 0x80008000u) && a.flags) atomicOr(a.flags, 1u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
     uint32_t crun[CPG];
 #pragma unroll
     for (int j = 0; j < CPG; j++) crun[j] = p2x2;
+    uint32_t ovf = 0;
     uint32_t* Cdst = (uint32_t*)(a.C + ((ptrdiff_t)(vr0 - (BS - 1)) * width1 + x0 + cb0) * D) + dp0 + dpi;
     const size_t crow = (size_t)width1 * D2;
     const uint32_t* ppb = pdw + dpi * CW_PDS + cb0;
@@ -454,6 +460,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
             for (int j = 0; j < CPG; j++) {
                 if (j < ncb) {
                     rp[j] = hs[j];
+                    ovf |= crun[j];
                     if (emit && !((a.dbg & 1) && crun[j] != 0x12345u)) Cdst[(size_t)j * D2] = crun[j];
                 }
             }
@@ -462,6 +469,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
         Cdst += crow;
         slot = slot + 1 == BS ? 0 : slot + 1;
     }
+    if ((ovf & 0x80008000u) && a.flags) atomicOr(a.flags, 1u);
 }
 // ------------------------------------------------------------------------------------------
 // cost volumes of BOTH matchers of a frame from one pixel-cost pass (numDisparities 64 / 128)
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_warp_kernel(const C
 // (split arrive / wait: a warp runs at most one row ahead of the slowest).
 constexpr int CD_NS = 4;        // operand-table stages
 constexpr int CD_PDS = 88;      // pixel-cost strip stride per pair
-constexpr int CD_MAXT1 = 8;
+constexpr int CD_MAXT1 = 16;
 
 struct DualArgs {
     const uint4* desc[2];       // BT operand planes of the left view [0] and the right view [1]
@@ -497,24 +505,33 @@ struct DualArgs {
     int stride0;                // role-0 tile origins: t * stride0; role-1 origins: x1[t]
     int x1[CD_MAXT1];
     int emit, RA, RB;           // role-0 tiles also write columns RA <= x' < RB of C[1]
+    unsigned* flags;            // bit 0 is set when a cost value reaches 32768 (OpenCV's int16 would wrap there)
     int dbg;
 };
 
 template <int BS, int DD>
 struct CdCfg {
-    static constexpr int D = DD, D2 = DD / 2, SW2 = BS / 2, TXH = 64, TX = TXH - 2 * SW2;
-    static constexpr int NW = COST_THREADS / 32, DPW = D2 / NW, NG = 32 / DPW, CPG = (TX + NG - 1) / NG;
+    // 64 computed columns per tile (two per lane in phase A) up to 128 disparities; 32 at 256 disparities, where the
+    // ring of row sums (BS * D/2 * TX words) would not fit with more
+    static constexpr int D = DD, D2 = DD / 2, SW2 = BS / 2, TXH = DD > 128 ? 32 : 64, NHH = TXH / 32, TX = TXH - 2 * SW2;
+    static constexpr int NW = COST_THREADS / 32, DPW = D2 / NW, NG = 32 / DPW;
+    // phase B: lane <-> (pair, group of CPG columns).  D = 256: 4 groups of 8 columns (the last one idle): with 6-column
+    // groups no strip stride avoids 2-way bank conflicts on the tap loads
+    static constexpr int CPG = DD > 128 ? 8 : (TX + NG - 1) / NG;
+    static constexpr int PDS = DD > 128 ? 37 : CD_PDS;    // pixel-cost strip stride per pair (conflict-free tap loads)
     static constexpr int NEMAX = TXH + D;                 // right-operand entries per channel and stage
     static constexpr int STAGE_U4 = 2 * NEMAX + 2 * TXH;  // [R0 | R1 | L0 | L1]
     // staged row: column stride in words.  D = 128: 68 (== 4 mod 32: the phase-B lanes (pair, 7-column group) hit 32
-    // banks, the sheared walk moves by -(2 * 68 + 1) == -9 words per lane and wraps by 56 * 68 == 0 mod 32)
-    static constexpr int CS = D2 % 32 == 0 && D2 >= 64 ? D2 + 4 : D2 + 1;
-    static constexpr int NH = D2 / 32;                    // 32-word halves of a right-volume vector
+    // banks, the sheared walk moves by -(2 * 68 + 1) == -9 words per lane and wraps by 56 * 68 == 0 mod 32); D = 256:
+    // 129 (8-column groups: 8 * 129 == 8 mod 32); D = 64: 33 (2-way conflicts on the staging stores at best)
+    static constexpr int CS = DD == 128 ? D2 + 4 : D2 + 1;
+    static constexpr int NH = D2 / 32;                    // 32-word pieces of a right-volume vector
     static constexpr size_t smem_bytes() {
-        return (size_t)CD_NS * STAGE_U4 * 16 + (size_t)D2 * CD_PDS * 4 + (size_t)BS * D2 * TX * 4 + (size_t)2 * TX * CS * 4 +
-               (size_t)(2 * CD_NS + 4) * 8;
+        return (size_t)CD_NS * STAGE_U4 * 16 + (size_t)D2 * PDS * 4 + (size_t)BS * D2 * TX * 4 + (size_t)2 * TX * CS * 4 +
+               (size_t)(2 * CD_NS + 4) * 8 + 64;
     }
-    static_assert(DPW >= 1 && 32 % DPW == 0 && CPG <= COST_MAXCPG && D2 % 32 == 0, "tile geometry");
+    static_assert(DPW >= 1 && 32 % DPW == 0 && CPG <= COST_MAXCPG && CPG * NG >= TX && D2 % 32 == 0, "tile geometry");
+    static_assert(PDS >= ((TX - 1) / CPG) * CPG + CPG + BS - 1, "strip stride covers the last active group's taps");
 };
 
 __device__ __forceinline__ void cost_mbar_arrive(uint32_t bar) {
@@ -527,6 +544,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int D = K::D, D2 = K::D2, SW2 = K::SW2, TXH = K::TXH, TX = K::TX;
     constexpr int NW = K::NW, DPW = K::DPW, CPG = K::CPG, NEMAX = K::NEMAX, STAGE_U4 = K::STAGE_U4, CS = K::CS, NH = K::NH;
+    constexpr int NHH = K::NHH, PDS = K::PDS;
     const int width1 = a.width1, W = a.W;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -558,9 +576,9 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
     const int lc0 = max(0, SW2 - x0), lc1 = min(TXH, width1 - (x0 - SW2));
     uint4* tabs = (uint4*)smem_raw;                                              // [CD_NS][STAGE_U4]
     uint32_t* u32base = (uint32_t*)(tabs + CD_NS * STAGE_U4);
-    uint32_t* pdw = u32base + warp * DPW * CD_PDS;                               // this warp's pixel-cost strip [DPW][CD_PDS]
-    uint32_t* ringw = u32base + D2 * CD_PDS + (size_t)warp * BS * DPW * TX;      // this warp's row sums [BS][DPW][TX]
-    uint32_t* Ls = u32base + D2 * CD_PDS + (size_t)BS * D2 * TX;                 // staged rows [2][TX][CS]
+    uint32_t* pdw = u32base + warp * DPW * PDS;                               // this warp's pixel-cost strip [DPW][PDS]
+    uint32_t* ringw = u32base + D2 * PDS + (size_t)warp * BS * DPW * TX;      // this warp's row sums [BS][DPW][TX]
+    uint32_t* Ls = u32base + D2 * PDS + (size_t)BS * D2 * TX;                 // staged rows [2][TX][CS]
     const uint32_t bars = (uint32_t)__cvta_generic_to_shared(Ls + 2 * TX * CS);
     // bars + 8 s: full[s]; + 8 (CD_NS + s): empty[s]; + 8 (2 CD_NS + s): row staged[s]; + 8 (2 CD_NS + 2 + s): row written out[s]
     const uint32_t bar_lsf = bars + 8 * (2 * CD_NS), bar_lse = bars + 8 * (2 * CD_NS + 2);
@@ -590,9 +608,9 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
 
     // phase A role: tile columns lane and lane + 32, pairs dp0 .. dp0 + DPW - 1
     const int dp0 = warp * DPW;
-    int eoff[2], lcol[2];
+    int eoff[NHH], lcol[NHH];
 #pragma unroll
-    for (int hh = 0; hh < 2; hh++) {
+    for (int hh = 0; hh < NHH; hh++) {
         const int c = lane + 32 * hh;
         const int xc = min(max(x0 - SW2 + c, 0), width1 - 1);
         eoff[hh] = xc - xa + D - 2 - 2 * dp0;
@@ -606,13 +624,13 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
     uint32_t crun[CPG];
 #pragma unroll
     for (int j = 0; j < CPG; j++) crun[j] = p2x2;
-    const uint32_t* ppb = pdw + dpi * CD_PDS + cb0;
+    const uint32_t* ppb = pdw + dpi * PDS + cb0;
     uint32_t* rpb = ringw + dpi * TX + cb0;
     uint32_t* lsb = Ls + cb0 * CS + dp0 + dpi;                 // + stage * TX * CS, + j * CS
     int slot = 0;
+    uint32_t ovf = 0;
     // write-out role: sheared walk constants, cw[h] = (-2 w) mod TX for w = 32 h + lane
-    const int cw0 = (TX * 8 - 2 * lane) % TX, cw1 = (TX * 8 - 2 * (32 + lane)) % TX;
-    static_assert(NH <= 2, "sheared walk: at most two 32-word halves per vector");
+    const int cw0 = (TX * 16 - 2 * lane) % TX;                 // + TX - (64 h) % TX per piece h
     uint32_t* Cown32 = (uint32_t*)a.C[role];
     uint32_t* Cother32 = (uint32_t*)a.C[1];
 
@@ -638,8 +656,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
             for (int unit = warp; unit < TX * NH; unit += NW) {
                 const int s = unit / NH, h = unit - s * NH;
                 const int w = 32 * h + lane;
-                int u = s + ((NH == 1 || h == 0) ? cw0 : cw1);
-                if (u >= TX) u -= TX;
+                int u = (s + cw0 + TX * 16 - 64 * h) % TX;
                 const int xq = x0 + u + 1 + 2 * w;             // right-volume column of this word
                 if (u < TX - 1 && xq >= a.RA && xq < a.RB) {
                     const uint32_t Aw = ls[(u + 1) * CS + (D2 - 1 - w)], Bw = ls[u * CS + (D2 - 1 - w)];
@@ -666,24 +683,28 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
             // ---- phase A
             if (!(a.dbg & 4))
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
+            for (int hh = 0; hh < NHH; hh++) {
                 const uint4 l0 = T0[2 * NEMAX + lcol[hh]], l1 = T0[2 * NEMAX + TXH + lcol[hh]];
                 const uint32_t u0 = __byte_perm(l0.x, l0.x, 0x3232), nu0 = __byte_perm(l0.y, l0.y, 0x3232);
                 const uint32_t ul0 = __byte_perm(l0.z, l0.z, 0x3232), nuh0 = __byte_perm(l0.w, l0.w, 0x3232);
                 const uint32_t u1 = __byte_perm(l1.x, l1.x, 0x3232), nu1 = __byte_perm(l1.y, l1.y, 0x3232);
                 const uint32_t ul1 = __byte_perm(l1.z, l1.z, 0x3232), nuh1 = __byte_perm(l1.w, l1.w, 0x3232);
-                uint4 e0[DPW], e1[DPW];
+                constexpr int NB = DPW < 4 ? DPW : 4;  // pairs per batch: all table loads, then the arithmetic, then the stores
 #pragma unroll
-                for (int i = 0; i < DPW; i++) { e0[i] = T0[eoff[hh] - 2 * i]; e1[i] = T0[NEMAX + eoff[hh] - 2 * i]; }
-                uint32_t c[DPW];
+                for (int i0 = 0; i0 < DPW; i0 += NB) {
+                    uint4 e0[NB], e1[NB];
 #pragma unroll
-                for (int i = 0; i < DPW; i++) {
-                    const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
-                    const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
-                    c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                    for (int i = 0; i < NB; i++) { e0[i] = T0[eoff[hh] - 2 * (i0 + i)]; e1[i] = T0[NEMAX + eoff[hh] - 2 * (i0 + i)]; }
+                    uint32_t c[NB];
+#pragma unroll
+                    for (int i = 0; i < NB; i++) {
+                        const uint32_t c0 = bt_pair(u0, nu0, ul0, nuh0, e0[i]);
+                        const uint32_t c1 = bt_pair(u1, nu1, ul1, nuh1, e1[i]);
+                        c[i] = c0 + ((c1 >> 2) & 0x3fff3fffu);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NB; i++) pdw[(i0 + i) * PDS + lane + 32 * hh] = c[i];
                 }
-#pragma unroll
-                for (int i = 0; i < DPW; i++) pdw[i * CD_PDS + lane + 32 * hh] = c[i];
             }
             __syncwarp();
             if (lane == 0) cost_mbar_arrive(bars + 8 * (CD_NS + s));
@@ -713,6 +734,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
                 for (int j = 0; j < CPG; j++) {
                     if (j < ncb) {
                         rp[j] = hs[j];
+                        ovf |= crun[j];
                         if (emit) lp[j * CS] = crun[j];
                     }
                 }
@@ -728,6 +750,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
             if (lane == 0) cost_mbar_arrive(bar_lse + 8 * ((e - 1) & 1));
         }
     }
+    if ((ovf & 0x80008000u) && a.flags) atomicOr(a.flags, 1u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -759,13 +782,14 @@ static void cost_bands(const Geom& g, int H, int want, CostArgs& ca) {
 }
 
 static int cost_single_staged(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, int16_t* C);
+static bool cost_dual_cfg(int bs, int D);
 
 int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, int16_t* C) {
     const int W = g.W, H = g.H;
     CostArgs ca;
     ca.Ldesc = dL; ca.Rdesc = dR; ca.C = C;
     ca.W = W; ca.H = H; ca.minD = g.minD; ca.D = g.D; ca.minX1 = g.minX1; ca.width1 = g.width1;
-    ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2;
+    ca.SW2 = g.SW2; ca.bs = g.bs; ca.P2 = g.P2; ca.flags = L.flags;
     static const int cost_dbg = getenv("L3D_COST_DBG") ? atoi(getenv("L3D_COST_DBG")) : 0;
     ca.dbg = cost_dbg;
     const int D2 = g.D / 2;
@@ -786,7 +810,7 @@ int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, i
     static const bool no_warp_cost = getenv("L3D_COST_CLASSIC") != nullptr;
     static const bool no_staged = getenv("L3D_COST_NO_STAGED") != nullptr;
     const bool warp_form = !no_warp_cost && ((g.D == 128 && g.bs == 9) || (g.D == 64 && g.bs == 5));
-    if (warp_form && !no_staged && g.nseg == 1) return cost_single_staged(L, g, dL, dR, C);
+    if (!no_warp_cost && !no_staged && g.nseg == 1 && cost_dual_cfg(g.bs, g.D)) return cost_single_staged(L, g, dL, dR, C);
     if (warp_form) {
         // warp-decoupled form: 64-column tiles
         ca.TXH = CW_TXH; ca.TX = CW_TXH - 2 * g.SW2;
@@ -815,7 +839,7 @@ int sgbm_cost_single(Lane& L, const Geom& g, const uint4* dL, const uint4* dR, i
 }
 
 // the (blockSize, numDisparities) pairs the dual kernel is instantiated for
-static bool cost_dual_cfg(int bs, int D) { return (bs == 9 && D == 128) || (bs == 5 && D == 64); }
+static bool cost_dual_cfg(int bs, int D) { return (bs == 9 && D == 128) || (bs == 5 && D == 64) || (bs == 11 && D == 256); }
 
 template <int BS, int DD>
 static int launch_cost_dual(Lane& L, const DualArgs& da) {
@@ -829,8 +853,40 @@ static int launch_cost_dual(Lane& L, const DualArgs& da) {
 static int launch_cost_dual_any(Lane& L, int bs, int D, const DualArgs& da) {
     if (bs == 9 && D == 128) return launch_cost_dual<9, 128>(L, da);
     if (bs == 5 && D == 64) return launch_cost_dual<5, 64>(L, da);
+    if (bs == 11 && D == 256) return launch_cost_dual<11, 256>(L, da);
     set_err(L.err, "sgbm_cost_dual: no instantiation for blockSize %d / numDisparities %d", bs, D);
     return L3D_ERR_UNSUPPORTED;
+}
+
+static int cost_dual_tx(int bs, int D) { return (D > 128 ? 32 : 64) - 2 * (bs / 2); }
+
+// Band split of a launch: nt0 tiles whose CTAs cost w0 per row and nt1 tiles at w1 per row, every CTA walks
+// (band rows + bs - 1) rows; one CTA per SM.  Picks the bands per tile of both roles that minimise the finish time of
+// a greedy assignment of the CTAs (in launch order: role 0 first) to the SMs.
+static void cost_pick_bands(int H, int bs, int nt0, double w0, int nt1, double w1, int& b0_out, int& b1_out) {
+    const int maxb = std::max(1, std::min(64, H / (2 * bs)));
+    double bestt = 1e30;
+    b0_out = b1_out = 1;
+    std::vector<double> sm(NUM_SMS);
+    for (int b0 = 1; b0 <= maxb; b0++) {
+        for (int b1 = 1; b1 <= (nt1 ? maxb : 1); b1++) {
+            const double t0 = w0 * (cdiv(H, b0) + bs - 1), t1 = w1 * (cdiv(H, b1) + bs - 1);
+            std::fill(sm.begin(), sm.end(), 0.0);
+            const int n0 = nt0 * b0, n1 = nt1 * b1;
+            if (n0 + n1 > 4096) continue;
+            // CTAs of equal length: fill round-robin onto the earliest-free SM
+            for (int i = 0; i < n0 + n1; i++) {
+                int k = 0;
+                for (int q = 1; q < NUM_SMS; q++) if (sm[q] < sm[k]) k = q;
+                sm[k] += i < n0 ? t0 : t1;
+            }
+            double t = 0;
+            for (double v : sm) t = std::max(t, v);
+            // inside the frame pipeline other kernels fill idle SMs, so total work (halo rows of short bands) counts too
+            t += 0.3 * (n0 * t0 + n1 * t1) / NUM_SMS + 1e-3 * (b0 + b1);
+            if (t < bestt) { bestt = t; b0_out = b0; b1_out = b1; }
+        }
+    }
 }
 
 // one volume through the staged-row kernel (role 0 only, nothing emitted into a second volume)
@@ -839,10 +895,18 @@ static int cost_single_staged(Lane& L, const Geom& g, const uint4* dL, const uin
     da.desc[0] = dL; da.desc[1] = dR; da.C[0] = C; da.C[1] = nullptr;
     da.W = g.W; da.H = g.H; da.width1 = g.width1; da.P2 = g.P2;
     da.viewL[0] = 0; da.minD[0] = g.minD; da.minX1[0] = g.minX1;
-    const int TX = 64 - 2 * g.SW2;
+    const int TX = cost_dual_tx(g.bs, g.D);
     da.stride0 = TX; da.ntiles[0] = cdiv(g.width1, TX); da.ntiles[1] = 0; da.nbands[1] = 1;
-    da.nbands[0] = std::max(1, std::min(NUM_SMS / da.ntiles[0], g.H / (2 * g.bs) > 0 ? g.H / (2 * g.bs) : 1));
-    da.emit = 0; da.RA = da.RB = 0;
+    static std::map<long long, int> cache;  // (H, bs, tiles) -> bands
+    const long long key = ((long long)g.H << 32) | ((long long)g.bs << 24) | da.ntiles[0];
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int b0, b1;
+        cost_pick_bands(g.H, g.bs, da.ntiles[0], 1.0, 0, 0.0, b0, b1);
+        it = cache.emplace(key, b0).first;
+    }
+    da.nbands[0] = it->second;
+    da.emit = 0; da.RA = da.RB = 0; da.flags = L.flags;
     static const int cost_dbg = getenv("L3D_COST_DBG") ? atoi(getenv("L3D_COST_DBG")) : 0;
     da.dbg = cost_dbg;
     return launch_cost_dual_any(L, g.bs, g.D, da);
@@ -857,7 +921,7 @@ bool sgbm_cost_dual_ok(const Geom& gl, const Geom& gr) {
 int sgbm_cost_dual(Lane& L, const Geom& gl, const Geom& gr, const uint4* dLv, const uint4* dRv, int16_t* Cl, int16_t* Cr) {
     L3D_ARG(L, sgbm_cost_dual_ok(gl, gr), "sgbm_cost_dual geometry");
     const int D = gl.D, SW2 = gl.SW2, W1 = gl.width1, H = gl.H;
-    const int TX = 64 - 2 * SW2;
+    const int TX = cost_dual_tx(gl.bs, D);
     DualArgs da = {};
     da.desc[0] = dLv; da.desc[1] = dRv; da.C[0] = Cl; da.C[1] = Cr;
     da.W = gl.W; da.H = H; da.width1 = W1; da.P2 = gl.P2;
@@ -872,25 +936,27 @@ int sgbm_cost_dual(Lane& L, const Geom& gl, const Geom& gr, const uint4* dLv, co
     da.RB = std::max(da.RA, W1 - TX);
     da.emit = da.RB > da.RA;
     int nt1 = 0;
-    for (int x = 0; x < da.RA; x += TX) da.x1[nt1++] = x;
-    if (da.RB < W1) da.x1[nt1++] = da.RB;
-    L3D_ARG(L, nt1 <= CD_MAXT1, "sgbm_cost_dual: border tiles");
-    da.ntiles[1] = nt1;
-    // bands: one wave of CTAs; a role-0 row costs about 1.35 role-1 rows (it also writes the sheared copy)
-    const int maxb = std::max(1, H / (2 * gl.bs));
-    int best0 = 1, best1 = 1;
-    double bestt = 1e30;
-    for (int b0 = 1; b0 <= maxb; b0++) {
-        for (int b1 = 1; b1 <= maxb; b1++) {
-            if (da.ntiles[0] * b0 + nt1 * b1 > NUM_SMS && !(b0 == 1 && b1 == 1)) continue;
-            const double t0 = 1.35 * (cdiv(H, b0) + gl.bs - 1), t1 = nt1 ? 1.0 * (cdiv(H, b1) + gl.bs - 1) : 0.0;
-            const double t = std::max(t0, t1) + 1e-3 * (b0 + b1);
-            if (t < bestt) { bestt = t; best0 = b0; best1 = b1; }
-        }
+    for (int x = 0; x < da.RA && nt1 < CD_MAXT1; x += TX) da.x1[nt1++] = x;
+    L3D_ARG(L, nt1 * TX >= da.RA, "sgbm_cost_dual: border tiles");
+    if (da.RB < W1) {
+        L3D_ARG(L, nt1 < CD_MAXT1, "sgbm_cost_dual: border tiles");
+        da.x1[nt1++] = da.RB;
     }
-    da.nbands[0] = best0; da.nbands[1] = best1;
+    da.ntiles[1] = nt1; da.flags = L.flags;
+    // a role-0 row costs about 1.35 role-1 rows (it also writes the sheared copy)
+    static std::map<long long, std::pair<int, int>> cache;  // (H, bs, tiles) -> bands of both roles
+    const long long key = ((long long)H << 40) | ((long long)gl.bs << 32) | ((long long)da.ntiles[0] << 8) | nt1;
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int b0, b1;
+        cost_pick_bands(H, gl.bs, da.ntiles[0], 1.35, nt1, 1.0, b0, b1);
+        it = cache.emplace(key, std::make_pair(b0, b1)).first;
+    }
+    da.nbands[0] = it->second.first; da.nbands[1] = it->second.second;
     static const int cost_dbg = getenv("L3D_COST_DBG") ? atoi(getenv("L3D_COST_DBG")) : 0;
     da.dbg = cost_dbg;
+    if (getenv("L3D_DEBUG_CLUSTERS"))
+        fprintf(stderr, "[l3d] cost dual: %d x %d + %d x %d CTAs, RA %d RB %d\n", da.ntiles[0], da.nbands[0], nt1, da.nbands[1], da.RA, da.RB);
     return launch_cost_dual_any(L, gl.bs, D, da);
 }
 

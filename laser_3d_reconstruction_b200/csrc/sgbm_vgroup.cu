@@ -26,9 +26,9 @@ namespace l3d {
 namespace cg = cooperative_groups;
 
 constexpr int VG_CLUSTER_MAX = 16;  // cluster sizes used: 8 (portable) and 16 (non-portable)
-constexpr int VG_WARPS = 16;
-constexpr int VG_THREADS = VG_WARPS * 32;
-constexpr int VG_MAXCPW = 9;     // columns per warp: the cluster spans 8 * 16 * 9 = 1152 columns
+constexpr int VG_WARPS = 16;     // warps per CTA (D <= 128); D = 256 runs 8 warps per CTA with up to 255 registers each
+constexpr int VG_MAXCPW = 9;     // columns per warp at 16 warps: the cluster spans 8 * 16 * 9 = 1152 columns
+constexpr int VG_MAXCPW8 = 13;   // columns per warp at 8 warps (D = 256): 16 * 8 * 13 = 1664 columns
 constexpr int VG_MAXJOBS = 64;
 // 16 warps x 120 registers leave 4096 registers of the SM free: the one-warp CTAs of the back-half kernels (FGS
 // solver, ...) can then share an SM with an aggregation CTA instead of blocking a whole cluster from launching
@@ -51,9 +51,9 @@ struct VGroupArgs {
     int minD[VG_MAXJOBS], minX1[VG_MAXJOBS], uniq[VG_MAXJOBS];
 };
 
-static size_t vgroup_smem_bytes(int D, int cpw) {
-    const size_t strip = (size_t)VG_WARPS * cpw * D * 2;
-    const size_t halo = (size_t)2 * 2 * VG_WARPS * (D * 2 + 16);
+static size_t vgroup_smem_bytes(int D, int cpw, int nwarps) {
+    const size_t strip = (size_t)nwarps * cpw * D * 2;
+    const size_t halo = (size_t)2 * 2 * nwarps * (D * 2 + 16);
     return 2 * 2 * strip + halo + 64;  // + 6 mbarriers (2 row stages, 2 x 2 remote-halo parities)
 }
 
@@ -134,9 +134,13 @@ __device__ __noinline__ bool vg_not_unique(typename VgVec<NP>::T wv, unsigned ke
     return __any_sync(0xffffffffu, rej) && minS < 32767;
 }
 
-// NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities); CPW = columns per warp
-template <int NP, int CPW, bool FINAL>
-__global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
+// NP = D / 64 words per lane (D in {64, 128, 256}: all 32 lanes hold disparities); CPW = columns per warp; NW = warps per
+// CTA.  D = 256 at 1920 columns: a column's state is 15 registers, the 1664 columns of width1 spread over the largest
+// cluster (16 CTAs) leave 104 per CTA -- 8 warps x 13 columns (195 state registers of the 255 a 256-thread CTA may
+// use; each warp carries 39 independent recurrences per row, so two warps per sub-partition still fill the ALU pipe).
+template <int NP, int CPW, bool FINAL, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) __maxnreg__(NW == 16 ? VG_MAXREG : 255) sgbm_vgroup_kernel(const VGroupArgs a) {
+    constexpr int VG_WARPS = NW, VG_THREADS = NW * 32;
     typedef typename VgVec<NP>::T vec;
     constexpr uint32_t INF = 0x7fff7fffu;
     extern __shared__ __align__(128) unsigned char vg_smem[];
@@ -386,20 +390,26 @@ __global__ void __maxnreg__(VG_MAXREG) sgbm_vgroup_kernel(const VGroupArgs a) {
 
 // Host entry: aggregate the three previous-row paths of pass `dir` for `njobs` volumes at once.
 // Returns L3D_ERR_UNSUPPORTED when the geometry does not fit (caller falls back to the scan kernels).
-static int vgroup_cluster_size(int width1, int D) {
+// launch shape for a geometry: CTAs per cluster (= per job), warps per CTA, columns per warp; false = not covered
+struct VGShape { int cluster, nwarps, cpw; };
+static bool vgroup_shape(int width1, int D, VGShape& s) {
     // 8 CTAs per job when the per-warp state fits (measured: more jobs resident, better throughput than 16);
-    // 16 (non-portable) only for volumes wider than 8 * 16 * cpw_max columns
-    const int maxcpw = D == 256 ? 4 : VG_MAXCPW;
-    if (cdiv(width1, 8 * VG_WARPS) <= maxcpw) return 8;
-    if (cdiv(width1, 16 * VG_WARPS) <= maxcpw) return 16;
-    return 0;
+    // 16 (non-portable) only for volumes wider than that
+    const int cand[4][3] = {{8, 16, D == 256 ? 4 : VG_MAXCPW}, {16, 16, D == 256 ? 4 : VG_MAXCPW},
+                            {8, 8, D == 256 ? VG_MAXCPW8 : 0}, {16, 8, D == 256 ? VG_MAXCPW8 : 0}};
+    for (int i = 0; i < 4; i++) {
+        const int cl = cand[i][0], nw = cand[i][1], maxcpw = cand[i][2];
+        if (!maxcpw) continue;
+        const int cpw = cdiv(width1, cl * nw);
+        if (cpw <= maxcpw && vgroup_smem_bytes(D, cpw, nw) <= 227 * 1024) { s.cluster = cl; s.nwarps = nw; s.cpw = cpw; return true; }
+    }
+    return false;
 }
 
 bool vgroup_supported(int width1, int H, int D) {
     if (!(D == 64 || D == 128 || D == 256) || width1 < 1 || H < 1) return false;
-    const int cl = vgroup_cluster_size(width1, D);
-    if (!cl) return false;
-    return vgroup_smem_bytes(D, cdiv(width1, cl * VG_WARPS)) <= 220 * 1024;
+    VGShape s;
+    return vgroup_shape(width1, D, s);
 }
 
 int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
@@ -419,12 +429,14 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
         a.final = wta ? 1 : 0; a.W = wta ? wta[0].W : 0;
         a.zero = 0;
         a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir;
-        a.cluster = vgroup_cluster_size(width1, D);
-        a.cpw = cdiv(width1, a.cluster * VG_WARPS);
-        const size_t smem = vgroup_smem_bytes(D, a.cpw);
+        VGShape shp;
+        vgroup_shape(width1, D, shp);
+        a.cluster = shp.cluster;
+        a.cpw = shp.cpw;
+        const size_t smem = vgroup_smem_bytes(D, a.cpw, shp.nwarps);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(a.cluster, nj);
-        cfg.blockDim = dim3(VG_THREADS);
+        cfg.blockDim = dim3(shp.nwarps * 32);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = L.stream;
         cudaLaunchAttribute attr[1];
@@ -445,15 +457,19 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
         L.launches++;                                                                                                 \
         rc = L3D_OK;                                                                                                  \
     }
-#define VG_CASE(NPV, CPWV)                                                                                            \
-    if (D == 64 * NPV && a.cpw == CPWV) {                                                                             \
-        if (a.final) VG_LAUNCH((sgbm_vgroup_kernel<NPV, CPWV, true>))                                                 \
-        else VG_LAUNCH((sgbm_vgroup_kernel<NPV, CPWV, false>))                                                        \
+#define VG_CASE_W(NPV, CPWV, NWV)                                                                                     \
+    if (D == 64 * NPV && a.cpw == CPWV && shp.nwarps == NWV) {                                                        \
+        if (a.final) VG_LAUNCH((sgbm_vgroup_kernel<NPV, CPWV, true, NWV>))                                            \
+        else VG_LAUNCH((sgbm_vgroup_kernel<NPV, CPWV, false, NWV>))                                                   \
     }
+#define VG_CASE(NPV, CPWV) VG_CASE_W(NPV, CPWV, 16)
 #define VG_NP(NPV) VG_CASE(NPV, 1) VG_CASE(NPV, 2) VG_CASE(NPV, 3) VG_CASE(NPV, 4) VG_CASE(NPV, 5) VG_CASE(NPV, 6) \
                    VG_CASE(NPV, 7) VG_CASE(NPV, 8) VG_CASE(NPV, 9)
         VG_NP(1) VG_NP(2)
         VG_CASE(4, 1) VG_CASE(4, 2) VG_CASE(4, 3) VG_CASE(4, 4)
+        VG_CASE_W(4, 5, 8) VG_CASE_W(4, 6, 8) VG_CASE_W(4, 7, 8) VG_CASE_W(4, 8, 8) VG_CASE_W(4, 9, 8) VG_CASE_W(4, 10, 8)
+        VG_CASE_W(4, 11, 8) VG_CASE_W(4, 12, 8) VG_CASE_W(4, 13, 8)
+#undef VG_CASE_W
 #undef VG_NP
 #undef VG_CASE
 #undef VG_LAUNCH

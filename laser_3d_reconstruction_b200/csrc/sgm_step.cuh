@@ -3,10 +3,13 @@
 //
 // A warp owns one pixel's disparity range, lane l holds 2*NP consecutive disparities as NP packed u16x2 words.
 // With delta = min_d(I) + P2 the step is
-//     O[d] = C[d] + min(I[d] - delta, I[d-1] + P1 - delta, I[d+1] + P1 - delta, 0)
-// which is OpenCV's  C + min(L[d], L[d+-1] + P1, delta) - delta  with the subtraction folded into the operands:
-// three VIADDMNMX.S16x2 and one VIADD.16x2 per word.  -delta and P1 - delta are taken modulo 2^16; every true
-// intermediate lies in [-P2, 32767], so the wrapped s16 arithmetic is exact.
+//     T[d] = min(I[d], I[d-1] + P1, I[d+1] + P1)          (two VIADDMNMX.U16x2; independent of delta)
+//     O[d] = C[d] + min(T[d] - delta, 0)                  (one VIADDMNMX.S16x2, one VIADD.16x2)
+// which is OpenCV's  C + min(L[d], L[d+-1] + P1, delta) - delta.  Only the last two operations wait for the
+// warp-wide minimum of the previous step, so the loop-carried chain through the reduction is
+// CREDUX -> IMAD -> VIADDMNMX -> VIADD -> (min tree) -> CREDUX; the neighbour exchange (SHFL, PRMT, two VIADDMNMX) runs
+// beside it.  -delta is taken modulo 2^16; T - delta lies in [-P2, 32767], so the wrapped s16 arithmetic is exact;
+// I + P1 < 2^16 unsigned.
 //
 // Pipe balance (sm_100: the integer ALU pipe and the FMA pipe each accept one warp instruction every second cycle
 // per SM sub-partition, so an all-ALU instruction stream tops out at half the issue rate; the cluster-fused
@@ -53,8 +56,8 @@ __device__ __forceinline__ uint32_t sgm_mulhi(uint32_t a, uint32_t b) {
     return d;
 }
 
-// k2 = (0x10000 - P2) * 0x10001, p1x2 = P1 * 0x10001; neither k2 - minI2 nor (k2 - minI2) + p1x2 can carry between the
-// halves (minI <= 32767, P1 < P2 <= 16000).  In and out may be the same registers (every output word is computed
+// k2 = (0x10000 - P2) * 0x10001, p1x2 = P1 * 0x10001; k2 - minI2 cannot carry between the halves (minI <= 32767,
+// P1 < P2 <= 16000).  In and out may be the same registers (every output word is computed
 // before any is stored).  Returns the warp-wide minimum of O in both halves.
 // FULL = false: lanes with `active` == false hold no disparities (D < 64 * NP); they keep O = MAX_COST so that neither
 // the neighbour exchange nor the min-reduction sees them.
@@ -65,7 +68,6 @@ __device__ __forceinline__ uint32_t sgm_step(uint32_t (&O)[NP], const uint32_t (
     const uint32_t up = __shfl_up_sync(0xffffffffu, I[NP - 1], 1);
     const uint32_t dn = __shfl_down_sync(0xffffffffu, I[0], 1);
     const uint32_t nd2 = sgm_madlo(minI2, s.neg1, k2);   // -(minI + P2) mod 2^16, both halves
-    const uint32_t pm2 = nd2 + p1x2;                     // P1 - (minI + P2) mod 2^16
     uint32_t F[NP + 1];                                  // F[k] = (I[k-1] >> 16) | (I[k] << 16): dm1 of word k, dp1 of word k-1
     F[0] = __byte_perm(up, I[0], s.selA);
     F[NP] = __byte_perm(I[NP - 1], dn, s.selB);
@@ -75,10 +77,9 @@ __device__ __forceinline__ uint32_t sgm_step(uint32_t (&O)[NP], const uint32_t (
     uint32_t Ln[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) {
-        uint32_t t = __viaddmin_s16x2(I[k], nd2, s.zero);
-        t = __viaddmin_s16x2(F[k], pm2, t);
-        t = __viaddmin_s16x2(F[k + 1], pm2, t);
-        Ln[k] = __vadd2(Cv[k], t);
+        uint32_t t = __viaddmin_u16x2(F[k], p1x2, I[k]);
+        t = __viaddmin_u16x2(F[k + 1], p1x2, t);
+        Ln[k] = __vadd2(Cv[k], __viaddmin_s16x2(t, nd2, s.zero));
         if (!FULL && !active) Ln[k] = 0x7fff7fffu;
     }
     uint32_t mn = Ln[0];

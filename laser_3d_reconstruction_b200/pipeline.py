@@ -143,30 +143,40 @@ class FramePipeline:
         self.ctx.check(self.lib.l3d_pipeline_kernel_time(self.h, name.encode(), C.byref(t), C.byref(k)), "l3d_pipeline_kernel_time")
         return t.value, k.value
 
+    @property
+    def points_needed(self):
+        """largest 2D point count a frame of the last run produced; > cfg.max_points means truncated point lists"""
+        return int(self.lib.l3d_pipeline_points_needed(self.h))
+
     def fetch(self, frame):
+        """Everything frame slot `frame` of the last run produced.  points_2d: float64 for the Simple extractor (its
+        exact centroids), float32 for the Steger variants -- the dtypes the reference's extractors return."""
         W, H, cap = self.cfg.W, self.cfg.H, self.cfg.max_points
         rect = np.empty((H, W, 3), np.uint8)
         depth = np.empty((H, W), np.float32)
         disp = np.empty((H, W), np.int16)
-        xy = np.empty((cap, 2), np.float32)
-        xyz = np.empty((cap, 3), np.float64)
+        self.ctx.check(self.lib.l3d_pipeline_fetch(self.h, int(frame), N._ptr(rect), N._ptr(depth), N._ptr(disp), None,
+                                                   None, None, None), "l3d_pipeline_fetch")
+        xy, xyz = self.fetch_points(frame, want_2d=True)
+        if self.cfg.extractor != N.EXTRACT_SIMPLE:
+            xy = xy.astype(np.float32)
+        return dict(left_rect=rect, depth=depth, disp16=disp, points_2d=xy, points_3d=xyz)
+
+    def fetch_points(self, frame, want_2d=False):
+        """The 3D points (and optionally the 2D centres) of frame slot `frame` of the last run (device -> host);
+        buffers are sized from the frame's own counts, clamped to the pipeline's max_points."""
         nxy, nxyz = C.c_int(), C.c_int()
-        self.ctx.check(self.lib.l3d_pipeline_fetch(self.h, int(frame), N._ptr(rect), N._ptr(depth), N._ptr(disp), N._ptr(xy),
-                                                   N._ptr(xyz), C.byref(nxy), C.byref(nxyz)), "l3d_pipeline_fetch")
-        return dict(left_rect=rect, depth=depth, disp16=disp, points_2d=xy[:min(nxy.value, cap)], points_3d=xyz[:nxyz.value])
-
-
-def _fetch_points(self, frame, n_hint=None):
-    """Only the 3D points of frame slot `frame` of the last run (device -> host)."""
-    cap = self.cfg.max_points if n_hint is None else max(int(n_hint), 1)
-    xyz = np.empty((cap, 3), np.float64)
-    nxy, nxyz = C.c_int(), C.c_int()
-    self.ctx.check(self.lib.l3d_pipeline_fetch(self.h, int(frame), None, None, None, None, N._ptr(xyz),
-                                               C.byref(nxy), C.byref(nxyz)), "l3d_pipeline_fetch")
-    return xyz[:nxyz.value]
-
-
-FramePipeline.fetch_points = _fetch_points
+        self.ctx.check(self.lib.l3d_pipeline_fetch_points(self.h, int(frame), None, 0, None, 0, C.byref(nxy), C.byref(nxyz)),
+                       "l3d_pipeline_fetch_points")
+        cap = self.cfg.max_points
+        m2 = min(nxy.value, cap) if want_2d else 0
+        m3 = min(nxyz.value, cap)
+        xy = np.empty((m2, 2), np.float64)
+        xyz = np.empty((m3, 3), np.float64)
+        self.ctx.check(self.lib.l3d_pipeline_fetch_points(self.h, int(frame), N._ptr(xy) if m2 else None, m2,
+                                                          N._ptr(xyz) if m3 else None, m3, C.byref(nxy), C.byref(nxyz)),
+                       "l3d_pipeline_fetch_points")
+        return (xy, xyz) if want_2d else xyz
 
 
 def _pack_points_dev(self, frame_ids, table_ptr):

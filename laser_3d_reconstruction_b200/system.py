@@ -35,6 +35,7 @@ class LaserReconstructionSystem:
         self.verbose = verbose
         self._pipe = None
         self._pipe_key = None
+        self._pipe_cap = None
 
     def _say(self, *a):
         if self.verbose:
@@ -113,18 +114,18 @@ class LaserReconstructionSystem:
                 self.point_cloud.extend(points_3d.tolist())
 
     # ---- batched, device-resident form ---------------------------------------------------------
-    def _pipeline(self, lanes):
+    def _pipeline(self, lanes, cap=None):
         cam = self.camera
         W, H = cam.single_width, cam.single_height
         dcfg = cam._depth_config()
         simple = isinstance(self.laser_extractor, SimpleLaserExtractor)
         ex = self.laser_extractor
-        key = (W, H, lanes, simple, bytes(dcfg))
+        cap = max(H, 20000, int(cap or 0))
+        key = (W, H, lanes, simple, bytes(dcfg), cap)
         if self._pipe is not None and self._pipe_key == key:
             return self._pipe
         if self._pipe is not None:
             self._pipe.close()
-        cap = max(H, 20000)
         if simple:
             pc = _pl.make_pipeline_config(W, H, dcfg.left.numDisparities, dcfg.left.blockSize, dcfg.left.mode, None,
                                           self.reconstructor.K, extractor=N.EXTRACT_SIMPLE, lanes=lanes, max_points=cap,
@@ -154,13 +155,22 @@ class LaserReconstructionSystem:
         lefts = np.ascontiguousarray(lefts, np.uint8)
         rights = np.ascontiguousarray(rights, np.uint8)
         n = lefts.shape[0]
-        fp = self._pipeline(lanes)
+        fp = self._pipeline(lanes, self._pipe_cap)
         fp.run_host(lefts, rights)
+        if fp.points_needed > fp.cfg.max_points:
+            # a frame found more laser points than the pipeline's point lists hold (FastSteger emits one per bright
+            # pixel: a saturated patch can exceed any fixed bound): nothing may be dropped silently -- the single-frame
+            # calls grow their buffers too -- so the pipeline is rebuilt with room for them and the batch runs again
+            self._pipe_cap = min(lefts.shape[1] * lefts.shape[2], 2 * fp.points_needed)
+            fp = self._pipeline(lanes, self._pipe_cap)
+            fp.run_host(lefts, rights)
+            if fp.points_needed > fp.cfg.max_points:
+                raise N.L3DError("process_frames: %d laser points in one frame exceed the point list capacity %d"
+                                 % (fp.points_needed, fp.cfg.max_points))
         out = []
         for i in range(n):
             got = fp.fetch(i)
-            pts2 = [(np.float64(x), np.float64(y)) for x, y in got["points_2d"]] if isinstance(
-                self.laser_extractor, SimpleLaserExtractor) else [(x, y) for x, y in got["points_2d"]]
+            pts2 = [(x, y) for x, y in got["points_2d"]]  # np.float64 pairs (Simple) / np.float32 pairs (Steger), as the reference
             p3 = got["points_3d"]
             if len(p3) > 0:
                 p3 = p3[~np.isnan(p3).any(axis=1)]

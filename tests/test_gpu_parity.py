@@ -111,7 +111,8 @@ def test_sgbm_small_all_roles(ctx, mode, shape):
 # the matcher pair of get_frames() in one call: one pixel-cost pass feeds both cost volumes (sgbm_cost_dual_kernel);
 # widths chosen so that the sheared range [RA, RB) is empty, a few columns, and most of the volume
 PAIR_SHAPES = [(200, 40, 64, 5), (330, 50, 64, 5), (320, 360, 64, 5), (300, 30, 128, 9), (420, 44, 128, 9),
-               (533, 37, 128, 9), (1280, 720, 128, 9), (260, 40, 32, 5), (400, 40, 128, 7)]
+               (533, 37, 128, 9), (1280, 720, 128, 9), (260, 40, 32, 5), (400, 40, 128, 7), (300, 30, 256, 11),
+               (600, 40, 256, 11), (1920, 48, 256, 11)]
 
 
 @pytest.mark.parametrize("mode", [1, 0, 3, 2])
@@ -137,6 +138,29 @@ def test_sgbm_pair_shared_cost_pass(ctx, mode, shape):
         eq(Cr, oCr, "%s m%d right cost volume" % (shape, mode))
     eq(dl, cv2.StereoSGBM_create(**mut).compute(lg, rg), "%s m%d left disparity vs cv2" % (shape, mode))
     eq(dr, cv2.StereoSGBM_create(**right).compute(rg, lg), "%s m%d right disparity vs cv2" % (shape, mode))
+
+
+def test_sgbm_int16_domain_guard(ctx):
+    """cv2 keeps the cost volume in int16 and wraps when block sum + P2 reaches 32768; this library carries unsigned 16-bit
+    pairs, so beyond that point the bits would differ silently.  The cost kernels flag the event on the device and the
+    call fails with L3D_ERR_UNSUPPORTED instead.  With the reference's own penalties (P2 = 96 bs^2) an adversarial
+    sawtooth pair at block 11 stays inside the domain (max C = 30976) and must equal cv2."""
+    W, H, D = 200, 48, 32
+    x = np.arange(W)
+    saw = ((x % 32) * 8).astype(np.uint8)
+    l, r = np.tile(saw, (H, 1)), np.tile(255 - saw, (H, 1))
+    noise = np.random.default_rng(1).integers(0, 256, (H, W), dtype=np.uint8)
+    kw = dict(minDisparity=0, numDisparities=D, blockSize=11, P1=2904, P2=11616, disp12MaxDiff=1, preFilterCap=63,
+              uniquenessRatio=10, speckleWindowSize=0, speckleRange=0, mode=1)
+    eq(ctx.sgbm_compute(N.SgbmParams(**kw), l, r), cv2.StereoSGBM_create(**kw).compute(l, r), "sawtooth, reference penalties")
+    for (a, b, bs) in ((l, r, 11), (noise, 255 - noise, 15)):
+        bad = dict(kw, blockSize=bs, P1=4000, P2=16000)
+        with pytest.raises(N.L3DError, match="int16"):
+            ctx.sgbm_compute(N.SgbmParams(**bad), a, b)
+        with pytest.raises(N.L3DError, match="int16"):
+            ctx.sgbm_compute_pair(N.SgbmParams(**bad), N.SgbmParams(**dict(bad, minDisparity=-(D - 1))), a, b)
+    # the context stays usable
+    eq(ctx.sgbm_compute(N.SgbmParams(**kw), l, r), cv2.StereoSGBM_create(**kw).compute(l, r), "after the error")
 
 
 @pytest.mark.parametrize("mode", [2, 0, 1, 3])
@@ -603,7 +627,8 @@ def test_pipeline_graph_replay_host_buffers(ctx):
         fp.close()
 
 
-@pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5)])
+@pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5),
+                                      (1920, 36, 256, 11), (1500, 30, 256, 5)])  # the last two: 8 warps x 13 / 10 columns, 16-CTA clusters
 def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
     """Cluster-fused aggregation on volumes that do not fill the cluster's column strips: the last CTA / last warps own
     fewer (or no) valid columns, neighbour-CTA halo hand-off (st.async + mbarrier) still has to deliver "no predecessor"

@@ -102,12 +102,12 @@ int main() {
     cudaMemcpy(cost, hc, ncost * 4, cudaMemcpyHostToDevice);
     uint32_t* host = new uint32_t[148 * 512];
     run<2, 0>("alu, literal 0 (round 1)", cost, out, host, cyc, P1, P2);
-    run<2, 1>("register 0, madlo delta", cost, out, host, cyc, P1, P2);
-    run<2, 2>("+ interior funnels on FMA", cost, out, host, cyc, P1, P2);
+    run<2, 1>("register 0, delta last", cost, out, host, cyc, P1, P2);
+    run<2, 2>("delta last + FMA funnels", cost, out, host, cyc, P1, P2);
     run<4, 0>("alu, literal 0 (round 1)", cost, out, host, cyc, P1, P2);
-    run<4, 1>("register 0, madlo delta", cost, out, host, cyc, P1, P2);
-    run<4, 2>("+ interior funnels on FMA", cost, out, host, cyc, P1, P2);
+    run<4, 1>("register 0, delta last", cost, out, host, cyc, P1, P2);
+    run<4, 2>("delta last + FMA funnels", cost, out, host, cyc, P1, P2);
     run<1, 0>("alu, literal 0 (round 1)", cost, out, host, cyc, P1, P2);
-    run<1, 2>("+ interior funnels on FMA", cost, out, host, cyc, P1, P2);
+    run<1, 2>("delta last + FMA funnels", cost, out, host, cyc, P1, P2);
     return 0;
 }
