@@ -119,7 +119,19 @@ typedef struct {
     int min_disp, num_disp;     /* of the left matcher */
     int dd_radius;              /* depth-discontinuity radius = ceil(0.5*blockSize) for SGBM */
     int lrc_thresh;             /* 24 */
+    int solver;                 /* 0: partitioned parallel tridiagonal solves (default); 1: serial Thomas solves in the
+                                 * oracle's f32 operation order (bit-identical to oracle/csrc/orc_wls.c) */
+    int variant;                /* L3D_WLS_* bits: readings of opencv_contrib the oracle cannot pin (cv2.ximgproc is not
+                                 * installed anywhere this was built); 0 = the documented defaults, see DESIGN.md */
 } l3d_wls_params;
+enum {
+    L3D_WLS_LAMBDA_PER_PASS = 1,   /* lambda is attenuated after every pass (x, y) instead of after each iteration */
+    L3D_WLS_LRC_OUTSIDE_ZERO = 2,  /* a pixel whose matching column falls outside the right ROI gets confidence 0
+                                    * (default: it keeps its own depth-discontinuity confidence) */
+    L3D_WLS_BOX_FULL_IMAGE = 4,    /* the variance box filters read across the ROI edge into the full disparity image
+                                    * (default: they run on a copy of the ROI, REFLECT_101 at the ROI edge) */
+    L3D_WLS_CONF_CLAMP_1 = 8       /* 1 - 0.001 var is clamped to [0, 1] (default: only below at 0) */
+};
 /* wls_filter.filter(dl, guide, disparity_map_right=dr) (camera/single_usb_stereo_camera.py:328-332) */
 int l3d_wls_filter(l3d_ctx* ctx, const l3d_wls_params* p, const int16_t* dl, const int16_t* dr,
                    const uint8_t* guide, int W, int H, int16_t* out, float* conf_out);

@@ -34,7 +34,12 @@ class BmParams(C.Structure):
 
 class WlsParams(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("sigma_color", C.c_double), ("min_disp", C.c_int),
-                ("num_disp", C.c_int), ("dd_radius", C.c_int), ("lrc_thresh", C.c_int)]
+                ("num_disp", C.c_int), ("dd_radius", C.c_int), ("lrc_thresh", C.c_int),
+                ("solver", C.c_int), ("variant", C.c_int)]
+
+
+WLS_SOLVER_PARALLEL, WLS_SOLVER_SERIAL = 0, 1
+WLS_LAMBDA_PER_PASS, WLS_LRC_OUTSIDE_ZERO, WLS_BOX_FULL_IMAGE, WLS_CONF_CLAMP_1 = 1, 2, 4, 8
 
 
 class DepthConfig(C.Structure):

@@ -23,8 +23,9 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 // horizontal (2r+1) sums of d and d*d for the left ROI (x0..) and the right ROI (0..)
+// full: the taps come from the whole image row (reflected at the image border) instead of the ROI copy (L3D_WLS_BOX_FULL_IMAGE)
 __global__ void wls_hbox_kernel(const int16_t* __restrict__ dl, const int16_t* __restrict__ dr, int W, int x0,
-                                int w, int h, int r, float* __restrict__ aL, float* __restrict__ bL,
+                                int w, int h, int r, int full, float* __restrict__ aL, float* __restrict__ bL,
                                 float* __restrict__ aR, float* __restrict__ bR) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
@@ -33,8 +34,14 @@ __global__ void wls_hbox_kernel(const int16_t* __restrict__ dl, const int16_t* _
     const int16_t* rr = dr + (size_t)y * W;
     float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f;
     for (int k = -r; k <= r; k++) {
-        int xx = reflect101(x + k, w);
-        float v = (float)rl[xx], u = (float)rr[xx];
+        float v, u;
+        if (full) {
+            v = (float)dl[(size_t)y * W + reflect101(x0 + x + k, W)];
+            u = (float)dr[(size_t)y * W + reflect101(x + k, W)];
+        } else {
+            const int xx = reflect101(x + k, w);
+            v = (float)rl[xx]; u = (float)rr[xx];
+        }
         sa = __fadd_rn(sa, v); sb = __fadd_rn(sb, __fmul_rn(v, v));
         ta = __fadd_rn(ta, u); tb = __fadd_rn(tb, __fmul_rn(u, u));
     }
@@ -44,7 +51,7 @@ __global__ void wls_hbox_kernel(const int16_t* __restrict__ dl, const int16_t* _
 
 __global__ void wls_vbox_conf_kernel(const float* __restrict__ aL, const float* __restrict__ bL,
                                      const float* __restrict__ aR, const float* __restrict__ bR, int w, int h,
-                                     int r, float* __restrict__ cl, float* __restrict__ cr) {
+                                     int r, int clamp1, float* __restrict__ cl, float* __restrict__ cr) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     if (x >= w) return;
@@ -58,15 +65,17 @@ __global__ void wls_vbox_conf_kernel(const float* __restrict__ aL, const float* 
     float ma = __fmul_rn(sa, inv), mb = __fmul_rn(sb, inv);
     float c = __fsub_rn(1.0f, __fmul_rn(0.001f, __fsub_rn(mb, __fmul_rn(ma, ma))));
     size_t i = (size_t)y * w + x;
+    if (clamp1 && c > 1.f) c = 1.f;
     cl[i] = c < 0.f ? 0.f : c;
     ma = __fmul_rn(ta, inv); mb = __fmul_rn(tb, inv);
     c = __fsub_rn(1.0f, __fmul_rn(0.001f, __fsub_rn(mb, __fmul_rn(ma, ma))));
+    if (clamp1 && c > 1.f) c = 1.f;
     cr[i] = c < 0.f ? 0.f : c;
 }
 
 __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __restrict__ dr,
                                const uint8_t* __restrict__ guide, const float* __restrict__ lut, int W, int x0,
-                               int w, int h, int thresh, const float* __restrict__ cl, const float* __restrict__ cr,
+                               int w, int h, int thresh, int outside_zero, const float* __restrict__ cl, const float* __restrict__ cr,
                                float* __restrict__ conf, float* __restrict__ num, float* __restrict__ den,
                                float* __restrict__ ch, float* __restrict__ cv) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,7 +90,7 @@ __global__ void wls_lrc_kernel(const int16_t* __restrict__ dl, const int16_t* __
         int rr = dr[(size_t)y * W + ridx];
         if (abs(l + rr) < thresh) c = fminf(c, cr[(size_t)y * w + ridx]);
         else c = 0.f;
-    }
+    } else if (outside_zero) c = 0.f;
     c = __fmul_rn(255.0f, c);
     conf[i] = c;
     num[i] = __fmul_rn(c, (float)l);
@@ -305,6 +314,157 @@ __global__ void __launch_bounds__(32) fgs_rows_kernel(float* num, float* den, co
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same solves as a PARALLEL (partitioned) tridiagonal solver: one warp per line, the line split into 32 chunks.
+// The serial kernels above repeat the oracle's operation order (bit-identical, 2 x len dependent division steps
+// per line: 1.3 ms per frame at 1280x720, all of it latency); this form has about 3 x len / 32 dependent steps and
+// takes the solver off the single-frame critical path.  Results differ from the serial order in the last bits of
+// the f32 solution (tolerance class: the int16 output differs by at most 1 LSB, on well under 0.1 % of the pixels).
+//
+// Line system (fgs_filter.cpp):  a_j u_{j-1} + b_j u_j + c_j u_{j+1} = f_j,  c_j = lam w_j (w = LUT weight <= 0),
+// a_j = c_{j-1},  b_j = 1 - a_j - c_j;  two right-hand sides (numerator and denominator plane) share the matrix.
+// Lane l owns the chunk [s, e].
+//   up sweep    (e-1 .. s, nothing stored): row s as   E u_{s-1} + u_s + G u_e = H
+//   down sweep  (s .. e, stored per element): D_j = c_j / beta_j, AB_j = alpha_j / beta_j, g_j = phi_j / beta_j  with
+//               beta_j = b_j - a_j D_{j-1}: row j as   AB_j u_{s-1} + u_j + D_j u_{j+1} = g_j
+//   reduced system in the chunk ends u_e (one row per lane: row e with u_{s'} of the next chunk replaced by that
+//               chunk's row-s form), solved across the lanes by parallel cyclic reduction with warp shuffles
+//   back sweep  (e-1 .. s): u_j = g_j - AB_j u_{s-1} - D_j u_{j+1}
+// Lines are staged in shared memory (coalesced in and out); a lane walks its chunk with an odd element stride
+// between lanes, so every step of a sweep hits 32 different banks.
+constexpr int FGSP_ROWS = 4;   // lines (= warps) per CTA in the row pass
+constexpr int FGSP_COLS = 8;   // lines per CTA in the column pass: 8 adjacent columns = one 32-byte sector per image row
+
+__device__ __forceinline__ void fgsp_solve_line(const float* __restrict__ wgt, float* g1, float* g2, float* Dd, float* AB,
+                                                int n, float lam, int lane) {
+    int m = (n + 31) / 32;
+    if (m < 2) m = 2;
+    m |= 1;                                            // odd chunk length: lane stride == m mod 32 is odd
+    const int s = lane * m, e = min(s + m, n) - 1;     // chunk [s, e]; empty when s >= n
+    const bool act = s < n;
+    const int cnt = act ? e - s + 1 : 0;
+    // ---- up sweep: row s in terms of (u_{s-1}, u_s, u_e)
+    float E = 0.f, G = -1.f, H1 = 0.f, H2 = 0.f;
+    for (int j = e - 1; j >= s && act; j--) {
+        const float c = __fmul_rn(lam, wgt[j]), a = j > 0 ? __fmul_rn(lam, wgt[j - 1]) : 0.f;
+        const float b = 1.0f - a - c;
+        const float ib = __frcp_rn(b - c * E);
+        E = a * ib;
+        G = -c * G * ib;
+        H1 = (g1[j] - c * H1) * ib;
+        H2 = (g2[j] - c * H2) * ib;
+    }
+    // ---- down sweep
+    float Dp = 0.f, ABp = -1.f, p1 = 0.f, p2 = 0.f;
+    for (int j = s; j <= e && act; j++) {
+        const float c = __fmul_rn(lam, wgt[j]), a = j > 0 ? __fmul_rn(lam, wgt[j - 1]) : 0.f;
+        const float b = 1.0f - a - c;
+        const float ib = __frcp_rn(b - a * Dp);
+        Dp = c * ib;
+        ABp = -a * ABp * ib;
+        p1 = (g1[j] - a * p1) * ib;
+        p2 = (g2[j] - a * p2) * ib;
+        Dd[j] = Dp; AB[j] = ABp; g1[j] = p1; g2[j] = p2;
+    }
+    // ---- reduced system over the chunk ends: A u_e(l-1) + B u_e(l) + C u_e(l+1) = F
+    const int ncnt = __shfl_down_sync(0xffffffffu, cnt, 1);
+    const float En = __shfl_down_sync(0xffffffffu, E, 1), Gn = __shfl_down_sync(0xffffffffu, G, 1);
+    const float H1n = __shfl_down_sync(0xffffffffu, H1, 1), H2n = __shfl_down_sync(0xffffffffu, H2, 1);
+    float A = 0.f, B = 1.f, Cc = 0.f, F1 = 0.f, F2 = 0.f;
+    if (act) {
+        A = ABp; F1 = p1; F2 = p2;
+        const bool has_next = lane < 31 && ncnt > 0;
+        if (has_next && ncnt == 1) Cc = Dp;                       // the next chunk's first element is its end
+        else if (has_next) { B = 1.0f - Dp * En; Cc = -Dp * Gn; F1 = p1 - Dp * H1n; F2 = p2 - Dp * H2n; }
+    }
+#pragma unroll
+    for (int dist = 1; dist < 32; dist <<= 1) {
+        float Am = __shfl_up_sync(0xffffffffu, A, dist), Bm = __shfl_up_sync(0xffffffffu, B, dist);
+        float Cm = __shfl_up_sync(0xffffffffu, Cc, dist), F1m = __shfl_up_sync(0xffffffffu, F1, dist), F2m = __shfl_up_sync(0xffffffffu, F2, dist);
+        float Ap = __shfl_down_sync(0xffffffffu, A, dist), Bp = __shfl_down_sync(0xffffffffu, B, dist);
+        float Cp = __shfl_down_sync(0xffffffffu, Cc, dist), F1p = __shfl_down_sync(0xffffffffu, F1, dist), F2p = __shfl_down_sync(0xffffffffu, F2, dist);
+        if (lane < dist) { Am = 0.f; Bm = 1.f; Cm = 0.f; F1m = 0.f; F2m = 0.f; }
+        if (lane + dist > 31) { Ap = 0.f; Bp = 1.f; Cp = 0.f; F1p = 0.f; F2p = 0.f; }
+        const float k1 = A * __frcp_rn(Bm), k2 = Cc * __frcp_rn(Bp);
+        B = B - Cm * k1 - Ap * k2;
+        F1 = F1 - F1m * k1 - F1p * k2;
+        F2 = F2 - F2m * k1 - F2p * k2;
+        A = -Am * k1;
+        Cc = -Cp * k2;
+    }
+    const float ib = __frcp_rn(B);
+    const float ue1 = F1 * ib, ue2 = F2 * ib;
+    float up1 = __shfl_up_sync(0xffffffffu, ue1, 1), up2 = __shfl_up_sync(0xffffffffu, ue2, 1);
+    if (lane == 0) { up1 = 0.f; up2 = 0.f; }
+    // ---- back sweep
+    if (act) {
+        float n1 = ue1, n2 = ue2;
+        g1[e] = n1; g2[e] = n2;
+        for (int j = e - 1; j >= s; j--) {
+            const float d = Dd[j], ab = AB[j];
+            n1 = g1[j] - ab * up1 - d * n1;
+            n2 = g2[j] - ab * up2 - d * n2;
+            g1[j] = n1; g2[j] = n2;
+        }
+    }
+}
+
+static size_t fgsp_smem_bytes(int lines, int len) { return (size_t)lines * 5 * ((size_t)len + 8) * sizeof(float); }
+
+// row pass: warp <-> image row; num / den are solved in place
+__global__ void __launch_bounds__(FGSP_ROWS * 32) fgs_rows_par_kernel(float* num, float* den, const float* __restrict__ wgt,
+                                                                     int w, int h, float lam) {
+    extern __shared__ __align__(16) float fsm[];
+    const int LP = w + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * FGSP_ROWS + warp;
+    float* base = fsm + (size_t)warp * 5 * LP;
+    float *sw = base, *s1 = base + LP, *s2 = base + 2 * LP, *sD = base + 3 * LP, *sA = base + 4 * LP;
+    if (row < h) {
+        const size_t off = (size_t)row * w;
+        for (int i = lane; i < w; i += 32) { sw[i] = wgt[off + i]; s1[i] = num[off + i]; s2[i] = den[off + i]; }
+    }
+    __syncwarp();
+    if (row < h) fgsp_solve_line(sw, s1, s2, sD, sA, w, lam, lane);
+    __syncwarp();
+    if (row < h) {
+        const size_t off = (size_t)row * w;
+        for (int i = lane; i < w; i += 32) { num[off + i] = s1[i]; den[off + i] = s2[i]; }
+    }
+}
+
+// column pass: a CTA stages FGSP_COLS adjacent columns (32 contiguous bytes per image row), warp <-> column
+__global__ void __launch_bounds__(FGSP_COLS * 32) fgs_cols_par_kernel(float* num, float* den, const float* __restrict__ wgt,
+                                                                     int w, int h, float lam) {
+    extern __shared__ __align__(16) float fsm[];
+    const int LP = ((h + 31) / 32) * 32 + 4;  // == 4 mod 32: the 8 columns x 4 rows a warp stages per request hit 32 banks
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col0 = blockIdx.x * FGSP_COLS;
+    const int ncol = min(FGSP_COLS, w - col0);
+    const int tc = threadIdx.x & (FGSP_COLS - 1), tr = threadIdx.x / FGSP_COLS;  // staging role: column, row phase
+    constexpr int RPI = FGSP_COLS * 32 / FGSP_COLS;                               // rows per staging iteration
+    if (tc < ncol) {
+        float *sw = fsm + (size_t)tc * 5 * LP, *s1 = sw + LP, *s2 = sw + 2 * LP;
+        for (int r = tr; r < h; r += RPI) {
+            const size_t g = (size_t)r * w + col0 + tc;
+            sw[r] = wgt[g]; s1[r] = num[g]; s2[r] = den[g];
+        }
+    }
+    __syncthreads();
+    if (warp < ncol) {
+        float* base = fsm + (size_t)warp * 5 * LP;
+        fgsp_solve_line(base, base + LP, base + 2 * LP, base + 3 * LP, base + 4 * LP, h, lam, lane);
+    }
+    __syncthreads();
+    if (tc < ncol) {
+        const float *s1 = fsm + (size_t)tc * 5 * LP + LP, *s2 = s1 + LP;
+        for (int r = tr; r < h; r += RPI) {
+            const size_t g = (size_t)r * w + col0 + tc;
+            num[g] = s1[r]; den[g] = s2[r];
+        }
+    }
+}
+
 __global__ void wls_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den,
                                     const float* __restrict__ conf, int W, int H, int x0, int w, int outside,
                                     int16_t* __restrict__ out, float* __restrict__ conf_out) {
@@ -358,16 +518,29 @@ int dev_wls(Lane& L, const l3d_wls_params& p, const int16_t* dl, const int16_t* 
     if (rc != L3D_OK) return rc;
     dim3 g(cdiv(w, 128), h);
     L.t_begin("wls");
-    L3D_LAUNCH(L, wls_hbox_kernel, g, 128, 0, dl, dr, W, x0, w, h, p.dd_radius, aL, bL, aR, bR);
-    L3D_LAUNCH(L, wls_vbox_conf_kernel, g, 128, 0, aL, bL, aR, bR, w, h, p.dd_radius, cl, cr);
+    L3D_LAUNCH(L, wls_hbox_kernel, g, 128, 0, dl, dr, W, x0, w, h, p.dd_radius, (p.variant & L3D_WLS_BOX_FULL_IMAGE) ? 1 : 0, aL, bL, aR, bR);
+    L3D_LAUNCH(L, wls_vbox_conf_kernel, g, 128, 0, aL, bL, aR, bR, w, h, p.dd_radius, (p.variant & L3D_WLS_CONF_CLAMP_1) ? 1 : 0, cl, cr);
     // aL/bL are free now: reuse as num/den
     float *num = aL, *den = bL;
-    L3D_LAUNCH(L, wls_lrc_kernel, g, 128, 0, dl, dr, guide, lut, W, x0, w, h, p.lrc_thresh, cl, cr, conf, num, den, ch, cv);
+    L3D_LAUNCH(L, wls_lrc_kernel, g, 128, 0, dl, dr, guide, lut, W, x0, w, h, p.lrc_thresh, (p.variant & L3D_WLS_LRC_OUTSIDE_ZERO) ? 1 : 0, cl, cr, conf, num, den, ch,
+               cv);
     float lam = (float)p.lambda;
     float* Dscr = aR;  // aR/bR are free as well: elimination factors of the current pass
+    // solver: 0 = partitioned parallel solves (default), 1 = serial solves in the oracle's operation order (bit-identical
+    // to oracle/csrc/orc_wls.c); L3D_FGS_SERIAL=1 forces the serial form everywhere
+    static const bool force_serial = getenv("L3D_FGS_SERIAL") && atoi(getenv("L3D_FGS_SERIAL")) > 0;
+    const size_t smr = fgsp_smem_bytes(FGSP_ROWS, w), smc = (size_t)FGSP_COLS * 5 * (((h + 31) / 32) * 32 + 4) * sizeof(float);
+    const bool parallel = !force_serial && p.solver != 1 && smr <= 200 * 1024 && smc <= 200 * 1024 && w >= 2 && h >= 2;
+    if (parallel) {
+        L3D_CHECK(L, cudaFuncSetAttribute(fgs_rows_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+        L3D_CHECK(L, cudaFuncSetAttribute(fgs_cols_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+    }
     for (int it = 0; it < 3; it++) {
-        L3D_LAUNCH(L, fgs_rows_kernel, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
-        L3D_LAUNCH(L, fgs_cols_kernel<FGS_CPW>, cdiv(w, FGS_CPW), 32, 0, num, den, cv, Dscr, w, h, lam);
+        if (parallel) L3D_LAUNCH(L, fgs_rows_par_kernel, cdiv(h, FGSP_ROWS), FGSP_ROWS * 32, smr, num, den, ch, w, h, lam);
+        else L3D_LAUNCH(L, fgs_rows_kernel, cdiv(h, FGS_LPW), 32, 0, num, den, ch, Dscr, w, h, lam);
+        if (p.variant & L3D_WLS_LAMBDA_PER_PASS) lam *= 0.25f;
+        if (parallel) L3D_LAUNCH(L, fgs_cols_par_kernel, cdiv(w, FGSP_COLS), FGSP_COLS * 32, smc, num, den, cv, w, h, lam);
+        else L3D_LAUNCH(L, fgs_cols_kernel<FGS_CPW>, cdiv(w, FGS_CPW), 32, 0, num, den, cv, Dscr, w, h, lam);
         lam *= 0.25f;
     }
     L3D_LAUNCH(L, wls_finalize_kernel, dim3(cdiv(W, 128), H), 128, 0, num, den, conf, W, H, x0, w, outside, out, conf_out);

@@ -123,13 +123,13 @@ def filter_speckles(a, new_val, max_size, max_diff):
 
 
 def wls_filter(dl, dr, guide, min_disp, num_disp, dd_radius, lam=8000.0, sigma_color=1.5,
-               lrc_thresh=24, want_conf=False):
+               lrc_thresh=24, want_conf=False, variant=0):
     dl, dr, guide = _c(dl, np.int16), _c(dr, np.int16), _c(guide, np.uint8)
     H, W = dl.shape
     out = np.empty((H, W), np.int16)
     conf = np.empty((H, W), np.float32) if want_conf else None
-    lib().orc_wls_filter(_p(dl), _p(dr), _p(guide), W, H, int(min_disp), int(num_disp), int(dd_radius),
-                         C.c_double(lam), C.c_double(sigma_color), int(lrc_thresh), _p(out), _p(conf))
+    lib().orc_wls_filter_v(_p(dl), _p(dr), _p(guide), W, H, int(min_disp), int(num_disp), int(dd_radius),
+                           C.c_double(lam), C.c_double(sigma_color), int(lrc_thresh), int(variant), _p(out), _p(conf))
     return (out, conf) if want_conf else out
 
 

@@ -51,6 +51,11 @@ void orc_filter_speckles(int16_t* img, int W, int H, int newVal, int maxSize, in
 void orc_wls_filter(const int16_t* dl, const int16_t* dr, const uint8_t* guide, int W, int H,
                     int min_disp, int num_disp, int dd_radius, double lambda, double sigma_color,
                     int lrc_thresh, int16_t* out, float* conf_out);
+/* the same with the unpinned points of the restatement switchable (bits as L3D_WLS_* of include/l3d.h) */
+enum { ORC_WLS_LAMBDA_PER_PASS = 1, ORC_WLS_LRC_OUTSIDE_ZERO = 2, ORC_WLS_BOX_FULL_IMAGE = 4, ORC_WLS_CONF_CLAMP_1 = 8 };
+void orc_wls_filter_v(const int16_t* dl, const int16_t* dr, const uint8_t* guide, int W, int H,
+                      int min_disp, int num_disp, int dd_radius, double lambda, double sigma_color,
+                      int lrc_thresh, int variant, int16_t* out, float* conf_out);
 
 /* disparity(int16 x16) -> depth: camera/single_usb_stereo_camera.py:335-346 (Q branch) */
 void orc_disp_to_depth_q(const int16_t* disp16, int W, int H, const double* Q, float* depth);

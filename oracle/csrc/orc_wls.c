@@ -42,31 +42,60 @@ static void box_f32(const float* s, int w, int h, int r, float* d) {
     free(t);
 }
 
-/* 1 - 0.001*var(disparity) clamped below at 0, on the ROI copy */
-static void discontinuity_map(const int16_t* disp, int W, int x0, int w, int h, int r, float* dst) {
+/* (2r+1)^2 box mean whose horizontal taps come from the FULL image row (columns x0+x+k reflected at the image border):
+ * variant ORC_WLS_BOX_FULL_IMAGE */
+static void box_full(const int16_t* disp, int W, int x0, int w, int h, int r, int squared, float* d) {
+    float* t = (float*)malloc(sizeof(float) * (size_t)w * h);
+    float inv = 1.0f / (float)((2 * r + 1) * (2 * r + 1));
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float a = 0;
+            for (int k = -r; k <= r; k++) {
+                float v = (float)disp[(long)y * W + reflect101(x0 + x + k, W)];
+                a += squared ? v * v : v;
+            }
+            t[(long)y * w + x] = a;
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float a = 0;
+            for (int k = -r; k <= r; k++) a += t[(long)reflect101(y + k, h) * w + x];
+            d[(long)y * w + x] = a * inv;
+        }
+    free(t);
+}
+
+/* 1 - 0.001*var(disparity) clamped below at 0 (variant: to [0,1]), on the ROI copy (variant: across the ROI edge) */
+static void discontinuity_map(const int16_t* disp, int W, int x0, int w, int h, int r, int variant, float* dst) {
     size_t n = (size_t)w * h;
     float* a = (float*)malloc(sizeof(float) * n);
     float* b = (float*)malloc(sizeof(float) * n);
     float* ma = (float*)malloc(sizeof(float) * n);
     float* mb = (float*)malloc(sizeof(float) * n);
-    for (int y = 0; y < h; y++)
-        for (int x = 0; x < w; x++) {
-            float v = (float)disp[(long)y * W + x0 + x];
-            a[(long)y * w + x] = v;
-            b[(long)y * w + x] = v * v;
-        }
-    box_f32(a, w, h, r, ma);
-    box_f32(b, w, h, r, mb);
+    if (variant & ORC_WLS_BOX_FULL_IMAGE) {
+        box_full(disp, W, x0, w, h, r, 0, ma);
+        box_full(disp, W, x0, w, h, r, 1, mb);
+    } else {
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                float v = (float)disp[(long)y * W + x0 + x];
+                a[(long)y * w + x] = v;
+                b[(long)y * w + x] = v * v;
+            }
+        box_f32(a, w, h, r, ma);
+        box_f32(b, w, h, r, mb);
+    }
     for (size_t i = 0; i < n; i++) {
         float var = mb[i] - ma[i] * ma[i];
         float c = 1.0f - 0.001f * var;
+        if ((variant & ORC_WLS_CONF_CLAMP_1) && c > 1.0f) c = 1.0f;
         dst[i] = c < 0.0f ? 0.0f : c;
     }
     free(a); free(b); free(ma); free(mb);
 }
 
 /* one Fast-Global-Smoother solve over the w x h image u (in place); ch/cv = -exp(-|dg|/sigma) */
-static void fgs_solve(float* u, int w, int h, const float* ch, const float* cv, double lambda0) {
+static void fgs_solve(float* u, int w, int h, const float* ch, const float* cv, double lambda0, int variant) {
     float* D = (float*)malloc(sizeof(float) * (size_t)(w > h ? w : h));
     float lam = (float)lambda0;
     for (int it = 0; it < 3; it++) {
@@ -83,6 +112,7 @@ static void fgs_solve(float* u, int w, int h, const float* ch, const float* cv, 
             }
             for (int j = w - 2; j >= 0; j--) r[j] = r[j] - D[j] * r[j + 1];
         }
+        if (variant & ORC_WLS_LAMBDA_PER_PASS) lam *= 0.25f;
         for (int x = 0; x < w; x++) { /* vertical pass */
             float den = 1.0f - lam * cv[x];
             D[0] = (lam * cv[x]) / den;
@@ -104,6 +134,14 @@ static void fgs_solve(float* u, int w, int h, const float* ch, const float* cv, 
 void orc_wls_filter(const int16_t* dl, const int16_t* dr, const uint8_t* guide, int W, int H,
                     int min_disp, int num_disp, int dd_radius, double lambda, double sigma_color,
                     int lrc_thresh, int16_t* out, float* conf_out) {
+    orc_wls_filter_v(dl, dr, guide, W, H, min_disp, num_disp, dd_radius, lambda, sigma_color, lrc_thresh, 0, out, conf_out);
+}
+
+/* variant: ORC_WLS_* bits -- the points of opencv_contrib's implementation this restatement cannot pin;
+ * 0 = the documented reading, each bit switches one point to the alternative reading */
+void orc_wls_filter_v(const int16_t* dl, const int16_t* dr, const uint8_t* guide, int W, int H,
+                      int min_disp, int num_disp, int dd_radius, double lambda, double sigma_color,
+                      int lrc_thresh, int variant, int16_t* out, float* conf_out) {
     int x0 = min_disp + num_disp; if (x0 < 0) x0 = 0;
     int w = W - x0, h = H;
     int16_t outside = (int16_t)(16 * (min_disp - 1));
@@ -113,8 +151,8 @@ void orc_wls_filter(const int16_t* dl, const int16_t* dr, const uint8_t* guide, 
     size_t n = (size_t)w * h;
     float* cl = (float*)malloc(sizeof(float) * n);
     float* cr = (float*)malloc(sizeof(float) * n);
-    discontinuity_map(dl, W, x0, w, h, dd_radius, cl); /* left ROI  = columns [x0, W)   */
-    discontinuity_map(dr, W, 0, w, h, dd_radius, cr);  /* right ROI = columns [0, W-x0) */
+    discontinuity_map(dl, W, x0, w, h, dd_radius, variant, cl); /* left ROI  = columns [x0, W)   */
+    discontinuity_map(dr, W, 0, w, h, dd_radius, variant, cr);  /* right ROI = columns [0, W-x0) */
     float* conf = (float*)malloc(sizeof(float) * n);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
@@ -128,7 +166,7 @@ void orc_wls_filter(const int16_t* dl, const int16_t* dr, const uint8_t* guide, 
                     float c2 = cr[(long)y * w + ridx];
                     c = c < c2 ? c : c2;
                 } else c = 0.0f;
-            }
+            } else if (variant & ORC_WLS_LRC_OUTSIDE_ZERO) c = 0.0f;
             conf[(long)y * w + x] = 255.0f * c;
         }
     /* guide weights */
@@ -152,8 +190,8 @@ void orc_wls_filter(const int16_t* dl, const int16_t* dr, const uint8_t* guide, 
             num[i] = conf[i] * (float)dl[(long)y * W + x0 + x];
             den[i] = conf[i];
         }
-    fgs_solve(num, w, h, ch, cv, lambda);
-    fgs_solve(den, w, h, ch, cv, lambda);
+    fgs_solve(num, w, h, ch, cv, lambda, variant);
+    fgs_solve(den, w, h, ch, cv, lambda, variant);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             long i = (long)y * w + x;

@@ -193,3 +193,38 @@ def test_wls_restatement_properties():
     assert np.all(out[:, D + 12:] == 160)
     assert conf.max() <= 255.0 + 1e-3
     assert np.array_equal(out, cref.wls_filter(dl, dr, guide, 0, D, 3))
+
+
+def wls_case(W, H, D, seed):
+    """left/right disparity maps that are mostly LR-consistent (so the confidence is not zero everywhere): a constant
+    patch at 587/16 px (in f32 its box variance rounds to -0.03, confidence 1.00003), a smooth ramp with a little noise,
+    some invalid pixels, and the invalid borders a real matcher pair leaves outside the two ROIs"""
+    rng = np.random.default_rng(seed)
+    guide = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 1.2)
+    x = np.arange(W)[None, :].repeat(H, 0)
+    d = np.where(x < W // 2, 587, 6 * 16 + (x - W // 2) * 2).astype(np.int32)
+    dl = (d + np.where(x < W // 2, 0, rng.integers(-3, 4, (H, W)))).astype(np.int16)
+    dl[rng.random((H, W)) < 0.03] = -16
+    dl[:, :D] = -16
+    dr = (-d + rng.integers(-3, 4, (H, W))).astype(np.int16)
+    dr[:, : W // 2] = -587
+    dr[:, W - D:] = -16 * D
+    return dl, dr, guide
+
+
+def test_wls_oracle_variants_switch_one_point_each():
+    """oracle/csrc/orc_wls.c: the unpinned points of the restatement are switchable; variant 0 is the legacy entry
+    point, and every bit changes the result on an input built to exercise it."""
+    from oracle import cref
+    W, H, D = 150, 33, 48
+    dl, dr, guide = wls_case(W, H, D, 3)
+    base, bconf = cref.wls_filter(dl, dr, guide, 0, D, 3, 8000.0, 1.5, want_conf=True)
+    assert base.shape == (H, W) and (base[:, :D] == -16).all()
+    outs = {}
+    for bit in (1, 2, 4, 8):
+        o, c = cref.wls_filter(dl, dr, guide, 0, D, 3, 8000.0, 1.5, want_conf=True, variant=bit)
+        assert not np.array_equal(o, base), "variant bit %d had no effect" % bit
+        outs[bit] = o
+        if bit == 1:
+            assert np.array_equal(c, bconf)  # lambda schedule: the confidence map is untouched
+    assert not np.array_equal(outs[2], outs[8])
