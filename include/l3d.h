@@ -163,6 +163,11 @@ int l3d_simple_extract(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, const int
                        const int* hsv_hi, int bright_thr, double min_area, uint8_t* mask_morph,
                        uint8_t* mask_final, double* xy, int* n);
 
+/* Steps (1)-(3) of the same function alone (core/laser_extractor.py:56-64): mask = inRange(cvtColor(bgr, HSV), lo, hi) &
+ * (cvtColor(bgr, GRAY) > bright_thr), 0 / 255 per pixel (bright_thr < 0: the HSV range test alone). */
+int l3d_colour_mask(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, const int* hsv_lo, const int* hsv_hi,
+                    int bright_thr, uint8_t* mask);
+
 /* -------- K4b: Steger extractors ----------------------------------------------------------- */
 enum {
     L3D_STEGER_FAST = 0,      /* FastStegerExtractor.extract_centerline   core/laser_extractor.py:160-261 */
@@ -204,6 +209,10 @@ typedef struct {
  * xyz: up to n rows of 3 f64; *n_out rows written (invalid points dropped, order kept). */
 int l3d_reconstruct(l3d_ctx* ctx, const l3d_recon_params* p, const double* xy, int n,
                     const float* img, int W, int H, double* xyz, int* n_out);
+/* ImprovedLaserReconstructor.create_laser_depth_map (improved_reconstruction.py:154-186): out (f32, W x H) is zero except at
+ * the rounded laser pixels with disparity > 1, where it holds fx * baseline / disparity if that lies in (0, 10) m. */
+int l3d_laser_depth_map(l3d_ctx* ctx, const double* xy, int n, const float* disp, int W, int H, double fx,
+                        double baseline, float* out);
 
 /* -------- batched, device-resident frame pipeline (bench + LaserReconstructionSystem.process_frame) */
 typedef struct l3d_pipeline l3d_pipeline;

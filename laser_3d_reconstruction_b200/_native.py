@@ -74,7 +74,7 @@ EXPORTS = (
     "l3d_ctx_create l3d_ctx_destroy l3d_last_error l3d_sync l3d_device_count l3d_version l3d_launch_count "
     "l3d_set_rectify_maps l3d_init_undistort_rectify_map l3d_remap_gray l3d_bgr2gray l3d_sgbm_compute l3d_sgbm_compute_pair l3d_sgbm_debug l3d_sgbm_volume_rows "
     "l3d_sgbm_vgroup_time l3d_bm_compute l3d_median3_s16 l3d_filter_speckles l3d_wls_filter l3d_disp_to_depth l3d_compute_depth "
-    "l3d_simple_extract l3d_steger_extract l3d_reconstruct l3d_voxel_downsample l3d_statistical_outlier_removal l3d_pipeline_create l3d_pipeline_destroy "
+    "l3d_simple_extract l3d_colour_mask l3d_steger_extract l3d_reconstruct l3d_laser_depth_map l3d_voxel_downsample l3d_statistical_outlier_removal l3d_pipeline_create l3d_pipeline_destroy "
     "l3d_pipeline_set_maps l3d_pipeline_run_dev l3d_pipeline_run_host l3d_pipeline_fetch l3d_pipeline_fetch_points l3d_pipeline_points_needed "
     "l3d_pipeline_pack_points_dev l3d_pipeline_launch_count l3d_pipeline_graph_replays l3d_pipeline_last_ms l3d_pipeline_set_timing l3d_pipeline_kernel_time "
     "l3d_host_alloc l3d_host_free l3d_dev_alloc l3d_dev_free l3d_memcpy_h2d l3d_memcpy_d2h"
@@ -136,6 +136,17 @@ def _arr(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def _rows_u8c3(a):
+    """HxWx3 uint8 image whose ROWS may be strided (the views `_split_frame` returns: frame[:, :mid], frame[:, mid:]):
+    returned as it is -- the C ABI takes a row stride, so the side-by-side split costs no copy.  Anything else is made
+    contiguous."""
+    a = np.asarray(a)
+    if (a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3 and a.strides[2] == 1 and a.strides[1] == 3
+            and a.strides[0] >= 3 * a.shape[1]):
+        return a
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
 class Context:
     """One GPU context (stream + scratch).  Not thread-safe; create one per thread."""
 
@@ -191,7 +202,7 @@ class Context:
         return W, H
 
     def remap_gray(self, eye, src_bgr, out_shape):
-        src = _arr(src_bgr, np.uint8)
+        src = _rows_u8c3(src_bgr)
         if src.ndim != 3 or src.shape[2] != 3:
             raise ValueError("remap_gray expects an HxWx3 uint8 image")
         H, W = out_shape
@@ -319,16 +330,40 @@ class Context:
         return out
 
     def compute_depth(self, cfg, left_bgr, right_bgr, want_disp=False):
-        l, r = _arr(left_bgr, np.uint8), _arr(right_bgr, np.uint8)
+        l, r = _rows_u8c3(left_bgr), _rows_u8c3(right_bgr)
         if l.ndim != 3 or l.shape[2] != 3 or l.shape != r.shape:
             raise ValueError("compute_depth expects two HxWx3 uint8 images of equal size")
+        if l.strides[0] != r.strides[0]:  # one row stride for both views in the ABI
+            l, r = _arr(l, np.uint8), _arr(r, np.uint8)
         H, W = l.shape[:2]
         rect = np.empty((H, W, 3), np.uint8)
         depth = np.empty((H, W), np.float32)
         disp = np.empty((H, W), np.int16) if want_disp else None
-        self.check(self.lib.l3d_compute_depth(self.h, C.byref(cfg), _ptr(l), _ptr(r), W, H, C.c_long(3 * W), _ptr(rect),
+        self.check(self.lib.l3d_compute_depth(self.h, C.byref(cfg), _ptr(l), _ptr(r), W, H, C.c_long(l.strides[0]), _ptr(rect),
                                               _ptr(depth), _ptr(disp)), "l3d_compute_depth")
         return (rect, depth, disp) if want_disp else (rect, depth)
+
+    def colour_mask(self, bgr, hsv_lo, hsv_hi, bright_thr=-1):
+        """inRange(HSV) & (gray > bright_thr) as a 0/255 mask (core/laser_extractor.py:56-64)"""
+        bgr = _arr(bgr, np.uint8)
+        if bgr.ndim != 3 or bgr.shape[2] != 3:
+            raise ValueError("expects an HxWx3 BGR uint8 image")
+        H, W = bgr.shape[:2]
+        lo = (C.c_int * 3)(*[int(v) for v in hsv_lo])
+        hi = (C.c_int * 3)(*[int(v) for v in hsv_hi])
+        mask = np.empty((H, W), np.uint8)
+        self.check(self.lib.l3d_colour_mask(self.h, _ptr(bgr), W, H, lo, hi, int(bright_thr), _ptr(mask)), "l3d_colour_mask")
+        return mask
+
+    def laser_depth_map(self, xy, disp, fx, baseline):
+        """ImprovedLaserReconstructor.create_laser_depth_map (improved_reconstruction.py:154-186)"""
+        disp = _arr(disp, np.float32)
+        H, W = disp.shape
+        xy = _arr(np.asarray(xy, np.float64).reshape(-1, 2), np.float64)
+        out = np.empty((H, W), np.float32)
+        self.check(self.lib.l3d_laser_depth_map(self.h, _ptr(xy) if len(xy) else None, len(xy), _ptr(disp), W, H,
+                                                C.c_double(fx), C.c_double(baseline), _ptr(out)), "l3d_laser_depth_map")
+        return out
 
     def simple_extract(self, bgr, hsv_lo, hsv_hi, bright_thr, min_area, want_masks=False):
         bgr = _arr(bgr, np.uint8)
@@ -374,14 +409,20 @@ class Context:
         return out[:n_out.value]
 
 
-# ---- per-process default contexts (one per device) ----------------------------------------
-_default = {}
+# ---- default contexts: one per (thread, device) ---------------------------------------------
+# A Context owns one stream and grow-only scratch buffers and is not thread-safe (include/l3d.h: one l3d_ctx per
+# (thread, GPU)), so the reference-API classes -- which share "the" context of their device -- get a separate one in
+# every thread that uses them (e.g. a capture thread next to a processing thread).
+_default = threading.local()
 
 
 def default_context(device=0):
-    """The process-wide Context of `device` used by the reference-API classes.  Raises L3DError
+    """The calling thread's Context of `device`, used by the reference-API classes.  Raises L3DError
     when the CUDA library or a GPU is missing: there is no CPU fallback."""
-    ctx = _default.get(device)
+    table = getattr(_default, "ctx", None)
+    if table is None:
+        table = _default.ctx = {}
+    ctx = table.get(device)
     if ctx is None or ctx.h is None:
-        ctx = _default[device] = Context(device)
+        ctx = table[device] = Context(device)
     return ctx

@@ -2,6 +2,8 @@
 #include <chrono>
 #include <stdexcept>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "sgbm.cuh"
 
 namespace l3d {
@@ -52,13 +54,22 @@ cudaEvent_t Lane::new_event() {
     if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
     return ev_pool[ev_used++];
 }
+// Kernel groups (sgbm_cost, sgbm_scan_k*, sgbm_vgroup_*, sgbm_wta, wls, remap, extract, recon) are bracketed by NVTX ranges
+// when L3D_NVTX=1 (host-side push/pop around the enqueue: they show up as ranges over the launches in Nsight Systems /
+// ncu --nvtx) and by CUDA events when timing is on (bench roofline leg).
+static bool nvtx_on() {
+    static const bool on = getenv("L3D_NVTX") && atoi(getenv("L3D_NVTX")) > 0;
+    return on;
+}
 void Lane::t_begin(const char* name) {
+    if (nvtx_on()) nvtxRangePushA(name);
     if (!timing) return;
     TimerRec r; r.a = new_event(); r.b = nullptr;
     cudaEventRecord(r.a, stream);
     timers[name].push_back(r);
 }
 void Lane::t_end(const char* name) {
+    if (nvtx_on()) nvtxRangePop();
     if (!timing) return;
     auto& v = timers[name];
     if (v.empty() || v.back().b) return;
@@ -208,7 +219,8 @@ int l3d_remap_gray(l3d_ctx* ctx, int eye, const uint8_t* src_bgr, int sw, int sh
     Lane& L = ctx->lane;
     const RectMap& m = ctx->maps[eye];
     NEED(ctx, m.map, "rectification maps not set for this eye");
-    size_t nsrc = (size_t)src_stride * sh, n = (size_t)m.W * m.H;
+    // a strided view (the halves _split_frame returns) ends with its last ROW, not with a whole stride
+    size_t nsrc = (size_t)src_stride * (sh - 1) + 3 * (size_t)sw, n = (size_t)m.W * m.H;
     uint8_t* s = L.get<uint8_t>(S_SRC_L, nsrc);
     uint8_t* r = L.get<uint8_t>(S_RECT_L, n * 3);
     uint8_t* g = L.get<uint8_t>(S_GRAY_L, n);
@@ -502,6 +514,7 @@ static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps
     size_t n = (size_t)W * H;
     uint8_t* gl = L.get<uint8_t>(S_GRAY_L, n);
     uint8_t* gr = L.get<uint8_t>(S_GRAY_R, n);
+    L.t_begin("remap");
     if (cfg.use_maps) {
         L3D_ARG(L, maps[0].map && maps[1].map, "rectification maps not set");
         L3D_ARG(L, maps[0].W == W && maps[0].H == H && maps[1].W == W && maps[1].H == H, "map size != image size");
@@ -511,6 +524,7 @@ static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps
         RC(dev_copy_gray(L, lsrc, W, H, stride, rectL, gl));
         RC(dev_copy_gray(L, rsrc, W, H, stride, nullptr, gr));
     }
+    L.t_end("remap");
     uint4* dL = L.get<uint4>(S_DESC_L, 2 * n);  // two operand planes per view (sgbm_prefilter_kernel)
     uint4* dR = L.get<uint4>(S_DESC_R, 2 * n);
     dr.has_right = cfg.use_wls != 0;
@@ -554,7 +568,7 @@ int l3d_compute_depth(l3d_ctx* ctx, const l3d_depth_config* cfg, const uint8_t* 
     NEED(ctx, cfg && left_bgr && right_bgr && depth && W > 0 && H > 0 && stride >= 3L * W, "compute_depth arguments");
     CK(ctx, cudaSetDevice(ctx->device));
     Lane& L = ctx->lane;
-    size_t n = (size_t)W * H, ns = (size_t)stride * H;
+    size_t n = (size_t)W * H, ns = (size_t)stride * (H - 1) + 3 * (size_t)W;  // strided views end with their last row
     uint8_t* sl = L.get<uint8_t>(S_SRC_L, ns);
     uint8_t* sr = L.get<uint8_t>(S_SRC_R, ns);
     uint8_t* rl = L.get<uint8_t>(S_RECT_L, n * 3);
@@ -637,6 +651,42 @@ int l3d_reconstruct(l3d_ctx* ctx, const l3d_recon_params* p, const double* xy, i
     RC(d2h(ctx, n_out, dn, sizeof(int)));
     CK(ctx, cudaStreamSynchronize(L.stream));
     if (*n_out > 0) { RC(d2h(ctx, xyz, dxyz, sizeof(double) * 3 * (size_t)*n_out)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_laser_depth_map(l3d_ctx* ctx, const double* xy, int n, const float* disp, int W, int H, double fx,
+                        double baseline, float* out) {
+    API_BEGIN(ctx)
+    NEED(ctx, n >= 0 && disp && out && W > 0 && H > 0 && (n == 0 || xy), "laser_depth_map arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    const size_t np = (size_t)W * H;
+    float* dimg = L.get<float>(S_DEPTH, np);
+    float* dout = L.get<float>(S_IO_D, np);
+    double* dxy = L.get<double>(S_RC_XY, (size_t)2 * std::max(n, 1));
+    RC(h2d(ctx, dimg, disp, np * 4));
+    if (n > 0) RC(h2d(ctx, dxy, xy, sizeof(double) * 2 * (size_t)n));
+    RC(dev_laser_depth_map(L, dxy, n, dimg, W, H, fx, baseline, dout));
+    RC(d2h(ctx, out, dout, np * 4));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    return L3D_OK;
+    API_END(ctx)
+}
+
+int l3d_colour_mask(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, const int* hsv_lo, const int* hsv_hi, int bright_thr,
+                    uint8_t* mask) {
+    API_BEGIN(ctx)
+    NEED(ctx, bgr && hsv_lo && hsv_hi && mask && W > 0 && H > 0, "colour_mask arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Lane& L = ctx->lane;
+    const size_t np = (size_t)W * H;
+    uint8_t* s = L.get<uint8_t>(S_SRC_L, np * 3);
+    uint8_t* m = L.get<uint8_t>(S_IO_A, np);
+    RC(h2d(ctx, s, bgr, np * 3));
+    RC(dev_colour_mask(L, s, W, H, hsv_lo, hsv_hi, bright_thr, m));
+    RC(d2h(ctx, mask, m, np));
+    CK(ctx, cudaStreamSynchronize(L.stream));
     return L3D_OK;
     API_END(ctx)
 }
@@ -791,6 +841,7 @@ static int pipe_extract(l3d_pipeline* p, Lane& L, FrameOut& o) {
         return L3D_OK;
     }
     const double* xy64 = nullptr; const float* xy32 = nullptr;
+    L.t_begin("extract");
     if (c.extractor == 4) {
         RC(dev_simple(L, o.rect, W, H, c.simple_hsv_lo, c.simple_hsv_hi, c.simple_bright_thr, c.simple_min_area,
                       nullptr, nullptr, o.xy64, o.n_xy));
@@ -799,8 +850,11 @@ static int pipe_extract(l3d_pipeline* p, Lane& L, FrameOut& o) {
         RC(dev_steger(L, c.steger, o.rect, 3, W, H, o.xy, c.max_points, o.n_xy));
         xy32 = o.xy;
     }
+    L.t_end("extract");
     const float* img = (c.recon.kind == L3D_RECON_PLANE) ? nullptr : o.depth;
+    L.t_begin("recon");
     RC(dev_recon(L, c.recon, xy64, xy32, o.n_xy, c.max_points, img, W, H, o.xyz, o.n_xyz));
+    L.t_end("recon");
     return L3D_OK;
 }
 

@@ -161,6 +161,9 @@ int dev_simple(Lane& L, const uint8_t* bgr, int W, int H, const int* lo, const i
                double min_area, uint8_t* mask_morph, uint8_t* mask_final, double* xy, int* n_dev);
 int dev_steger(Lane& L, const l3d_steger_params& p, const uint8_t* img, int channels, int W, int H,
                float* xy, int cap, int* n_dev);
+int dev_colour_mask(Lane& L, const uint8_t* bgr, int W, int H, const int* lo, const int* hi, int thr, uint8_t* mask255);
+int dev_laser_depth_map(Lane& L, const double* xy, int n, const float* disp, int W, int H, double fx, double baseline,
+                        float* out);
 int dev_recon(Lane& L, const l3d_recon_params& p, const double* xy, const float* xy_f32,
               const int* n_dev, int n_max, const float* img, int W, int H, double* xyz, int* n_out_dev);
 

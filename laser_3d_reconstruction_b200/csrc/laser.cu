@@ -236,6 +236,18 @@ int dev_simple(Lane& L, const uint8_t* bgr, int W, int H, const int* lo, const i
     return L3D_OK;
 }
 
+// steps (1)-(3) of SimpleLaserExtractor.extract_centerline alone (core/laser_extractor.py:56-64): inRange(HSV) & (gray > thr)
+// as a 0/255 mask -- the exhaustive colour-cube tests go through this
+int dev_colour_mask(Lane& L, const uint8_t* bgr, int W, int H, const int* lo, const int* hi, int thr, uint8_t* mask255) {
+    const size_t n = (size_t)W * H;
+    uint8_t* m0 = L.get<uint8_t>(S_SM_MASK0, n);
+    HsvRange rg;
+    for (int k = 0; k < 3; k++) { rg.lo[k] = lo[k]; rg.hi[k] = hi[k]; }
+    L3D_LAUNCH(L, colour_mask_kernel, cdiv(n, 256), 256, 0, bgr, (int)n, rg, thr, m0, (uint8_t*)nullptr);
+    L3D_LAUNCH(L, mask_to_255_kernel, cdiv(n, 256), 256, 0, m0, (int)n, mask255);
+    return L3D_OK;
+}
+
 // ============================================================================================
 // Steger
 // ============================================================================================

@@ -106,6 +106,45 @@ __global__ void vx_scatter_kernel(const int* __restrict__ slot_of, const int* __
     const int r = rank_of_slot[slot_of[i]];
     bucket[offset[r] + atomicAdd(fill + r, 1)] = i;
 }
+// The mean of a voxel is numpy's sequential sum over its members IN INPUT ORDER, so the member indices (scattered in
+// arbitrary order above) have to be sorted first.  Voxels with up to VX_SMALL members: one thread per voxel, insertion
+// sort.  Larger ones (a static laser line accumulated over many frames puts 1e3 .. 1e5 points into one 2 mm voxel; the
+// quadratic sort would run for seconds in one thread): one CTA per voxel, bitonic sort in place, then the sequential sum.
+constexpr int VX_SMALL = 48;
+constexpr int VX_BIG_THREADS = 256;
+
+__device__ void vx_sum_store(const double* __restrict__ pts, const int* __restrict__ b, int m, int f32, double* __restrict__ o);
+
+__global__ void __launch_bounds__(VX_BIG_THREADS) vx_mean_big_kernel(const double* __restrict__ pts, int* __restrict__ bucket,
+                                                                      const int* __restrict__ offset, const int* __restrict__ cnt,
+                                                                      int nvox, int f32, double* __restrict__ out) {
+    const int r = blockIdx.x;
+    if (r >= nvox) return;
+    const int m = cnt[r];
+    if (m <= VX_SMALL) return;  // handled by vx_mean_kernel
+    int* b = bucket + offset[r];
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    // bitonic network over p2 virtual slots in its all-ascending form (every merge starts with the "flip" partner
+    // i ^ (k - 1)): slots >= m hold +infinity, and as every comparator puts the smaller value into the lower slot, a
+    // comparator with a virtual partner never moves anything
+    auto cmpswap = [&](int i, int l) {
+        if (l > i && l < m) {
+            const int a = b[i], c = b[l];
+            if (a > c) { b[i] = c; b[l] = a; }
+        }
+    };
+    for (int k = 2; k <= p2; k <<= 1) {
+        for (int i = threadIdx.x; i < m; i += VX_BIG_THREADS) cmpswap(i, i ^ (k - 1));
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += VX_BIG_THREADS) cmpswap(i, i ^ j);
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) vx_sum_store(pts, b, m, f32, out + (size_t)r * 3);
+}
+
 // one thread per voxel: put its member indices into input order, sum sequentially in f64, divide by the count
 __global__ void vx_mean_kernel(const double* __restrict__ pts, int* __restrict__ bucket, const int* __restrict__ offset,
                                const int* __restrict__ cnt, int nvox, int f32, double* __restrict__ out) {
@@ -113,12 +152,19 @@ __global__ void vx_mean_kernel(const double* __restrict__ pts, int* __restrict__
     if (r >= nvox) return;
     int* b = bucket + offset[r];
     const int m = cnt[r];
+    if (m > VX_SMALL) return;  // vx_mean_big_kernel
     for (int i = 1; i < m; i++) {  // insertion sort (voxels hold a handful of points)
         const int v = b[i];
         int j = i - 1;
         while (j >= 0 && b[j] > v) { b[j + 1] = b[j]; j--; }
         b[j + 1] = v;
     }
+    vx_sum_store(pts, b, m, f32, out + (size_t)r * 3);
+}
+
+// numpy's mean of the member rows in input order (b sorted): sequential sum, then the division
+__device__ void vx_sum_store(const double* __restrict__ pts, const int* __restrict__ b, int m, int f32, double* __restrict__ out) {
+    const int r = 0;
     if (f32) {  // np.mean of float32 rows: float32 running sum, float32 division
         float fx = 0.f, fy = 0.f, fz = 0.f;
         for (int i = 0; i < m; i++) {
@@ -178,6 +224,7 @@ int dev_voxel_downsample(Lane& L, const double* pts, int n, double voxel, int f3
     if (rc != L3D_OK) return rc;
     L3D_LAUNCH(L, vx_scatter_kernel, g, 256, 0, slot_of, rank_of_slot, offset, fill, n, bucket);
     L3D_LAUNCH(L, vx_mean_kernel, cdiv(nvox, 128), 128, 0, pts, bucket, offset, cnt_ranked, nvox, f32, out);
+    L3D_LAUNCH(L, vx_mean_big_kernel, nvox, VX_BIG_THREADS, 0, pts, bucket, offset, cnt_ranked, nvox, f32, out);
     *nvox_host = nvox;
     return L3D_OK;
 }

@@ -128,6 +128,31 @@ __global__ void recon_emit_kernel(const double* __restrict__ tmp, const int* __r
     xyz[3 * o] = tmp[3 * (size_t)i]; xyz[3 * o + 1] = tmp[3 * (size_t)i + 1]; xyz[3 * o + 2] = tmp[3 * (size_t)i + 2];
 }
 
+// ImprovedLaserReconstructor.create_laser_depth_map (improved_reconstruction.py:154-186): depth only at the rounded laser
+// pixels.  px = int(round(x)) (half to even), bounds, disparity > 1.0 and not NaN, depth = (fx * baseline) / disparity in
+// f64 (np.float64 scalars times an np.float32 element), kept if 0 < depth < 10, stored as f32.  Two points that round to
+// the same pixel write the same value (it depends on the pixel's disparity only), so the scatter needs no order.
+__global__ void laser_depth_map_kernel(const double* __restrict__ xy, int n, const float* __restrict__ disp, int W, int H,
+                                       double fxb, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = xy[2 * i], y = xy[2 * i + 1];
+    if (!(fabs(x) < 2147483647.0 && fabs(y) < 2147483647.0)) return;
+    const int px = (int)rint(x), py = (int)rint(y);
+    if (px < 0 || px >= W || py < 0 || py >= H) return;
+    const float d = disp[(size_t)py * W + px];
+    if (!(d > 1.0f) || isnan(d)) return;
+    const double depth = __ddiv_rn(fxb, (double)d);
+    if (depth > 0 && depth < 10.0) out[(size_t)py * W + px] = (float)depth;
+}
+
+int dev_laser_depth_map(Lane& L, const double* xy, int n, const float* disp, int W, int H, double fx, double baseline,
+                        float* out) {
+    L3D_CHECK(L, cudaMemsetAsync(out, 0, sizeof(float) * (size_t)W * H, L.stream));
+    if (n > 0) L3D_LAUNCH(L, laser_depth_map_kernel, cdiv(n, 128), 128, 0, xy, n, disp, W, H, fx * baseline, out);
+    return L3D_OK;
+}
+
 static bool inv3(const double* m, double* o) {
     double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
     double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);

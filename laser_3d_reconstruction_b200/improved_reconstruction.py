@@ -54,31 +54,15 @@ class ImprovedLaserReconstructor:
 
     def create_laser_depth_map(self, laser_points: List[Tuple[float, float]], disparity_map: np.ndarray,
                                image_shape: Tuple[int, int]) -> np.ndarray:
-        """:154-186: depth only at the (rounded) laser pixels, `disparity > 1.0`.  Built from the
-        same GPU reconstruction (Z of reconstruct_from_disparity with min_disparity just above 1)."""
+        """:154-186: depth only at the (rounded) laser pixels with `disparity > 1.0`, one scatter kernel
+        (l3d_laser_depth_map); bounds follow `image_shape` like the reference's."""
         h, w = image_shape
-        out = np.zeros((h, w), np.float32)
-        if len(laser_points) == 0:
-            return out
         disp = np.asarray(disparity_map, np.float32)
-        xy = np.asarray(laser_points, np.float64).reshape(-1, 2)
-        px = np.rint(xy[:, 0]).astype(np.int64)
-        py = np.rint(xy[:, 1]).astype(np.int64)
-        ok = (px >= 0) & (px < w) & (py >= 0) & (py < h)
-        if not ok.any():
-            return out
-        # points that survive the reference's tests, in order; Z from the device kernel
-        md = float(np.nextafter(np.float32(1.0), np.float32(2.0)))  # "> 1.0" on float32 values
-        pts = self._run(N.RECON_DISPARITY, [tuple(p) for p in xy[ok]], disp[:h, :w], md)
-        d = disp[py[ok].clip(0, disp.shape[0] - 1), px[ok].clip(0, disp.shape[1] - 1)]
-        with np.errstate(all="ignore"):
-            z = (float(self.fx) * float(self.baseline)) / d.astype(np.float64)
-        keep = (d > 1.0) & ~np.isnan(d) & ~np.isinf(d) & (z > 0) & (z < 10.0)
-        if len(pts) == int(keep.sum()):
-            out[py[ok][keep], px[ok][keep]] = pts[:, 2]
-        else:  # shapes disagree only if disparity_map is smaller than image_shape: follow the reference's bounds
-            raise ValueError("disparity_map smaller than image_shape")
-        return out
+        if disp.shape[0] < h or disp.shape[1] < w:
+            raise IndexError("disparity_map smaller than image_shape")  # the reference indexes out of bounds here
+        if len(laser_points) == 0:
+            return np.zeros((h, w), np.float32)
+        return N.default_context(self.device).laser_depth_map(laser_points, np.ascontiguousarray(disp[:h, :w]), float(self.fx), float(self.baseline))
 
 
 def fix_roi_alignment(left_rect, right_rect, roi_left, roi_right):

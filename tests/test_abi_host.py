@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes as the C compiler lays them out (ints 4, doubles 8, natural alignment)
     assert C.sizeof(N.SgbmParams) == 11 * 4
-    assert C.sizeof(N.WlsParams) == 2 * 8 + 4 * 4
-    assert C.sizeof(N.DepthConfig) == 44 + 44 + 32 + 12 + 4 + 16 * 8
+    assert C.sizeof(N.WlsParams) == 2 * 8 + 6 * 4  # + solver, variant
+    assert C.sizeof(N.DepthConfig) == 44 + 44 + 40 + 12 + 4 + 16 * 8
     assert C.sizeof(N.StegerParams) == 8 + 8 + 8 + 8 + 16 + 12 + 12
     assert N.ReconParams.K.offset == 8 and N.ReconParams.window.offset == 8 + 72 + 32 + 8 + 8 + 5 * 8
 

@@ -67,11 +67,56 @@ def test_remap_noncontiguous_view_and_real_pair(ctx, golden_real):
         eq(ctx.remap_gray(1, r, (240, 320))[0], g["rrect_" + tag], "right rect")
 
 
-def test_gray_exhaustive_slice(ctx):
-    v = np.unique(np.concatenate([np.arange(0, 256, 5), [254, 255]])).astype(np.uint8)
-    b, g, r = np.meshgrid(v, v, v, indexing="ij")
-    img = np.ascontiguousarray(np.stack([b, g, r], -1).reshape(len(v), -1, 3))
-    eq(ctx.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+def colour_cube(r0, r1):
+    """all 2^16 (B, G) combinations for every R in [r0, r1): slices of the full 2^24 colour cube"""
+    b, g = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    planes = [np.stack([b, g, np.full_like(b, r)], -1) for r in range(r0, r1)]
+    return np.ascontiguousarray(np.concatenate(planes, 0))
+
+
+def test_colour_arithmetic_full_cube(ctx):
+    """SURVEY 8c pin (iii): BGR->gray, BGR->HSV and inRange over ALL 2^24 colours, on the GPU, against cv2 -- gray through
+    l3d_bgr2gray, HSV through l3d_colour_mask with range boxes that cut every channel (incl. the hue wrap at 0 / 179 and
+    the S / V extremes), bit-exact."""
+    boxes = [((50, 100, 180), (70, 255, 255)), ((40, 50, 100), (80, 255, 255)), ((0, 0, 0), (0, 255, 255)),
+             ((179, 1, 1), (179, 255, 255)), ((0, 0, 0), (179, 0, 255)), ((90, 128, 0), (150, 129, 127)),
+             ((10, 254, 254), (170, 255, 255)), ((0, 1, 1), (179, 254, 254))]
+    for r0 in range(0, 256, 32):
+        img = colour_cube(r0, r0 + 32)  # 8192 x 256 x 3
+        eq(ctx.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), "gray, R in [%d, %d)" % (r0, r0 + 32))
+        hsv = cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
+        for lo, hi in boxes:
+            eq(ctx.colour_mask(img, lo, hi), cv2.inRange(hsv, np.array(lo, np.uint8), np.array(hi, np.uint8)),
+               "inRange(HSV) %s-%s, R in [%d, %d)" % (lo, hi, r0, r0 + 32))
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        want = cv2.inRange(hsv, np.array(boxes[0][0], np.uint8), np.array(boxes[0][1], np.uint8)) & ((gray > 200) * np.uint8(255))
+        eq(ctx.colour_mask(img, boxes[0][0], boxes[0][1], 200), want, "config.py colour + brightness mask")
+
+
+def test_sgbm_more_real_pairs(ctx, golden_real):
+    """Four more of the reference's 28 calibration pairs (tests/golden/real_pairs.npz from the REAL camera class): the
+    rectified views (CRC32 of cv2.remap's output), the as-constructed 3WAY matcher's int16 disparity and the depth image."""
+    import os
+    import zlib
+    g = golden_real
+    more = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_pairs.npz")))
+    size = (320, 240)
+    R1, R2, P1, P2, Q, _, _ = cv2.stereoRectify(g["K_left"], g["dist_left"], g["K_right"], g["dist_right"], size,
+                                                g["R"], g["T"], flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
+    mlx, mly = cv2.initUndistortRectifyMap(g["K_left"], g["dist_left"], R1, P1, size, cv2.CV_32FC1)
+    mrx, mry = cv2.initUndistortRectifyMap(g["K_right"], g["dist_right"], R2, P2, size, cv2.CV_32FC1)
+    ctx.set_rectify_maps(0, mlx, mly)
+    ctx.set_rectify_maps(1, mrx, mry)
+    base, _, _ = ref_ops.sgbm_param_sets(64, 5, 2)
+    crc = lambda a: zlib.crc32(np.ascontiguousarray(a).tobytes())
+    for tag in ("c", "d", "e", "f"):
+        frame = more["frame_" + tag]
+        lrect, lg = ctx.remap_gray(0, frame[:, :320], (240, 320))
+        rrect, rg = ctx.remap_gray(1, frame[:, 320:], (240, 320))
+        assert crc(lrect) == int(more["lrect_crc_" + tag]) and crc(rrect) == int(more["rrect_crc_" + tag]), tag
+        d16 = ctx.sgbm_compute(N.SgbmParams(**base), lg, rg)
+        eq(d16, more["disp16_" + tag], "real pair " + tag)
+        assert crc(ctx.disp_to_depth(d16, Q)) == int(more["depth_crc_" + tag]), tag
 
 
 # ---- K2 SGBM -------------------------------------------------------------------------------
