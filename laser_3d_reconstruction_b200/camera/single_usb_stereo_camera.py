@@ -2,10 +2,12 @@
 the per-frame depth path (:311-359: remap -> gray -> SGBM left/right -> WLS -> depth) running in the
 sm_100a kernels of libl3d.so.
 
-What stays on the host, in cv2, because it is not the hot path: the UVC capture
-(``cv2.VideoCapture``, hardware I/O) and the init-time calibration maths
-(``cv2.stereoRectify`` / ``cv2.initUndistortRectifyMap``, :162-206).  There is no CPU fallback for
-the per-frame work: a missing library or GPU raises.
+What stays in cv2 because it is hardware I/O: the UVC capture (``cv2.VideoCapture``) and the MJPG decode behind it.  The
+init-time calibration maths (:162-206) needs no cv2: ``cv2.stereoRectify`` is restated in ``rectify.py`` (host,
+float64) and ``cv2.initUndistortRectifyMap`` is a kernel of the library with ``gpu_maps=True`` (the default keeps
+cv2's function for the maps; both give the same f32 maps).  The side-by-side split (:143-150) costs no copy: the two
+views go to the library as strided rows.  There is no CPU fallback for the per-frame work: a missing library or GPU
+raises.
 
 New, keyword-only: ``num_disparities``, ``block_size``, ``sgbm_mode``, ``use_wls``, ``device``,
 ``verbose`` (defaults reproduce the reference: 64/5 below 400 px per eye else 96/7, MODE_SGBM_3WAY,
@@ -20,6 +22,7 @@ import numpy as np
 
 from .. import _native as N
 from .. import stereo
+from .rectify import CALIB_ZERO_DISPARITY, stereo_rectify
 
 
 class SingleUSBStereoCameraManager:
@@ -108,7 +111,7 @@ class SingleUSBStereoCameraManager:
         return frame[:mid, :], frame[mid:, :]
 
     def _load_calibration(self) -> bool:
-        """reference :152-213 (init-time, stays in cv2)."""
+        """reference :152-213: calibration file -> rectification matrices (rectify.py) -> maps (GPU kernel with gpu_maps)."""
         if not os.path.exists(self.calibration_file):
             self._say(f"  标定文件不存在: {self.calibration_file}")
             return False
@@ -122,9 +125,11 @@ class SingleUSBStereoCameraManager:
             self.R = np.array(calib['R'])
             self.T = np.array(calib['T'])
             size = (self.single_width, self.single_height)
-            self.R1, self.R2, self.P1, self.P2, self.Q, _roi_l, _roi_r = cv2.stereoRectify(
+            # cv2.stereoRectify(..., flags=cv2.CALIB_ZERO_DISPARITY, alpha=0) restated in rectify.py (P1, P2, Q bit-identical to
+            # cv2 4.x, R1 / R2 to the last bit or two, the maps built from them identical): no cv2 call at init time
+            self.R1, self.R2, self.P1, self.P2, self.Q, _roi_l, _roi_r = stereo_rectify(
                 self.camera_matrix_left, self.dist_coeffs_left, self.camera_matrix_right, self.dist_coeffs_right,
-                size, self.R, self.T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
+                size, self.R, self.T, flags=CALIB_ZERO_DISPARITY, alpha=0)
             if self._gpu_maps:
                 ctx = self._context()
                 self.map_left_x, self.map_left_y = ctx.init_undistort_rectify_map(

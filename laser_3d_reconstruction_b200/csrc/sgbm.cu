@@ -99,6 +99,8 @@ struct ScanArgs {
     const int16_t* C; int16_t* S;
     int width1, D, nact, P1, P2;
     uint32_t zero;  // 0, as a value the compiler cannot see (sgm_step.cuh)
+    int hp_mode;    // horizontal pair: 0 = each warp runs on through the other half, 1 = each warp turns round at the middle
+    int hp_row0;    // horizontal pair: first volume row of this launch (row waves)
     int kind;   // 0 ->, 1 <-, 2 down, 3 down-right, 4 down-left, 5 up, 6 up-left, 7 up-right
     int store;  // 1: S = L ; 0: S = min(S + L, 32767)
     int HV, nseg;
@@ -440,9 +442,10 @@ __global__ void __launch_bounds__(32) sgbm_scan_kernel(const ScanArgs a) {
 template <int NP, bool FULL>
 __global__ void __launch_bounds__(64) sgbm_scan_hpair_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char scan_smem[];
+    __shared__ uint32_t xch[2][32][NP + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* my_smem = scan_smem + (size_t)warp * scan_smem_bytes_dev(a.D);
-    const int vr = blockIdx.x, width1 = a.width1, mid = width1 / 2;
+    const int vr = a.hp_row0 + blockIdx.x, width1 = a.width1, mid = width1 / 2;
     ScanLine s1, s2;
     s1.vr = s2.vr = vr; s1.dvr = s2.dvr = 0;
     if (warp == 0) { s1.x = 0; s1.n = mid; s1.dx = 1; s2.x = mid; s2.n = width1 - mid; s2.dx = 1; }
@@ -452,7 +455,22 @@ __global__ void __launch_bounds__(64) sgbm_scan_hpair_kernel(const ScanArgs a) {
     for (int k = 0; k < NP; k++) L[k] = (FULL || lane < a.nact) ? 0u : INF2;
     uint32_t minL = 0;
     scan_run<NP, SCAN_STORE, FULL, HPAIR_NST>(a, s1, my_smem, L, minL, lane);
-    __syncthreads();  // the other warp's S stores of its first half are visible before we accumulate onto them
+    if (a.hp_mode == 1) {
+        // turn round: the two warps exchange their path states at the middle and each walks back over ITS OWN half with
+        // the other direction's path -- the vectors it needs first are the ones it touched last (L2 reuse distance grows
+        // from zero instead of being half a row for every vector)
+#pragma unroll
+        for (int k = 0; k < NP; k++) xch[warp][lane][k] = L[k];
+        xch[warp][lane][NP] = minL;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NP; k++) L[k] = xch[warp ^ 1][lane][k];
+        minL = xch[warp ^ 1][lane][NP];
+        if (warp == 0) { s2.x = mid - 1; s2.n = mid; s2.dx = -1; }
+        else { s2.x = mid; s2.n = width1 - mid; s2.dx = 1; }
+    } else {
+        __syncthreads();  // the other warp's S stores of its first half are visible before we accumulate onto them
+    }
     scan_run<NP, SCAN_ACCUM, FULL, HPAIR_NST>(a, s2, my_smem, L, minL, lane);
 }
 
@@ -758,14 +776,28 @@ static int launch_scan_t(Lane& L, const ScanArgs& sa, int lines) {
     return L3D_OK;
 }
 template <int NP>
-static int launch_hpair(Lane& L, const ScanArgs& sa) {
-    const size_t smem = 2 * scan_smem_bytes_dev(sa.D);
-    if (sa.nact == 32) {
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, true>), sa.HV, 64, smem, sa);
-    } else {
-        L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, false>), sa.HV, 64, smem, sa);
+static int launch_hpair(Lane& L, const ScanArgs& sa0) {
+    const size_t smem = 2 * scan_smem_bytes_dev(sa0.D);
+    static const int hp_mode = getenv("L3D_HPAIR_MODE") ? atoi(getenv("L3D_HPAIR_MODE")) : 1;
+    // Row slices.  Alone, ONE launch over all rows is fastest (the two serial recurrences per row need every row in flight
+    // to cover their latency: 0.168 ms against 0.213 ms in three slices at config 3) -- that is what single calls and the
+    // kernel-timing leg use.  Inside the frame pipeline three slices let the other streams' kernels (above all the
+    // aggregation clusters, which need whole free SMs) start sooner: +2 % frames/s (tools/skip_probe.py, L3D_HPAIR_WAVES).
+    static const int hp_waves_env = getenv("L3D_HPAIR_WAVES") ? std::max(1, atoi(getenv("L3D_HPAIR_WAVES"))) : 0;
+    const int hp_waves = hp_waves_env ? hp_waves_env : ((L.back_stream && !L.timing && sa0.HV >= 360) ? 3 : 1);
+    ScanArgs sa = sa0;
+    sa.hp_mode = hp_mode;
+    const int per = cdiv(sa.HV, hp_waves);
+    for (int r0 = 0; r0 < sa.HV; r0 += per) {
+        const int rows = std::min(per, sa.HV - r0);
+        sa.hp_row0 = r0;
+        if (sa.nact == 32) {
+            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, true>), rows, 64, smem, sa);
+        } else {
+            L3D_CHECK(L, cudaFuncSetAttribute(sgbm_scan_hpair_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            L3D_LAUNCH(L, (sgbm_scan_hpair_kernel<NP, false>), rows, 64, smem, sa);
+        }
     }
     return L3D_OK;
 }
@@ -795,7 +827,7 @@ static void scan_args_of(const SgbmRun& r, ScanArgs& sa) {
     sa.HV = g.HV; sa.nseg = g.nseg;
     for (int s = 0; s < MAXSEG; s++) { sa.seg_vr0[s] = g.seg_vr0[s]; sa.seg_rows[s] = g.seg_rows[s]; }
     sa.raw = r.raw; sa.disp2key = r.d2; sa.W = r.W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
-    sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0; sa.zero = 0;
+    sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0; sa.zero = 0; sa.hp_mode = 0; sa.hp_row0 = 0;
     sa.tway = g.mode == 2;
     for (int s = 0; s < MAXSEG; s++) { sa.seg_y0[s] = g.seg_y0[s]; sa.seg_emit[s] = g.seg_emit[s]; }
 }

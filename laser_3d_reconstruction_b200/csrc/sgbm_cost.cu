@@ -506,6 +506,7 @@ struct DualArgs {
     int x1[CD_MAXT1];
     int emit, RA, RB;           // role-0 tiles also write columns RA <= x' < RB of C[1]
     unsigned* flags;            // bit 0 is set when a cost value reaches 32768 (OpenCV's int16 would wrap there)
+    int cta0;                   // first CTA of this launch (a launch may be split so that other streams' kernels get in between)
     int dbg;
 };
 
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     // ---- CTA -> (role, tile, band)
-    int cta = blockIdx.x;
+    int cta = a.cta0 + blockIdx.x;
     const int n0 = a.ntiles[0] * a.nbands[0];
     const int role = cta >= n0 ? 1 : 0;
     if (role) cta -= n0;
@@ -653,15 +654,22 @@ __global__ void __launch_bounds__(COST_THREADS, 1) sgbm_cost_dual_kernel(const D
             }
         }
         if (emitR && !(a.dbg & 8)) {
-            for (int unit = warp; unit < TX * NH; unit += NW) {
-                const int s = unit / NH, h = unit - s * NH;
-                const int w = 32 * h + lane;
-                int u = (s + cw0 + TX * 16 - 64 * h) % TX;
-                const int xq = x0 + u + 1 + 2 * w;             // right-volume column of this word
-                if (u < TX - 1 && xq >= a.RA && xq < a.RB) {
-                    const uint32_t Aw = ls[(u + 1) * CS + (D2 - 1 - w)], Bw = ls[u * CS + (D2 - 1 - w)];
-                    Cother32[(rowbase + xq) * D2 + w] = __byte_perm(Aw, Bw, 0x5432);
-                }
+            // units (wrapped line s, 32-word piece h) are dealt to the warps round robin: unit = warp + NW i, so a warp
+            // keeps its piece h = warp % NH and its line advances by NW / NH per unit -- column, staged-row address and
+            // global address all move by constants (with one conditional wrap)
+            constexpr int SSTEP = NW / NH;                     // line step per unit
+            constexpr int NU = (TX * NH + NW - 1) / NW;        // units per warp (the last one may not exist)
+            const int h = warp % NH, w = 32 * h + lane;
+            int sline = warp / NH;
+            int u = (sline + cw0 + TX * 16 - 64 * h) % TX;
+            const uint32_t* lsp = ls + u * CS + (D2 - 1 - w);                           // column u; column u + 1 is CS further
+            uint32_t* gp = Cother32 + (rowbase + x0 + u + 1 + 2 * w) * D2 + w;
+            int xq = x0 + u + 1 + 2 * w;                       // right-volume column of this word
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                if (sline < TX && u < TX - 1 && xq >= a.RA && xq < a.RB) *gp = __byte_perm(lsp[CS], lsp[0], 0x5432);
+                sline += SSTEP; u += SSTEP; lsp += SSTEP * CS; gp += SSTEP * D2; xq += SSTEP;
+                if (u >= TX) { u -= TX; lsp -= TX * CS; gp -= TX * D2; xq -= TX; }
             }
         }
     };
@@ -847,7 +855,13 @@ static int launch_cost_dual(Lane& L, const DualArgs& da) {
     const int ncta = da.ntiles[0] * da.nbands[0] + da.ntiles[1] * da.nbands[1];
     L3D_CHECK(L, cudaFuncSetAttribute((sgbm_cost_dual_kernel<BS, DD>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)K::smem_bytes()));
-    L3D_LAUNCH(L, (sgbm_cost_dual_kernel<BS, DD>), ncta, COST_THREADS, K::smem_bytes(), da);
+    static const int split = getenv("L3D_COST_SPLIT") ? std::max(1, atoi(getenv("L3D_COST_SPLIT"))) : 1;
+    const int per = cdiv(ncta, split);
+    DualArgs d = da;
+    for (int c0 = 0; c0 < ncta; c0 += per) {
+        d.cta0 = c0;
+        L3D_LAUNCH(L, (sgbm_cost_dual_kernel<BS, DD>), std::min(per, ncta - c0), COST_THREADS, K::smem_bytes(), d);
+    }
     return L3D_OK;
 }
 static int launch_cost_dual_any(Lane& L, int bs, int D, const DualArgs& da) {

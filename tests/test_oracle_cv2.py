@@ -274,3 +274,44 @@ def test_oracle_on_all_28_real_pairs(golden_real):
             assert np.array_equal(more["frame_" + t], np.hstack([l, r]))
             assert np.array_equal(more["disp16_" + t], want)
             assert int(more["lrect_crc_" + t]) == zlib.crc32(lrect.tobytes())
+
+
+def test_stereo_rectify_vs_cv2(golden_real):
+    """cv2.stereoRectify restated on the host (camera/rectify.py; reference call
+    camera/single_usb_stereo_camera.py:176-187).  On the shipped calibration P1, P2, Q and both ROIs equal cv2 4.x bit for
+    bit at every alpha; R1 / R2 differ by at most the last bits (OpenCV re-orthogonalises R with its own Jacobi SVD) and
+    the f32 rectification maps built from them are identical.  Synthetic rigs (horizontal / vertical baselines, 5 and 8
+    distortion coefficients, with and without CALIB_ZERO_DISPARITY): <= 1e-12 relative, ROIs equal."""
+    from laser_3d_reconstruction_b200.camera.rectify import stereo_rectify
+    g = golden_real
+    K1, d1, K2, d2, R, T = g["K_left"], g["dist_left"], g["K_right"], g["dist_right"], g["R"], g["T"]
+
+    def rel(a, b):
+        return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())
+
+    for size in ((320, 240), (640, 480)):
+        for alpha in (0, -1, 1, 0.5):
+            want = cv2.stereoRectify(K1, d1, K2, d2, size, R, T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=alpha)
+            got = stereo_rectify(K1, d1, K2, d2, size, R, T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=alpha)
+            assert rel(got[0], want[0]) < 1e-15 and rel(got[1], want[1]) < 1e-15
+            assert all(rel(got[i], want[i]) < 1e-14 for i in (2, 3, 4))
+            assert got[5] == tuple(want[5]) and got[6] == tuple(want[6])
+            if alpha == 0:  # the reference's call
+                assert all(np.array_equal(got[i], want[i]) for i in (2, 3, 4)), "P1, P2, Q bit-identical"
+                for K, d, Rg, Rw, Pg, Pw in ((K1, d1, got[0], want[0], got[2], want[2]), (K2, d2, got[1], want[1], got[3], want[3])):
+                    a = cv2.initUndistortRectifyMap(K, d, Rg, Pg, size, cv2.CV_32FC1)
+                    b = cv2.initUndistortRectifyMap(K, d, Rw, Pw, size, cv2.CV_32FC1)
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    rng = np.random.default_rng(0)
+    for trial in range(8):
+        f = 300 + rng.random() * 200
+        Ka = np.array([[f, 0, 160 + rng.normal() * 5], [0, f * 1.01, 120 + rng.normal() * 5], [0, 0, 1]])
+        Kb = Ka.copy(); Kb[0, 0] *= 1.02; Kb[0, 2] += 3
+        da, db = rng.normal(0, 0.02, (1, 5 if trial % 2 else 8)), rng.normal(0, 0.02, (1, 5 if trial % 2 else 8))
+        Rm = cv2.Rodrigues(rng.normal(0, 0.02, 3))[0]
+        Tm = np.array([[-0.06], [0.002], [0.001]]) if trial < 5 else np.array([[0.001], [-0.05], [0.002]])
+        fl = cv2.CALIB_ZERO_DISPARITY if trial % 3 else 0
+        want = cv2.stereoRectify(Ka, da, Kb, db, (320, 240), Rm, Tm, flags=fl, alpha=0)
+        got = stereo_rectify(Ka, da, Kb, db, (320, 240), Rm, Tm, flags=fl, alpha=0)
+        assert all(rel(got[i], want[i]) < 1e-12 for i in range(5)), trial
+        assert got[5] == tuple(want[5]) and got[6] == tuple(want[6])

@@ -17,6 +17,21 @@ METRICS = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+    ("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "fmaheavy%"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+    ("sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "uniform%"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu_cyc%"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_cyc%"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_wf%"),
+    ("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "lsu_wb%"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall_mio"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("smsp__inst_executed.sum", "inst"),
     ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
     ("launch__shared_mem_per_block_dynamic", "dsmem"),

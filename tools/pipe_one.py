@@ -3,7 +3,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from laser_3d_reconstruction_b200 import _native as N, pipeline, synth
-W, H, D, BS = 1280, 720, 128, 9
+W, H, D, BS = {'c1': (320, 360, 64, 5), 'c3': (1280, 720, 128, 9), 'c4': (1920, 1080, 256, 11)}[os.environ.get('L3D_PROBE_CFG', 'c3')]
 K, Q = synth.camera_model(W, H)
 maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
 nfr = int(sys.argv[2]) if len(sys.argv) > 2 else 32
