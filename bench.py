@@ -313,11 +313,12 @@ def single_frame_latency(ctx, pair, maps, K, Q, reps=10):
     ctx.set_rectify_maps(1, maps[2], maps[3])
     dcfg = pipeline.depth_config(D, BS, MODE, Q, use_wls=CFG["wls"])
     if CFG["extractor"] == "simple":
-        ex = l3d.SimpleLaserExtractor(hsv_lower=[50, 100, 180], hsv_upper=[70, 255, 255], brightness_threshold=200, min_area=50)
+        ex = l3d.SimpleLaserExtractor(hsv_lower=[50, 100, 180], hsv_upper=[70, 255, 255], brightness_threshold=200, min_area=50,
+                                      verbose=False)
     elif CFG["extractor"] == "fast":
-        ex = l3d.FastStegerExtractor(sigma=3.0)
+        ex = l3d.FastStegerExtractor(sigma=3.0, verbose=False)
     else:
-        ex = l3d.ImprovedStegerExtractor(sigma=3.0)
+        ex = l3d.ImprovedStegerExtractor(sigma=3.0, verbose=False)
     rec = l3d.Reconstructor(K, synth.LASER_PLANE, CFG["recon"] == "plane_refraction")
     t = {"compute_depth": [], "extract_centerline": [], "reconstruct": []}
     for i in range(reps + 2):
