@@ -243,6 +243,46 @@ def test_sgbm_c4_full_size(ctx):
     eq(ctx.sgbm_compute(N.SgbmParams(**mut), lg, rg), cv2.StereoSGBM_create(**mut).compute(lg, rg), "c4")
 
 
+def test_c4_full_pipeline(ctx):
+    """BASELINE config 4 through the whole frame pipeline at full size (1920x1080, 256 disparities, block 11, MODE_HH,
+    matcher pair + WLS + ImprovedSteger + 3D): the grouped pipeline (shared pixel-cost pass on 32-column tiles,
+    cluster-fused aggregation with 8 warps x 13 columns per CTA on 16-CTA clusters) must equal the lane-per-frame
+    pipeline (direction-split aggregation) bit for bit, the matcher pair must equal cv2, and the frame must pass the
+    north_star acceptance list against the reference path."""
+    W, H, D, bs, mode = 1920, 1080, 256, 11, 1
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, 70 + s) for s in range(2)]
+    idx = [0, 1, 0, 1, 0, 1, 0]  # one full lane set of seven frames
+    L = np.stack([frames[i][0] for i in idx])
+    R = np.stack([frames[i][1] for i in idx])
+    results = {}
+    for lanes in (2, 7):
+        cfg = pipeline.make_pipeline_config(W, H, D, bs, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=20000)
+        fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+        try:
+            n = 2 if lanes == 2 else 7
+            dl, dr = fp.upload(L[:n]), fp.upload(R[:n])
+            fp.run_dev(dl, dr, n)
+            results[lanes] = [fp.fetch(i) for i in (0, 1)] + ([fp.fetch(6)] if lanes == 7 else [])
+        finally:
+            fp.close()
+    for i in (0, 1):
+        for k in ("left_rect", "depth", "disp16", "points_2d", "points_3d"):
+            eq(results[2][i][k], results[7][i][k], "c4 grouped vs per-lane %s frame %d" % (k, i))
+    eq(results[7][2]["disp16"], results[7][0]["disp16"], "same input in another lane of the set")
+    wrect, wdepth, aux = ref_ops.depth_path(frames[1][0], frames[1][1], maps, D, bs, mode, Q, want_all=True)
+    got = results[7][1]
+    eq(got["left_rect"], wrect, "c4 rectified image vs cv2.remap")
+    _, mut, right = ref_ops.sgbm_param_sets(D, bs, mode)
+    dl16, dr16 = ctx.sgbm_compute_pair(N.SgbmParams(**mut), N.SgbmParams(**right), aux["lg"], aux["rg"])
+    eq(dl16, aux["dl"], "c4 left disparity vs cv2")
+    eq(dr16, aux["dr"], "c4 right disparity vs cv2")
+    diff = np.abs(got["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999
+    assert point_sets_agree(got["points_2d"], ref_ops.improved_steger_extract(wrect))
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_sgbm_noise_saturation(ctx, mode):
     rng = np.random.default_rng(0)
