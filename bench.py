@@ -484,7 +484,7 @@ def run_gpu(args, rank, world, local_rank):
             fp1.run_dev(dL, dR, nr)
         fp1.set_timing(True)
         fp1.run_dev(dL, dR, nr)
-        names = ["sgbm_cost", "sgbm_scan_k0", "sgbm_vgroup_down", "sgbm_vgroup_up", "sgbm_wta", "wls"] + \
+        names = ["sgbm_cost", "sgbm_scan_k0", "sgbm_vgroup_down", "sgbm_vgroup_up", "sgbm_vwave_down", "sgbm_vwave_up", "sgbm_wta", "wls"] + \
                 ["sgbm_scan_k%d" % kk for kk in range(1, 8)]
         groups = {}
         for g in names:

@@ -508,6 +508,7 @@ int l3d_disp_to_depth(l3d_ctx* ctx, const int16_t* disp16, int W, int H, const d
 struct DepthRuns {
     SgbmRun left, right;
     bool has_right = false;
+    bool vwave = false;  // the grouped pipeline aggregates this frame's volumes with the wavefront kernel
 };
 static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps, const uint8_t* lsrc,
                        const uint8_t* rsrc, int W, int H, long stride, uint8_t* rectL, DepthRuns& dr) {
@@ -528,6 +529,7 @@ static int depth_front(Lane& L, const l3d_depth_config& cfg, const RectMap* maps
     uint4* dL = L.get<uint4>(S_DESC_L, 2 * n);  // two operand planes per view (sgbm_prefilter_kernel)
     uint4* dR = L.get<uint4>(S_DESC_R, 2 * n);
     dr.has_right = cfg.use_wls != 0;
+    dr.left.no_hpair = dr.right.no_hpair = dr.vwave;
     // the right matcher sees the views swapped: same BT operands, roles exchanged, one pixel-cost pass for both volumes
     if (dr.has_right) RC(sgbm_front_pair(L, cfg.left, cfg.right, gl, gr, W, H, dL, dR, dr.left, dr.right));
     else RC(sgbm_front(L, cfg.left, gl, gr, W, H, 0, dL, dR, true, dr.left));
@@ -1021,6 +1023,9 @@ static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t*
     const int gsz = pipe_group_size(p);
     const int nsets = p->timing ? 1 : std::max(1, std::min(l3d_pipeline::MAXSETS, nl / gsz));  // lane sets alternate
     const int nchunks = (nframes + gsz - 1) / gsz;
+    const l3d_sgbm_params& lp = c.depth.left;
+    const bool use_vwave = sgbm_vwave_ok((W + std::min(lp.minDisparity, 0)) - std::max(lp.minDisparity + lp.numDisparities, 0), H,
+                                         lp.numDisparities, lp.mode);
     for (int i = 0; i < l3d_pipeline::MAXSETS; i++) {
         p->mid[i].t_reset(); p->mid[i].timing = p->timing;
         // only streams that get work: every stream that forks from `main` has to join it again (graph capture)
@@ -1044,6 +1049,7 @@ static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t*
                 l = sl; r = sr;
             }
             DepthRuns& dr = p->runs[li];
+            dr.vwave = use_vwave;
             static const bool dbg_marks_on = getenv("L3D_DEBUG_PHASES") != nullptr;
             if (dbg_marks_on) p->mark("front0", f, L.stream);
             RC(depth_front(L, c.depth, p->maps, l, r, W, H, 3L * W, p->outs[f].rect, dr));
@@ -1056,7 +1062,8 @@ static int pipe_run_grouped(l3d_pipeline* p, const uint8_t* left, const uint8_t*
         static const bool dbg_phases = getenv("L3D_DEBUG_PHASES") != nullptr;
         cudaEvent_t d0 = nullptr, d1 = nullptr;
         if (dbg_phases) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventRecord(d0, M.stream); }
-        RC(sgbm_middle_vgroup(M, list.data(), (int)list.size(), false));
+        if (use_vwave) RC(sgbm_middle_vwave(M, list.data(), (int)list.size()));
+        else RC(sgbm_middle_vgroup(M, list.data(), (int)list.size(), false));
         if (dbg_phases) { cudaEventRecord(d1, M.stream); p->dbg_events.push_back({d0, d1}); }
         CK(ctx, cudaEventRecord(p->ev_mid[set], M.stream));
         for (int i = 0; i < ng; i++) {

@@ -147,6 +147,10 @@ bool vgroup_supported(int width1, int H, int D);
 struct VGroupWta { int16_t* raw; unsigned* d2; int W, minD, minX1, uniq; };
 int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
                     int P2, int dir, const VGroupWta* wta);
+// four paths per pass as a warp-skewed wavefront (sgbm_vwave.cu): wta == nullptr first pass (S written), else last pass
+bool vwave_supported(int width1, int H, int D);
+int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
+                   int P2, int dir, const VGroupWta* wta);
 int dev_voxel_downsample(Lane& L, const double* pts, int n, double voxel, int f32, double* out, int* nvox_host);
 int dev_outlier_removal(Lane& L, const double* pts, int n, int nb_neighbors, double std_ratio, double* out, int* nout_host);
 int dev_bm(Lane& L, const l3d_bm_params& p, const uint8_t* left, const uint8_t* right, int W, int H, int16_t* disp);

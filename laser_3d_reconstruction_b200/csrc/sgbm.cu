@@ -835,7 +835,7 @@ static void scan_args_of(const SgbmRun& r, ScanArgs& sa) {
 // front, first part: geometry, invalid-filled raw image, scratch volumes, disp2 vote buffer
 // set: 0 / 1 selects the scratch slots (the pipeline keeps the left and the right matcher's volumes alive together)
 static int sgbm_front_begin(Lane& L, const l3d_sgbm_params& p, int W, int H, int set, SgbmRun& r) {
-    r.p = p; r.W = W; r.H = H; r.wta_done = false;
+    r.p = p; r.W = W; r.H = H; r.wta_done = false;  // r.no_hpair is the caller's choice and survives
     r.C = nullptr; r.S = nullptr; r.d2 = nullptr;
     Geom& g = r.g;
     int rc = make_geom(p, W, H, g, L.err);
@@ -866,6 +866,7 @@ static int sgbm_front_end(Lane& L, SgbmRun& r) {
         const size_t rowel = (size_t)g.width1 * g.D;
         L3D_LAUNCH(L, fill_s16_kernel, cdiv(rowel * (H - y0), 256), 256, 0, r.C + rowel * y0, rowel * (H - y0), (int16_t)g.P2);
     }
+    if (r.no_hpair) return L3D_OK;
     ScanArgs sa;
     scan_args_of(r, sa);
     L.t_begin("sgbm_scan_k0");
@@ -1048,6 +1049,39 @@ int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns, bool keep_S) {
         rc = dev_sgbm_vgroup(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, -1, last);
         L.t_end("sgbm_vgroup_up");
     }
+    return rc;
+}
+
+// can all eight paths of this geometry go through the wavefront kernel?  (MODE_HH only: its two passes carry four paths each)
+bool sgbm_vwave_ok(int width1, int H, int D, int mode) {
+    static const bool off = getenv("L3D_NO_VWAVE") && atoi(getenv("L3D_NO_VWAVE")) > 0;
+    return !off && mode == 1 && width1 > 0 && vwave_supported(width1, H, D);
+}
+
+// MODE_HH's eight paths of a set of runs that share one geometry: pass 1 (left-to-right, down-right, down, down-left)
+// writes S, pass 2 (the mirrored four) accumulates and runs the winner-takes-all on the finished rows.
+int sgbm_middle_vwave(Lane& L, SgbmRun* const* runs, int nruns) {
+    if (nruns <= 0) return L3D_OK;
+    const Geom& g = runs[0]->g;
+    std::vector<const int16_t*> Cp(nruns);
+    std::vector<int16_t*> Sp(nruns);
+    std::vector<VGroupWta> wta(nruns);
+    for (int i = 0; i < nruns; i++) {
+        const Geom& h = runs[i]->g;
+        L3D_ARG(L, h.width1 == g.width1 && h.HV == g.HV && h.D == g.D && h.P1 == g.P1 && h.P2 == g.P2 && h.mode == 1 &&
+                       runs[i]->W == runs[0]->W && runs[i]->no_hpair,
+                "vwave: runs of one launch must share geometry and penalties");
+        Cp[i] = runs[i]->C; Sp[i] = runs[i]->S;
+        wta[i] = VGroupWta{runs[i]->raw, runs[i]->d2, runs[i]->W, h.minD, h.minX1, h.uniq};
+        runs[i]->wta_done = true;
+    }
+    L.t_begin("sgbm_vwave_down");
+    int rc = dev_sgbm_vwave(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, +1, nullptr);
+    L.t_end("sgbm_vwave_down");
+    if (rc != L3D_OK) return rc;
+    L.t_begin("sgbm_vwave_up");
+    rc = dev_sgbm_vwave(L, Cp.data(), Sp.data(), nruns, g.width1, g.HV, g.D, g.P1, g.P2, -1, wta.data());
+    L.t_end("sgbm_vwave_up");
     return rc;
 }
 

@@ -28,6 +28,7 @@ struct SgbmRun {
     int16_t* raw = nullptr;
     unsigned* d2 = nullptr;
     bool wta_done = false;
+    bool no_hpair = false;  // the horizontal paths are aggregated by the wavefront kernel (sgbm_vwave.cu), not in the front
 };
 
 // ---- sgbm_cost.cu
@@ -50,6 +51,9 @@ int sgbm_front_pair(Lane& L, const l3d_sgbm_params& pl, const l3d_sgbm_params& p
 bool sgbm_vgroup_ok(const SgbmRun& r);
 int sgbm_middle_split(Lane& L, SgbmRun& r, bool keep_S);
 int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns, bool keep_S);
+// all eight paths of MODE_HH in two wavefront passes (runs fronted with no_hpair)
+bool sgbm_vwave_ok(int width1, int H, int D, int mode);
+int sgbm_middle_vwave(Lane& L, SgbmRun* const* runs, int nruns);
 int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg);
 
 }  // namespace l3d

@@ -691,7 +691,7 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
             dl, dr = fp.upload(L), fp.upload(R)
             for _ in range(5):  # steady state: scratch reuse across runs; a launch-bound step (this size is) is captured
                 fp.run_dev(dl, dr, len(frames))  # on its third occurrence and replayed as a CUDA graph afterwards
-            if lanes == 14:
+            if lanes == 14 and mode != 1:  # (MODE_HH runs two wavefront launches per lane set: the step is no longer launch-bound)
                 assert fp.graph_replays >= 1, "the repeated 320x360 step should have been replayed as a CUDA graph"
             results[lanes] = [fp.fetch(i) for i in range(len(frames))]
         finally:

@@ -22,7 +22,7 @@ fp.set_timing(True)
 for r in range(reps):
     fp.run_dev(dL, dR, nfr)
     out = []
-    for g in ["sgbm_cost", "sgbm_scan_k0", "sgbm_scan_k2", "sgbm_scan_k5", "sgbm_wta", "sgbm_vgroup_down", "sgbm_vgroup_up", "wls"]:
+    for g in ["sgbm_cost", "sgbm_scan_k0", "sgbm_wta", "sgbm_vgroup_down", "sgbm_vgroup_up", "sgbm_vwave_down", "sgbm_vwave_up", "wls"]:
         t, k = fp.kernel_time(g)
         out.append("%s %.4f" % (g, t / (nfr if g == "wls" else 2 * nfr)))
     print("  ".join(out), flush=True)
