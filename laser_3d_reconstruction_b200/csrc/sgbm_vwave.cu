@@ -114,6 +114,11 @@ template <> __device__ __forceinline__ void vw_st_local_vec<2>(uint32_t addr, co
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
 }
 
+// stage index of a double-buffered resource: a compile-time value when the row loop is unrolled by two (every stage offset
+// an immediate), a register otherwise (one copy of the row body: half the instruction footprint)
+template <int V> struct VwStageCt { __device__ __forceinline__ constexpr int get() const { return V; } };
+struct VwStageRt { int v; __device__ __forceinline__ int get() const { return v; } };
+
 template <int NP> struct VwVec;
 template <> struct VwVec<1> { typedef uint32_t T; };
 template <> struct VwVec<2> { typedef uint2 T; };
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(VW_THREADS, 1) sgbm_vwave_kernel(const VWaveAr
     constexpr uint32_t rowb = (uint32_t)CPW * B, slot = B + 16;
     constexpr uint32_t WB = 4 * rowb + (LAST ? rowb : 0) + 6 * slot + 128;  // shared memory per warp
     constexpr int DIR = LAST ? -1 : 1;
+    constexpr bool UNROLL2 = !LAST;
     extern __shared__ __align__(128) unsigned char vw_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -261,9 +267,11 @@ __global__ void __launch_bounds__(VW_THREADS, 1) sgbm_vwave_kernel(const VWaveAr
     auto JB = [&](int j) -> int { return FULL ? (DIR > 0 ? j : CPW - 1 - j) : jbr[FULL ? 0 : j]; };
     auto valid = [&](int j) -> bool { return FULL || j < ncols; };
 
-    // one row; ST = it & 1 as a compile-time value (the row loop is unrolled by two: every stage offset is an immediate)
+    // one row; ST = it & 1.  Pass 1 unrolls the row loop by two (ST a compile-time value).  The last pass keeps ONE copy of
+    // its longer body: two copies (42 KB of code, 16 warps per SM all at different places of it) ran with 13 % of the
+    // stall samples on instruction fetch (profiles/r2_vwave_kernels.md).
     auto do_row = [&](const int it, auto st_tag) {
-        constexpr int ST = decltype(st_tag)::value;
+        const int ST = st_tag.get();
         const uint32_t ph = (uint32_t)((it >> 1) & 1);      // phase of the it-th use of a double-buffered resource
         vw_mbar_wait(bar_tma + 8 * ST, ph);
         const vec* cs = (const vec*)(Cbuf + ST * rowb) + lane;   // cs[JB(j) * 32]: pass column j
@@ -444,12 +452,17 @@ __global__ void __launch_bounds__(VW_THREADS, 1) sgbm_vwave_kernel(const VWaveAr
         __syncwarp();
     };
     if (active) {
-        int it = 0;
-        for (; it + 1 < H; it += 2) {
-            do_row(it, std::integral_constant<int, 0>());
-            do_row(it + 1, std::integral_constant<int, 1>());
+        if (UNROLL2) {
+            int it = 0;
+            for (; it + 1 < H; it += 2) {
+                do_row(it, VwStageCt<0>());
+                do_row(it + 1, VwStageCt<1>());
+            }
+            if (it < H) do_row(it, VwStageCt<0>());
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < H; it++) do_row(it, VwStageRt{it & 1});
         }
-        if (it < H) do_row(it, std::integral_constant<int, 0>());
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     cluster.sync();  // no CTA exits while a neighbour may still write into its shared memory or signal its barriers

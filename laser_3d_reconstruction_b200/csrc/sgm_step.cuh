@@ -3,7 +3,7 @@
 //
 // A warp owns one pixel's disparity range, lane l holds 2*NP consecutive disparities as NP packed u16x2 words.
 // With delta = min_d(I) + P2 the step is
-//     T[d] = min(I[d], I[d-1] + P1, I[d+1] + P1)          (two VIADDMNMX.U16x2; independent of delta)
+//     T[d] = min(I[d], I[d-1] + P1, I[d+1] + P1)          (I + P1 once per word on the FMA pipe, one VIMNMX3.U16x2)
 //     O[d] = C[d] + min(T[d] - delta, 0)                  (one VIADDMNMX.S16x2, one VIADD.16x2)
 // which is OpenCV's  C + min(L[d], L[d+-1] + P1, delta) - delta.  Only the last two operations wait for the
 // warp-wide minimum of the previous step, so the loop-carried chain through the reduction is
@@ -23,7 +23,12 @@
 //     and 31 use a selector that feeds the word's own value into the missing slot -- L[d] + P1 - delta >= L[d] - delta
 //     never wins); with FMAFUNNEL the NP - 1 interior ones become (x << 16) + (y >> 16) = IMAD(x, 65536,
 //     IMAD.HI(y, 65536)) with the multiplier in a register, which ptxas keeps on the FMA pipe (tools/ubench/sgmstep.cu
-//     measures all forms).
+//     measures all forms);
+//   * I + P1 is carry-free in both halves (I + P1 < 2^16), so it is ONE 32-bit multiply-add per word with an opaque
+//     multiplier 1 (FMA pipe); the neighbour words are funnelled from the sums and T is a single three-input minimum
+//     instead of two add-min instructions: 12 instead of 14 ALU-pipe instructions per step at D = 128 (ubench: 30.0 ->
+//     28.7 cycles per step and sub-partition; 50.9 -> 45.7 at D = 256).  Moving C + min(T - delta, 0) to the FMA pipe as
+//     min(T, delta) + (C - delta) was measured too (30.4): two more IMADs per word cost more than the ALU slot they free.
 #pragma once
 #include <cstdint>
 
@@ -35,13 +40,14 @@ struct SgmLane {
     uint32_t zero;        // 0, opaque
     uint32_t neg1;        // 0xffffffff, opaque
     uint32_t m64k;        // 65536, opaque
+    uint32_t one;         // 1, opaque
 };
 // zero_param = 0: a value the compiler cannot see (kernel parameter)
 __device__ __forceinline__ SgmLane sgm_lane_init(int lane, uint32_t zero_param) {
     SgmLane s;
     s.selA = lane == 0 ? 0x5454u : 0x5432u;
     s.selB = lane == 31 ? 0x3232u : 0x5432u;
-    s.zero = zero_param; s.neg1 = ~zero_param; s.m64k = zero_param + 65536u;
+    s.zero = zero_param; s.neg1 = ~zero_param; s.m64k = zero_param + 65536u; s.one = zero_param + 1u;
     return s;
 }
 
@@ -65,20 +71,22 @@ template <int NP, bool FMAFUNNEL = false, bool FULL = true>
 __device__ __forceinline__ uint32_t sgm_step(uint32_t (&O)[NP], const uint32_t (&I)[NP], uint32_t minI2,
                                              const uint32_t (&Cv)[NP], uint32_t p1x2, uint32_t k2, const SgmLane& s,
                                              bool active = true) {
-    const uint32_t up = __shfl_up_sync(0xffffffffu, I[NP - 1], 1);
-    const uint32_t dn = __shfl_down_sync(0xffffffffu, I[0], 1);
+    uint32_t Ip[NP];                                     // I + P1, both halves (no carry: I + P1 < 2^16)
+#pragma unroll
+    for (int k = 0; k < NP; k++) Ip[k] = sgm_madlo(I[k], s.one, p1x2);
+    const uint32_t up = __shfl_up_sync(0xffffffffu, Ip[NP - 1], 1);
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, Ip[0], 1);
     const uint32_t nd2 = sgm_madlo(minI2, s.neg1, k2);   // -(minI + P2) mod 2^16, both halves
-    uint32_t F[NP + 1];                                  // F[k] = (I[k-1] >> 16) | (I[k] << 16): dm1 of word k, dp1 of word k-1
-    F[0] = __byte_perm(up, I[0], s.selA);
-    F[NP] = __byte_perm(I[NP - 1], dn, s.selB);
+    uint32_t F[NP + 1];                                  // F[k] = (Ip[k-1] >> 16) | (Ip[k] << 16): dm1 of word k, dp1 of word k-1
+    F[0] = __byte_perm(up, Ip[0], s.selA);
+    F[NP] = __byte_perm(Ip[NP - 1], dn, s.selB);
 #pragma unroll
     for (int k = 1; k < NP; k++)
-        F[k] = FMAFUNNEL ? sgm_madlo(I[k], s.m64k, sgm_mulhi(I[k - 1], s.m64k)) : __byte_perm(I[k - 1], I[k], 0x5432);
+        F[k] = FMAFUNNEL ? sgm_madlo(Ip[k], s.m64k, sgm_mulhi(Ip[k - 1], s.m64k)) : __byte_perm(Ip[k - 1], Ip[k], 0x5432);
     uint32_t Ln[NP];
 #pragma unroll
     for (int k = 0; k < NP; k++) {
-        uint32_t t = __viaddmin_u16x2(F[k], p1x2, I[k]);
-        t = __viaddmin_u16x2(F[k + 1], p1x2, t);
+        const uint32_t t = __vimin3_u16x2(I[k], F[k], F[k + 1]);
         Ln[k] = __vadd2(Cv[k], __viaddmin_s16x2(t, nd2, s.zero));
         if (!FULL && !active) Ln[k] = 0x7fff7fffu;
     }
