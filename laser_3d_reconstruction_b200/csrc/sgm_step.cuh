@@ -4,11 +4,13 @@
 // A warp owns one pixel's disparity range, lane l holds 2*NP consecutive disparities as NP packed u16x2 words.
 // With delta = min_d(I) + P2 the step is
 //     T[d] = min(I[d], I[d-1] + P1, I[d+1] + P1)          (I + P1 once per word on the FMA pipe, one VIMNMX3.U16x2)
-//     O[d] = C[d] + min(T[d] - delta, 0)                  (one VIADDMNMX.S16x2, one VIADD.16x2)
+//     O[d] = min(T[d] + (C[d] - delta), C[d])             (one VIADD.16x2, one VIADDMNMX.U16x2)
 // which is OpenCV's  C + min(L[d], L[d+-1] + P1, delta) - delta.  Only the last two operations wait for the
 // warp-wide minimum of the previous step, so the loop-carried chain through the reduction is
 // CREDUX -> IMAD -> VIADDMNMX -> VIADD -> (min tree) -> CREDUX; the neighbour exchange (SHFL, PRMT, two VIADDMNMX) runs
-// beside it.  -delta is taken modulo 2^16; T - delta lies in [-P2, 32767], so the wrapped s16 arithmetic is exact;
+// beside it.  -delta and C - delta are taken modulo 2^16; T + C - delta lies in [0, 2^16) because T >= min(I), delta =
+// min(I) + P2 and C >= P2 (OpenCV's C carries P2), so the wrapped sum is the exact value and the unsigned minimum with C
+// is the step's result; no zero operand is needed (the earlier form C + min(T - delta, 0) needed one: see below).
 // I + P1 < 2^16 unsigned.
 //
 // Pipe balance (sm_100: the integer ALU pipe and the FMA pipe each accept one warp instruction every second cycle
@@ -87,7 +89,7 @@ __device__ __forceinline__ uint32_t sgm_step(uint32_t (&O)[NP], const uint32_t (
 #pragma unroll
     for (int k = 0; k < NP; k++) {
         const uint32_t t = __vimin3_u16x2(I[k], F[k], F[k + 1]);
-        Ln[k] = __vadd2(Cv[k], __viaddmin_s16x2(t, nd2, s.zero));
+        Ln[k] = __viaddmin_u16x2(t, __vadd2(Cv[k], nd2), Cv[k]);  // min(T + (C - delta), C), all modulo 2^16 (see above)
         if (!FULL && !active) Ln[k] = 0x7fff7fffu;
     }
     uint32_t mn = Ln[0];

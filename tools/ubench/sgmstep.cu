@@ -59,7 +59,14 @@ __device__ __forceinline__ uint32_t step_fma(uint32_t (&O)[NP], const uint32_t (
 #pragma unroll
     for (int k = 1; k < NP; k++) F[k] = __byte_perm(Ip[k - 1], Ip[k], 0x5432);
     uint32_t Ln[NP];
-    if (FORM == 3) {
+    if (FORM == 9) {   // FORM 3 with L = min(T + (C - delta), C): no zero operand
+        const uint32_t nd2 = sgm_madlo(minI2, s.neg1, k2);
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            const uint32_t t = __vimin3_u16x2(I[k], F[k], F[k + 1]);
+            Ln[k] = __viaddmin_u16x2(t, __vadd2(Cv[k], nd2), Cv[k]);
+        }
+    } else if (FORM == 3) {
         const uint32_t nd2 = sgm_madlo(minI2, s.neg1, k2);
 #pragma unroll
         for (int k = 0; k < NP; k++) {
@@ -173,6 +180,9 @@ int main() {
     run<2, 3>("I+P1 by IMAD, VIMNMX3", cost, out, host, cyc, P1, P2);
     run<2, 4>("+ L = min(T,delta) + (C-delta)", cost, out, host, cyc, P1, P2);
     run<2, 5>("+ two CREDUX min tree", cost, out, host, cyc, P1, P2);
+    run<2, 9>("form 3, min(T + (C-delta), C)", cost, out, host, cyc, P1, P2);
+    run<4, 9>("form 3, min(T + (C-delta), C)", cost, out, host, cyc, P1, P2);
+    run<1, 9>("form 3, min(T + (C-delta), C)", cost, out, host, cyc, P1, P2);
     run<2, 6>("form 4 without the reduction", cost, out, host, cyc, P1, P2);
     run<2, 7>("form 4, shuffle butterfly", cost, out, host, cyc, P1, P2);
     run<2, 8>("form 4, redux.sync asm", cost, out, host, cyc, P1, P2);
