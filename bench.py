@@ -509,7 +509,8 @@ def run_gpu(args, rank, world, local_rank):
             pass
         out["roofline"] = {
             "bound": "hbm", "kernel": "sgbm matcher run = cost volume (one pixel-cost pass feeds both matchers' volumes) + "
-                                      "horizontal paths + previous-row paths (all passes) + WTA",
+                                      "aggregation (config 3: two wavefront passes of four paths each, WTA fused into the second; other "
+                                      "geometries: horizontal pair + cluster-fused previous-row passes) + WTA",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "algorithmic_bytes_per_run": sgbm_algorithmic_bytes(), "ms_per_run": sgbm_ms, "traffic": traffic,
