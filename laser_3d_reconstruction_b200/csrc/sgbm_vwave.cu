@@ -295,7 +295,10 @@ __global__ void __launch_bounds__(VW_THREADS, 1) sgbm_vwave_kernel(const VWaveAr
             vw_unpack<NP>(*(const vec*)(q + slot + lane * sizeof(vec)), inA);
             inAm = *(const uint32_t*)(q + slot + B);
             __syncwarp();
-            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(left_free_bar + 8 * ST, rel_arrive); else vw_mbar_arrive(left_free_bar + 8 * ST); }
+            // the "slot free" arrive carries a (zero) term computed from what was just read: it cannot issue before the
+            // loads have returned, which is all the relaxed remote form needs
+            const uint32_t dep = (LH[0] | inA[0] | mH | inAm) & sl.zero;
+            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(left_free_bar + 8 * ST + dep, rel_arrive); else vw_mbar_arrive(left_free_bar + 8 * ST); }
         }
         // ---- horizontal path: along the row through my columns
 #pragma unroll
@@ -368,7 +371,8 @@ __global__ void __launch_bounds__(VW_THREADS, 1) sgbm_vwave_kernel(const VWaveAr
                 vw_unpack<NP>(*(const vec*)(q + lane * sizeof(vec)), inB);
                 inBm = *(const uint32_t*)(q + B);
                 __syncwarp();
-                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(right_free_bar + 8 * (ST ^ 1), rel_arrive); else vw_mbar_arrive(right_free_bar + 8 * (ST ^ 1)); }
+                const uint32_t dep = (inB[0] | inBm) & sl.zero;
+                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(right_free_bar + 8 * (ST ^ 1) + dep, rel_arrive); else vw_mbar_arrive(right_free_bar + 8 * (ST ^ 1)); }
             }
             vw_unpack<NP>(cs[JB(CPW - 1) * 32], Cw);
             mB[CPW - 1] = sgm_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, sl);

@@ -737,11 +737,12 @@ def test_pipeline_graph_replay_host_buffers(ctx):
 
 
 @pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5),
-                                      (1920, 36, 256, 11), (1500, 30, 256, 5)])  # the last two: 8 warps x 13 / 10 columns, 16-CTA clusters
+                                      (1920, 36, 256, 11), (1500, 30, 256, 5),  # these two: 8 warps x 13 / 10 columns, 16-CTA clusters
+                                      (1280, 720, 128, 9)])  # config 3 at full height: the wavefront kernel's fill, steady state and drain
 def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
-    """Cluster-fused aggregation on volumes that do not fill the cluster's column strips: the last CTA / last warps own
-    fewer (or no) valid columns, neighbour-CTA halo hand-off (st.async + mbarrier) still has to deliver "no predecessor"
-    there.  Grouped (14 lanes) == lane-per-frame (2 lanes, direction-split kernels) bit for bit, and the raw matcher
+    """Cluster-fused aggregation (MODE_HH at D <= 128: the two-pass wavefront kernel sgbm_vwave.cu, else sgbm_vgroup.cu) on
+    volumes that do not fill the cluster's column strips: the last CTA / last warps own fewer (or no) valid columns,
+    neighbour-CTA hand-off (st.async + mbarrier) still has to deliver "no predecessor" there.  Grouped (14 lanes) == lane-per-frame (2 lanes, direction-split kernels) bit for bit, and the raw matcher
     output equals cv2."""
     mode = 1
     K, Q = synth.camera_model(W, H)
