@@ -149,6 +149,7 @@ int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njo
                     int P2, int dir, const VGroupWta* wta);
 // four paths per pass as a warp-skewed wavefront (sgbm_vwave.cu): wta == nullptr first pass (S written), else last pass
 bool vwave_supported(int width1, int H, int D);
+bool vwave_pays(int width1, int H, int D);  // ... and is it the faster choice there (measured)
 int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
                    int P2, int dir, const VGroupWta* wta);
 int dev_voxel_downsample(Lane& L, const double* pts, int n, double voxel, int f32, double* out, int* nvox_host);

@@ -1053,9 +1053,14 @@ int sgbm_middle_vgroup(Lane& L, SgbmRun* const* runs, int nruns, bool keep_S) {
 }
 
 // can all eight paths of this geometry go through the wavefront kernel?  (MODE_HH only: its two passes carry four paths each)
+// L3D_VWAVE (read at every call, so that a test can switch it): 0 = never, 1 = wherever the kernel covers the geometry,
+// unset = where it is the faster choice (vwave_pays)
 bool sgbm_vwave_ok(int width1, int H, int D, int mode) {
     static const bool off = getenv("L3D_NO_VWAVE") && atoi(getenv("L3D_NO_VWAVE")) > 0;
-    return !off && mode == 1 && width1 > 0 && vwave_supported(width1, H, D);
+    const char* e = getenv("L3D_VWAVE");
+    const int policy = e ? atoi(e) : -1;
+    if (off || policy == 0 || mode != 1 || width1 <= 0) return false;
+    return policy == 1 ? vwave_supported(width1, H, D) : vwave_pays(width1, H, D);
 }
 
 // MODE_HH's eight paths of a set of runs that share one geometry: pass 1 (left-to-right, down-right, down, down-left)

@@ -486,6 +486,16 @@ bool vwave_supported(int width1, int H, int D) {
     return width1 >= 1 && H >= 1 && vwave_shape(width1, D, cl, cpw);
 }
 
+// Does the wavefront kernel beat horizontal pair + cluster-fused passes on this geometry?  Measured in the frame pipeline
+// (frames/s with / without, MODE_HH + WLS, 28 lanes; gpurun_out/geoms.log): 1280x720 D=128 +18 %, 1280x360 D=128 +14 %,
+// 960x540 D=128 (7 columns per warp) +7.5 %, 640x480 D=128 (4) +5.5 %, 512x512 D=128 (3) -4 %; D=64: 800x600 -1 %,
+// 640x480 -1.5 %, 320x360 (2 columns per warp) -9 %.  The fill and drain of the wavefront (one horizontal chain + hand-off
+// per strip) do not shrink with the strips, and at D=64 the bytes the other kernels move twice are half as many.
+bool vwave_pays(int width1, int H, int D) {
+    int cl, cpw;
+    return width1 >= 1 && H >= 1 && vwave_shape(width1, D, cl, cpw) && D == 128 && cpw >= 4;
+}
+
 // Aggregate four paths of pass `dir` for `njobs` volumes at once; wta != nullptr: last pass (S is read, accumulated,
 // reduced by the winner-takes-all and NOT written back), else first pass (S is written, not read).
 int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,

@@ -691,7 +691,7 @@ def test_grouped_pipeline_cluster_aggregation(ctx, mode):
             dl, dr = fp.upload(L), fp.upload(R)
             for _ in range(5):  # steady state: scratch reuse across runs; a launch-bound step (this size is) is captured
                 fp.run_dev(dl, dr, len(frames))  # on its third occurrence and replayed as a CUDA graph afterwards
-            if lanes == 14 and mode != 1:  # (MODE_HH runs two wavefront launches per lane set: the step is no longer launch-bound)
+            if lanes == 14:
                 assert fp.graph_replays >= 1, "the repeated 320x360 step should have been replayed as a CUDA graph"
             results[lanes] = [fp.fetch(i) for i in range(len(frames))]
         finally:
@@ -739,33 +739,90 @@ def test_pipeline_graph_replay_host_buffers(ctx):
 @pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5),
                                       (1920, 36, 256, 11), (1500, 30, 256, 5),  # these two: 8 warps x 13 / 10 columns, 16-CTA clusters
                                       (1280, 720, 128, 9)])  # config 3 at full height: the wavefront kernel's fill, steady state and drain
-def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs):
+@pytest.mark.parametrize("policy", [None, "1"])  # L3D_VWAVE: default = the wavefront kernel where it pays, 1 = wherever it applies
+def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs, policy):
     """Cluster-fused aggregation (MODE_HH at D <= 128: the two-pass wavefront kernel sgbm_vwave.cu, else sgbm_vgroup.cu) on
     volumes that do not fill the cluster's column strips: the last CTA / last warps own fewer (or no) valid columns,
     neighbour-CTA hand-off (st.async + mbarrier) still has to deliver "no predecessor" there.  Grouped (14 lanes) == lane-per-frame (2 lanes, direction-split kernels) bit for bit, and the raw matcher
     output equals cv2."""
+    import os
     mode = 1
+    if policy is not None and (D > 128 or (W, H) == (1280, 720)):
+        pytest.skip("the wavefront kernel does not cover D = 256; config 3 takes it by default")
     K, Q = synth.camera_model(W, H)
     maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
     frames = [synth.stereo_pair(W, H, D, 40 + s) for s in range(8)]
     L = np.stack([f[0] for f in frames])
     R = np.stack([f[1] for f in frames])
     results = {}
-    for lanes in (2, 14):
-        cfg = pipeline.make_pipeline_config(W, H, D, bs, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=8000)
-        fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
-        try:
-            dl, dr = fp.upload(L), fp.upload(R)
-            fp.run_dev(dl, dr, len(frames))
-            results[lanes] = [fp.fetch(i) for i in range(len(frames))]
-        finally:
-            fp.close()
+    saved = os.environ.get("L3D_VWAVE")
+    if policy is not None:
+        os.environ["L3D_VWAVE"] = policy  # read by the library at every pipeline run
+    try:
+        for lanes in (2, 14):
+            cfg = pipeline.make_pipeline_config(W, H, D, bs, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=8000)
+            fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+            try:
+                dl, dr = fp.upload(L), fp.upload(R)
+                fp.run_dev(dl, dr, len(frames))
+                results[lanes] = [fp.fetch(i) for i in range(len(frames))]
+            finally:
+                fp.close()
+    finally:
+        if saved is None:
+            os.environ.pop("L3D_VWAVE", None)
+        else:
+            os.environ["L3D_VWAVE"] = saved
     for i in range(len(frames)):
         for k in ("left_rect", "depth", "disp16", "points_2d", "points_3d"):
             eq(results[2][i][k], results[14][i][k], "ragged grouped vs per-lane %s frame %d" % (k, i))
     wrect, wdepth, aux = ref_ops.depth_path(frames[7][0], frames[7][1], maps, D, bs, mode, Q, want_all=True)
     diff = np.abs(results[14][7]["disp16"].astype(np.int32) - aux["df"].astype(np.int32))
     assert (diff <= 1).mean() >= 0.999
+
+
+@pytest.mark.parametrize("W,H,D,bs", [(640, 200, 128, 9), (437, 50, 64, 5)])
+def test_grouped_pipeline_without_wls_uniqueness(ctx, W, H, D, bs):
+    """use_wls = False: one matcher per frame with the reference's own parameters (uniquenessRatio 10, disp12MaxDiff 1,
+    speckle filter): the fused winner-takes-all of the cluster kernels (wavefront kernel forced on: L3D_VWAVE=1) runs
+    OpenCV's uniqueness test.  Grouped (15 lanes) == lane-per-frame (2 lanes, direction-split kernels + stand-alone WTA)
+    bit for bit, and the disparity equals cv2's."""
+    import os
+    import cv2
+    mode = 1
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, 60 + s) for s in range(9)]
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    results = {}
+    saved = os.environ.get("L3D_VWAVE")
+    os.environ["L3D_VWAVE"] = "1"
+    try:
+        for lanes in (2, 15):
+            cfg = pipeline.make_pipeline_config(W, H, D, bs, mode, Q, K, extractor=N.STEGER_IMPROVED, lanes=lanes, max_points=8000,
+                                                use_wls=False)
+            fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+            try:
+                dl, dr = fp.upload(L), fp.upload(R)
+                fp.run_dev(dl, dr, len(frames))
+                results[lanes] = [fp.fetch(i) for i in range(len(frames))]
+            finally:
+                fp.close()
+    finally:
+        if saved is None:
+            os.environ.pop("L3D_VWAVE", None)
+        else:
+            os.environ["L3D_VWAVE"] = saved
+    for i in range(len(frames)):
+        for k in ("left_rect", "depth", "disp16", "points_2d", "points_3d"):
+            eq(results[2][i][k], results[15][i][k], "no-WLS grouped vs per-lane %s frame %d" % (k, i))
+    lrect = cv2.remap(frames[8][0], maps[0], maps[1], cv2.INTER_LINEAR)
+    rrect = cv2.remap(frames[8][1], maps[2], maps[3], cv2.INTER_LINEAR)
+    want = cv2.StereoSGBM_create(minDisparity=0, numDisparities=D, blockSize=bs, P1=24 * bs * bs, P2=96 * bs * bs, disp12MaxDiff=1,
+                                 preFilterCap=63, uniquenessRatio=10, speckleWindowSize=100, speckleRange=32, mode=mode).compute(
+        cv2.cvtColor(lrect, cv2.COLOR_BGR2GRAY), cv2.cvtColor(rrect, cv2.COLOR_BGR2GRAY))
+    eq(results[15][8]["disp16"], want, "no-WLS grouped disparity vs cv2")
 
 
 @pytest.mark.parametrize("switch,cases", [

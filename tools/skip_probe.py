@@ -11,6 +11,8 @@ if os.environ.get('L3D_PROBE_CFG') == 'c4':
     W, H, D, BS = 1920, 1080, 256, 11
 if os.environ.get('L3D_PROBE_CFG') == 'c1':
     W, H, D, BS = 320, 360, 64, 5
+if os.environ.get('L3D_PROBE_GEOM'):  # "W,H,D,BS"
+    W, H, D, BS = (int(v) for v in os.environ['L3D_PROBE_GEOM'].split(','))
 lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 14
 nfr = int(sys.argv[2]) if len(sys.argv) > 2 else 56
 K, Q = synth.camera_model(W, H)
