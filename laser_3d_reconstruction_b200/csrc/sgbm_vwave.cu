@@ -1,481 +1,21 @@
-// sgbm_vwave.cu -- FOUR SGM paths per pass on a thread-block cluster, as a warp-skewed wavefront: the whole aggregation of
-// cv2.StereoSGBM MODE_HH (camera/single_usb_stereo_camera.py:324-325) in two passes that move exactly the algorithmic
-// bytes (every pass reads C once and reads-or-writes S once).
-//
-// S is a saturating sum of eight non-negative path costs, so the paths may be grouped into passes freely:
-//   pass 1 (rows top-down, columns left-to-right):   H from (x-1, y),  A from (x-1, y-1),  V from (x, y-1),  B from (x+1, y-1)
-//   pass 2 = the same kernel on the volume mirrored in x and y: from (x+1, y), (x+1, y+1), (x, y+1), (x-1, y+1)
-// H needs the LEFT neighbour of the same row, B the RIGHT neighbour of the previous row.  In row lock-step (sgbm_vgroup.cu)
-// the two cannot share a pass.  Here warp g (owner of CPW adjacent columns, all warps of the cluster numbered left to
-// right) simply runs one row BEHIND warp g-1: it exports the B state of its FIRST column early in a row and imports its
-// right neighbour's (one row back, produced at about the same time) just before its LAST column.  Nothing is in
-// lock-step: every warp streams its own rows of C (and S) by TMA bulk copies with its own mbarriers and talks to its two
-// neighbours only, through double-buffered slots with full / empty mbarriers -- plain shared memory inside a CTA,
-// st.async + remote arrive between the CTAs of the cluster.  The price of the skew is (warps per cluster - 1) row-times of
-// pipeline fill and drain per pass.
-//
-// What it replaces: sgbm_scan_hpair_kernel (both horizontal paths: 4.3 volume-passes of DRAM traffic, because a pixel's
-// two horizontal costs meet half a row apart) and the two sgbm_vgroup_kernel passes (3 + 2 volume-passes).
-#include <cooperative_groups.h>
-
-#include <type_traits>
-
-#include "common.cuh"
-#include "sgm_step.cuh"
+// sgbm_vwave.cu -- host side of the wavefront aggregation (kernel: sgbm_vwave.cuh) and its D <= 128 instantiations
+#include "sgbm_vwave.cuh"
 
 namespace l3d {
-namespace cg = cooperative_groups;
 
-constexpr int VW_WARPS = 16;
-constexpr int VW_THREADS = VW_WARPS * 32;
-constexpr int VW_MAXCPW = 9;
-constexpr int VW_MAXJOBS = 64;
-constexpr int VW_MAXREG = 128;
-
-struct VWaveArgs {
-    const int16_t* C[VW_MAXJOBS];
-    int16_t* S[VW_MAXJOBS];
-    int width1, H, D, P1, P2;
-    int dir;       // +1: pass 1 (rows top-down, strips left-to-right); -1: pass 2 (the volume mirrored in x and y)
-    int cluster;   // CTAs per cluster (= per job)
-    int W;         // image width (WTA outputs)
-    uint32_t zero; // 0, as a value the compiler cannot see (sgm_step.cuh)
-    int flags;     // experiment switches (L3D_VW_FLAGS): 1 = release-form remote arrives
-    int16_t* raw[VW_MAXJOBS];
-    unsigned* d2[VW_MAXJOBS];
-    int minD[VW_MAXJOBS], minX1[VW_MAXJOBS], uniq[VW_MAXJOBS];
-};
-
-// shared memory per warp: C rows [2][CPW * B], S rows [2][CPW * B], left-edge slots [2][2 * (B + 16)], right-edge slots
-// [2][B + 16], 10 mbarriers
-static size_t vwave_warp_bytes(int D, int cpw, bool last) {
-    const size_t B = (size_t)D * 2, row = (size_t)cpw * B, slot = B + 16;
-    return 4 * row + (last ? row : 0) + 6 * slot + 128;
-}
-static size_t vwave_smem_bytes(int D, int cpw, bool last) { return VW_WARPS * vwave_warp_bytes(D, cpw, last) + 128; }
-
-__device__ __forceinline__ void vw_mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void vw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void vw_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// A barrier in another CTA of the cluster.  Only "slot free" signals travel this way: the consumer has READ the slot (its
-// LDS results are in registers, the warp has re-converged) and nothing it wrote has to become visible to the producer, so
-// the arrive is relaxed.  The release form costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive: the two
-// edge warps of a CTA spent half their time there and the whole wavefront ran at their pace (profiles/r2_vwave_kernels.md).
-__device__ __forceinline__ void vw_mbar_arrive_remote(uint32_t rbar, bool release) {
-    if (release) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-    else asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-}
-__device__ __forceinline__ void vw_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "VW_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra VW_DONE_%=;\n\t"
-        "bra VW_WAIT_%=;\n\t"
-        "VW_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void vw_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void vw_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t vw_mapa(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void vw_st_async(uint32_t raddr, uint32_t v, uint32_t rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                 ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
-}
-template <int NP> __device__ __forceinline__ void vw_st_async_vec(uint32_t raddr, const uint32_t (&v)[NP], uint32_t rbar);
-template <> __device__ __forceinline__ void vw_st_async_vec<1>(uint32_t raddr, const uint32_t (&v)[1], uint32_t rbar) {
-    vw_st_async(raddr, v[0], rbar);
-}
-template <> __device__ __forceinline__ void vw_st_async_vec<2>(uint32_t raddr, const uint32_t (&v)[2], uint32_t rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
-                 ::"r"(raddr), "r"(v[0]), "r"(v[1]), "r"(rbar) : "memory");
-}
-
-// a lane's NP words into a slot of this CTA's shared memory (address in the shared window)
-template <int NP> __device__ __forceinline__ void vw_st_local_vec(uint32_t addr, const uint32_t (&v)[NP]);
-template <> __device__ __forceinline__ void vw_st_local_vec<1>(uint32_t addr, const uint32_t (&v)[1]) {
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v[0]) : "memory");
-}
-template <> __device__ __forceinline__ void vw_st_local_vec<2>(uint32_t addr, const uint32_t (&v)[2]) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
-}
-
-// stage index of a double-buffered resource: a compile-time value when the row loop is unrolled by two (every stage offset
-// an immediate), a register otherwise (one copy of the row body: half the instruction footprint)
-template <int V> struct VwStageCt { __device__ __forceinline__ constexpr int get() const { return V; } };
-struct VwStageRt { int v; __device__ __forceinline__ int get() const { return v; } };
-
-template <int NP> struct VwVec;
-template <> struct VwVec<1> { typedef uint32_t T; };
-template <> struct VwVec<2> { typedef uint2 T; };
-template <int NP> __device__ __forceinline__ void vw_unpack(const typename VwVec<NP>::T& v, uint32_t (&o)[NP]);
-template <> __device__ __forceinline__ void vw_unpack<1>(const uint32_t& v, uint32_t (&o)[1]) { o[0] = v; }
-template <> __device__ __forceinline__ void vw_unpack<2>(const uint2& v, uint32_t (&o)[2]) { o[0] = v.x; o[1] = v.y; }
-template <int NP> __device__ __forceinline__ typename VwVec<NP>::T vw_pack(const uint32_t (&o)[NP]);
-template <> __device__ __forceinline__ uint32_t vw_pack<1>(const uint32_t (&o)[1]) { return o[0]; }
-template <> __device__ __forceinline__ uint2 vw_pack<2>(const uint32_t (&o)[2]) { return make_uint2(o[0], o[1]); }
-
-// OpenCV's uniqueness test (modes SGBM / HH), see wta_not_unique in sgbm.cu; out of line, uniquenessRatio > 0 only
-template <int NP>
-__device__ __noinline__ bool vw_not_unique(typename VwVec<NP>::T wv, unsigned key, int uniq, unsigned dkey) {
-    uint32_t w[NP];
-    vw_unpack<NP>(wv, w);
-    const int minS = (int)(key >> 8), best = (int)(key & 255u);
-    bool rej = false;
-#pragma unroll
-    for (int q = 0; q < NP; q++) {
-        const int s0 = (int)(w[q] & 0xffffu), s1 = (int)(w[q] >> 16);
-        const int d0 = (int)dkey + 2 * q;
-        if (s0 * (100 - uniq) < minS * 100 && abs(best - d0) > 1) rej = true;
-        if (s1 * (100 - uniq) < minS * 100 && abs(best - d0 - 1) > 1) rej = true;
-    }
-    return __any_sync(0xffffffffu, rej) && minS < 32767;
-}
-
-// NP = D / 64 words per lane (D in {64, 128}); CPW = columns per warp
-// LAST = false: pass 1 (rows top-down, columns left-to-right), S = sum of the four path costs (S is not read), written back
-// LAST = true:  pass 2 (the volume mirrored in x and y), S += the four path costs, winner-takes-all on the finished
-//               rows, S not written back
-// FULL:         width1 is a multiple of CPW (every strip has CPW columns): all column offsets are immediates
-//
-// One row of a warp (row-time), in this order so that the left-to-right chain of the horizontal path moves on after
-// about a fifth of a row-time (fill and drain of the wavefront: ~0.2 x warps row-times instead of 1 x warps):
-//   left edge in  {H after the left neighbour's last column of THIS row, its A state after the PREVIOUS row}
-//   H chain       CPW dependent steps; each column's cost is parked in shared memory for the S sum
-//   left edge out {H after my last column, my last column's A state as it still is: after the previous row}
-//   B, column 0   -> right edge out (the left neighbour needs it for its NEXT row, late in its row-time)
-//   A columns, B columns 1 .. CPW-2, right edge in (the right neighbour's B state after the previous row), B column CPW-1
-//   V + S sum (+ winner-takes-all keys) per column, epilogue, TMA store / loads
-template <int NP, int CPW, bool LAST, bool FULL>
-__global__ void __launch_bounds__(VW_THREADS, 1) sgbm_vwave_kernel(const VWaveArgs a) {
-    typedef typename VwVec<NP>::T vec;
-    constexpr uint32_t INF = 0x7fff7fffu;
-    constexpr uint32_t B = 128u * NP;                      // bytes per pixel vector (D = 64 NP disparities)
-    constexpr uint32_t rowb = (uint32_t)CPW * B, slot = B + 16;
-    constexpr uint32_t WB = 4 * rowb + (LAST ? rowb : 0) + 6 * slot + 128;  // shared memory per warp
-    constexpr int DIR = LAST ? -1 : 1;
-    constexpr bool UNROLL2 = !LAST;
-    extern __shared__ __align__(128) unsigned char vw_smem[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    const int CL = a.cluster;
-    const int job = blockIdx.y;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int lane = threadIdx.x & 31;
-    const int width1 = a.width1, H = a.H;
-    const bool rel_arrive = (a.flags & 1) != 0;
-    const int g = rank * VW_WARPS + warp;                  // strip number, left to right in pass coordinates
-    const int u0 = g * CPW;                                // first column (pass coordinates) of this warp
-    const int ncols = FULL ? (u0 < width1 ? CPW : 0) : max(0, min(CPW, width1 - u0));  // valid columns
-    const int nstrips = (width1 + CPW - 1) / CPW;
-    const bool has_left = g > 0, has_right = g + 1 < nstrips;
-    // memory block of a row: image columns [xb, xb + ncols); pass column j <-> block column (DIR > 0 ? j : ncols - 1 - j)
-    const int xb = DIR > 0 ? u0 : max(width1 - u0 - CPW, 0);
-    unsigned char* wbase = vw_smem + (size_t)warp * WB;
-    unsigned char* Cbuf = wbase;                           // [2][rowb]
-    unsigned char* Sbuf = wbase + 2 * rowb;                // [2][rowb]
-    unsigned char* Lin = Sbuf + 2 * rowb;                  // [2][2 * slot]: {H vector, H min, A vector, A min} from the left neighbour
-    unsigned char* Rin = Lin + 2 * 2 * slot;               // [2][slot]: {B vector, B min} from the right neighbour
-    unsigned char* Hrow = Rin + 2 * slot + 128;            // LAST only: [rowb] the horizontal path's costs of the current row
-    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(Rin + 2 * slot);
-    // bars + 8 i: 0-1 row landed (TMA) | 2-3 left slot full | 4-5 right slot full | 6-7 my outgoing left-edge slot (in the
-    // right neighbour) free | 8-9 my outgoing right-edge slot (in the left neighbour) free
-    const uint32_t bar_tma = bars, bar_lf = bars + 16, bar_rf = bars + 32, bar_le = bars + 48, bar_re = bars + 64;
-    const char* Cg = (const char*)a.C[job];
-    char* Sg = (char*)a.S[job];
-    const int uniq = a.uniq[job], minD = a.minD[job], minX1 = a.minX1[job];
-    int16_t* rawg = a.raw[job];
-    unsigned* d2g = a.d2[job];
-    const unsigned dkey = (unsigned)(lane * 2 * NP);
-    const unsigned dpair = dkey | ((dkey + 1u) << 8);
-
-    if (lane == 0) {
-        // a slot is filled either by plain stores + one arrive (same CTA) or by st.async bytes + the consumer's own
-        // expect_tx arrive (neighbour CTA): one arrival per phase in both cases
-        for (int i = 0; i < 10; i++) vw_mbar_init(bars + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    cluster.sync();  // every warp's barriers exist before a neighbour signals them
-
-    // where the edges go
-    const bool left_remote = warp == 0 && rank > 0;                   // my left neighbour lives in the previous CTA
-    const bool right_remote = warp == VW_WARPS - 1 && rank < CL - 1;  // my right neighbour lives in the next CTA
-    constexpr uint32_t OFF_LIN = 4 * rowb, OFF_RIN = 4 * rowb + 4 * slot, OFF_BARS = 4 * rowb + 6 * slot;
-    // outgoing left-edge data (H, A) -> right neighbour's Lin; outgoing right-edge data (B) -> left neighbour's Rin.
-    // All as shared-window addresses: the same 32-bit arithmetic serves local (shared::cta) and remote (shared::cluster).
-    uint32_t outL = 0, outL_bar = 0, outR = 0, outR_bar = 0;   // neighbour's slot + its "full" barrier
-    uint32_t left_free_bar = 0, right_free_bar = 0;            // neighbour's "my outgoing slot is free" barriers (what I signal)
-    const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
-    if (has_right) {
-        const uint32_t nb = right_remote ? vw_mapa((uint32_t)__cvta_generic_to_shared(vw_smem), (uint32_t)(rank + 1)) : wbase_s + WB;
-        outL = nb + OFF_LIN; outL_bar = nb + OFF_BARS + 16; right_free_bar = nb + OFF_BARS + 64;
-    }
-    if (has_left) {
-        const uint32_t nb = left_remote ? vw_mapa((uint32_t)__cvta_generic_to_shared(vw_smem) + (VW_WARPS - 1) * WB, (uint32_t)(rank - 1))
-                                        : wbase_s - WB;
-        outR = nb + OFF_RIN; outR_bar = nb + OFF_BARS + 32; left_free_bar = nb + OFF_BARS + 48;
-    }
-
-    auto load_row = [&](int it) {  // lane 0: C (and S) of my columns of the it-th processed row into stage it & 1
-        const int row = DIR > 0 ? it : H - 1 - it;
-        const uint32_t bytes = (uint32_t)ncols * B;
-        const uint32_t bar = bar_tma + 8 * (it & 1);
-        const size_t off = ((size_t)row * width1 + xb) * B;
-        vw_mbar_expect_tx(bar, LAST ? 2 * bytes : bytes);
-        vw_bulk_g2s((uint32_t)__cvta_generic_to_shared(Cbuf + (it & 1) * rowb), Cg + off, bytes, bar);
-        if (LAST) vw_bulk_g2s((uint32_t)__cvta_generic_to_shared(Sbuf + (it & 1) * rowb), Sg + off, bytes, bar);
-    };
-    const bool active = ncols > 0;
-    if (active && lane == 0) {
-        load_row(0);
-        if (H > 1) load_row(1);
-    }
-
-    // path state: A = diagonal fed from the left neighbour column, V = vertical, Bp = diagonal fed from the right
-    uint32_t LA[CPW][NP], LV[CPW][NP], LB[CPW][NP];
-    uint32_t mA[CPW], mV[CPW], mB[CPW];
-#pragma unroll
-    for (int j = 0; j < CPW; j++) {
-#pragma unroll
-        for (int k = 0; k < NP; k++) { LA[j][k] = 0; LV[j][k] = 0; LB[j][k] = 0; }
-        mA[j] = 0; mV[j] = 0; mB[j] = 0;
-    }
-    const uint32_t p1x2 = (uint32_t)a.P1 * 0x10001u;
-    const uint32_t k2 = (0x10000u - (uint32_t)a.P2) * 0x10001u;
-    const SgmLane sl = sgm_lane_init(lane, a.zero);
-    // block column (in vectors of the warp: x 32 lanes) of pass column j
-    int jbr[FULL ? 1 : CPW];
-    if (!FULL) {
-#pragma unroll
-        for (int j = 0; j < CPW; j++) jbr[FULL ? 0 : j] = j < ncols ? (DIR > 0 ? j : ncols - 1 - j) : 0;
-    }
-    auto JB = [&](int j) -> int { return FULL ? (DIR > 0 ? j : CPW - 1 - j) : jbr[FULL ? 0 : j]; };
-    auto valid = [&](int j) -> bool { return FULL || j < ncols; };
-
-    // one row; ST = it & 1.  Pass 1 unrolls the row loop by two (ST a compile-time value).  The last pass keeps ONE copy of
-    // its longer body: two copies (42 KB of code, 16 warps per SM all at different places of it) ran with 13 % of the
-    // stall samples on instruction fetch (profiles/r2_vwave_kernels.md).
-    auto do_row = [&](const int it, auto st_tag) {
-        const int ST = st_tag.get();
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);      // phase of the it-th use of a double-buffered resource
-        vw_mbar_wait(bar_tma + 8 * ST, ph);
-        const vec* cs = (const vec*)(Cbuf + ST * rowb) + lane;   // cs[JB(j) * 32]: pass column j
-        vec* ss = (vec*)(Sbuf + ST * rowb) + lane;
-        vec* hs = (vec*)(LAST ? Hrow : Sbuf + ST * rowb) + lane;  // where the horizontal path parks its costs
-        uint32_t Cw[NP];
-        // ---- left edge in
-        uint32_t LH[NP], mH = 0, inA[NP], inAm = 0;
-#pragma unroll
-        for (int k = 0; k < NP; k++) { LH[k] = 0; inA[k] = 0; }
-        if (has_left) {
-            const uint32_t hb = bar_lf + 8 * ST;
-            if (left_remote) {
-                if (lane == 0) vw_mbar_expect_tx(hb, 2 * (B + 4u));
-                __syncwarp();
-            }
-            vw_mbar_wait(hb, ph);
-            const unsigned char* q = Lin + ST * 2 * slot;
-            vw_unpack<NP>(*(const vec*)(q + lane * sizeof(vec)), LH);
-            mH = *(const uint32_t*)(q + B);
-            vw_unpack<NP>(*(const vec*)(q + slot + lane * sizeof(vec)), inA);
-            inAm = *(const uint32_t*)(q + slot + B);
-            __syncwarp();
-            // the "slot free" arrive carries a (zero) term computed from what was just read: it cannot issue before the
-            // loads have returned, which is all the relaxed remote form needs
-            const uint32_t dep = (LH[0] | inA[0] | mH | inAm) & sl.zero;
-            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(left_free_bar + 8 * ST + dep, rel_arrive); else vw_mbar_arrive(left_free_bar + 8 * ST); }
-        }
-        // ---- horizontal path: along the row through my columns
-#pragma unroll
-        for (int j = 0; j < CPW; j++) {
-            vw_unpack<NP>(cs[JB(j) * 32], Cw);
-            mH = sgm_step<NP>(LH, LH, mH, Cw, p1x2, k2, sl);
-            if (valid(j)) hs[JB(j) * 32] = vw_pack<NP>(LH);
-        }
-        // ---- left edge out
-        if (has_right) {
-            if (it >= 2) vw_mbar_wait(bar_le + 8 * ST, ph ^ 1u);
-            const uint32_t q = outL + ST * 2 * slot, rb = outL_bar + 8 * ST;
-            if (!right_remote) {
-                vw_st_local_vec<NP>(q + lane * (uint32_t)sizeof(vec), LH);
-                vw_st_local_vec<NP>(q + slot + lane * (uint32_t)sizeof(vec), LA[CPW - 1]);
-                if (lane == 0) {
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + B), "r"(mH) : "memory");
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + slot + B), "r"(mA[CPW - 1]) : "memory");
-                }
-                __syncwarp();
-                if (lane == 0) vw_mbar_arrive(rb);
-            } else {
-                vw_st_async_vec<NP>(q + lane * (uint32_t)sizeof(vec), LH, rb);
-                vw_st_async_vec<NP>(q + slot + lane * (uint32_t)sizeof(vec), LA[CPW - 1], rb);
-                if (lane == 0) { vw_st_async(q + B, mH, rb); vw_st_async(q + slot + B, mA[CPW - 1], rb); }
-            }
-        }
-        // ---- B path, first column, and right edge out
-        vw_unpack<NP>(cs[JB(0) * 32], Cw);
-        mB[0] = sgm_step<NP>(LB[0], LB[1], mB[1], Cw, p1x2, k2, sl);
-        if (has_left && it + 1 < H) {
-            if (it >= 2) vw_mbar_wait(bar_re + 8 * ST, ph ^ 1u);        // the neighbour has read the slot's previous content
-            const uint32_t q = outR + ST * slot, rb = outR_bar + 8 * ST;
-            if (!left_remote) {
-                vw_st_local_vec<NP>(q + lane * (uint32_t)sizeof(vec), LB[0]);
-                if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + B), "r"(mB[0]) : "memory");
-                __syncwarp();
-                if (lane == 0) vw_mbar_arrive(rb);
-            } else {
-                vw_st_async_vec<NP>(q + lane * (uint32_t)sizeof(vec), LB[0], rb);
-                if (lane == 0) vw_st_async(q + B, mB[0], rb);
-            }
-        }
-        // ---- diagonal A (fed from the left): in place, right to left (column j reads column j-1's old state)
-#pragma unroll
-        for (int j = CPW - 1; j >= 1; j--) {
-            vw_unpack<NP>(cs[JB(j) * 32], Cw);
-            mA[j] = sgm_step<NP>(LA[j], LA[j - 1], mA[j - 1], Cw, p1x2, k2, sl);
-        }
-        vw_unpack<NP>(cs[JB(0) * 32], Cw);
-        mA[0] = sgm_step<NP>(LA[0], inA, inAm, Cw, p1x2, k2, sl);
-        // ---- diagonal B (fed from the right): in place, left to right; the last column needs the right neighbour's state
-#pragma unroll
-        for (int j = 1; j < CPW - 1; j++) {
-            vw_unpack<NP>(cs[JB(j) * 32], Cw);
-            mB[j] = sgm_step<NP>(LB[j], LB[j + 1], mB[j + 1], Cw, p1x2, k2, sl);
-        }
-        {
-            uint32_t inB[NP], inBm = 0;
-#pragma unroll
-            for (int k = 0; k < NP; k++) inB[k] = 0;
-            if (has_right && it > 0) {  // B state of the neighbour's first column after row it - 1 (stage ST ^ 1)
-                const uint32_t hb = bar_rf + 8 * (ST ^ 1);
-                if (right_remote) {
-                    if (lane == 0) vw_mbar_expect_tx(hb, B + 4u);
-                    __syncwarp();
-                }
-                vw_mbar_wait(hb, (uint32_t)(((it - 1) >> 1) & 1));
-                const unsigned char* q = Rin + (ST ^ 1) * slot;
-                vw_unpack<NP>(*(const vec*)(q + lane * sizeof(vec)), inB);
-                inBm = *(const uint32_t*)(q + B);
-                __syncwarp();
-                const uint32_t dep = (inB[0] | inBm) & sl.zero;
-                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(right_free_bar + 8 * (ST ^ 1) + dep, rel_arrive); else vw_mbar_arrive(right_free_bar + 8 * (ST ^ 1)); }
-            }
-            vw_unpack<NP>(cs[JB(CPW - 1) * 32], Cw);
-            mB[CPW - 1] = sgm_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, sl);
-        }
-        if (!FULL && ncols < CPW) {
-            // columns outside the volume: their state must read as "no predecessor" (0) for the last valid column
-#pragma unroll
-            for (int j = 0; j < CPW; j++) {
-                if (j >= ncols) {
-#pragma unroll
-                    for (int k = 0; k < NP; k++) LB[j][k] = 0;
-                    mB[j] = 0;
-                }
-            }
-        }
-        // ---- vertical path + S row
-        unsigned wkey = 0xffffffffu;
-        bool wrej = false;
-#pragma unroll
-        for (int j = 0; j < CPW; j++) {
-            vw_unpack<NP>(cs[JB(j) * 32], Cw);
-            mV[j] = sgm_step<NP>(LV[j], LV[j], mV[j], Cw, p1x2, k2, sl);
-            uint32_t Sw[NP], Hw[NP];
-            vw_unpack<NP>(hs[JB(j) * 32], Hw);
-            if (LAST) vw_unpack<NP>(ss[JB(j) * 32], Sw);
-#pragma unroll
-            for (int k = 0; k < NP; k++) {
-                uint32_t s3 = __viaddmin_u16x2(LA[j][k], LB[j][k], INF);
-                const uint32_t s4 = __viaddmin_u16x2(LV[j][k], Hw[k], INF);
-                s3 = __viaddmin_u16x2(s3, s4, INF);
-                Sw[k] = LAST ? __viaddmin_u16x2(Sw[k], s3, INF) : s3;
-            }
-            if (valid(j)) ss[JB(j) * 32] = vw_pack<NP>(Sw);  // columns outside the volume alias block column 0: never stored
-            if (LAST) {
-                unsigned key = 0xffffffffu;
-#pragma unroll
-                for (int k = 0; k < NP; k++) {
-                    const unsigned dk = dpair + 0x0202u * (unsigned)k;
-                    key = min(key, min(__byte_perm(Sw[k], dk, 0x7104), __byte_perm(Sw[k], dk, 0x7325)));
-                }
-                key = __reduce_min_sync(0xffffffffu, key);
-                bool rej = false;
-                if (uniq > 0) rej = vw_not_unique<NP>(vw_pack<NP>(Sw), key, uniq, dkey);
-                if (lane == j) { wkey = key; wrej = rej; }
-            }
-        }
-        if (LAST) {
-            __syncwarp();
-            const int u = u0 + lane;                                   // pass column of lane's pixel
-            const int minS = (int)(wkey >> 8), d = (int)(wkey & 255u);
-            if (lane < ncols && minS < 32767 && !wrej) {
-                const int y = DIR > 0 ? it : H - 1 - it;
-                const int x = DIR > 0 ? u : width1 - 1 - u;
-                const int x2 = x + minX1 - d - minD;
-                if (x2 >= 0 && x2 < a.W + 2)
-                    atomicMax(d2g + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
-                int dd = d * 16;
-                if (0 < d && d < 64 * NP - 1) {
-                    const int jbl = DIR > 0 ? lane : ncols - 1 - lane;
-                    const uint16_t* Sp = (const uint16_t*)(Sbuf + ST * rowb + (size_t)jbl * B);
-                    const int sm = Sp[d - 1], sp = Sp[d + 1];
-                    const int denom2 = max(sm + sp - 2 * minS, 1);
-                    dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
-                }
-                rawg[(size_t)y * a.W + x + minX1] = (int16_t)(dd + minD * 16);
-            }
-        }
-        // ---- S row out (first pass), next-but-one row in
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-            if (!LAST) {
-                const int row = DIR > 0 ? it : H - 1 - it;
-                vw_bulk_s2g(Sg + ((size_t)row * width1 + xb) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + ST * rowb), (uint32_t)ncols * B);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // the other stage's store (row it - 1) must have read its buffer before row it + 1 writes into it
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            }
-            if (it + 2 < H) load_row(it + 2);
-        }
-        __syncwarp();
-    };
-    if (active) {
-        if (UNROLL2) {
-            int it = 0;
-            for (; it + 1 < H; it += 2) {
-                do_row(it, VwStageCt<0>());
-                do_row(it + 1, VwStageCt<1>());
-            }
-            if (it < H) do_row(it, VwStageCt<0>());
-        } else {
-#pragma unroll 1
-            for (int it = 0; it < H; it++) do_row(it, VwStageRt{it & 1});
-        }
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    cluster.sync();  // no CTA exits while a neighbour may still write into its shared memory or signal its barriers
-}
-
+// geometry -> (CTAs per cluster, columns per warp).  D <= 128: 16 warps per CTA, 2..9 columns per warp, the smallest of an
+// 8- or a 16-CTA cluster that covers width1; D = 256: 8 warps per CTA, 16-CTA cluster, 10..13 columns per warp (narrower
+// volumes stay on the other kernels: the instantiations are expensive)
 static bool vwave_shape(int width1, int D, int& cluster, int& cpw) {
+    if (D == 256) {
+        const int c = cdiv(width1, 16 * vwave_warps(D));
+        if (c < 10 || c > VW_MAXCPW256 || vwave_smem_bytes(D, c, true) > 227 * 1024) return false;
+        cluster = 16; cpw = c;
+        return true;
+    }
     if (!(D == 64 || D == 128)) return false;
     for (int cl = 8; cl <= 16; cl *= 2) {
-        const int c = cdiv(width1, cl * VW_WARPS);
+        const int c = cdiv(width1, cl * vwave_warps(D));
         if (c <= VW_MAXCPW && c >= 2 && vwave_smem_bytes(D, c, true) <= 227 * 1024) { cluster = cl; cpw = c; return true; }
     }
     return false;
@@ -493,7 +33,9 @@ bool vwave_supported(int width1, int H, int D) {
 // per strip) do not shrink with the strips, and at D=64 the bytes the other kernels move twice are half as many.
 bool vwave_pays(int width1, int H, int D) {
     int cl, cpw;
-    return width1 >= 1 && H >= 1 && vwave_shape(width1, D, cl, cpw) && D == 128 && cpw >= 4;
+    if (!(width1 >= 1 && H >= 1 && vwave_shape(width1, D, cl, cpw))) return false;
+    if (D == 256) return true;   // config 4 (13 columns per warp): see DESIGN.md for the measurement
+    return D == 128 && cpw >= 4;
 }
 
 // Aggregate four paths of pass `dir` for `njobs` volumes at once; wta != nullptr: last pass (S is read, accumulated,
@@ -502,6 +44,7 @@ int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njob
                    int P2, int dir, const VGroupWta* wta) {
     int cl = 0, cpw = 0;
     L3D_ARG(L, H >= 1 && vwave_shape(width1, D, cl, cpw), "vwave geometry");
+    L3D_ARG(L, (dir > 0) == (wta == nullptr), "vwave: pass 1 runs top-down without the WTA, pass 2 bottom-up with it");
     for (int j0 = 0; j0 < njobs; j0 += VW_MAXJOBS) {
         VWaveArgs a;
         const int nj = std::min(VW_MAXJOBS, njobs - j0);
@@ -516,40 +59,16 @@ int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njob
         static const int vw_flags = getenv("L3D_VW_FLAGS") ? atoi(getenv("L3D_VW_FLAGS")) : 0;
         a.W = wta ? wta[0].W : 0; a.zero = 0; a.flags = vw_flags;
         a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir; a.cluster = cl;
-        L3D_ARG(L, (dir > 0) == (wta == nullptr), "vwave: pass 1 runs top-down without the WTA, pass 2 bottom-up with it");
-        const size_t smem = vwave_smem_bytes(D, cpw, wta != nullptr);
-        const bool full = width1 % cpw == 0;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(cl, nj);
-        cfg.blockDim = dim3(VW_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = L.stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        const bool last = wta != nullptr, full = width1 % cpw == 0;
+        const size_t smem = vwave_smem_bytes(D, cpw, last);
         int rc = L3D_ERR_UNSUPPORTED;
-#define VW_LAUNCH(KERN)                                                                                               \
-    {                                                                                                                 \
-        L3D_CHECK(L, cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-        L3D_CHECK(L, cudaFuncSetAttribute(KERN, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));                  \
-        if (!dbg_skip("sgbm_vwave_kernel")) L3D_CHECK(L, cudaLaunchKernelEx(&cfg, KERN, a));                          \
-        L.launches++;                                                                                                 \
-        rc = L3D_OK;                                                                                                  \
-    }
-#define VW_CASE(NPV, CPWV)                                                                                            \
-    if (D == 64 * NPV && cpw == CPWV) {                                                                               \
-        if (wta && full) VW_LAUNCH((sgbm_vwave_kernel<NPV, CPWV, true, true>))                                        \
-        else if (wta) VW_LAUNCH((sgbm_vwave_kernel<NPV, CPWV, true, false>))                                          \
-        else if (full) VW_LAUNCH((sgbm_vwave_kernel<NPV, CPWV, false, true>))                                         \
-        else VW_LAUNCH((sgbm_vwave_kernel<NPV, CPWV, false, false>))                                                  \
-    }
+        if (D == 256) rc = vwave_launch_256(L, a, cpw, nj, last, full, smem);
+#define VW_CASE(NPV, CPWV) else if (D == 64 * NPV && cpw == CPWV) rc = vwave_launch_shape<NPV, CPWV, 16>(L, a, nj, last, full, smem);
 #define VW_NP(NPV) VW_CASE(NPV, 2) VW_CASE(NPV, 3) VW_CASE(NPV, 4) VW_CASE(NPV, 5) VW_CASE(NPV, 6) VW_CASE(NPV, 7) \
                    VW_CASE(NPV, 8) VW_CASE(NPV, 9)
         VW_NP(1) VW_NP(2)
 #undef VW_NP
 #undef VW_CASE
-#undef VW_LAUNCH
         if (rc != L3D_OK) return rc;
     }
     return L3D_OK;
