@@ -53,11 +53,11 @@ CONFIGS = {
                cpu_frames_per_core=8,
                workload="c3: 1280x720 per eye, 128 disparities, block 9, SGBM MODE_HH (left+right matcher) + WLS(8000,1.5) "
                         "+ ImprovedSteger sigma 3 + reconstruct_from_depth"),
-    "c4": dict(W=1920, H=1080, D=256, BS=11, MODE=1, wls=True, extractor="improved", recon="depth", frames=256, lanes=14,
+    "c4": dict(W=1920, H=1080, D=256, BS=11, MODE=1, wls=True, extractor="improved", recon="depth", frames=256, lanes=21,
                cpu_frames_per_core=1,
                workload="c4: 1920x1080 per eye, 256 disparities, block 11, SGBM MODE_HH (left+right matcher) + WLS(8000,1.5) "
                         "+ ImprovedSteger sigma 3 + reconstruct_from_depth, 256 frames per GPU and step streamed through "
-                        "14 lanes of scratch volumes"),
+                        "21 lanes of scratch volumes"),
     "c5": dict(W=1280, H=720, D=128, BS=9, MODE=1, wls=True, extractor="improved", recon="depth", frames=112, lanes=28,
                cpu_frames_per_core=8, job_frames=4096,
                workload="c5: 4096 frames of c3 (1280x720, 128 disparities, block 9, MODE_HH + WLS + ImprovedSteger) sharded "
