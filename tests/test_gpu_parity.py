@@ -738,7 +738,8 @@ def test_pipeline_graph_replay_host_buffers(ctx):
 
 @pytest.mark.parametrize("W,H,D,bs", [(1100, 64, 128, 9), (437, 50, 64, 5), (300, 33, 64, 7), (1920, 40, 128, 9), (700, 30, 256, 5),
                                       (1920, 36, 256, 11), (1500, 30, 256, 5),  # these two: 8 warps x 13 / 10 columns, 16-CTA clusters
-                                      (1280, 720, 128, 9)])  # config 3 at full height: the wavefront kernel's fill, steady state and drain
+                                      (1280, 720, 128, 9),  # config 3 at full height: the wavefront kernel's fill, steady state and drain
+                                      (640, 5, 128, 5), (700, 3, 128, 5)])  # fewer rows than pipeline stages of the row loop
 @pytest.mark.parametrize("policy", [None, "1"])  # L3D_VWAVE: default = the wavefront kernel where it pays, 1 = wherever it applies
 def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs, policy):
     """Cluster-fused aggregation (MODE_HH at D <= 128: the two-pass wavefront kernel sgbm_vwave.cu, else sgbm_vgroup.cu) on
