@@ -782,6 +782,34 @@ def test_grouped_pipeline_ragged_geometry(ctx, W, H, D, bs, policy):
     assert (diff <= 1).mean() >= 0.999
 
 
+def test_grouped_pipeline_is_deterministic(ctx):
+    """The same frames through the grouped pipeline (wavefront aggregation: mbarrier hand-offs between skewed warps, relaxed
+    remote arrives, st.async slots) twelve times: every output bit equals the first run's.  (tools/stress_determinism.py is
+    the long form: config 3 / config 4 sizes, dozens of runs.)"""
+    W, H, D, bs = 640, 240, 128, 7
+    K, Q = synth.camera_model(W, H)
+    maps = synth.warp_maps(W, H, 0) + synth.warp_maps(W, H, 1)
+    frames = [synth.stereo_pair(W, H, D, 80 + s) for s in range(14)]
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    cfg = pipeline.make_pipeline_config(W, H, D, bs, 1, Q, K, extractor=N.STEGER_IMPROVED, lanes=14, max_points=8000)
+    fp = pipeline.FramePipeline(cfg, maps=maps, ctx=ctx)
+    try:
+        dl, dr = fp.upload(L), fp.upload(R)
+        first = None
+        for run in range(12):
+            fp.run_dev(dl, dr, len(frames))
+            got = [fp.fetch(i) for i in range(len(frames))]
+            if first is None:
+                first = got
+                continue
+            for i in range(len(frames)):
+                for k in ("disp16", "depth", "points_3d"):
+                    eq(first[i][k], got[i][k], "run %d frame %d %s vs run 0" % (run, i, k))
+    finally:
+        fp.close()
+
+
 @pytest.mark.parametrize("W,H,D,bs", [(640, 200, 128, 9), (437, 50, 64, 5)])
 def test_grouped_pipeline_without_wls_uniqueness(ctx, W, H, D, bs):
     """use_wls = False: one matcher per frame with the reference's own parameters (uniquenessRatio 10, disp12MaxDiff 1,
