@@ -980,7 +980,7 @@ int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg) {
         for (int s = 0; s < MAXSEG; s++) {
             wa.seg_vr0[s] = g.seg_vr0[s]; wa.seg_y0[s] = g.seg_y0[s]; wa.seg_rows[s] = g.seg_rows[s]; wa.seg_emit[s] = g.seg_emit[s];
         }
-        L.t_begin("sgbm_wta");
+        if (!r.wta_done) L.t_begin("sgbm_wta");   // (fused into the last aggregation pass otherwise: nothing to time here)
         if (r.wta_done) {
         } else if (g.mode != 2) {
             const int wgrid = cdiv(cdiv((long)g.HV * g.width1, 32), WTA_WARPS);
@@ -1006,7 +1006,7 @@ int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg) {
                 else L3D_LAUNCH(L, sgbm_wta_lean3_kernel<4>, wgrid, WTA_WARPS * 32, 0, wa);
             }
         }
-        L.t_end("sgbm_wta");
+        if (!r.wta_done) L.t_end("sgbm_wta");
         L3D_LAUNCH(L, sgbm_lrcheck_kernel, dim3(cdiv(g.width1, 128), H), 128, 0, r.raw, r.d2, W, H, g.minX1, g.maxX1, g.minD, g.d12);
         if (dbg) {
             const size_t nvol = (size_t)g.HV * g.width1 * g.D;
