@@ -56,8 +56,7 @@ int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njob
                 a.minX1[j] = wta[j0 + j].minX1; a.uniq[j] = wta[j0 + j].uniq;
             }
         }
-        static const int vw_flags = getenv("L3D_VW_FLAGS") ? atoi(getenv("L3D_VW_FLAGS")) : 0;
-        a.W = wta ? wta[0].W : 0; a.zero = 0; a.flags = vw_flags;
+        a.W = wta ? wta[0].W : 0; a.zero = 0;
         a.width1 = width1; a.H = H; a.D = D; a.P1 = P1; a.P2 = P2; a.dir = dir; a.cluster = cl;
         const bool last = wta != nullptr, full = width1 % cpw == 0;
         const size_t smem = vwave_smem_bytes(D, cpw, last);

@@ -40,7 +40,6 @@ struct VWaveArgs {
     int cluster;   // CTAs per cluster (= per job)
     int W;         // image width (WTA outputs)
     uint32_t zero; // 0, as a value the compiler cannot see (sgm_step.cuh)
-    int flags;     // experiment switches (L3D_VW_FLAGS): 1 = release-form remote arrives
     int16_t* raw[VW_MAXJOBS];
     unsigned* d2[VW_MAXJOBS];
     int minD[VW_MAXJOBS], minX1[VW_MAXJOBS], uniq[VW_MAXJOBS];
@@ -71,9 +70,8 @@ __device__ __forceinline__ void vw_mbar_arrive(uint32_t bar) {
 // LDS results are in registers, the warp has re-converged) and nothing it wrote has to become visible to the producer, so
 // the arrive is relaxed.  The release form costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive: the two
 // edge warps of a CTA spent half their time there and the whole wavefront ran at their pace (profiles/r2_vwave_kernels.md).
-__device__ __forceinline__ void vw_mbar_arrive_remote(uint32_t rbar, bool release) {
-    if (release) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-    else asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+__device__ __forceinline__ void vw_mbar_arrive_remote(uint32_t rbar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
 __device__ __forceinline__ void vw_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -197,7 +195,6 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int width1 = a.width1, H = a.H;
-    const bool rel_arrive = (a.flags & 1) != 0;
     const int g = rank * VW_WARPS + warp;                  // strip number, left to right in pass coordinates
     const int u0 = g * CPW;                                // first column (pass coordinates) of this warp
     const int ncols = FULL ? (u0 < width1 ? CPW : 0) : max(0, min(CPW, width1 - u0));  // valid columns
@@ -324,7 +321,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
             // the "slot free" arrive carries a (zero) term computed from what was just read: it cannot issue before the
             // loads have returned, which is all the relaxed remote form needs
             const uint32_t dep = (LH[0] | inA[0] | mH | inAm) & sl.zero;
-            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(left_free_bar + 8 * SS + dep, rel_arrive); else vw_mbar_arrive(left_free_bar + 8 * SS); }
+            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(left_free_bar + 8 * SS + dep); else vw_mbar_arrive(left_free_bar + 8 * SS); }
         }
         // ---- horizontal path: along the row through my columns
         auto h_column = [&](const int jb, const bool ok) {   // jb: block column of the pass column; ok: it is inside the volume
@@ -417,7 +414,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
                 inBm = *(const uint32_t*)(q + B);
                 __syncwarp();
                 const uint32_t dep = (inB[0] | inBm) & sl.zero;
-                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(right_free_bar + 8 * SE + dep, rel_arrive); else vw_mbar_arrive(right_free_bar + 8 * SE); }
+                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(right_free_bar + 8 * SE + dep); else vw_mbar_arrive(right_free_bar + 8 * SE); }
             }
             vw_unpack<NP>(cs[JB(CPW - 1) * 32], Cw);
             mB[CPW - 1] = sgm_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, sl);
