@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         if (ROLLH) {
             // the chain touches no per-column registers, so it can be a real loop: D = 256 needs the instruction footprint
             // (the unrolled last pass was 48 KB of code and ran with 52 % of its stall samples on instruction fetch)
-#pragma unroll 1
+#pragma unroll 2
             for (int j = 0; j < CPW; j++) {
                 const bool ok = FULL || j < ncols;
                 const int jb = FULL ? (DIR > 0 ? j : CPW - 1 - j) : (ok ? (DIR > 0 ? j : ncols - 1 - j) : 0);
@@ -469,8 +469,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         if (LAST && ROLLH) {
             // winner-takes-all keys from the finished S row in shared memory, as a real loop (instruction footprint, see
             // the horizontal chain); every lane reads back what it stored itself
-#pragma unroll 1
-            for (int j = 0; j < (FULL ? CPW : ncols); j++) {
+#pragma unroll 4
+            for (int j = 0; j < (FULL ? CPW : ncols); j++) {   // (four columns in flight: the reductions overlap)
                 uint32_t Sw[NP];
                 vw_unpack<NP>(ss[(DIR > 0 ? j : (FULL ? CPW : ncols) - 1 - j) * 32], Sw);
                 wta_column(Sw, j);
