@@ -144,7 +144,7 @@ int dev_sgbm(Lane& L, const l3d_sgbm_params& p, const uint8_t* left, const uint8
 // cluster-fused aggregation of the three previous-row paths of one pass (sgbm_vgroup.cu)
 bool vgroup_supported(int width1, int H, int D);
 // per-job WTA outputs when a pass is the last one (nullptr array: S is written back instead)
-struct VGroupWta { int16_t* raw; unsigned* d2; int W, minD, minX1, uniq; };
+struct VGroupWta { int16_t* raw; unsigned* d2; int W, minD, minX1, uniq; uint2* rec = nullptr; };
 int dev_sgbm_vgroup(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
                     int P2, int dir, const VGroupWta* wta);
 // four paths per pass as a warp-skewed wavefront (sgbm_vwave.cu): wta == nullptr first pass (S written), else last pass

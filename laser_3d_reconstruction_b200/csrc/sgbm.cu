@@ -848,7 +848,9 @@ static int sgbm_front_begin(Lane& L, const l3d_sgbm_params& p, int W, int H, int
     const size_t nvol = (size_t)g.HV * g.width1 * g.D;
     r.C = L.get<int16_t>(set ? S_COST2 : S_COST, nvol);
     r.S = L.get<int16_t>(set ? S_AGGR2 : S_AGGR, nvol);
-    r.d2 = L.get<unsigned>(set ? S_DISP22 : S_DISP2, (size_t)H * (W + 2));
+    const size_t nd2 = ((size_t)H * (W + 2) + 1) & ~(size_t)1;   // vote words, padded so that the records behind them are 8-byte aligned
+    r.d2 = L.get<unsigned>(set ? S_DISP22 : S_DISP2, nd2 + 2 * (size_t)g.HV * g.width1);
+    r.wrec = (uint2*)(r.d2 + nd2);
     L3D_CHECK(L, cudaMemsetAsync(r.d2, 0, (size_t)H * (W + 2) * sizeof(unsigned), L.stream));
     return L3D_OK;
 }
@@ -1077,7 +1079,7 @@ int sgbm_middle_vwave(Lane& L, SgbmRun* const* runs, int nruns) {
                        runs[i]->W == runs[0]->W && runs[i]->no_hpair,
                 "vwave: runs of one launch must share geometry and penalties");
         Cp[i] = runs[i]->C; Sp[i] = runs[i]->S;
-        wta[i] = VGroupWta{runs[i]->raw, runs[i]->d2, runs[i]->W, h.minD, h.minX1, h.uniq};
+        wta[i] = VGroupWta{runs[i]->raw, runs[i]->d2, runs[i]->W, h.minD, h.minX1, h.uniq, runs[i]->wrec};
         runs[i]->wta_done = true;
     }
     L.t_begin("sgbm_vwave_down");

@@ -27,6 +27,7 @@ struct SgbmRun {
     int16_t* S = nullptr;
     int16_t* raw = nullptr;
     unsigned* d2 = nullptr;
+    uint2* wrec = nullptr;   // per-pixel winner records of the wavefront kernel's last pass (behind d2 in the same scratch slot)
     bool wta_done = false;
     bool no_hpair = false;  // the horizontal paths are aggregated by the wavefront kernel (sgbm_vwave.cu), not in the front
 };

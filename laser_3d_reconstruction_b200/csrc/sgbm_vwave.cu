@@ -38,6 +38,39 @@ bool vwave_pays(int width1, int H, int D) {
     return D == 128 && cpw >= 4;
 }
 
+// The per-pixel tail of the winner-takes-all for all volumes of a last-pass launch: disp2 vote (order-independent atomicMax
+// key, sgbm.cu), OpenCV's sub-pixel step with its truncating division, raw disparity.  One thread per pixel over the dense
+// records the last pass left.
+struct VWaveFinishArgs {
+    const uint2* rec[VW_MAXJOBS];
+    int16_t* raw[VW_MAXJOBS];
+    unsigned* d2[VW_MAXJOBS];
+    int minD[VW_MAXJOBS], minX1[VW_MAXJOBS];
+    int width1, H, D, W;
+};
+__global__ void __launch_bounds__(256) vw_finish_kernel(const VWaveFinishArgs a) {
+    const int job = blockIdx.y;
+    const int n = a.width1 * a.H;
+    const int minD = a.minD[job], minX1 = a.minX1[job];
+    const uint2* __restrict__ recs = a.rec[job];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint2 rec = recs[i];
+        if (rec.x == 0xffffffffu) continue;
+        const int y = i / a.width1, x = i - y * a.width1;
+        const int minS = (int)(rec.x >> 8), d = (int)(rec.x & 255u);
+        const int x2 = x + minX1 - d - minD;
+        if (x2 >= 0 && x2 < a.W + 2)
+            atomicMax(a.d2[job] + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
+        int dd = d * 16;
+        if (0 < d && d < a.D - 1) {
+            const int sm = (int)(rec.y & 0xffffu), sp = (int)(rec.y >> 16);
+            const int denom2 = max(sm + sp - 2 * minS, 1);
+            dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
+        }
+        a.raw[job][(size_t)y * a.W + x + minX1] = (int16_t)(dd + minD * 16);
+    }
+}
+
 // Aggregate four paths of pass `dir` for `njobs` volumes at once; wta != nullptr: last pass (S is read, accumulated,
 // reduced by the winner-takes-all and NOT written back), else first pass (S is written, not read).
 int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njobs, int width1, int H, int D, int P1,
@@ -50,10 +83,10 @@ int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njob
         const int nj = std::min(VW_MAXJOBS, njobs - j0);
         for (int j = 0; j < nj; j++) {
             a.C[j] = C[j0 + j]; a.S[j] = S[j0 + j];
-            a.raw[j] = nullptr; a.d2[j] = nullptr; a.minD[j] = 0; a.minX1[j] = 0; a.uniq[j] = 0;
+            a.rec[j] = nullptr; a.uniq[j] = 0;
             if (wta) {
-                a.raw[j] = wta[j0 + j].raw; a.d2[j] = wta[j0 + j].d2; a.minD[j] = wta[j0 + j].minD;
-                a.minX1[j] = wta[j0 + j].minX1; a.uniq[j] = wta[j0 + j].uniq;
+                L3D_ARG(L, wta[j0 + j].rec != nullptr, "vwave: the last pass needs a record buffer");
+                a.rec[j] = wta[j0 + j].rec; a.uniq[j] = wta[j0 + j].uniq;
             }
         }
         a.W = wta ? wta[0].W : 0; a.zero = 0;
@@ -69,6 +102,15 @@ int dev_sgbm_vwave(Lane& L, const int16_t* const* C, int16_t* const* S, int njob
 #undef VW_NP
 #undef VW_CASE
         if (rc != L3D_OK) return rc;
+        if (wta) {
+            VWaveFinishArgs f;
+            for (int j = 0; j < nj; j++) {
+                f.rec[j] = wta[j0 + j].rec; f.raw[j] = wta[j0 + j].raw; f.d2[j] = wta[j0 + j].d2;
+                f.minD[j] = wta[j0 + j].minD; f.minX1[j] = wta[j0 + j].minX1;
+            }
+            f.width1 = width1; f.H = H; f.D = D; f.W = a.W;
+            L3D_LAUNCH(L, vw_finish_kernel, dim3(std::min(cdiv(width1 * H, 256 * 4), 1024), nj), 256, 0, f);
+        }
     }
     return L3D_OK;
 }

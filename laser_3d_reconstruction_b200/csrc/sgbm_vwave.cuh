@@ -40,9 +40,8 @@ struct VWaveArgs {
     int cluster;   // CTAs per cluster (= per job)
     int W;         // image width (WTA outputs)
     uint32_t zero; // 0, as a value the compiler cannot see (sgm_step.cuh)
-    int16_t* raw[VW_MAXJOBS];
-    unsigned* d2[VW_MAXJOBS];
-    int minD[VW_MAXJOBS], minX1[VW_MAXJOBS], uniq[VW_MAXJOBS];
+    uint2* rec[VW_MAXJOBS];   // last pass: per-pixel winner records [H][width1] for vw_finish_kernel
+    int uniq[VW_MAXJOBS];
 };
 
 // shared memory per warp: C rows [2][CPW * B], S rows [2][CPW * B], left-edge slots [2][2 * (B + 16)], right-edge slots
@@ -214,9 +213,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
     const uint32_t bar_tma = bars, bar_lf = bars + 16, bar_rf = bars + 32, bar_le = bars + 48, bar_re = bars + 64;
     const char* Cg = (const char*)a.C[job];
     char* Sg = (char*)a.S[job];
-    const int uniq = a.uniq[job], minD = a.minD[job], minX1 = a.minX1[job];
-    int16_t* rawg = a.raw[job];
-    unsigned* d2g = a.d2[job];
+    const int uniq = a.uniq[job];
+    uint2* recg = a.rec[job];
     const unsigned dkey = (unsigned)(lane * 2 * NP);
     const unsigned dpair = dkey | ((dkey + 1u) << 8);
 
@@ -477,24 +475,22 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
             }
         }
         if (LAST) {
+            // One record per finished pixel: the winner key and the two S neighbours of the minimum.  The disp2 vote, the
+            // sub-pixel division and the store of the raw disparity are vw_finish_kernel's job (one thread per pixel): here
+            // 9 of 32 lanes ran ~100 dependent instructions per row, 19 % of the pass's stall samples.
             __syncwarp();
-            const int u = u0 + lane;                                   // pass column of lane's pixel
-            const int minS = (int)(wkey >> 8), d = (int)(wkey & 255u);
-            if (lane < ncols && minS < 32767 && !wrej) {
+            if (lane < ncols) {
+                const int u = u0 + lane;                               // pass column of lane's pixel
                 const int y = DIR > 0 ? it : H - 1 - it;
                 const int x = DIR > 0 ? u : width1 - 1 - u;
-                const int x2 = x + minX1 - d - minD;
-                if (x2 >= 0 && x2 < a.W + 2)
-                    atomicMax(d2g + (size_t)y * (a.W + 2) + x2, ((unsigned)(0x7fff - minS) << 16) | (unsigned)x);
-                int dd = d * 16;
-                if (0 < d && d < 64 * NP - 1) {
+                const int d = (int)(wkey & 255u);
+                uint2 rec = make_uint2(0xffffffffu, 0u);
+                if ((wkey >> 8) < 32767u && !wrej) {
                     const int jbl = DIR > 0 ? lane : ncols - 1 - lane;
                     const uint16_t* Sp = (const uint16_t*)(Sbuf + ST * rowb + (size_t)jbl * B);
-                    const int sm = Sp[d - 1], sp = Sp[d + 1];
-                    const int denom2 = max(sm + sp - 2 * minS, 1);
-                    dd += ((sm - sp) * 16 + denom2) / (denom2 * 2);
+                    rec = make_uint2(wkey, (unsigned)Sp[max(d - 1, 0)] | ((unsigned)Sp[min(d + 1, 64 * NP - 1)] << 16));
                 }
-                rawg[(size_t)y * a.W + x + minX1] = (int16_t)(dd + minD * 16);
+                recg[(size_t)y * width1 + x] = rec;
             }
         }
         // ---- S row out (first pass), next-but-one row in
