@@ -49,10 +49,13 @@ struct VWaveArgs {
 // D = 256: the neighbour slots are single-buffered and the last pass adds the horizontal path's costs into the S row in
 // place (no row of its own), so that 8 warps x 4 row buffers of 13 x 512 bytes fit 227 KB
 static inline int vwave_warps(int D) { return D > 128 ? 8 : 16; }
+// distance of a warp's two stage blocks [C row | S row | 64 bytes of mbarriers | three neighbour slots] (see the kernel),
+// a multiple of 128 bytes so that both blocks' rows are aligned alike for the bulk copies
+__host__ __device__ constexpr uint32_t vwave_delta(uint32_t rowb, uint32_t slot) { return (2 * rowb + 64 + 3 * slot + 127u) & ~127u; }
 static inline size_t vwave_warp_bytes(int D, int cpw, bool last) {
-    const size_t B = (size_t)D * 2, row = (size_t)cpw * B, slot = B + 16;
-    if (D > 128) return 4 * row + 3 * slot + 128;
-    return 4 * row + (last ? row : 0) + 6 * slot + 128;
+    const uint32_t B = (uint32_t)D * 2, row = (uint32_t)cpw * B, slot = B + 16, delta = vwave_delta(row, slot);
+    if (D > 128) return ((size_t)delta + 2 * row + 64 + 127) & ~(size_t)127;   // single-buffered slots: block 1 is [C | S | barriers]
+    return 2 * (size_t)delta + (last ? row : 0);   // (rows are multiples of 128 bytes)
 }
 static inline size_t vwave_smem_bytes(int D, int cpw, bool last) { return vwave_warps(D) * vwave_warp_bytes(D, cpw, last) + 128; }
 
@@ -178,12 +181,18 @@ template <int NP, int CPW, bool LAST, bool FULL, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs a) {
     constexpr int VW_WARPS = NW;
     constexpr bool SB = NP > 2, HIP = NP > 2, ROLLH = NP > 2;
-    constexpr uint32_t NSS = SB ? 1 : 2;                   // stages of a neighbour slot
     typedef typename VwVec<NP>::T vec;
     constexpr uint32_t INF = 0x7fff7fffu;
     constexpr uint32_t B = 128u * NP;                      // bytes per pixel vector (D = 64 NP disparities)
     constexpr uint32_t rowb = (uint32_t)CPW * B, slot = B + 16;
-    constexpr uint32_t WB = 4 * rowb + (LAST && !HIP ? rowb : 0) + 3 * NSS * slot + 128;  // shared memory per warp
+    // Shared memory of a warp: two STAGE BLOCKS a fixed distance DELTA apart, each [C row | S row | 5 mbarriers | Lin: H slot,
+    // A slot | Rin slot], so that every address that depends on the stage of a row is (one register: block base) + (a
+    // compile-time offset) -- with the stage as a register (one copy of the row body) the addresses cost one toggle per
+    // row instead of a multiply-add each.  Single-buffered slots (SB) live in block 0 only; block 1 is then [C | S | bars].
+    constexpr uint32_t O_C = 0, O_S = rowb, O_BAR = 2 * rowb, O_LIN = 2 * rowb + 64, O_RIN = O_LIN + 2 * slot;
+    constexpr uint32_t DELTA = vwave_delta(rowb, slot);
+    constexpr uint32_t WBS = SB ? ((DELTA + 2 * rowb + 64 + 127u) & ~127u) : 2 * DELTA;   // both blocks
+    constexpr uint32_t WB = WBS + (LAST && !HIP ? rowb : 0);                         // + the horizontal path's row
     constexpr int DIR = LAST ? -1 : 1;
     constexpr bool UNROLL2 = !LAST && NP <= 2;
     extern __shared__ __align__(128) unsigned char vw_smem[];
@@ -202,15 +211,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
     // memory block of a row: image columns [xb, xb + ncols); pass column j <-> block column (DIR > 0 ? j : ncols - 1 - j)
     const int xb = DIR > 0 ? u0 : max(width1 - u0 - CPW, 0);
     unsigned char* wbase = vw_smem + (size_t)warp * WB;
-    unsigned char* Cbuf = wbase;                           // [2][rowb]
-    unsigned char* Sbuf = wbase + 2 * rowb;                // [2][rowb]
-    unsigned char* Lin = Sbuf + 2 * rowb;                  // [NSS][2 * slot]: {H vector, H min, A vector, A min} from the left neighbour
-    unsigned char* Rin = Lin + NSS * 2 * slot;             // [NSS][slot]: {B vector, B min} from the right neighbour
-    unsigned char* Hrow = Rin + NSS * slot + 128;          // LAST && !HIP only: [rowb] the horizontal path's costs of the current row
-    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(Rin + NSS * slot);
-    // bars + 8 i: 0-1 row landed (TMA) | 2-3 left slot full | 4-5 right slot full | 6-7 my outgoing left-edge slot (in the
-    // right neighbour) free | 8-9 my outgoing right-edge slot (in the left neighbour) free
-    const uint32_t bar_tma = bars, bar_lf = bars + 16, bar_rf = bars + 32, bar_le = bars + 48, bar_re = bars + 64;
+    unsigned char* Hrow = wbase + WBS;                     // LAST && !HIP only: [rowb] the horizontal path's costs of the current row
+    // barriers of a block, at O_BAR: +0 row landed (TMA) | +8 left slot (Lin) full | +16 right slot (Rin) full | +24 my
+    // outgoing left-edge slot (in the right neighbour) free | +32 my outgoing right-edge slot (in the left neighbour) free
+    constexpr uint32_t B_TMA = O_BAR, B_LF = O_BAR + 8, B_RF = O_BAR + 16, B_LE = O_BAR + 24, B_RE = O_BAR + 32;
     const char* Cg = (const char*)a.C[job];
     char* Sg = (char*)a.S[job];
     const int uniq = a.uniq[job];
@@ -221,7 +225,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
     if (lane == 0) {
         // a slot is filled either by plain stores + one arrive (same CTA) or by st.async bytes + the consumer's own
         // expect_tx arrive (neighbour CTA): one arrival per phase in both cases
-        for (int i = 0; i < 10; i++) vw_mbar_init(bars + 8 * i, 1);
+        const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(wbase);
+        for (int i = 0; i < 5; i++) { vw_mbar_init(w0 + O_BAR + 8 * i, 1); vw_mbar_init(w0 + DELTA + O_BAR + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -230,30 +235,28 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
     // where the edges go
     const bool left_remote = warp == 0 && rank > 0;                   // my left neighbour lives in the previous CTA
     const bool right_remote = warp == VW_WARPS - 1 && rank < CL - 1;  // my right neighbour lives in the next CTA
-    constexpr uint32_t OFF_LIN = 4 * rowb, OFF_RIN = 4 * rowb + 2 * NSS * slot, OFF_BARS = 4 * rowb + 3 * NSS * slot;
     // outgoing left-edge data (H, A) -> right neighbour's Lin; outgoing right-edge data (B) -> left neighbour's Rin.
     // All as shared-window addresses: the same 32-bit arithmetic serves local (shared::cta) and remote (shared::cluster).
-    uint32_t outL = 0, outL_bar = 0, outR = 0, outR_bar = 0;   // neighbour's slot + its "full" barrier
-    uint32_t left_free_bar = 0, right_free_bar = 0;            // neighbour's "my outgoing slot is free" barriers (what I signal)
+    uint32_t nbR = 0, nbL = 0;   // block 0 of the right / left neighbour's shared memory (this CTA's or, mapped, the next one's)
     const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
     if (has_right) {
         const uint32_t nb = right_remote ? vw_mapa((uint32_t)__cvta_generic_to_shared(vw_smem), (uint32_t)(rank + 1)) : wbase_s + WB;
-        outL = nb + OFF_LIN; outL_bar = nb + OFF_BARS + 16; right_free_bar = nb + OFF_BARS + 64;
+        nbR = nb;   // its Lin (+ O_LIN) and Lin-full barrier (+ B_LF) take my {H, A}; its B_RE is where I signal "Rin slot read"
     }
     if (has_left) {
         const uint32_t nb = left_remote ? vw_mapa((uint32_t)__cvta_generic_to_shared(vw_smem) + (VW_WARPS - 1) * WB, (uint32_t)(rank - 1))
                                         : wbase_s - WB;
-        outR = nb + OFF_RIN; outR_bar = nb + OFF_BARS + 32; left_free_bar = nb + OFF_BARS + 48;
+        nbL = nb;   // its Rin (+ O_RIN) and Rin-full barrier (+ B_RF) take my B; its B_LE is where I signal "Lin slot read"
     }
 
     auto load_row = [&](int it) {  // lane 0: C (and S) of my columns of the it-th processed row into stage it & 1
         const int row = DIR > 0 ? it : H - 1 - it;
         const uint32_t bytes = (uint32_t)ncols * B;
-        const uint32_t bar = bar_tma + 8 * (it & 1);
+        const uint32_t blk = wbase_s + (uint32_t)(it & 1) * DELTA, bar = blk + B_TMA;
         const size_t off = ((size_t)row * width1 + xb) * B;
         vw_mbar_expect_tx(bar, LAST ? 2 * bytes : bytes);
-        vw_bulk_g2s((uint32_t)__cvta_generic_to_shared(Cbuf + (it & 1) * rowb), Cg + off, bytes, bar);
-        if (LAST) vw_bulk_g2s((uint32_t)__cvta_generic_to_shared(Sbuf + (it & 1) * rowb), Sg + off, bytes, bar);
+        vw_bulk_g2s(blk + O_C, Cg + off, bytes, bar);
+        if (LAST) vw_bulk_g2s(blk + O_S, Sg + off, bytes, bar);
     };
     const bool active = ncols > 0;
     if (active && lane == 0) {
@@ -294,23 +297,28 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         const uint32_t sph = SB ? (uint32_t)(it & 1) : ph;
         const bool reuse = SB ? it >= 1 : it >= 2;
         const uint32_t fph = sph ^ 1u;
-        vw_mbar_wait(bar_tma + 8 * ST, ph);
-        const vec* cs = (const vec*)(Cbuf + ST * rowb) + lane;   // cs[JB(j) * 32]: pass column j
-        vec* ss = (vec*)(Sbuf + ST * rowb) + lane;
-        vec* hs = (vec*)(LAST && !HIP ? Hrow : Sbuf + ST * rowb) + lane;  // where the horizontal path parks its costs
+        // block bases: this row's stage (C, S, TMA barrier), the slots' stage (SS), the stage of the right neighbour's previous
+        // row (SE, right edge in); the same offsets in the neighbours' shared memory
+        const uint32_t so = (uint32_t)ST * DELTA, sso = (uint32_t)SS * DELTA;
+        unsigned char* blk = wbase + so;
+        const uint32_t blk_s = wbase_s + so, sblk_s = wbase_s + sso;
+        vw_mbar_wait(blk_s + B_TMA, ph);
+        const vec* cs = (const vec*)(blk + O_C) + lane;   // cs[JB(j) * 32]: pass column j
+        vec* ss = (vec*)(blk + O_S) + lane;
+        vec* hs = (vec*)(LAST && !HIP ? Hrow : blk + O_S) + lane;  // where the horizontal path parks its costs
         uint32_t Cw[NP];
         // ---- left edge in
         uint32_t LH[NP], mH = 0, inA[NP], inAm = 0;
 #pragma unroll
         for (int k = 0; k < NP; k++) { LH[k] = 0; inA[k] = 0; }
         if (has_left) {
-            const uint32_t hb = bar_lf + 8 * SS;
+            const uint32_t hb = sblk_s + B_LF;
             if (left_remote) {
                 if (lane == 0) vw_mbar_expect_tx(hb, 2 * (B + 4u));
                 __syncwarp();
             }
             vw_mbar_wait(hb, sph);
-            const unsigned char* q = Lin + SS * 2 * slot;
+            const unsigned char* q = wbase + sso + O_LIN;
             vw_unpack<NP>(*(const vec*)(q + lane * sizeof(vec)), LH);
             mH = *(const uint32_t*)(q + B);
             vw_unpack<NP>(*(const vec*)(q + slot + lane * sizeof(vec)), inA);
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
             // the "slot free" arrive carries a (zero) term computed from what was just read: it cannot issue before the
             // loads have returned, which is all the relaxed remote form needs
             const uint32_t dep = (LH[0] | inA[0] | mH | inAm) & sl.zero;
-            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(left_free_bar + 8 * SS + dep); else vw_mbar_arrive(left_free_bar + 8 * SS); }
+            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(nbL + sso + B_LE + dep); else vw_mbar_arrive(nbL + sso + B_LE); }
         }
         // ---- horizontal path: along the row through my columns
         auto h_column = [&](const int jb, const bool ok) {   // jb: block column of the pass column; ok: it is inside the volume
@@ -348,8 +356,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         }
         // ---- left edge out
         if (has_right) {
-            if (reuse) vw_mbar_wait(bar_le + 8 * SS, fph);
-            const uint32_t q = outL + SS * 2 * slot, rb = outL_bar + 8 * SS;
+            if (reuse) vw_mbar_wait(sblk_s + B_LE, fph);
+            const uint32_t q = nbR + sso + O_LIN, rb = nbR + sso + B_LF;
             if (!right_remote) {
                 vw_st_local_vec<NP>(q + lane * (uint32_t)sizeof(vec), LH);
                 vw_st_local_vec<NP>(q + slot + lane * (uint32_t)sizeof(vec), LA[CPW - 1]);
@@ -369,8 +377,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         vw_unpack<NP>(cs[JB(0) * 32], Cw);
         mB[0] = sgm_step<NP>(LB[0], LB[1], mB[1], Cw, p1x2, k2, sl);
         if (has_left && it + 1 < H) {
-            if (reuse) vw_mbar_wait(bar_re + 8 * SS, fph);              // the neighbour has read the slot's previous content
-            const uint32_t q = outR + SS * slot, rb = outR_bar + 8 * SS;
+            if (reuse) vw_mbar_wait(sblk_s + B_RE, fph);                // the neighbour has read the slot's previous content
+            const uint32_t q = nbL + sso + O_RIN, rb = nbL + sso + B_RF;
             if (!left_remote) {
                 vw_st_local_vec<NP>(q + lane * (uint32_t)sizeof(vec), LB[0]);
                 if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + B), "r"(mB[0]) : "memory");
@@ -400,19 +408,19 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
 #pragma unroll
             for (int k = 0; k < NP; k++) inB[k] = 0;
             if (has_right && it > 0) {  // B state of the neighbour's first column after row it - 1 (its stage and phase)
-                const int SE = SB ? 0 : (ST ^ 1);
-                const uint32_t hb = bar_rf + 8 * SE;
+                const uint32_t seo = SB ? 0u : DELTA - so;   // the other stage's block
+                const uint32_t hb = wbase_s + seo + B_RF;
                 if (right_remote) {
                     if (lane == 0) vw_mbar_expect_tx(hb, B + 4u);
                     __syncwarp();
                 }
                 vw_mbar_wait(hb, SB ? (uint32_t)((it - 1) & 1) : (uint32_t)(((it - 1) >> 1) & 1));
-                const unsigned char* q = Rin + SE * slot;
+                const unsigned char* q = wbase + seo + O_RIN;
                 vw_unpack<NP>(*(const vec*)(q + lane * sizeof(vec)), inB);
                 inBm = *(const uint32_t*)(q + B);
                 __syncwarp();
                 const uint32_t dep = (inB[0] | inBm) & sl.zero;
-                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(right_free_bar + 8 * SE + dep); else vw_mbar_arrive(right_free_bar + 8 * SE); }
+                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(nbR + seo + B_RE + dep); else vw_mbar_arrive(nbR + seo + B_RE); }
             }
             vw_unpack<NP>(cs[JB(CPW - 1) * 32], Cw);
             mB[CPW - 1] = sgm_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, sl);
@@ -487,7 +495,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
                 uint2 rec = make_uint2(0xffffffffu, 0u);
                 if ((wkey >> 8) < 32767u && !wrej) {
                     const int jbl = DIR > 0 ? lane : ncols - 1 - lane;
-                    const uint16_t* Sp = (const uint16_t*)(Sbuf + ST * rowb + (size_t)jbl * B);
+                    const uint16_t* Sp = (const uint16_t*)(blk + O_S + (size_t)jbl * B);
                     rec = make_uint2(wkey, (unsigned)Sp[max(d - 1, 0)] | ((unsigned)Sp[min(d + 1, 64 * NP - 1)] << 16));
                 }
                 recg[(size_t)y * width1 + x] = rec;
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         if (lane == 0) {
             if (!LAST) {
                 const int row = DIR > 0 ? it : H - 1 - it;
-                vw_bulk_s2g(Sg + ((size_t)row * width1 + xb) * B, (uint32_t)__cvta_generic_to_shared(Sbuf + ST * rowb), (uint32_t)ncols * B);
+                vw_bulk_s2g(Sg + ((size_t)row * width1 + xb) * B, blk_s + O_S, (uint32_t)ncols * B);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 // the other stage's store (row it - 1) must have read its buffer before row it + 1 writes into it
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
