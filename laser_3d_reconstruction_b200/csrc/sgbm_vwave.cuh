@@ -100,6 +100,25 @@ __device__ __forceinline__ void vw_st_async(uint32_t raddr, uint32_t v, uint32_t
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                  ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
 }
+// One-lane operations as PREDICATED instructions instead of `if (lane == 0)` branches: a divergent region makes the whole warp
+// wait at its reconvergence point until lane 0's barrier instruction has gone through (measured: ~180 cycles per
+// `if (lane == 0) mbarrier.arrive`, six such regions per row); a predicated instruction is just issued.
+__device__ __forceinline__ void vw_mbar_arrive_if(uint32_t bar, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void vw_mbar_arrive_remote_if(uint32_t rbar, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(rbar), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void vw_mbar_expect_tx_if(uint32_t bar, uint32_t bytes, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void vw_st_async_if(uint32_t raddr, uint32_t v, uint32_t rbar, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n\t}"
+                 ::"r"(raddr), "r"(v), "r"(rbar), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void vw_st_shared_if(uint32_t addr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
 template <int NP> __device__ __forceinline__ void vw_st_async_vec(uint32_t raddr, const uint32_t (&v)[NP], uint32_t rbar);
 template <> __device__ __forceinline__ void vw_st_async_vec<1>(uint32_t raddr, const uint32_t (&v)[1], uint32_t rbar) {
     vw_st_async(raddr, v[0], rbar);
@@ -202,6 +221,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
     const int job = blockIdx.y;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    const bool lane0 = lane == 0;
     const int width1 = a.width1, H = a.H;
     const int g = rank * VW_WARPS + warp;                  // strip number, left to right in pass coordinates
     const int u0 = g * CPW;                                // first column (pass coordinates) of this warp
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
         if (has_left) {
             const uint32_t hb = sblk_s + B_LF;
             if (left_remote) {
-                if (lane == 0) vw_mbar_expect_tx(hb, 2 * (B + 4u));
+                vw_mbar_expect_tx_if(hb, 2 * (B + 4u), lane0);
                 __syncwarp();
             }
             vw_mbar_wait(hb, sph);
@@ -327,7 +347,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
             // the "slot free" arrive carries a (zero) term computed from what was just read: it cannot issue before the
             // loads have returned, which is all the relaxed remote form needs
             const uint32_t dep = (LH[0] | inA[0] | mH | inAm) & sl.zero;
-            if (lane == 0) { if (left_remote) vw_mbar_arrive_remote(nbL + sso + B_LE + dep); else vw_mbar_arrive(nbL + sso + B_LE); }
+            if (left_remote) vw_mbar_arrive_remote_if(nbL + sso + B_LE + dep, lane0); else vw_mbar_arrive_if(nbL + sso + B_LE, lane0);
         }
         // ---- horizontal path: along the row through my columns
         auto h_column = [&](const int jb, const bool ok) {   // jb: block column of the pass column; ok: it is inside the volume
@@ -361,16 +381,15 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
             if (!right_remote) {
                 vw_st_local_vec<NP>(q + lane * (uint32_t)sizeof(vec), LH);
                 vw_st_local_vec<NP>(q + slot + lane * (uint32_t)sizeof(vec), LA[CPW - 1]);
-                if (lane == 0) {
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + B), "r"(mH) : "memory");
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + slot + B), "r"(mA[CPW - 1]) : "memory");
-                }
+                vw_st_shared_if(q + B, mH, lane0);
+                vw_st_shared_if(q + slot + B, mA[CPW - 1], lane0);
                 __syncwarp();
-                if (lane == 0) vw_mbar_arrive(rb);
+                vw_mbar_arrive_if(rb, lane0);
             } else {
                 vw_st_async_vec<NP>(q + lane * (uint32_t)sizeof(vec), LH, rb);
                 vw_st_async_vec<NP>(q + slot + lane * (uint32_t)sizeof(vec), LA[CPW - 1], rb);
-                if (lane == 0) { vw_st_async(q + B, mH, rb); vw_st_async(q + slot + B, mA[CPW - 1], rb); }
+                vw_st_async_if(q + B, mH, rb, lane0);
+                vw_st_async_if(q + slot + B, mA[CPW - 1], rb, lane0);
             }
         }
         // ---- B path, first column, and right edge out
@@ -381,12 +400,12 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
             const uint32_t q = nbL + sso + O_RIN, rb = nbL + sso + B_RF;
             if (!left_remote) {
                 vw_st_local_vec<NP>(q + lane * (uint32_t)sizeof(vec), LB[0]);
-                if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(q + B), "r"(mB[0]) : "memory");
+                vw_st_shared_if(q + B, mB[0], lane0);
                 __syncwarp();
-                if (lane == 0) vw_mbar_arrive(rb);
+                vw_mbar_arrive_if(rb, lane0);
             } else {
                 vw_st_async_vec<NP>(q + lane * (uint32_t)sizeof(vec), LB[0], rb);
-                if (lane == 0) vw_st_async(q + B, mB[0], rb);
+                vw_st_async_if(q + B, mB[0], rb, lane0);
             }
         }
         // ---- diagonal A (fed from the left): in place, right to left (column j reads column j-1's old state)
@@ -411,7 +430,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
                 const uint32_t seo = SB ? 0u : DELTA - so;   // the other stage's block
                 const uint32_t hb = wbase_s + seo + B_RF;
                 if (right_remote) {
-                    if (lane == 0) vw_mbar_expect_tx(hb, B + 4u);
+                    vw_mbar_expect_tx_if(hb, B + 4u, lane0);
                     __syncwarp();
                 }
                 vw_mbar_wait(hb, SB ? (uint32_t)((it - 1) & 1) : (uint32_t)(((it - 1) >> 1) & 1));
@@ -420,7 +439,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sgbm_vwave_kernel(const VWaveArgs 
                 inBm = *(const uint32_t*)(q + B);
                 __syncwarp();
                 const uint32_t dep = (inB[0] | inBm) & sl.zero;
-                if (lane == 0) { if (right_remote) vw_mbar_arrive_remote(nbR + seo + B_RE + dep); else vw_mbar_arrive(nbR + seo + B_RE); }
+                if (right_remote) vw_mbar_arrive_remote_if(nbR + seo + B_RE + dep, lane0); else vw_mbar_arrive_if(nbR + seo + B_RE, lane0);
             }
             vw_unpack<NP>(cs[JB(CPW - 1) * 32], Cw);
             mB[CPW - 1] = sgm_step<NP>(LB[CPW - 1], inB, inBm, Cw, p1x2, k2, sl);
