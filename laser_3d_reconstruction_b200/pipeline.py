@@ -6,6 +6,7 @@ the GPUs of one box (no collective on the hot path; NCCL only gathers the point 
 """
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 
@@ -113,8 +114,19 @@ class FramePipeline:
         return np.frombuffer(counts, np.int32).copy()
 
     def run_host(self, left, right, depth_out=None, xyz_out=None):
-        """left/right: (n,H,W,3) uint8 host arrays (pinned for full overlap)."""
+        """left/right: (n,H,W,3) uint8 host arrays (pinned for full overlap); depth_out (n,H,W) float32 and
+        xyz_out (n,max_points,3) float64 are optional C-contiguous result buffers."""
         n = left.shape[0]
+        want = (n, self.cfg.H, self.cfg.W, 3)
+        for name, a in (("left", left), ("right", right)):
+            if a.dtype != np.uint8 or a.shape != want or not a.flags.c_contiguous:
+                raise N.L3DError("run_host: %s must be a C-contiguous uint8 array of shape %s" % (name, want))
+        if depth_out is not None and (depth_out.dtype != np.float32 or not depth_out.flags.c_contiguous
+                                      or depth_out.size < n * self.cfg.H * self.cfg.W):
+            raise N.L3DError("run_host: depth_out must be C-contiguous float32 with room for %d frames" % n)
+        if xyz_out is not None and (xyz_out.dtype != np.float64 or not xyz_out.flags.c_contiguous
+                                    or xyz_out.size < n * self.cfg.max_points * 3):
+            raise N.L3DError("run_host: xyz_out must be C-contiguous float64 with room for %d x max_points x 3" % n)
         counts = (C.c_int * n)()
         self.ctx.check(self.lib.l3d_pipeline_run_host(self.h, C.c_void_p(left.ctypes.data), C.c_void_p(right.ctypes.data), n,
                                                       C.c_void_p(depth_out.ctypes.data) if depth_out is not None else None,
@@ -178,19 +190,15 @@ class FramePipeline:
                        "l3d_pipeline_fetch_points")
         return (xy, xyz) if want_2d else xyz
 
-
-def _pack_points_dev(self, frame_ids, table_ptr):
-    """Pack the last run's point clouds into the caller's device table (rows frame_id,x,y,z; f64).
-    table_ptr: device pointer with room for sum(counts)*4 doubles.  Returns the number of rows."""
-    n = len(frame_ids)
-    ids = (C.c_int * n)(*[int(f) for f in frame_ids])
-    total = C.c_longlong(0)
-    self.ctx.check(self.lib.l3d_pipeline_pack_points_dev(self.h, n, ids, C.c_void_p(table_ptr), C.byref(total)),
-                   "l3d_pipeline_pack_points_dev")
-    return int(total.value)
-
-
-FramePipeline.pack_points_dev = _pack_points_dev
+    def pack_points_dev(self, frame_ids, table_ptr):
+        """Pack the last run's point clouds into the caller's device table (rows frame_id,x,y,z; f64).
+        table_ptr: device pointer with room for sum(counts)*4 doubles.  Returns the number of rows."""
+        n = len(frame_ids)
+        ids = (C.c_int * n)(*[int(f) for f in frame_ids])
+        total = C.c_longlong(0)
+        self.ctx.check(self.lib.l3d_pipeline_pack_points_dev(self.h, n, ids, C.c_void_p(table_ptr), C.byref(total)),
+                       "l3d_pipeline_pack_points_dev")
+        return int(total.value)
 
 
 def pinned_empty(shape, dtype):
@@ -202,12 +210,10 @@ def pinned_empty(shape, dtype):
     if not p:
         raise N.L3DError("pinned allocation of %d bytes failed" % nbytes)
     buf = (C.c_char * nbytes).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _PINNED.append((p, buf))  # page-locked blocks live until process exit
-    return arr
-
-
-_PINNED = []
+    # every view of the array keeps `buf` alive; the block is unpinned with the last one (not at interpreter exit:
+    # the CUDA runtime may be gone by then and the process is ending anyway)
+    weakref.finalize(buf, lib.l3d_host_free, p).atexit = False
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 from .sharding import shard_frames  # noqa: E402,F401  (frame-wise sharding)
