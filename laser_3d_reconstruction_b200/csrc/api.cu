@@ -5,6 +5,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "sgbm.cuh"
+#include "hostcopy.cuh"
 
 namespace l3d {
 
@@ -84,6 +85,7 @@ using namespace l3d;
 
 #define API_BEGIN(ctxp)                                                                    \
     if (!(ctxp)) return L3D_ERR_ARG;                                                       \
+    (ctxp)->stager->begin();                                                               \
     try {
 #define API_END(ctxp)                                                                      \
     } catch (const std::exception& ex) {                                                   \
@@ -150,12 +152,13 @@ int l3d_ctx_create(int device, l3d_ctx** out) {
     if (e != cudaSuccess) { set_err(&g_create_err, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return L3D_ERR_CUDA; }
     l3d_ctx* c = new l3d_ctx();
     c->device = device;
+    c->stager = new HostStager();
     c->lane.err = &c->err;
     e = cudaStreamCreateWithFlags(&c->lane.stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { set_err(&g_create_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return L3D_ERR_CUDA; }
+    if (e != cudaSuccess) { set_err(&g_create_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete c->stager; delete c; return L3D_ERR_CUDA; }
     e = cudaMalloc(&c->lane.flags, 16);
     if (e == cudaSuccess) e = cudaMemset(c->lane.flags, 0, 16);
-    if (e != cudaSuccess) { set_err(&g_create_err, "cudaMalloc: %s", cudaGetErrorString(e)); delete c; return L3D_ERR_CUDA; }
+    if (e != cudaSuccess) { set_err(&g_create_err, "cudaMalloc: %s", cudaGetErrorString(e)); delete c->stager; delete c; return L3D_ERR_CUDA; }
     *out = c;
     return L3D_OK;
 }
@@ -166,6 +169,7 @@ void l3d_ctx_destroy(l3d_ctx* ctx) {
     ctx->lane.release();
     if (ctx->lane.flags) cudaFree(ctx->lane.flags);
     for (auto& m : ctx->maps) if (m.map) cudaFree(m.map);
+    delete ctx->stager;
     delete ctx;
 }
 
@@ -180,12 +184,20 @@ int l3d_sync(l3d_ctx* ctx) {
 long long l3d_launch_count(l3d_ctx* ctx) { return ctx ? ctx->lane.launches : 0; }
 
 // ---- small helpers -----------------------------------------------------------------------
+// Host <-> device copies of the single-frame calls.  Large ones are staged through the context's page-locked arena with a
+// few copy threads (hostcopy.cuh); a staged d2h lands in the caller's memory in finish(), which every call ends with.
 static int h2d(l3d_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->lane.stream));
+    if (ctx->stager->wants(bytes)) CK(ctx, ctx->stager->h2d(dst, src, bytes, ctx->lane.stream));
+    else CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->lane.stream));
     return L3D_OK;
 }
 static int d2h(l3d_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->lane.stream));
+    if (ctx->stager->wants(bytes)) CK(ctx, ctx->stager->d2h(dst, src, bytes, ctx->lane.stream));
+    else CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->lane.stream));
+    return L3D_OK;
+}
+static int finish(l3d_ctx* ctx) {
+    CK(ctx, ctx->stager->finish(ctx->lane.stream));
     return L3D_OK;
 }
 static int set_maps(l3d_ctx* ctx, Lane& L, RectMap& m, const float* mapx, const float* mapy, int W, int H) {
@@ -228,7 +240,7 @@ int l3d_remap_gray(l3d_ctx* ctx, int eye, const uint8_t* src_bgr, int sw, int sh
     RC(dev_remap_gray(L, m, s, sw, sh, src_stride, r, g));
     if (rect_bgr) RC(d2h(ctx, rect_bgr, r, n * 3));
     if (gray) RC(d2h(ctx, gray, g, n));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -244,7 +256,7 @@ int l3d_bgr2gray(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray) 
     RC(h2d(ctx, s, bgr, n * 3));
     RC(dev_copy_gray(L, s, W, H, 3L * W, nullptr, g));
     RC(d2h(ctx, gray, g, n));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -283,7 +295,7 @@ int l3d_sgbm_debug(l3d_ctx* ctx, const l3d_sgbm_params* p, const uint8_t* left, 
     if (raw) RC(d2h(ctx, raw, dbg.raw, n * 2));
     if (C_out && dbg.C) RC(d2h(ctx, C_out, dbg.C, nvol * 2));
     if (S_out && dbg.S) RC(d2h(ctx, S_out, dbg.S, nvol * 2));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return check_flags(ctx, L.flags);
     API_END(ctx)
 }
@@ -314,7 +326,7 @@ int l3d_sgbm_compute_pair(l3d_ctx* ctx, const l3d_sgbm_params* pl, const l3d_sgb
     RC(sgbm_back(L, rr, dr, nullptr));
     RC(d2h(ctx, disp_left, dl, n * 2));
     RC(d2h(ctx, disp_right, dr, n * 2));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return check_flags(ctx, L.flags);
     API_END(ctx)
 }
@@ -347,7 +359,7 @@ static int cloud_op(l3d_ctx* ctx, const double* points, int n, double* out, int*
     if (op == 0) RC(dev_voxel_downsample(L, dp, n, a, f32, dout, &m));
     else RC(dev_outlier_removal(L, dp, n, k, a, dout, &m));
     if (m > 0) RC(d2h(ctx, out, dout, (size_t)m * 24));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     *n_out = m;
     return L3D_OK;
     API_END(ctx)
@@ -373,7 +385,7 @@ int l3d_init_undistort_rectify_map(l3d_ctx* ctx, const double* K, const double* 
     RC(dev_init_undistort_map(L, K, dist, ndist, iR, W, H, mx, my));
     RC(d2h(ctx, mapx, mx, n * 4));
     RC(d2h(ctx, mapy, my, n * 4));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -392,7 +404,7 @@ int l3d_bm_compute(l3d_ctx* ctx, const l3d_bm_params* p, const uint8_t* left, co
     RC(h2d(ctx, r, right, n));
     RC(dev_bm(L, *p, l, r, W, H, d));
     RC(d2h(ctx, disp, d, n * 2));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -443,7 +455,7 @@ int l3d_median3_s16(l3d_ctx* ctx, const int16_t* src, int W, int H, int16_t* dst
     RC(h2d(ctx, a, src, n * 2));
     RC(dev_median3(L, a, W, H, b));
     RC(d2h(ctx, dst, b, n * 2));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -458,7 +470,7 @@ int l3d_filter_speckles(l3d_ctx* ctx, int16_t* img, int W, int H, int newVal, in
     RC(h2d(ctx, a, img, n * 2));
     RC(dev_speckles(L, a, W, H, newVal, maxSize, maxDiff));
     RC(d2h(ctx, img, a, n * 2));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -481,7 +493,7 @@ int l3d_wls_filter(l3d_ctx* ctx, const l3d_wls_params* p, const int16_t* dl, con
     RC(dev_wls(L, *p, a, b, g, W, H, o, cf));
     RC(d2h(ctx, out, o, n * 2));
     if (conf_out) RC(d2h(ctx, conf_out, cf, n * 4));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -497,7 +509,7 @@ int l3d_disp_to_depth(l3d_ctx* ctx, const int16_t* disp16, int W, int H, const d
     RC(h2d(ctx, a, disp16, n * 2));
     RC(dev_depth(L, a, W, H, Q, d));
     RC(d2h(ctx, depth, d, n * 4));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -578,11 +590,17 @@ int l3d_compute_depth(l3d_ctx* ctx, const l3d_depth_config* cfg, const uint8_t* 
     int16_t* df = L.get<int16_t>(S_DISP_F, n);
     RC(h2d(ctx, sl, left_bgr, ns));
     RC(h2d(ctx, sr, right_bgr, ns));
-    RC(depth_path(L, *cfg, ctx->maps, sl, sr, W, H, stride, rl, dp, df));
+    // depth_path() with the rectified view sent back as soon as it exists: its DMA and the copy into the caller's array
+    // run under the matchers
+    DepthRuns dr;
+    RC(depth_front(L, *cfg, ctx->maps, sl, sr, W, H, stride, rl, dr));
     if (left_rect) RC(d2h(ctx, left_rect, rl, n * 3));
+    RC(sgbm_middle_split(L, dr.left, false));
+    if (dr.has_right) RC(sgbm_middle_split(L, dr.right, false));
+    RC(depth_back(L, *cfg, dr, W, H, dp, df));
     RC(d2h(ctx, depth, dp, n * 4));
     if (disp_out) RC(d2h(ctx, disp_out, df, n * 2));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return check_flags(ctx, L.flags);
     API_END(ctx)
 }
@@ -604,8 +622,8 @@ int l3d_simple_extract(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, const int
     RC(d2h(ctx, n, dn, sizeof(int)));
     if (mask_morph) RC(d2h(ctx, mask_morph, mm, np));
     if (mask_final) RC(d2h(ctx, mask_final, mm + np, np));
-    CK(ctx, cudaStreamSynchronize(L.stream));
-    if (*n > 0) { RC(d2h(ctx, xy, dxy, sizeof(double) * 2 * (size_t)*n)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    RC(finish(ctx));
+    if (*n > 0) { RC(d2h(ctx, xy, dxy, sizeof(double) * 2 * (size_t)*n)); RC(finish(ctx)); }
     return L3D_OK;
     API_END(ctx)
 }
@@ -623,9 +641,9 @@ int l3d_steger_extract(l3d_ctx* ctx, const l3d_steger_params* p, const uint8_t* 
     RC(h2d(ctx, s, img, nb));
     RC(dev_steger(L, *p, s, channels, W, H, dxy, cap, dn));
     RC(d2h(ctx, n, dn, sizeof(int)));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     int m = std::min(*n, cap);
-    if (m > 0) { RC(d2h(ctx, xy, dxy, sizeof(float) * 2 * (size_t)m)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    if (m > 0) { RC(d2h(ctx, xy, dxy, sizeof(float) * 2 * (size_t)m)); RC(finish(ctx)); }
     return L3D_OK;
     API_END(ctx)
 }
@@ -651,8 +669,8 @@ int l3d_reconstruct(l3d_ctx* ctx, const l3d_recon_params* p, const double* xy, i
     RC(h2d(ctx, dxy, xy, sizeof(double) * 2 * (size_t)n));
     RC(dev_recon(L, *p, dxy, nullptr, nullptr, n, dimg, W, H, dxyz, dn));
     RC(d2h(ctx, n_out, dn, sizeof(int)));
-    CK(ctx, cudaStreamSynchronize(L.stream));
-    if (*n_out > 0) { RC(d2h(ctx, xyz, dxyz, sizeof(double) * 3 * (size_t)*n_out)); CK(ctx, cudaStreamSynchronize(L.stream)); }
+    RC(finish(ctx));
+    if (*n_out > 0) { RC(d2h(ctx, xyz, dxyz, sizeof(double) * 3 * (size_t)*n_out)); RC(finish(ctx)); }
     return L3D_OK;
     API_END(ctx)
 }
@@ -671,7 +689,7 @@ int l3d_laser_depth_map(l3d_ctx* ctx, const double* xy, int n, const float* disp
     if (n > 0) RC(h2d(ctx, dxy, xy, sizeof(double) * 2 * (size_t)n));
     RC(dev_laser_depth_map(L, dxy, n, dimg, W, H, fx, baseline, dout));
     RC(d2h(ctx, out, dout, np * 4));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }
@@ -688,7 +706,7 @@ int l3d_colour_mask(l3d_ctx* ctx, const uint8_t* bgr, int W, int H, const int* h
     RC(h2d(ctx, s, bgr, np * 3));
     RC(dev_colour_mask(L, s, W, H, hsv_lo, hsv_hi, bright_thr, m));
     RC(d2h(ctx, mask, m, np));
-    CK(ctx, cudaStreamSynchronize(L.stream));
+    RC(finish(ctx));
     return L3D_OK;
     API_END(ctx)
 }

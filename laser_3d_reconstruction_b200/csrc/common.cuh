@@ -174,8 +174,10 @@ int dev_recon(Lane& L, const l3d_recon_params& p, const double* xy, const float*
 
 }  // namespace l3d
 
+namespace l3d { class HostStager; }
 struct l3d_ctx {
     int device = 0;
+    l3d::HostStager* stager = nullptr;  // staged host <-> device copies of the single-frame calls (hostcopy.cuh)
     unsigned* flags_host = nullptr;  // pinned mirror of lane.flags
     std::string err;
     l3d::Lane lane;
