@@ -237,7 +237,8 @@ int l3d_pipeline_run_dev(l3d_pipeline* p, const uint8_t* left_dev, const uint8_t
  * (nframes*H*W f32, optional), xyz (nframes*max_points*3 f64) and counts. */
 int l3d_pipeline_run_host(l3d_pipeline* p, const uint8_t* left, const uint8_t* right, int nframes,
                           float* depth, double* xyz, int* counts);
-/* fetch results of the last run for frame slot i (device -> host); any pointer may be NULL */
+/* fetch results of the last run for frame slot i (device -> host); any pointer may be NULL.  xy (f32 pairs) and xyz
+ * (f64 triples) must hold max_points entries; l3d_pipeline_fetch_points is the form with explicit capacities. */
 int l3d_pipeline_fetch(l3d_pipeline* p, int frame, uint8_t* left_rect, float* depth, int16_t* disp,
                        float* xy, double* xyz, int* n_xy, int* n_xyz);
 /* Laser points of frame slot i of the last run, with explicit capacities: up to xy_cap 2D centres (f64; the Simple
