@@ -16,22 +16,28 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #include <cuda_runtime.h>
 
 namespace l3d {
 
 class CopyPool {
   public:
-    explicit CopyPool(int nthreads) : workers_(nthreads > 1 ? nthreads - 1 : 0) {}
+    explicit CopyPool(int nthreads) : workers_(nthreads > 1 ? nthreads - 1 : 0), pid_(getpid()) {}
     ~CopyPool() {
         if (th_.empty()) return;
+        if (getpid() != pid_) {   // a fork()ed child: the worker threads do not exist here, nothing to join
+            new std::vector<std::thread>(std::move(th_));
+            return;
+        }
         { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
     // memcpy split over the calling thread and the workers; returns when every part is done
     void copy(void* dst, const void* src, size_t bytes) {
-        if (workers_ == 0 || bytes < kParallelMin) { memcpy(dst, src, bytes); return; }
+        if (workers_ == 0 || bytes < kParallelMin || getpid() != pid_) { memcpy(dst, src, bytes); return; }
         if (th_.empty()) for (int i = 0; i < workers_; i++) th_.emplace_back(&CopyPool::run, this, i + 1);
         const size_t parts = (size_t)workers_ + 1;
         part_ = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
@@ -68,6 +74,7 @@ class CopyPool {
         }
     }
     const int workers_;
+    const pid_t pid_;   // the process that owns the worker threads (they do not survive a fork)
     std::vector<std::thread> th_;
     std::mutex m_;
     std::condition_variable cv_;
