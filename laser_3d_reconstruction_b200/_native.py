@@ -4,6 +4,7 @@ There is NO CPU fallback: if the shared library is missing it is built with nvcc
 if no CUDA device is visible when a context is requested, an exception is raised.
 """
 import ctypes as C
+import itertools
 import os
 import threading
 
@@ -359,7 +360,7 @@ class Context:
         """ImprovedLaserReconstructor.create_laser_depth_map (improved_reconstruction.py:154-186)"""
         disp = _arr(disp, np.float32)
         H, W = disp.shape
-        xy = _arr(np.asarray(xy, np.float64).reshape(-1, 2), np.float64)
+        xy = _arr(points_to_array(xy), np.float64)
         out = np.empty((H, W), np.float32)
         self.check(self.lib.l3d_laser_depth_map(self.h, _ptr(xy) if len(xy) else None, len(xy), _ptr(disp), W, H,
                                                 C.c_double(fx), C.c_double(baseline), _ptr(out)), "l3d_laser_depth_map")
@@ -413,6 +414,25 @@ class Context:
 # A Context owns one stream and grow-only scratch buffers and is not thread-safe (include/l3d.h: one l3d_ctx per
 # (thread, GPU)), so the reference-API classes -- which share "the" context of their device -- get a separate one in
 # every thread that uses them (e.g. a capture thread next to a processing thread).
+def points_to_list(pts):
+    """(n, 2) array -> list of (x, y) tuples of Python floats, the reference extractors' return type.  Two column
+    `tolist()`s zipped: a third faster than building n two-element lists first (0.43 vs 0.63 ms for 4600 points)."""
+    a = np.asarray(pts, np.float64).reshape(-1, 2)
+    return list(zip(a[:, 0].tolist(), a[:, 1].tolist()))
+
+
+def points_to_array(points):
+    """list of (u, v) pairs (or anything array-like) -> (n, 2) float64.  A list of pairs is flattened by
+    `np.fromiter` over one chained iterator (about 2.5x faster than np.asarray on 4600 tuples)."""
+    if isinstance(points, (list, tuple)) and len(points) and isinstance(points[0], (tuple, list)):
+        try:
+            if set(map(len, points)) == {2}:   # every entry a pair: nothing can be mis-grouped by the flat iterator
+                return np.fromiter(itertools.chain.from_iterable(points), np.float64, 2 * len(points)).reshape(-1, 2)
+        except (TypeError, ValueError):
+            pass  # entries without a length or non-numeric: let numpy's own conversion raise or cope
+    return np.asarray(points, np.float64).reshape(-1, 2)
+
+
 _default = threading.local()
 
 

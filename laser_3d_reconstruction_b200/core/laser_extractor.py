@@ -43,14 +43,14 @@ class SimpleLaserExtractor:
         image = _check_image(image, allow_gray=False)
         pts = N.default_context(self.device).simple_extract(image, self.hsv_lower, self.hsv_upper,
                                                             self.brightness_threshold, self.min_area)
-        return list(map(tuple, np.asarray(pts, np.float64).tolist()))  # python floats, built at C speed
+        return N.points_to_list(pts)  # python floats, built at C speed
 
     def extract_masks(self, image: np.ndarray):
         """(mask after morphology :69, final contour mask :81-82, points) -- for parity tests."""
         image = _check_image(image, allow_gray=False)
         pts, m1, m2 = N.default_context(self.device).simple_extract(
             image, self.hsv_lower, self.hsv_upper, self.brightness_threshold, self.min_area, want_masks=True)
-        return m1, m2, list(map(tuple, np.asarray(pts, np.float64).tolist()))  # python floats, built at C speed
+        return m1, m2, N.points_to_list(pts)  # python floats, built at C speed
 
 
 class FastStegerExtractor:

@@ -34,7 +34,7 @@ class Reconstructor:
 
     @staticmethod
     def _points(laser_points):
-        return np.asarray(laser_points, np.float64).reshape(-1, 2)
+        return N.points_to_array(laser_points)
 
     def reconstruct_point(self, u: float, v: float) -> np.ndarray:
         """:30-70 -> [x, y, z], NaN when the ray misses the plane."""

@@ -35,7 +35,7 @@ class ImprovedLaserReconstructor:
         disp = np.asarray(disparity_map)
         if disp.ndim != 2:
             raise ValueError("disparity_map must be HxW")
-        xy = np.asarray(laser_points, np.float64).reshape(-1, 2)
+        xy = N.points_to_array(laser_points)
         out = N.default_context(self.device).reconstruct(self._params(kind, min_disparity, window), xy,
                                                          disp.astype(np.float32, copy=False))
         return out.astype(np.float32) if len(out) else np.array([])

@@ -25,7 +25,7 @@ class ImprovedStegerExtractor:
         image = _check_image(image, allow_gray=True)
         p = _steger_params(variant, self.sigma, self.brightness_threshold, self.response_threshold)
         pts = N.default_context(self.device).steger_extract(p, image)
-        return list(map(tuple, np.asarray(pts, np.float64).tolist()))  # python floats, built at C speed
+        return N.points_to_list(pts)  # python floats, built at C speed
 
     def extract_centerline(self, image: np.ndarray) -> List[Tuple[float, float]]:
         """improved_steger.py:39-126: every ridge pixel, raster order."""
@@ -57,4 +57,4 @@ class HybridLaserExtractor:
         p = _steger_params(N.STEGER_HYBRID, self.sigma, self.brightness_threshold, 0.5, None, self.hsv_lower,
                            self.hsv_upper)
         pts = N.default_context(self.device).steger_extract(p, image)
-        return list(map(tuple, np.asarray(pts, np.float64).tolist()))  # python floats, built at C speed
+        return N.points_to_list(pts)  # python floats, built at C speed

@@ -123,3 +123,30 @@ def test_shard_and_pack_roundtrip():
             for r in range(2)]
     back = sharding.unpack_clouds(np.concatenate(tabs), 5)
     assert all(np.array_equal(a, b) for a, b in zip(back, clouds))
+
+
+def test_point_list_conversions():
+    """The point lists the reference's API carries ([(x, y), ...]) <-> arrays: the fast conversions give what the plain
+    numpy ones give, for every input form a caller may hand over."""
+    from laser_3d_reconstruction_b200 import _native as N
+    rng = np.random.default_rng(3)
+    a32 = rng.random((500, 2), np.float32) * 1000
+    a64 = a32.astype(np.float64)
+    lst = N.points_to_list(a32)
+    assert lst == list(map(tuple, a64.tolist())) and type(lst[0]) is tuple and type(lst[0][0]) is float
+    assert N.points_to_list(np.empty((0, 2), np.float32)) == []
+    forms = [lst, [list(p) for p in lst], tuple(lst), [(x, y) for x, y in a32], a32, a64, a64.tolist(), a64[::2]]
+    for f in forms:
+        got = N.points_to_array(f)
+        want = np.asarray(f, np.float64).reshape(-1, 2)
+        assert got.dtype == np.float64 and got.shape == want.shape and np.array_equal(got, want)
+    assert N.points_to_array([]).shape == (0, 2)
+    assert np.array_equal(N.points_to_array([(1, 2)]), [[1.0, 2.0]])
+    mixed = [(1.0, 2.0), [3, 4.5], (np.float32(5.5), 6)]
+    assert np.array_equal(N.points_to_array(mixed), np.asarray(mixed, np.float64))
+    with pytest.raises((TypeError, ValueError)):
+        N.points_to_array([(1.0, 2.0), (3.0,), (4.0, 5.0)])   # ragged middle entry: numpy's own error, nothing silent
+    with pytest.raises((TypeError, ValueError)):
+        N.points_to_array([(1.0, 2.0), (3.0, 4.0, 5.0), (6.0,), (7.0, 8.0)])   # 2n values in all, but not n pairs
+    with pytest.raises((TypeError, ValueError)):
+        N.points_to_array([(1.0, "a"), (2.0, 3.0)])
