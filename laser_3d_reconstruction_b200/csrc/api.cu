@@ -1010,7 +1010,7 @@ int l3d_pipeline_set_maps(l3d_pipeline* p, int eye, const float* mapx, const flo
 }
 
 // Grouped mode: one aggregation launch should carry close to (but not more than) one wave of clusters --
-// 15 clusters of 8 CTAs are resident on a B200 (cudaOccupancyMaxActiveClusters) -- so a lane set is
+// 15 clusters of 8 CTAs (14 of 9) are resident on a B200 (cudaOccupancyMaxActiveClusters) -- so a lane set is
 // 7 frames with WLS (14 volumes) or 15 without; up to 4 sets alternate to overlap fronts/backs with
 // another set's aggregation.
 constexpr int VG_WAVE = 15;
