@@ -1,7 +1,53 @@
 // sgbm_vwave.cu -- host side of the wavefront aggregation (kernel: sgbm_vwave.cuh) and its D <= 128 instantiations
+#include <map>
+#include <mutex>
+
 #include "sgbm_vwave.cuh"
 
 namespace l3d {
+
+// How many clusters of `cluster` CTAs of the (last-pass) kernel can be resident at once on the current device
+// (cudaOccupancyMaxActiveClusters; cached per device and shape).  B200s differ in how their 148 SMs are spread over the
+// GPCs, and a cluster lives inside one GPC: a 20- or 18-SM GPC holds two 9-CTA clusters, a 16-SM GPC only one.
+template <int NP, int CPW>
+static int vwave_resident_query(int cluster, size_t smem) {
+    auto kern = sgbm_vwave_kernel<NP, CPW, true, true, 16>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster, VW_MAXJOBS);
+    cfg.blockDim = dim3(16 * 32);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+static int vwave_resident_clusters(int D, int cpw, int cluster) {
+    static std::mutex mu;
+    static std::map<long long, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const long long key = (((long long)dev * 512 + D) * 64 + cpw) * 64 + cluster;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const size_t smem = vwave_smem_bytes(D, cpw, true);
+    int n = 0;
+#define VW_Q(NPV, CPWV) if (D == 64 * NPV && cpw == CPWV) n = vwave_resident_query<NPV, CPWV>(cluster, smem);
+#define VW_QN(NPV) VW_Q(NPV, 2) VW_Q(NPV, 3) VW_Q(NPV, 4) VW_Q(NPV, 5) VW_Q(NPV, 6) VW_Q(NPV, 7) VW_Q(NPV, 8) VW_Q(NPV, 9)
+    VW_QN(1) VW_QN(2)
+#undef VW_QN
+#undef VW_Q
+    cache[key] = n;
+    return n;
+}
 
 // geometry -> (CTAs per cluster, columns per warp).  D <= 128: 16 warps per CTA, 2..9 columns per warp, a 9-CTA cluster
 // where it fits exactly (below), else the smallest of an 8- or a 16-CTA cluster that covers width1; D = 256: 8 warps per
@@ -27,7 +73,9 @@ static bool vwave_shape(int width1, int D, int& cluster, int& cpw) {
     // pipeline, whose other streams were using the 36 free SMs, is unchanged (1124 vs 1119 frames/s).
     if (forced == 0 && width1 % (9 * vwave_warps(D)) == 0) {
         const int c = width1 / (9 * vwave_warps(D));
-        if (c >= 2 && c < cdiv(width1, 8 * vwave_warps(D)) && c <= VW_MAXCPW && vwave_smem_bytes(D, c, true) <= 227 * 1024) {
+        // ... provided this GPU keeps a lane set's 14 volumes resident as 9-CTA clusters too (one wave per launch)
+        if (c >= 2 && c < cdiv(width1, 8 * vwave_warps(D)) && c <= VW_MAXCPW && vwave_smem_bytes(D, c, true) <= 227 * 1024 &&
+            vwave_resident_clusters(D, c, 9) >= 14) {
             cluster = 9; cpw = c;
             return true;
         }
