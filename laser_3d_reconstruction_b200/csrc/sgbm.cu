@@ -71,17 +71,25 @@ int make_geom(const l3d_sgbm_params& p, int W, int H, Geom& g, std::string* err)
         double t = 0.1 * stripe_sz; int ci = (int)t; if ((double)ci < t) ci++;
         int overlap = (g.bs / 2 + 1) + ci;
         g.nseg = 0; g.HV = 0;
+        for (int s = 0; s < MAXSEG; s++) g.seg_shift[s] = 0;
         for (int s = 0; s < nstripes; s++) {
             int y0 = std::max(std::min(s * stripe_sz - overlap, H), 0);
             int y1 = std::min((s + 1) * stripe_sz, H);
             if (y1 <= y0) continue;
             int i = g.nseg++;
             g.seg_vr0[i] = g.HV; g.seg_y0[i] = y0; g.seg_rows[i] = y1 - y0; g.seg_emit[i] = s * stripe_sz;
+            // OpenCV keeps every stripe in a buffer of its own (image row y at buffer row (s == 0 ? overlap : 0) + y - y0)
+            // and assembles output row i from buffer row overlap + i % stripe_sz of stripe i / stripe_sz.  Where the stripe
+            // start is clamped at the image top (s >= 1, s * stripe_sz < overlap: images of a few rows) the two do not meet:
+            // output row i shows the result of image row i + shift and the rows past the stripe end stay invalid.  Found by
+            // differential fuzzing of the oracle against cv2; restated in oracle/csrc/orc_sgbm.c.
+            g.seg_shift[i] = s >= 1 ? std::max(overlap - s * stripe_sz, 0) : 0;
             g.HV += y1 - y0;
         }
     } else {
         g.nseg = 1; g.HV = H;
         g.seg_vr0[0] = 0; g.seg_y0[0] = 0; g.seg_rows[0] = H; g.seg_emit[0] = 0;
+        for (int s = 0; s < MAXSEG; s++) g.seg_shift[s] = 0;
     }
     return L3D_OK;
 }
@@ -829,7 +837,8 @@ static void scan_args_of(const SgbmRun& r, ScanArgs& sa) {
     sa.raw = r.raw; sa.disp2key = r.d2; sa.W = r.W; sa.minD = g.minD; sa.minX1 = g.minX1; sa.uniq = g.uniq;
     sa.kind = 0; sa.store = 1; sa.lines_per_seg = 0; sa.zero = 0; sa.hp_mode = 0; sa.hp_row0 = 0;
     sa.tway = g.mode == 2;
-    for (int s = 0; s < MAXSEG; s++) { sa.seg_y0[s] = g.seg_y0[s]; sa.seg_emit[s] = g.seg_emit[s]; }
+    // (the winner-takes-all stage maps volume rows to OUTPUT rows: the stripe's first image row minus its shift, make_geom)
+    for (int s = 0; s < MAXSEG; s++) { sa.seg_y0[s] = g.seg_y0[s] - g.seg_shift[s]; sa.seg_emit[s] = g.seg_emit[s]; }
 }
 
 // front, first part: geometry, invalid-filled raw image, scratch volumes, disp2 vote buffer
@@ -980,7 +989,7 @@ int sgbm_back(Lane& L, SgbmRun& r, int16_t* disp, SgbmDebug* dbg) {
         wa.DPL = g.DPL; wa.minD = g.minD; wa.minX1 = g.minX1; wa.uniq = g.uniq; wa.mode = g.mode;
         wa.HV = g.HV; wa.nseg = g.nseg;
         for (int s = 0; s < MAXSEG; s++) {
-            wa.seg_vr0[s] = g.seg_vr0[s]; wa.seg_y0[s] = g.seg_y0[s]; wa.seg_rows[s] = g.seg_rows[s]; wa.seg_emit[s] = g.seg_emit[s];
+            wa.seg_vr0[s] = g.seg_vr0[s]; wa.seg_y0[s] = g.seg_y0[s] - g.seg_shift[s]; wa.seg_rows[s] = g.seg_rows[s]; wa.seg_emit[s] = g.seg_emit[s];
         }
         if (!r.wta_done) L.t_begin("sgbm_wta");   // (fused into the last aggregation pass otherwise: nothing to time here)
         if (r.wta_done) {

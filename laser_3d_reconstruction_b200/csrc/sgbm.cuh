@@ -13,6 +13,7 @@ struct Geom {
     int DPL, NP, nact;
     int HV, nseg;
     int seg_vr0[MAXSEG], seg_y0[MAXSEG], seg_rows[MAXSEG], seg_emit[MAXSEG];
+    int seg_shift[MAXSEG];  // SGBM_3WAY on images of a few rows: output row = computed row - shift (make_geom)
 };
 int make_geom(const l3d_sgbm_params& p, int W, int H, Geom& g, std::string* err);
 

@@ -321,6 +321,12 @@ static int sgbm_3way(const uint8_t* img1, const uint8_t* img2, int W, int H,
         int y0 = imax(imin(s * stripe_sz - overlap, H), 0);
         int y1 = imin((s + 1) * stripe_sz, H);
         int emit0 = s * stripe_sz;
+        /* OpenCV writes stripe s into a buffer of its own, image row y at buffer row (s == 0 ? overlap : 0) + (y - y0),
+         * and assembles output row i from buffer row overlap + i % stripe_sz of stripe i / stripe_sz.  When the stripe
+         * start is clamped at the image top (s >= 1 and s * stripe_sz < overlap: images of a few rows only) the two do
+         * not meet: output row i then shows the result of image row i + shift, rows past the stripe end stay invalid
+         * (found by differential fuzzing against cv2 4.13; stereosgbm.cpp SGBM3WayMainLoop / computeDisparity3WaySGBM). */
+        int shift = s >= 1 ? imax(overlap - s * stripe_sz, 0) : 0;
         if (y1 <= y0) continue;
         int16_t* C = (int16_t*)malloc(sizeof(int16_t) * row * (size_t)(y1 - y0));
         cost_volume(&cc, img1, img2, y0, y1, SW2, SH2, P2, C);
@@ -343,11 +349,11 @@ static int sgbm_3way(const uint8_t* img1, const uint8_t* img2, int W, int H,
                 int16_t* Hp = hor + (long)x * D;
                 for (int d = 0; d < D; d++) Hp[d] = (int16_t)sat16(La[d] + T[d]);
             }
-            if (y < emit0) {
+            if (y - shift < emit0) {
                 /* overlap rows: the right pass result is discarded, but nothing else depends on it */
                 continue;
             }
-            int16_t* d1 = disp + (long)y * W;
+            int16_t* d1 = disp + (long)(y - shift) * W;
             for (int x = 0; x < W; x++) { disp2[x] = (int16_t)INVALID_SCALED; disp2cost[x] = MAX_COST; }
             memset(La, 0, sizeof(int16_t) * D);
             int rightMin = 0;

@@ -314,6 +314,22 @@ def test_sgbm_properties_full_size(ctx):
     assert np.median(err) < 0.6  # the matcher recovers the rendered disparity field
 
 
+@pytest.mark.parametrize("bs,H", [(11, 8), (11, 20), (11, 24), (11, 28), (9, 20), (5, 12), (3, 8), (9, 5)])
+def test_sgbm_3way_tiny_images(ctx, bs, H):
+    """SGBM_3WAY on images of a few rows: OpenCV's shifted stripe rows (tests/test_oracle_cv2.py has the story) on the GPU,
+    through the stand-alone and the fused winner-takes-all."""
+    for D, W, seed in ((48, 194, 5), (16, 90, 9)):
+        lg, rg = gray_pair(W, H, D, seed)
+        for (uq, d12, sw) in ((0, 5, 200), (10, 1, 0)):
+            kw = dict(minDisparity=0, numDisparities=D, blockSize=bs, P1=100, P2=1000, disp12MaxDiff=d12, preFilterCap=63,
+                      uniquenessRatio=uq, speckleWindowSize=sw, speckleRange=2, mode=2)
+            want = cv2.StereoSGBM_create(**kw).compute(lg, rg)
+            p = N.SgbmParams(**kw)
+            eq(ctx.sgbm_compute(p, lg, rg), want, "3way tiny %s" % ((bs, H, D, uq),))
+            disp, raw = ctx.sgbm_compute(p, lg, rg, want_raw=True)
+            eq(disp, want, "3way tiny (S kept) %s" % ((bs, H, D, uq),))
+
+
 @pytest.mark.parametrize("H", [1, 2, 3, 5, 8])
 def test_sgbm_hh4_short_images(ctx, H):
     """MODE_HH4's constant bottom rows of C (oracle/csrc/orc_sgbm.c) on images shorter than the window."""

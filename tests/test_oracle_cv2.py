@@ -81,6 +81,19 @@ def test_sgbm_c1_and_saturation(mode):
     assert np.array_equal(cref.sgbm_compute(ln, rn, **kw), cv2.StereoSGBM_create(**kw).compute(ln, rn))
 
 
+@pytest.mark.parametrize("bs,H", [(11, 8), (11, 20), (11, 24), (11, 28), (9, 20), (7, 16), (5, 12), (3, 8), (5, 7), (9, 5)])
+def test_sgbm_3way_tiny_images(bs, H):
+    """SGBM_3WAY on images of a few rows: where a stripe's start is clamped at the image top (ceil(H / 4) < blockSize / 2 + 1
+    + ceil(0.1 ceil(H / 4))) OpenCV's stripe buffers and its final assembly do not meet and the output rows of that stripe
+    are the results of rows further down (found by differential fuzzing: tools/fuzz_oracle.py)."""
+    for D, W, seed in ((48, 194, 5), (16, 90, 9)):
+        lg, rg = gray_pair(W, H, D, seed)
+        for (uq, d12, sw) in ((0, 5, 200), (10, 1, 0)):
+            kw = dict(minDisparity=0, numDisparities=D, blockSize=bs, P1=100, P2=1000, disp12MaxDiff=d12, preFilterCap=63,
+                      uniquenessRatio=uq, speckleWindowSize=sw, speckleRange=2, mode=2)
+            assert np.array_equal(cref.sgbm_compute(lg, rg, **kw), cv2.StereoSGBM_create(**kw).compute(lg, rg)), (D, uq)
+
+
 @pytest.mark.parametrize("H", [1, 2, 3, 5, 8])
 def test_sgbm_hh4_short_images(H):
     """MODE_HH4 leaves the last blockSize/2 rows of the cost volume at P2 (no branch for window rows below the image
