@@ -10,6 +10,14 @@ One step cannot be repeated bit for bit: OpenCV first re-orthogonalises R with i
 rotation vector.  For a calibration file's R (orthonormal to ~1e-16) that changes the last bit or two of R1 / R2; the f32
 rectification maps built from the result are unchanged.  tests/test_oracle_cv2.py pins matrices (<= 1e-13), rectangles
 (==) and maps (==) against cv2 on the shipped calibration and on synthetic rigs.
+
+Differential fuzzing against cv2.stereoRectify over random rigs (4 / 5 / 8 / 12 / 14 distortion coefficients, horizontal and
+vertical baselines, every alpha; tools/fuzz_rectify.py, 2 400 rigs) pinned three more points: the OUTER rectangle spans the
+border points of the 9 x 9 grid only; points the inverse distortion model turns into NaN are skipped by OpenCV's MIN / MAX
+macros (and a rig that is NaN at the image corners yields NaN matrices and empty ROIs, as in cv2); coefficients 13 / 14 are
+the tilted-sensor model.  What cannot be pinned: at alpha = 0 one ROI edge lies exactly on the image border, so
+`ceil(0 +- 1e-14)` decides between (0, 0, w, h) and (0, 1, w, h - 1) on the last bits of R1 / R2 (about 1.5 % of random
+rigs differ from cv2 by that one pixel; the shipped calibration does not).
 """
 import numpy as np
 
@@ -78,9 +86,34 @@ def undistort_points(pts, K, dist, R=None, P=None, dtype=np.float32):
     if P is not None:
         P = np.asarray(P, np.float64)
         RR = P[:3, :3] @ RR
-    for i, (u, v) in enumerate(np.asarray(pts, dtype).astype(np.float64)):
+    pts64 = np.asarray(pts, dtype).astype(np.float64)
+    inv_tilt = _inv_tilt_matrix(k[12], k[13]) if (k[12] != 0 or k[13] != 0) else None
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):   # a folding model may overflow: NaN out, like cv2
+        _undistort_loop(pts64, out, k, cx, cy, ifx, ify, RR, inv_tilt)
+    return out
+
+
+def _inv_tilt_matrix(tau_x, tau_y):
+    """inverse of OpenCV's tilted-sensor projection (computeTiltProjectionMatrix; distortion coefficients 13 and 14)"""
+    cx_, sx_, cy_, sy_ = np.cos(tau_x), np.sin(tau_x), np.cos(tau_y), np.sin(tau_y)
+    rot_x = np.array([[1, 0, 0], [0, cx_, sx_], [0, -sx_, cx_]])
+    rot_y = np.array([[cy_, 0, -sy_], [0, 1, 0], [sy_, 0, cy_]])
+    rot_xy = rot_y @ rot_x
+    inv = 1.0 / rot_xy[2, 2]
+    inv_proj_z = np.array([[inv, 0, inv * rot_xy[0, 2]], [0, inv, inv * rot_xy[1, 2]], [0, 0, 1]])
+    return rot_xy.T @ inv_proj_z
+
+
+def _undistort_loop(pts64, out, k, cx, cy, ifx, ify, RR, inv_tilt=None):
+    for i, (u, v) in enumerate(pts64):
         x = (u - cx) * ifx
         y = (v - cy) * ify
+        if inv_tilt is not None:   # compensate the sensor tilt first
+            vx = inv_tilt[0, 0] * x + inv_tilt[0, 1] * y + inv_tilt[0, 2]
+            vy = inv_tilt[1, 0] * x + inv_tilt[1, 1] * y + inv_tilt[1, 2]
+            vz = inv_tilt[2, 0] * x + inv_tilt[2, 1] * y + inv_tilt[2, 2]
+            ip = 1.0 / vz if vz else 1.0
+            x, y = ip * vx, ip * vy
         x0, y0 = x, y
         for _ in range(5):
             r2 = x * x + y * y
@@ -97,7 +130,6 @@ def undistort_points(pts, K, dist, R=None, P=None, dtype=np.float32):
         ww = 1.0 / (RR[2, 0] * x + RR[2, 1] * y + RR[2, 2])
         out[i, 0] = xx * ww
         out[i, 1] = yy * ww
-    return out
 
 
 def _rectangles(K, dist, R, P, size):
@@ -107,10 +139,16 @@ def _rectangles(K, dist, R, P, size):
     w, h = size
     pts = np.array([[float(x) * (w - 1) / (N - 1), float(y) * (h - 1) / (N - 1)] for y in range(N) for x in range(N)], np.float64)
     u = undistort_points(pts, K, dist, R, P, dtype=np.float64).reshape(N, N, 2)
-    inner_x0, inner_x1 = u[:, 0, 0].max(), u[:, N - 1, 0].min()
-    inner_y0, inner_y1 = u[0, :, 1].max(), u[N - 1, :, 1].min()
-    outer_x0, outer_x1 = u[:, :, 0].min(), u[:, :, 0].max()
-    outer_y0, outer_y1 = u[:, :, 1].min(), u[:, :, 1].max()
+    # OpenCV folds the points in with MIN / MAX macros whose comparisons are false for a NaN operand, so a point the
+    # inverse distortion model cannot handle (it yields NaN there) is simply skipped
+    fmax, fmin = np.fmax.reduce, np.fmin.reduce
+    inner_x0, inner_x1 = fmax(u[:, 0, 0]), fmin(u[:, N - 1, 0])
+    inner_y0, inner_y1 = fmax(u[0, :, 1]), fmin(u[N - 1, :, 1])
+    # the outer rectangle spans the grid's BORDER points only (cv2 4.13; found by fuzzing against cv2.stereoRectify: with a
+    # distortion model that folds inside the image, interior grid points land far outside and would blow the rectangle up)
+    b = np.concatenate([u[0], u[N - 1], u[:, 0], u[:, N - 1]])
+    outer_x0, outer_x1 = fmin(b[:, 0]), fmax(b[:, 0])
+    outer_y0, outer_y1 = fmin(b[:, 1]), fmax(b[:, 1])
     inner = (inner_x0, inner_y0, inner_x1 - inner_x0, inner_y1 - inner_y0)
     outer = (outer_x0, outer_y0, outer_x1 - outer_x0, outer_y1 - outer_y0)
     return inner, outer
@@ -149,12 +187,13 @@ def stereo_rectify(K1, d1, K2, d2, size, R, T, flags=CALIB_ZERO_DISPARITY, alpha
         und = undistort_points(corners, A, Dk)  # f32 normalised points
         # cvProjectPoints2 with rotation Rk, zero translation, camera matrix diag(fc_new, fc_new, 1), no distortion -> f32
         proj = np.empty((4, 2), np.float32)
-        for i in range(4):
-            X = np.array([np.float64(und[i, 0]), np.float64(und[i, 1]), 1.0])
-            Y = Rk @ X
-            z = 1.0 / Y[2] if Y[2] != 0 else 1.0
-            proj[i, 0] = np.float32(Y[0] * z * fc_new)
-            proj[i, 1] = np.float32(Y[1] * z * fc_new)
+        with np.errstate(invalid="ignore", over="ignore"):   # NaN corners (a model that cannot be inverted there) pass through
+            for i in range(4):
+                X = np.array([np.float64(und[i, 0]), np.float64(und[i, 1]), 1.0])
+                Y = Rk @ X
+                z = 1.0 / Y[2] if Y[2] != 0 else 1.0
+                proj[i, 0] = np.float32(Y[0] * z * fc_new)
+                proj[i, 1] = np.float32(Y[1] * z * fc_new)
         avg = proj.astype(np.float64).sum(axis=0) / 4.0
         cc_new[k, 0] = (nx - 1) / 2 - avg[0]
         cc_new[k, 1] = (ny - 1) / 2 - avg[1]
@@ -194,6 +233,8 @@ def stereo_rectify(K1, d1, K2, d2, size, R, T, flags=CALIB_ZERO_DISPARITY, alpha
 
     def roi(inner, cx0, cy0, cx, cy):
         x, y, w, h = inner
+        if not np.all(np.isfinite([x, y, w, h, s, cx, cy, cx0, cy0])):
+            return (0, 0, 0, 0)   # a rig whose model cannot be inverted at the image corners: cv2 returns NaN matrices and empty ROIs
         x0, y0 = int(np.ceil((x - cx0) * s + cx)), int(np.ceil((y - cy0) * s + cy))
         w0, h0 = int(np.floor(w * s)), int(np.floor(h * s))
         xa, ya = max(x0, 0), max(y0, 0)

@@ -328,3 +328,49 @@ def test_stereo_rectify_vs_cv2(golden_real):
         got = stereo_rectify(Ka, da, Kb, db, (320, 240), Rm, Tm, flags=fl, alpha=0)
         assert all(rel(got[i], want[i]) < 1e-12 for i in range(5)), trial
         assert got[5] == tuple(want[5]) and got[6] == tuple(want[6])
+
+
+def test_stereo_rectify_random_rigs_vs_cv2():
+    """Random rigs (4 .. 14 distortion coefficients incl. the tilted-sensor pair, both baseline directions, every alpha,
+    strong distortion that folds inside the image): matrices <= 1e-11 relative, ROIs equal -- except at alpha = 0, where
+    an ROI edge sits exactly on the image border and the last bits of R1 / R2 decide between 0 and 1 (camera/rectify.py)."""
+    from laser_3d_reconstruction_b200.camera.rectify import stereo_rectify
+    rng = np.random.default_rng(11)
+    for it in range(60):
+        W, H = int(rng.choice([320, 640, 1280])), int(rng.choice([240, 480, 720]))
+        f = rng.uniform(0.6, 1.4) * W
+        Ks = [np.array([[f * rng.uniform(.97, 1.03), 0, W / 2 + rng.uniform(-20, 20)],
+                        [0, f * rng.uniform(.97, 1.03), H / 2 + rng.uniform(-20, 20)], [0, 0, 1]]) for _ in range(2)]
+        nd = int(rng.choice([4, 5, 8, 12, 14]))
+        ds = []
+        for _ in range(2):
+            d = np.zeros(nd)
+            d[0], d[1] = rng.uniform(-.3, .2), rng.uniform(-.1, .1)
+            d[2:4] = rng.uniform(-2e-3, 2e-3, 2)
+            if nd > 4:
+                d[4] = rng.uniform(-.05, .05)
+            if nd >= 8:
+                d[5:8] = rng.uniform(-.02, .02, 3)
+            if nd >= 12:
+                d[8:12] = rng.uniform(-1e-3, 1e-3, 4)
+            if nd >= 14:
+                d[12:14] = rng.uniform(-1e-2, 1e-2, 2)
+            ds.append(d)
+        R = cv2.Rodrigues(rng.uniform(-0.05, 0.05, 3))[0]
+        T = np.array([-rng.uniform(0.03, 0.2), rng.uniform(-0.005, 0.005), rng.uniform(-0.005, 0.005)])
+        if rng.random() < 0.25:
+            T = T[[1, 0, 2]]
+        flags = int(rng.choice([cv2.CALIB_ZERO_DISPARITY, 0]))
+        alpha = float(rng.choice([0, -1, 1, 0.5, 0.25]))
+        want = cv2.stereoRectify(Ks[0], ds[0], Ks[1], ds[1], (W, H), R, T, flags=flags, alpha=alpha)
+        got = stereo_rectify(Ks[0], ds[0], Ks[1], ds[1], (W, H), R, T, flags=flags, alpha=alpha)
+        for i in range(5):
+            if np.all(np.isfinite(want[i])):
+                assert np.abs(got[i] - want[i]).max() <= 1e-11 * max(np.abs(want[i]).max(), 1.0), (it, i)
+            else:
+                assert np.array_equal(np.isfinite(got[i]), np.isfinite(want[i])), (it, i)
+        for a, b in ((got[5], want[5]), (got[6], want[6])):
+            if alpha == 0:
+                assert all(abs(int(p) - int(q)) <= 1 for p, q in zip(a, b)), (it, a, tuple(b))
+            else:
+                assert tuple(a) == tuple(b), (it, a, tuple(b))
