@@ -374,3 +374,24 @@ def test_stereo_rectify_random_rigs_vs_cv2():
                 assert all(abs(int(p) - int(q)) <= 1 for p, q in zip(a, b)), (it, a, tuple(b))
             else:
                 assert tuple(a) == tuple(b), (it, a, tuple(b))
+
+
+def test_sgbm_random_parameter_sets_vs_cv2():
+    """A fixed-seed slice of tools/fuzz_oracle.py: random StereoSGBM parameter sets (all modes, both disparity signs, odd
+    penalties, preFilterCap / uniqueness / disp12MaxDiff / speckle settings) on random small images, oracle == cv2."""
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        D = int(rng.choice([16, 32, 48, 64, 96, 128]))
+        bs = int(rng.choice([1, 3, 5, 7, 9, 11]))
+        W, H = int(rng.integers(D + 20, D + 160)), int(rng.integers(8, 60))
+        minD = int(rng.choice([0, 0, -(D - 1), 3, -5, 16, -D // 2]))
+        P1 = int(rng.choice([24 * bs * bs, 8 * bs * bs, 10, 0, 100]))
+        P2 = max(int(rng.choice([96 * bs * bs, 32 * bs * bs, 200, 1000])), P1 + 1)
+        kw = dict(minDisparity=minD, numDisparities=D, blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=int(rng.choice([1, 0, -1, 2, 1000000, 5])),
+                  preFilterCap=int(rng.choice([63, 63, 31, 15, 1, 40])), uniquenessRatio=int(rng.choice([0, 10, 5, 15, 40])),
+                  speckleWindowSize=int(rng.choice([0, 100, 20, 200])), speckleRange=int(rng.choice([32, 1, 2, 16])),
+                  mode=int(rng.integers(0, 4)))
+        lg, rg = gray_pair(W, H, max(D, 16), int(rng.integers(0, 1000)), quant=int(rng.choice([0, 0, 8, 32])))
+        if rng.random() < 0.2:
+            lg, rg = rng.integers(0, 256, lg.shape, dtype=np.uint8), rng.integers(0, 256, rg.shape, dtype=np.uint8)
+        assert np.array_equal(cref.sgbm_compute(lg, rg, **kw), cv2.StereoSGBM_create(**kw).compute(lg, rg)), (it, W, H, kw)
