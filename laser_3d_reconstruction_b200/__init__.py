@@ -7,11 +7,11 @@ from .camera.single_usb_stereo_camera import SingleUSBStereoCameraManager
 from .config import Config
 from .core.laser_extractor import FastStegerExtractor, SimpleLaserExtractor
 from .core.reconstruction import Reconstructor
-from .improved_reconstruction import ImprovedLaserReconstructor, fix_roi_alignment
+from .improved_reconstruction import ImprovedLaserReconstructor, fix_roi_alignment, visualize_laser_depth
 from .improved_steger import HybridLaserExtractor, ImprovedStegerExtractor, StegerLaserExtractor
 from .system import LaserReconstructionSystem
 
 __version__ = "0.1.0"
 __all__ = ["SingleUSBStereoCameraManager", "SimpleLaserExtractor", "FastStegerExtractor", "ImprovedStegerExtractor",
            "StegerLaserExtractor", "HybridLaserExtractor", "Reconstructor", "ImprovedLaserReconstructor",
-           "fix_roi_alignment", "Config", "LaserReconstructionSystem"]
+           "fix_roi_alignment", "visualize_laser_depth", "Config", "LaserReconstructionSystem"]

@@ -46,3 +46,26 @@ class Config:
                 v = getattr(cls, key)
                 out[key] = v.tolist() if isinstance(v, np.ndarray) else v
         return out
+
+    @classmethod
+    def print_config(cls):
+        """reference config.py:114-147: the settings a run uses, by group, on stdout."""
+        rule = "=" * 60
+        groups = (
+            ("camera", (("id", cls.SINGLE_USB_CAMERA_ID), ("resolution", f"{cls.CAMERA_WIDTH}x{cls.CAMERA_HEIGHT}"),
+                        ("fps", cls.CAMERA_FPS), ("split mode", cls.SPLIT_MODE), ("calibration", cls.STEREO_CALIBRATION_FILE))),
+            ("stereo matching", (("disparities", cls.STEREO_NUM_DISPARITIES), ("block size", cls.STEREO_BLOCK_SIZE),
+                                 ("WLS filter", "on" if cls.STEREO_USE_WLS_FILTER else "off"))),
+            ("laser extraction", (("extractor", cls.LASER_EXTRACTOR_TYPE),) + (
+                (("HSV range", f"{cls.SIMPLE_LASER_HSV_LOWER} ~ {cls.SIMPLE_LASER_HSV_UPPER}"),
+                 ("brightness threshold", cls.SIMPLE_LASER_BRIGHTNESS_THRESHOLD)) if cls.LASER_EXTRACTOR_TYPE == 'simple' else
+                (("sigma", cls.STEGER_SIGMA), ("brightness threshold", cls.STEGER_BRIGHTNESS_THRESHOLD)))),
+            ("reconstruction", (("refraction correction", "on" if cls.USE_REFRACTION_CORRECTION else "off"),
+                                ("voxel size", cls.VOXEL_SIZE), ("output dir", cls.OUTPUT_DIR))),
+        )
+        print("\n" + rule + "\nlaser3d-b200 configuration (single USB stereo camera)\n" + rule)
+        for title, rows in groups:
+            print(f"\n{title}:")
+            for name, value in rows:
+                print(f"  {name}: {value}")
+        print(rule + "\n")

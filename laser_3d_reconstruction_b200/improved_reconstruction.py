@@ -73,3 +73,32 @@ def fix_roi_alignment(left_rect, right_rect, roi_left, roi_right):
     if x2 - x1 > 0 and y2 - y1 > 0:
         return left_rect[y1:y2, x1:x2], right_rect[y1:y2, x1:x2]
     return left_rect, right_rect
+
+
+def visualize_laser_depth(image, laser_points, depth_map, max_depth: float = 5.0):
+    """:230-279 -- host-side drawing for the demo windows: every laser point with a positive depth becomes a radius-2 dot in
+    the reference's four-segment colour ramp (near = blue-ish in BGR order, far = red-ish) on a copy of the image, and a
+    single pixel of a black image of the same size.  -> (vis, depth_colored)"""
+    import cv2
+    vis = image.copy()
+    h, w = image.shape[:2]
+    depth_colored = np.zeros((h, w, 3), dtype=np.uint8)
+    for x, y in laser_points:
+        px, py = int(round(x)), int(round(y))
+        if px < 0 or px >= w or py < 0 or py >= h:
+            continue
+        depth = depth_map[py, px]
+        if not depth > 0:
+            continue
+        t = np.clip(depth / max_depth, 0, 1)
+        if t < 0.25:
+            color = (255, int(t * 4 * 255), 0)
+        elif t < 0.5:
+            color = (int((0.5 - t) * 4 * 255), 255, 0)
+        elif t < 0.75:
+            color = (0, 255, int((t - 0.5) * 4 * 255))
+        else:
+            color = (0, int((1 - t) * 4 * 255), 255)
+        cv2.circle(vis, (px, py), 2, color, -1)
+        depth_colored[py, px] = color
+    return vis, depth_colored

@@ -57,3 +57,53 @@ class PointCloudProcessor:
         """The reference needs Open3D for PCD and otherwise writes PLY (:183-196); so does this."""
         print("需要Open3D才能保存PCD格式，改为保存PLY格式")
         self.save_ply(points, filename.replace('.pcd', '.ply'), colors)
+
+    # ---- the rest of the reference's public surface: host-side helpers around the two GPU calls ------------------
+    def estimate_normals(self, points: np.ndarray, radius: float = 0.01) -> np.ndarray:
+        """:216-237: an Open3D-only feature; without Open3D the reference says so and returns zeros."""
+        print("需要Open3D来计算法向量")
+        return np.zeros_like(points)
+
+    def compute_point_cloud_metrics(self, points: np.ndarray) -> dict:
+        """:239-278: count, centre, spread, bounding box, volume and the mean nearest-neighbour spacing (host numpy: a
+        report, not part of the per-frame path)."""
+        if len(points) == 0:
+            return {'num_points': 0, 'bbox': None, 'center': None, 'dimensions': None}
+        lo, hi = np.min(points, axis=0), np.max(points, axis=0)
+        metrics = {'num_points': len(points), 'center': np.mean(points, axis=0), 'std': np.std(points, axis=0),
+                   'min': lo, 'max': hi}
+        metrics['dimensions'] = hi - lo
+        metrics['volume'] = np.prod(metrics['dimensions'])
+        if len(points) > 1:
+            metrics['avg_point_spacing'] = _mean_nearest_neighbour_distance(np.asarray(points))
+        return metrics
+
+    def visualize(self, points: np.ndarray, colors: Optional[np.ndarray] = None, window_name: str = "3D Point Cloud"):
+        """:280-321: an Open3D viewer; without Open3D the reference prints the point count and returns."""
+        print("需要Open3D进行可视化")
+        print(f"点云包含 {len(points)} 个点")
+
+    def merge_and_clean(self, point_clouds: list, voxel_size: float = 0.002) -> np.ndarray:
+        """:323-349: stack the non-empty clouds, voxel down-sample, remove statistical outliers."""
+        if not point_clouds:
+            return np.array([])
+        merged = np.vstack([pc for pc in point_clouds if len(pc) > 0])
+        if len(merged) == 0:
+            return merged
+        return self.statistical_outlier_removal(self.voxel_downsample(merged, voxel_size))
+
+
+def _mean_nearest_neighbour_distance(points: np.ndarray) -> float:
+    """mean over the points of the distance to their nearest other point (the reference asks scipy's cKDTree for k = 2)"""
+    try:
+        from scipy.spatial import cKDTree
+        d, _ = cKDTree(points).query(points, k=2)
+        return np.mean(d[:, 1])
+    except ImportError:
+        p = np.asarray(points, np.float64)
+        best = np.empty(len(p))
+        for i0 in range(0, len(p), 1024):   # blocked brute force
+            d2 = ((p[i0:i0 + 1024, None, :] - p[None, :, :]) ** 2).sum(-1)
+            d2[np.arange(d2.shape[0]), np.arange(i0, i0 + d2.shape[0])] = np.inf
+            best[i0:i0 + 1024] = np.sqrt(d2.min(axis=1))
+        return np.mean(best)

@@ -150,3 +150,73 @@ def test_point_list_conversions():
         N.points_to_array([(1.0, 2.0), (3.0, 4.0, 5.0), (6.0,), (7.0, 8.0)])   # 2n values in all, but not n pairs
     with pytest.raises((TypeError, ValueError)):
         N.points_to_array([(1.0, "a"), (2.0, 3.0)])
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree exists in the build container only")
+def test_public_api_surface_matches_the_reference():
+    """Every public method of the reference's hot-path classes exists here with the same leading parameter names, and the
+    host-side helpers (Config, point-cloud metrics, visualize_laser_depth) give the reference's own results."""
+    import contextlib
+    import importlib
+    import inspect
+    import io
+    import sys
+    import laser_3d_reconstruction_b200 as l3d
+    from laser_3d_reconstruction_b200.camera import SingleUSBStereoCameraManager
+    from laser_3d_reconstruction_b200.utils import PointCloudProcessor
+    sys.path.insert(0, REFERENCE)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("config", "core", "camera", "utils")}
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            pairs = [("core.laser_extractor", "SimpleLaserExtractor", l3d.SimpleLaserExtractor),
+                     ("core.laser_extractor", "FastStegerExtractor", l3d.FastStegerExtractor),
+                     ("core.reconstruction", "Reconstructor", l3d.Reconstructor),
+                     ("improved_steger", "ImprovedStegerExtractor", l3d.ImprovedStegerExtractor),
+                     ("improved_steger", "HybridLaserExtractor", l3d.HybridLaserExtractor),
+                     ("improved_reconstruction", "ImprovedLaserReconstructor", l3d.ImprovedLaserReconstructor),
+                     ("camera.single_usb_stereo_camera", "SingleUSBStereoCameraManager", SingleUSBStereoCameraManager),
+                     ("utils.point_cloud", "PointCloudProcessor", PointCloudProcessor),
+                     ("config", "Config", l3d.Config)]
+            for mod, name, mine in pairs:
+                ref = getattr(importlib.import_module(mod), name)
+                for k, v in inspect.getmembers(ref, predicate=lambda f: inspect.isfunction(f) or inspect.ismethod(f)):
+                    if k.startswith("_") and k != "__init__":
+                        continue
+                    assert hasattr(mine, k), "%s.%s missing" % (name, k)
+                    want = list(inspect.signature(v).parameters)
+                    got = list(inspect.signature(getattr(mine, k)).parameters)
+                    assert got[:len(want)] == want, (name, k, want, got)
+            ref_ir = importlib.import_module("improved_reconstruction")
+            for fn in ("fix_roi_alignment", "visualize_laser_depth"):
+                assert hasattr(ref_ir, fn) and hasattr(l3d, fn)
+            # Config: same constants (USE_CUDA is the one deliberate difference)
+            RefConfig = importlib.import_module("config").Config
+            for k in dir(RefConfig):
+                if k.isupper() and k != "USE_CUDA":
+                    assert np.array_equal(getattr(RefConfig, k), getattr(l3d.Config, k)), k
+            # point-cloud metrics and the depth visualisation against the reference's own code
+            rng = np.random.default_rng(5)
+            cloud = rng.normal(size=(400, 3)) * [0.2, 0.1, 0.05] + [0, 0, 1]
+            want = importlib.import_module("utils.point_cloud").PointCloudProcessor().compute_point_cloud_metrics(cloud)
+            got = PointCloudProcessor(verbose=False).compute_point_cloud_metrics(cloud)
+            assert set(got) == set(want)
+            for k in want:
+                assert np.allclose(got[k], want[k], rtol=1e-12, atol=0), k
+            empty = PointCloudProcessor(verbose=False).compute_point_cloud_metrics(np.empty((0, 3)))
+            assert empty == {'num_points': 0, 'bbox': None, 'center': None, 'dimensions': None}
+            img = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)
+            depth = (rng.random((60, 80)) * 6).astype(np.float32)
+            depth[rng.random((60, 80)) < 0.3] = 0
+            pts = [(float(rng.uniform(-3, 83)), float(rng.uniform(-3, 63))) for _ in range(150)]
+            a = l3d.visualize_laser_depth(img, pts, depth, 5.0)
+            b = ref_ir.visualize_laser_depth(img, pts, depth, 5.0)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    finally:
+        sys.path.remove(REFERENCE)
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("config", "core", "camera", "utils", "improved_steger", "improved_reconstruction"):
+                sys.modules.pop(k, None)
+        sys.modules.update(saved)
