@@ -203,6 +203,41 @@ class LaserReconstructionSystem:
         self._say(f"✓ 点云已保存: {filepath}")
         return True
 
+    def run_realtime(self, duration=None, max_frames=None):
+        """main.py:235-343 without the windows: the capture -> process_frame loop until `duration` seconds have passed,
+        `max_frames` frames have been processed (an addition: a server has no key to press) or Ctrl-C; the accumulated
+        cloud is auto-saved every AUTO_SAVE_INTERVAL seconds, and saved once more at the end, as the reference does.
+        The reference's OpenCV windows and key handling are a GUI and stay out.  -> frames processed"""
+        import time
+        cfg = self.config
+        self.start_time = time.time()
+        last_save = time.time()
+        try:
+            while True:
+                if duration and (time.time() - self.start_time) > duration:
+                    self._say(f"\n达到设定时长 {duration} 秒")
+                    break
+                if max_frames is not None and self.frame_count >= max_frames:
+                    break
+                color_image, depth_image, laser_points = self.process_frame()
+                if color_image is None:
+                    continue
+                if time.time() - last_save > cfg.AUTO_SAVE_INTERVAL and len(self.point_cloud) >= cfg.MIN_POINT_CLOUD_SIZE:
+                    self._say("\n自动保存点云...")
+                    self.save_point_cloud()
+                    last_save = time.time()
+        except KeyboardInterrupt:
+            self._say("\n检测到键盘中断")
+        finally:
+            self.stop()
+            if len(self.point_cloud) >= cfg.MIN_POINT_CLOUD_SIZE:
+                self._say("\n保存最终点云...")
+                self.save_point_cloud("final_" + time.strftime("%Y%m%d_%H%M%S") + f".{cfg.SAVE_FORMAT}")
+            elapsed = max(time.time() - self.start_time, 1e-9)
+            self._say(f"\n重建完成:\n  总帧数: {self.frame_count}\n  总时长: {elapsed:.1f} 秒\n"
+                      f"  平均FPS: {self.frame_count / elapsed:.1f}\n  点云大小: {len(self.point_cloud)} 点")
+        return self.frame_count
+
     def stop(self):
         if self._pipe is not None:
             self._pipe.close()

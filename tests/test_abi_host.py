@@ -179,7 +179,7 @@ def test_public_api_surface_matches_the_reference():
                      ("improved_reconstruction", "ImprovedLaserReconstructor", l3d.ImprovedLaserReconstructor),
                      ("camera.single_usb_stereo_camera", "SingleUSBStereoCameraManager", SingleUSBStereoCameraManager),
                      ("utils.point_cloud", "PointCloudProcessor", PointCloudProcessor),
-                     ("config", "Config", l3d.Config)]
+                     ("config", "Config", l3d.Config), ("main", "LaserReconstructionSystem", l3d.LaserReconstructionSystem)]
             for mod, name, mine in pairs:
                 ref = getattr(importlib.import_module(mod), name)
                 for k, v in inspect.getmembers(ref, predicate=lambda f: inspect.isfunction(f) or inspect.ismethod(f)):
@@ -217,6 +217,66 @@ def test_public_api_surface_matches_the_reference():
     finally:
         sys.path.remove(REFERENCE)
         for k in list(sys.modules):
-            if k.split(".")[0] in ("config", "core", "camera", "utils", "improved_steger", "improved_reconstruction"):
+            if k.split(".")[0] in ("config", "core", "camera", "utils", "improved_steger", "improved_reconstruction", "main"):
                 sys.modules.pop(k, None)
         sys.modules.update(saved)
+
+
+def test_system_run_realtime_headless(tmp_path):
+    """LaserReconstructionSystem.run_realtime (main.py:235-343 without the windows): the loop, the dropped frames, the
+    auto-save and the final save, with stand-ins for the camera and the GPU stages (host logic only)."""
+    from laser_3d_reconstruction_b200.system import LaserReconstructionSystem
+
+    class Cam:
+        def __init__(self):
+            self.n, self.stopped = 0, False
+
+        def get_frames(self):
+            self.n += 1
+            if self.n % 3 == 0:
+                return None, None   # a dropped capture
+            return np.zeros((4, 6, 3), np.uint8), np.ones((4, 6), np.float32)
+
+        def stop(self):
+            self.stopped = True
+
+    class Ext:
+        def extract_centerline(self, img):
+            return [(1.0, 1.0), (2.0, 2.0)]
+
+    class Rec:
+        def reconstruct_from_depth(self, pts, depth):
+            return np.array([[0.0, 0.0, 1.0], [np.nan, 0.0, 1.0], [0.1, 0.0, 1.0]])
+
+    saved = []
+
+    class Proc:
+        def voxel_downsample(self, p, voxel_size):
+            return p
+
+        def statistical_outlier_removal(self, p, nb_neighbors, std_ratio):
+            return p
+
+        def save_ply(self, p, path):
+            saved.append((len(p), os.path.basename(path)))
+
+    class Cfg(l3d_Config()):
+        OUTPUT_DIR = str(tmp_path / "out")
+        MIN_POINT_CLOUD_SIZE = 4
+        AUTO_SAVE_INTERVAL = 0.0
+
+    s = LaserReconstructionSystem(Cfg(), verbose=False)
+    s.camera, s.laser_extractor, s.reconstructor, s.point_cloud_processor = Cam(), Ext(), Rec(), Proc()
+    assert s.run_realtime(max_frames=5) == 5
+    assert s.camera.stopped and s.camera.n == 7          # 5 processed + 2 dropped captures
+    assert len(s.point_cloud) == 10                       # two finite points per frame, the NaN row filtered (main.py:181-184)
+    assert saved and saved[-1][1].startswith("final_") and saved[-1][0] == 10
+    assert any(not name.startswith("final_") for _, name in saved)   # the auto-save ran inside the loop
+    s2 = LaserReconstructionSystem(Cfg(), verbose=False)
+    s2.camera, s2.laser_extractor, s2.reconstructor, s2.point_cloud_processor = Cam(), Ext(), Rec(), Proc()
+    assert s2.run_realtime(duration=0.05) > 0 and s2.camera.stopped
+
+
+def l3d_Config():
+    from laser_3d_reconstruction_b200.config import Config
+    return Config
