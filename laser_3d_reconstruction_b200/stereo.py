@@ -82,11 +82,47 @@ class StereoBM:
     def params(self):
         return N.BmParams(**self._p)
 
+    # cv2.StereoBM's remaining accessors.  What the kernels do not implement is refused when it is asked for, not ignored.
+    _pre_filter_size, _smaller_block_size, _roi1, _roi2 = 9, 0, (0, 0, 0, 0), (0, 0, 0, 0)
+
+    def getPreFilterType(self):
+        return 1  # cv2.StereoBM_PREFILTER_XSOBEL, OpenCV's default
+
+    def setPreFilterType(self, v):
+        if int(v) != 1:
+            raise ValueError("StereoBM: only PREFILTER_XSOBEL (1) is implemented")
+
+    def getPreFilterSize(self):
+        return self._pre_filter_size
+
+    def setPreFilterSize(self, v):   # the window of PREFILTER_NORMALIZED_RESPONSE; XSOBEL does not use it
+        self._pre_filter_size = int(v)
+
+    def getSmallerBlockSize(self):
+        return self._smaller_block_size
+
+    def setSmallerBlockSize(self, v):   # stored by OpenCV, read by nothing
+        self._smaller_block_size = int(v)
+
+    def getROI1(self):
+        return self._roi1
+
+    def setROI1(self, r):
+        self._roi1 = tuple(int(v) for v in r)
+
+    def getROI2(self):
+        return self._roi2
+
+    def setROI2(self, r):
+        self._roi2 = tuple(int(v) for v in r)
+
     def compute(self, left, right):
         """left/right: single-channel uint8 HxW -> int16 HxW disparity x16, invalid = (minD-1)*16."""
         left, right = np.asarray(left), np.asarray(right)
         if left.dtype != np.uint8 or right.dtype != np.uint8:
             raise TypeError("StereoBM.compute expects uint8 images")
+        if (self._roi1[2] > 0 and self._roi1[3] > 0) or (self._roi2[2] > 0 and self._roi2[3] > 0):
+            raise ValueError("StereoBM: valid-disparity rectangles from ROI1 / ROI2 are not implemented (leave them empty)")
         return N.default_context(self.device).bm_compute(self.params(), left, right)
 
 

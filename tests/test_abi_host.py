@@ -280,3 +280,28 @@ def test_system_run_realtime_headless(tmp_path):
 def l3d_Config():
     from laser_3d_reconstruction_b200.config import Config
     return Config
+
+
+def test_matcher_accessors_match_cv2_defaults():
+    """Every getter cv2.StereoSGBM / cv2.StereoBM exposes exists on the look-alikes and starts at OpenCV's default; setters
+    round-trip; what the kernels do not implement is refused."""
+    import cv2
+    for ref, mine in ((cv2.StereoSGBM_create(), stereo.StereoSGBM_create()), (cv2.StereoBM_create(), stereo.StereoBM_create()),
+                      (cv2.StereoSGBM_create(minDisparity=3, numDisparities=96, blockSize=7, P1=11, P2=99, mode=1),
+                       stereo.StereoSGBM_create(minDisparity=3, numDisparities=96, blockSize=7, P1=11, P2=99, mode=1)),
+                      (cv2.StereoBM_create(numDisparities=48, blockSize=9), stereo.StereoBM_create(numDisparities=48, blockSize=9))):
+        for name in dir(ref):
+            if name.startswith("get") and name != "getDefaultName":
+                assert hasattr(mine, name), name
+                want, got = getattr(ref, name)(), getattr(mine, name)()
+                assert tuple(np.ravel(want)) == tuple(np.ravel(got)), (type(ref).__name__, name, want, got)
+                setter = "set" + name[3:]
+                assert hasattr(mine, setter), setter
+    bm = stereo.StereoBM_create()
+    bm.setSmallerBlockSize(5); bm.setPreFilterSize(11); bm.setPreFilterType(1)
+    assert (bm.getSmallerBlockSize(), bm.getPreFilterSize(), bm.getPreFilterType()) == (5, 11, 1)
+    with pytest.raises(ValueError):
+        bm.setPreFilterType(0)
+    bm.setROI1((0, 0, 10, 10))
+    with pytest.raises(ValueError):
+        bm.compute(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8))
