@@ -165,6 +165,7 @@ class DisparityWLSFilter:
         self._sigma = 1.0
         self._lrc = 24
         self._conf = None
+        self._roi = (0, 0, 0, 0)
 
     def setLambda(self, v):
         self._lambda = float(v)
@@ -193,6 +194,12 @@ class DisparityWLSFilter:
     def getConfidenceMap(self):
         return self._conf
 
+    def getROI(self):
+        """(x, y, w, h) of the region the last `filter` call processed: the columns from minDisparity + numDisparities on
+        (the restatement's reading of ximgproc's valid-disparity ROI for a StereoSGBM, oracle/csrc/orc_wls.c:145); (0, 0, 0, 0)
+        before the first call."""
+        return self._roi
+
     def params(self):
         return N.WlsParams(self._lambda, self._sigma, self._min_disp, self._num_disp, self._dd_radius, self._lrc)
 
@@ -206,6 +213,9 @@ class DisparityWLSFilter:
         out, conf = N.default_context(self.device).wls_filter(self.params(), disparity_map_left, disparity_map_right,
                                                               guide, want_conf=True)
         self._conf = conf
+        H, W = np.asarray(disparity_map_left).shape[:2]
+        x0 = min(max(self._min_disp + self._num_disp, 0), W)
+        self._roi = (x0, 0, W - x0, H)
         return out
 
 
