@@ -190,12 +190,12 @@ def run_reference(args, rank):
     sample = "%d frames/step (one per worker), %d steps" % (nfr, args.steps)
     cfg = bench_config(args.frames or CFG["frames"], min(args.distinct, args.frames or CFG["frames"]),
                        args.lanes or CFG["lanes"], 1)
-    cfg["reference_frames_per_step"] = nfr
     out = {
         "impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "gde_per_s": fps * W * H * D / 1e9,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": cfg,
+        "config": cfg,   # exactly the GPU arm's object: the sample the CPU arm times per step is stated below, not here
+        "reference_frames_per_step": nfr,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port", "sample": sample,
                          "note": "cv2 %s StereoSGBM/remap/cvtColor (the binary the reference calls) driven by "
                                  "oracle/ref_ops.py; WLS = oracle C restatement (cv2.ximgproc absent); Steger = "
