@@ -24,17 +24,24 @@ namespace l3d {
 
 class CopyPool {
   public:
-    explicit CopyPool(int nthreads) : workers_(nthreads > 1 ? nthreads - 1 : 0), pid_(getpid()) {}
+    explicit CopyPool(int nthreads) : workers_(nthreads > 1 ? nthreads - 1 : 0), pid_(getpid()), sync_(new Sync) {}
     ~CopyPool() {
-        if (th_.empty()) return;
-        if (getpid() != pid_) {   // a fork()ed child: the worker threads do not exist here, nothing to join
+        if (getpid() != pid_) {
+            // a fork()ed child: the worker threads do not exist here.  Nothing to join, and the mutex / condition variable
+            // must not be destroyed either (their copied state still counts the parent's waiters: pthread_cond_destroy
+            // would wait for them forever) -- both are left behind.
             new std::vector<std::thread>(std::move(th_));
             return;
         }
-        { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
-        cv_.notify_all();
-        for (auto& t : th_) t.join();
+        if (!th_.empty()) {
+            { std::lock_guard<std::mutex> g(sync_->m); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
+            sync_->cv.notify_all();
+            for (auto& t : th_) t.join();
+        }
+        delete sync_;
     }
+    CopyPool(const CopyPool&) = delete;
+    CopyPool& operator=(const CopyPool&) = delete;
     // memcpy split over the calling thread and the workers; returns when every part is done
     void copy(void* dst, const void* src, size_t bytes) {
         if (workers_ == 0 || bytes < kParallelMin || getpid() != pid_) { memcpy(dst, src, bytes); return; }
@@ -44,8 +51,8 @@ class CopyPool {
         dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
         remaining_.store(workers_, std::memory_order_relaxed);
         gen_.fetch_add(1, std::memory_order_release);
-        { std::lock_guard<std::mutex> g(m_); }  // a worker between its predicate check and its wait sees the new gen
-        cv_.notify_all();
+        { std::lock_guard<std::mutex> g(sync_->m); }  // a worker between its predicate check and its wait sees the new gen
+        sync_->cv.notify_all();
         do_part(0);
         while (remaining_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
     }
@@ -64,8 +71,8 @@ class CopyPool {
             // copies come in bursts (two views up, three images down): poll briefly before sleeping
             for (int spin = 0; spin < 300 && gen_.load(std::memory_order_acquire) == seen; spin++) std::this_thread::yield();
             if (gen_.load(std::memory_order_acquire) == seen) {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                std::unique_lock<std::mutex> lk(sync_->m);
+                sync_->cv.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
             }
             seen = gen_.load(std::memory_order_acquire);
             if (stop_) return;
@@ -75,9 +82,9 @@ class CopyPool {
     }
     const int workers_;
     const pid_t pid_;   // the process that owns the worker threads (they do not survive a fork)
+    struct Sync { std::mutex m; std::condition_variable cv; };
+    Sync* const sync_;   // on the heap: a forked child leaves it alone (see the destructor)
     std::vector<std::thread> th_;
-    std::mutex m_;
-    std::condition_variable cv_;
     std::atomic<unsigned long long> gen_{0};
     std::atomic<int> remaining_{0};
     bool stop_ = false;

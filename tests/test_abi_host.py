@@ -305,3 +305,29 @@ def test_matcher_accessors_match_cv2_defaults():
     bm.setROI1((0, 0, 10, 10))
     with pytest.raises(ValueError):
         bm.compute(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8))
+
+
+@pytest.mark.parametrize("sanitize", [False, True])
+def test_copy_pool_host_only(tmp_path, sanitize):
+    """csrc/hostcopy.cuh's thread pool on the host alone (tests/csrc/copypool_test.cpp): exact copies for every size class
+    and thread count, bursts and idle gaps, clean shutdown, a forked child that copies and tears the pool down without
+    hanging; once more under ThreadSanitizer where g++ has it (no data race reports)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    exe = str(tmp_path / "copypool_test")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-I", cuda_inc, "-I", os.path.join(root, "laser_3d_reconstruction_b200", "csrc"),
+           os.path.join(root, "tests", "csrc", "copypool_test.cpp"), "-o", exe]
+    if sanitize:
+        cmd.insert(1, "-fsanitize=thread")
+    b = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    if b.returncode != 0:
+        if sanitize or not os.path.isdir(cuda_inc):
+            pytest.skip("toolchain cannot build this variant: " + b.stderr[-200:])
+        raise AssertionError(b.stderr)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "copypool ok" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-600:])
+    assert "ThreadSanitizer" not in r.stderr
