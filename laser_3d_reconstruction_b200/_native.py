@@ -421,6 +421,14 @@ def points_to_list(pts):
     return list(zip(a[:, 0].tolist(), a[:, 1].tolist()))
 
 
+def points_to_list_f32(pts):
+    """(n, 2) float32 array -> list of (np.float32, np.float32) tuples, FastStegerExtractor's return type in the reference
+    (core/laser_extractor.py:256 appends the float32 scalars as they are); zip of the two columns, ~9x faster than
+    unpacking row by row."""
+    a = np.asarray(pts, np.float32).reshape(-1, 2)
+    return list(zip(a[:, 0], a[:, 1]))
+
+
 def points_to_array(points):
     """list of (u, v) pairs (or anything array-like) -> (n, 2) float64.  A list of pairs is flattened by
     `np.fromiter` over one chained iterator (about 2.5x faster than np.asarray on 4600 tuples)."""

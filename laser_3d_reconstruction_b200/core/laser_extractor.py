@@ -84,7 +84,7 @@ class FastStegerExtractor:
             roi = (x0, y0, w, h)
         p = _steger_params(N.STEGER_FAST, self.sigma, self.brightness_threshold, roi=roi)
         pts = N.default_context(self.device).steger_extract(p, image)
-        return [(x, y) for x, y in pts]  # np.float32 pairs, like the reference
+        return N.points_to_list_f32(pts)  # np.float32 pairs, like the reference
 
     def extract_batch(self, images: List[np.ndarray]) -> List[List[Tuple[float, float]]]:
         """core/laser_extractor.py:279-285."""

@@ -135,6 +135,9 @@ def test_point_list_conversions():
     lst = N.points_to_list(a32)
     assert lst == list(map(tuple, a64.tolist())) and type(lst[0]) is tuple and type(lst[0][0]) is float
     assert N.points_to_list(np.empty((0, 2), np.float32)) == []
+    l32 = N.points_to_list_f32(a32)
+    assert l32 == [(x, y) for x, y in a32] and type(l32[0]) is tuple and type(l32[0][0]) is np.float32
+    assert N.points_to_list_f32(np.empty((0, 2), np.float32)) == [] and N.points_to_list_f32(a32[:1]) == [(a32[0, 0], a32[0, 1])]
     forms = [lst, [list(p) for p in lst], tuple(lst), [(x, y) for x, y in a32], a32, a64, a64.tolist(), a64[::2]]
     for f in forms:
         got = N.points_to_array(f)
