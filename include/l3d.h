@@ -24,7 +24,7 @@ typedef struct l3d_ctx l3d_ctx;
 enum { L3D_OK = 0, L3D_ERR_ARG = -1, L3D_ERR_CUDA = -2, L3D_ERR_UNSUPPORTED = -3, L3D_ERR_STATE = -4 };
 enum { L3D_MODE_SGBM = 0, L3D_MODE_HH = 1, L3D_MODE_SGBM_3WAY = 2, L3D_MODE_HH4 = 3 }; /* cv2.STEREO_SGBM_MODE_* */
 
-/* -------- context ------------------------------------------------------------------------ */
+/* -------- context (plumbing: the reference has no counterpart; it is what `import cv2` gives the Python process) -------- */
 int l3d_ctx_create(int device, l3d_ctx** out);
 void l3d_ctx_destroy(l3d_ctx* ctx);
 const char* l3d_last_error(l3d_ctx* ctx); /* ctx may be NULL: last create error */
@@ -109,7 +109,8 @@ int l3d_sgbm_volume_rows(const l3d_sgbm_params* p, int W, int H);
  * synthetic width1 x H x D volumes `reps` times and returns the mean CUDA-event time of one launch. */
 int l3d_sgbm_vgroup_time(l3d_ctx* ctx, int width1, int H, int D, int P1, int P2, int njobs, int dir, int reps,
                          float* ms_per_launch);
-/* cv2.medianBlur(disp, 3) and cv2.filterSpeckles as applied inside StereoSGBM.compute */
+/* cv2.medianBlur(disp, 3) and cv2.filterSpeckles as applied inside StereoSGBM.compute
+ * (camera/single_usb_stereo_camera.py:324-325 with speckleWindowSize / speckleRange of :266-267) */
 int l3d_median3_s16(l3d_ctx* ctx, const int16_t* src, int W, int H, int16_t* dst);
 int l3d_filter_speckles(l3d_ctx* ctx, int16_t* img, int W, int H, int newVal, int maxSize, int maxDiff);
 
@@ -214,7 +215,9 @@ int l3d_reconstruct(l3d_ctx* ctx, const l3d_recon_params* p, const double* xy, i
 int l3d_laser_depth_map(l3d_ctx* ctx, const double* xy, int n, const float* disp, int W, int H, double fx,
                         double baseline, float* out);
 
-/* -------- batched, device-resident frame pipeline (bench + LaserReconstructionSystem.process_frame) */
+/* -------- batched, device-resident frame pipeline: LaserReconstructionSystem.process_frame (main.py:164-189 = get_frames,
+ * camera/single_usb_stereo_camera.py:294-359, + extract_centerline + reconstruct_from_depth) for many frames per call;
+ * what bench.py times.  The launch-count / timing / packing calls below are measurement and sharding plumbing. */
 typedef struct l3d_pipeline l3d_pipeline;
 typedef struct {
     int W, H;                 /* per-eye size */
@@ -268,7 +271,7 @@ float l3d_pipeline_last_ms(l3d_pipeline* p);
  * launching stream; kernel_time returns their summed duration and count for the last run. */
 int l3d_pipeline_set_timing(l3d_pipeline* p, int on);
 int l3d_pipeline_kernel_time(l3d_pipeline* p, const char* which, float* ms, int* launches);
-/* pinned host allocation helpers (for the e2e path) */
+/* pinned host allocation helpers (for the e2e path; plumbing, no reference counterpart) */
 void* l3d_host_alloc(long bytes);
 void l3d_host_free(void* p);
 /* raw device helpers for bench.py/tests (so they need no torch to stage data) */
