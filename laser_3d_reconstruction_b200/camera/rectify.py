@@ -12,7 +12,7 @@ rectification maps built from the result are unchanged.  tests/test_oracle_cv2.p
 (==) and maps (==) against cv2 on the shipped calibration and on synthetic rigs.
 
 Differential fuzzing against cv2.stereoRectify over random rigs (4 / 5 / 8 / 12 / 14 distortion coefficients, horizontal and
-vertical baselines, every alpha; tools/fuzz_rectify.py, 2 400 rigs) pinned three more points: the OUTER rectangle spans the
+vertical baselines, every alpha; tests/fuzz/fuzz_rectify.py, 2 400 rigs) pinned three more points: the OUTER rectangle spans the
 border points of the 9 x 9 grid only; points the inverse distortion model turns into NaN are skipped by OpenCV's MIN / MAX
 macros (and a rig that is NaN at the image corners yields NaN matrices and empty ROIs, as in cv2); coefficients 13 / 14 are
 the tilted-sensor model.  What cannot be pinned: at alpha = 0 one ROI edge lies exactly on the image border, so

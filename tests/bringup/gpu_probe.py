@@ -1,5 +1,5 @@
 """GPU bring-up probe: every stage against the oracle / cv2 with verbose mismatch diagnostics, then
-a first timing of the c3 pipeline.  Run on the GPU box:  python tools/gpu_probe.py [quick]
+a first timing of the c3 pipeline.  Run on the GPU box:  python tests/bringup/gpu_probe.py [quick]
 (not a pytest; tests/ holds the real parity suite)."""
 import ctypes as C
 import os
@@ -10,7 +10,7 @@ import traceback
 import cv2
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from laser_3d_reconstruction_b200 import _native as N  # noqa: E402
 from laser_3d_reconstruction_b200 import synth  # noqa: E402

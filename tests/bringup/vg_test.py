@@ -2,7 +2,7 @@
 import os, sys, time
 os.environ["L3D_VGROUP"] = "1"
 import cv2, numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from laser_3d_reconstruction_b200 import _native as N, synth
 from oracle import cref

@@ -1,13 +1,13 @@
 """Differential fuzzing of the C restatement (oracle/csrc via oracle/cref.py) against the installed cv2 binary over random
 sizes and parameters: remap, median / speckle filters, reprojectImageTo3D depth, Simple-extractor masks (inRange + CLOSE +
-OPEN + contour fill), Gaussian / Sobel float filters.  SGBM: tools/fuzz_oracle.py; stereoRectify: tools/fuzz_rectify.py.
+OPEN + contour fill), Gaussian / Sobel float filters.  SGBM: tests/fuzz/fuzz_oracle.py; stereoRectify: tests/fuzz/fuzz_rectify.py.
 
-    python tools/fuzz_cref.py [seed] [iterations]
+    python tests/fuzz/fuzz_cref.py [seed] [iterations]
 """
 import os, sys
 import cv2
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import cref
 

@@ -3,12 +3,12 @@ installed cv2 binary over random parameter sets (disparity range and sign, block
 disp12MaxDiff, speckle filter, all four modes) and random small images (textured pairs, quantised pairs with cost ties, pure
 noise).  This is how the shifted stripe rows of SGBM_3WAY on images of a few rows were found.
 
-    python tools/fuzz_oracle.py [seed] [iterations] [sgbm|bm]
+    python tests/fuzz/fuzz_oracle.py [seed] [iterations] [sgbm|bm]
 """
 import os, sys
 import cv2
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import cref
 from laser_3d_reconstruction_b200 import synth

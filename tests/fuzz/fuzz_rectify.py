@@ -1,5 +1,12 @@
-import sys, numpy as np, cv2
-sys.path.insert(0,'/root/repo')
+"""Differential fuzzing of camera/rectify.py (the host restatement of cv2.stereoRectify) against cv2 over random rigs: 4 / 5 / 8 /
+12 / 14 distortion coefficients, both baseline directions, every alpha, with and without CALIB_ZERO_DISPARITY.
+
+    python tests/fuzz/fuzz_rectify.py <seed> <iterations>
+"""
+import os, sys
+import cv2
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from laser_3d_reconstruction_b200.camera.rectify import stereo_rectify
 rng=np.random.default_rng(int(sys.argv[1])); n=int(sys.argv[2])
 worst=0; bad=0

@@ -2,12 +2,12 @@
 classes imported from /root/reference (build container only): random frames with blobs, stripes, saturated patches and noise
 through every extractor, random points / depth / disparity maps through both reconstructors.
 
-    python tools/fuzz_ref_ops.py [seed] [iterations]
+    python tests/fuzz/fuzz_ref_ops.py [seed] [iterations]
 """
 import contextlib, io, os, sys
 import cv2
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, "/root/reference")
 from oracle import ref_ops
 

@@ -58,6 +58,11 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "liborc" not in txt, f
+    # ... and nothing under tools/ (measurement helpers) does either: whatever checks against the oracle lives in tests/
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", f), encoding="utf-8").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) and "liborc" not in txt, f
 
 
 def test_wls_creation_mutates_left_matcher():

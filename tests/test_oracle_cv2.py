@@ -85,7 +85,7 @@ def test_sgbm_c1_and_saturation(mode):
 def test_sgbm_3way_tiny_images(bs, H):
     """SGBM_3WAY on images of a few rows: where a stripe's start is clamped at the image top (ceil(H / 4) < blockSize / 2 + 1
     + ceil(0.1 ceil(H / 4))) OpenCV's stripe buffers and its final assembly do not meet and the output rows of that stripe
-    are the results of rows further down (found by differential fuzzing: tools/fuzz_oracle.py)."""
+    are the results of rows further down (found by differential fuzzing: tests/fuzz/fuzz_oracle.py)."""
     for D, W, seed in ((48, 194, 5), (16, 90, 9)):
         lg, rg = gray_pair(W, H, D, seed)
         for (uq, d12, sw) in ((0, 5, 200), (10, 1, 0)):
@@ -377,7 +377,7 @@ def test_stereo_rectify_random_rigs_vs_cv2():
 
 
 def test_sgbm_random_parameter_sets_vs_cv2():
-    """A fixed-seed slice of tools/fuzz_oracle.py: random StereoSGBM parameter sets (all modes, both disparity signs, odd
+    """A fixed-seed slice of tests/fuzz/fuzz_oracle.py: random StereoSGBM parameter sets (all modes, both disparity signs, odd
     penalties, preFilterCap / uniqueness / disp12MaxDiff / speckle settings) on random small images, oracle == cv2."""
     rng = np.random.default_rng(2024)
     for it in range(24):
