@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# scripts, not test modules: the differential fuzzers and the verbose bring-up checkers are run by hand
+collect_ignore_glob = ["fuzz/*", "bringup/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
